@@ -1,0 +1,233 @@
+#include "driver.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "glf.h"
+#include "params.h"
+#include "pedigree.h"
+#include "vcf_writer.h"
+
+namespace pmh {
+
+namespace {
+
+int fatal(const std::string &msg) {  // core/Error.cpp:10-23
+  printf("\nFATAL ERROR - \n%s\n\n", msg.c_str());
+  return 1;
+}
+
+std::vector<std::string> split_ws(const std::string &line) {
+  std::vector<std::string> out;
+  std::istringstream in(line);
+  std::string t;
+  while (in >> t) out.push_back(t);
+  return out;
+}
+
+// .gif: "<index> <glf path>" per line (src/main.cpp:15-37)
+bool read_glf_index(const std::string &path, std::map<std::string, std::string> *m, std::string *err) {
+  std::ifstream f(path);
+  if (!f) { *err = path + " open failed"; return false; }
+  std::string line;
+  while (std::getline(f, line)) {
+    auto tok = split_ws(line);
+    if (tok.size() < 2) continue;
+    (*m)[tok[0]] = tok[1];
+  }
+  return true;
+}
+
+struct Counters {  // src/main.cpp:264-282
+  unsigned minTotalDepthFilter = 0, maxTotalDepthFilter = 0, minMapQualFilter = 0, minPSFilter = 0;
+  int refBaseCounts[5] = {0, 0, 0, 0, 0};
+  int homoRef = 0, transitions = 0, transversions = 0, tstvs1 = 0, tstvs2 = 0, tvs1tvs2 = 0, nocall = 0;
+  int totalEntryCnt = 0;
+};
+
+// Counter updates of main.cpp:341-553 from one status word (see pm_call_glf_sites).
+void count_site(Counters &c, const pm_site_hdr &h, uint16_t st, const Options &opt) {
+  int code = st & 0xf, maxidx = ((st >> 4) & 0xf) - 1;
+  bool nocall = (st >> 8) & 1;
+  if (code == PM_SITE_BAD_REF) return;
+  c.refBaseCounts[h.ref_base]++;
+  switch (code) {
+    case PM_SITE_MIN_DEPTH: c.minTotalDepthFilter++; return;
+    case PM_SITE_MAX_DEPTH: c.maxTotalDepthFilter++; return;
+    case PM_SITE_MIN_PS: c.minPSFilter++; return;
+    case PM_SITE_MIN_MAPQ: c.minMapQualFilter++; return;
+    case PM_SITE_QUICK_SKIP: return;
+  }
+  if (nocall) { c.nocall++; if (!opt.force_call && !opt.out_all_sites) return; }
+  switch (maxidx) {
+    case 0: c.homoRef++; break;
+    case 1: c.transitions++; break;
+    case 2: case 3: c.transversions++; break;
+    case 4: c.tstvs1++; break;
+    case 5: c.tstvs2++; break;
+    case 6: c.tvs1tvs2++; break;
+  }
+}
+
+}  // namespace
+
+int run_cli(int argc, char **argv, const Engine &engine) {
+  Options opt;
+  std::string err;
+  bool parsed = opt.parse(argc, argv, &err);
+  opt.print_status();
+  if (!parsed) return fatal(err);
+  if (!opt.vcf_in.empty())
+    return fatal("--in_vcf (VCF input mode) is not implemented by this build yet");  // SURVEY.md §8, row "VCF mode"
+
+  std::map<std::string, std::string> glf_map;
+  if (!read_glf_index(opt.glf_index_file, &glf_map, &err)) return fatal(err);
+
+  Pedigree ped;
+  try {
+    ped.load(opt.dat_file, opt.ped_file);
+  } catch (const std::exception &e) {
+    return fatal(e.what());
+  }
+  FILE *vcf = fopen(opt.vcf_out.c_str(), "w");
+  if (!vcf) return fatal("vcfOutFile can not be opened for output!");
+
+  // PedigreeGLF::SetPedGLF, src/PedigreeGLF.cpp:117-163
+  std::vector<std::string> paths;
+  for (int idx : ped.columns()) {
+    const Person &p = ped.persons[idx];
+    if (p.glf_index == 0) { paths.emplace_back(); continue; }
+    auto it = glf_map.find(std::to_string(p.glf_index));
+    if (it == glf_map.end()) {
+      printf("\nWARNING - \nNo entry found for the glf with the key [%d]\n\n", p.glf_index);
+      paths.emplace_back();
+      continue;
+    }
+    paths.push_back(it->second);
+  }
+  GlfSet glf;
+  if (!glf.open(paths, &err)) return fatal(err);
+
+  std::set<std::string> positions;  // --pos: "chr:pos" (src/main.cpp:39-55)
+  if (!opt.pos_file.empty()) {
+    std::ifstream f(opt.pos_file);
+    if (!f) return fatal("Open position file " + opt.pos_file + " failed!");
+    std::string line;
+    while (std::getline(f, line)) {
+      auto tok = split_ws(line);
+      if (tok.size() >= 2) positions.insert(tok[0] + ":" + tok[1]);
+    }
+  }
+  std::map<std::string, int> chrs;
+  {
+    std::stringstream ss(opt.chrs2process);
+    std::string c;
+    while (std::getline(ss, c, ',')) if (!c.empty()) chrs[c]++;
+  }
+
+  pm_params par;
+  opt.to_params(&par);
+  double lut[256];
+  pm_fill_lut(lut);
+  void *ctx = engine.create(ped.view(), &par, lut, opt.device);
+  if (!ctx) return fatal(std::string("engine '") + engine.name + "': " + engine.last_error());
+
+  const int np = ped.n_person();
+  size_t batch = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)1 << 16;
+  // keep a batch of packed input below ~256 MB
+  while (batch > 1024 && batch * (size_t)np * sizeof(pm_person_site) > ((size_t)256 << 20)) batch >>= 1;
+  std::vector<pm_site_hdr> hdr(batch);
+  std::vector<pm_person_site> ps(batch * (size_t)np);
+  std::vector<uint16_t> status(batch);
+  std::vector<pm_site_result> res(batch);
+  std::vector<pm_person_result> pres(batch * (size_t)np);
+
+  VcfWriter writer(vcf, opt, ped);
+  time_t t0;
+  time(&t0);
+  printf("Analysis started on %s\n", ctime(&t0));
+  size_t out_cnt = 0;
+  int processed_chrs = 0;
+  bool stop = false;
+  try {
+    while (!stop && glf.next_section()) {
+      if (!chrs.empty() && processed_chrs >= (int)chrs.size()) break;
+      const std::string label = glf.label();
+      pm_site_hdr h;
+      std::vector<pm_person_site> one((size_t)np);
+      if (!chrs.empty() && chrs.count(label) == 0) { while (glf.next_site(&h, one.data())) {} continue; }
+      uint8_t chr_class = label == opt.chrX ? PM_CHR_X : label == opt.chrY ? PM_CHR_Y : label == opt.chrMT ? PM_CHR_MT : PM_CHR_AUTO;
+      Counters cnt;
+      processed_chrs++;
+      time_t tc;
+      time(&tc);
+      bool more = true;
+      while (more && !stop) {
+        size_t n = 0;
+        while (n < batch) {
+          if (!glf.next_site(&hdr[n], &ps[n * (size_t)np])) { more = false; break; }
+          if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
+          hdr[n].chr_class = chr_class;
+          if (!positions.empty() && positions.count(label + ":" + std::to_string(hdr[n].pos + 1)) == 0) continue;
+          n++;
+        }
+        if (n == 0) break;
+        size_t n_res = 0;
+        int rc = engine.call_glf(ctx, hdr.data(), ps.data(), n, status.data(), res.data(), pres.data(), batch, &n_res);
+        if (rc != PM_OK) {
+          engine.destroy(ctx);
+          fclose(vcf);
+          return fatal(std::string("engine '") + engine.name + "': " + engine.last_error());
+        }
+        for (size_t s = 0; s < n; s++) count_site(cnt, hdr[s], status[s], opt);
+        for (size_t r = 0; r < n_res; r++) {
+          uint32_t s = res[r].site;
+          writer.write_site(label, hdr[s], res[r], &ps[(size_t)s * np], &pres[r * (size_t)np]);
+          out_cnt++;
+          if (opt.force_call && out_cnt >= positions.size()) { stop = true; break; }  // main.cpp:593
+        }
+      }
+      if (stop) break;
+      // summary block, src/main.cpp:596-621
+      int totalBases = 0;
+      for (int i = 0; i < 5; i++) totalBases += cnt.refBaseCounts[i];
+      int other = cnt.tstvs1 + cnt.tstvs2 + cnt.tvs1tvs2;
+      printf("Summary of reference -- %s\n", label.c_str());
+      printf("Total Entry Count: %9d\n", cnt.totalEntryCnt);
+      printf("Total Base Cout: %9d\n", totalBases);
+      printf("Non-Polymorphic Count: %9d\n", cnt.homoRef);
+      printf("Transition Count: %9d\n", cnt.transitions);
+      printf("Transversion Count: %9d\n", cnt.transversions);
+      printf("Other Polymorphism Count: %9d\n", other);
+      printf("Filter counts:\n");
+      printf("\tminMapQual %u\n", cnt.minMapQualFilter);
+      printf("\tminTotalDepth %u\n", cnt.minTotalDepthFilter);
+      printf("\tmaxTotalDepth %u\n", cnt.maxTotalDepthFilter);
+      printf("Hard to call: %9d\n", cnt.nocall);
+      printf("Skipped bases: %u\n", (unsigned)(cnt.totalEntryCnt - cnt.homoRef - cnt.transitions - cnt.transversions - other));
+      time_t t1;
+      time(&t1);
+      printf("Analysis ended on %s\n", ctime(&t1));
+      printf("Running time is %u seconds\n\n", (unsigned)(t1 - tc));
+      fflush(vcf);
+    }
+  } catch (const std::exception &e) {
+    engine.destroy(ctx);
+    fclose(vcf);
+    return fatal(e.what());
+  }
+  engine.destroy(ctx);
+  fclose(vcf);
+  return 0;
+}
+
+}  // namespace pmh

@@ -20,24 +20,23 @@ CU_SRC    := $(wildcard polymutt_b200/csrc/*.cu)
 CU_HDR    := $(wildcard polymutt_b200/csrc/*.cuh) $(wildcard polymutt_b200/csrc/*.h) include/polymutt_b200.h
 
 LIB := polymutt_b200/lib/libpolymutt_b200.so
-HOSTLIB := polymutt_b200/lib/libpolymutt_host.so
 CLI := polymutt_b200/bin/polymutt-b200
 ORACLE_LIB := oracle/_build/libpm_oracle.so
 ORACLE_CLI := oracle/_build/polymutt_oracle_cli
+TOOLS := polymutt_b200/bin/pm-tools
 
-.PHONY: all lib cli hostlib oracle ref clean
-all: lib hostlib cli oracle
+.PHONY: all lib cli tools oracle ref clean
+all: lib cli tools oracle
 
 lib: $(LIB)
 $(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC) polymutt_b200/csrc/host/host_error.h
 	@mkdir -p polymutt_b200/lib
 	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_SRC) $(HOST_LIB_SRC) -Ipolymutt_b200/csrc/host -lcudart 2> polymutt_b200/lib/ptxas.log || (cat polymutt_b200/lib/ptxas.log; exit 1)
 
-# host-only helpers (pedigree loader, GLF pack/unpack, VCF writers) for the Python tests and tools
-hostlib: $(HOSTLIB)
-$(HOSTLIB): $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h) include/polymutt_b200.h
-	@mkdir -p polymutt_b200/lib
-	$(HOSTCXX) $(CXXFLAGS) -shared -o $@ $(FRONT_SRC) $(HOST_LIB_SRC) -lz
+tools: $(TOOLS)
+$(TOOLS): polymutt_b200/csrc/tools/pm_tools.cpp $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h)
+	@mkdir -p polymutt_b200/bin
+	$(HOSTCXX) $(CXXFLAGS) -o $@ polymutt_b200/csrc/tools/pm_tools.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/pedigree.cpp $(HOST_LIB_SRC) -lz
 
 cli: $(CLI)
 $(CLI): $(LIB) $(FRONT_SRC) polymutt_b200/csrc/host/main.cpp $(wildcard polymutt_b200/csrc/host/*.h)

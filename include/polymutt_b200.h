@@ -161,7 +161,7 @@ typedef struct pm_site_result {
   double   refit_llk;        /* --denovo, polymorphic winner: maxlogL refitted without mutation (main.cpp:570) */
 } pm_site_result;
 
-/* Per-(emitted site, person) result: postProb[f][j][0..9], bestGenoIdx, GQ, dosage. 104 bytes.
+/* Per-(emitted site, person) result: postProb[f][j][0..9], bestGenoIdx, GQ, dosage. 96 bytes.
  * post[0..2] are (11, 12, 22) posteriors unless ten_state != 0, where post[0..9] follow the
  * ten-genotype order (kids and extended pedigrees under --denovo). */
 typedef struct pm_person_result {
@@ -208,6 +208,24 @@ int pm_sync(pm_ctx *ctx);
 /* Device time (ms, CUDA events on the ctx stream) and launch count of the calling kernels
  * in the most recent pm_call_*; used by bench.py for the roofline numbers. */
 int pm_last_timing(pm_ctx *ctx, float *ms_main_kernel, float *ms_total, int *n_launches);
+
+/* Device-side stopwatch on the ctx stream (CUDA events): pm_timer_start records an event, pm_timer_stop
+ * records a second one, waits for it and returns the elapsed milliseconds.  bench.py brackets its K
+ * timed steps with these so that the number is taken on the stream the kernels are launched on. */
+int pm_timer_start(pm_ctx *ctx);
+int pm_timer_stop(pm_ctx *ctx, float *ms);
+
+/* Work counters accumulated by the site kernels since the last pm_reset_counters: hypotheses set up
+ * (coefficient builds), objective evaluations (Brent steps incl. the bracket point), sites evaluated
+ * (passed the filters) — the inputs of the algorithmic flop count in DESIGN.md. */
+typedef struct pm_counters {
+  unsigned long long hypotheses;
+  unsigned long long evaluations;
+  unsigned long long sites_evaluated;
+  unsigned long long sites_emitted;
+} pm_counters;
+int pm_get_counters(pm_ctx *ctx, pm_counters *out);
+int pm_reset_counters(pm_ctx *ctx);
 
 /* Microbenchmarks used as roofline denominators: sustained DFMA throughput (FLOP/s) and
  * device copy bandwidth (B/s) measured on this ctx's device. */

@@ -1,0 +1,449 @@
+// pm_capi.cu — the C ABI (include/polymutt_b200.h) over the sm_100a kernels: context set-up
+// (pedigree -> device descriptors, host-computed tables), device scratch management, the host-buffer
+// and device-buffer calling entry points, timing and the roofline microbenchmarks.
+//
+// There is no CPU path here: every entry point that computes needs a CUDA device and fails with
+// PM_ECUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "host/host_error.h"
+#include "pm_device.cuh"
+#include "pm_kernels.h"
+
+using pmh::fail;
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) return fail(PM_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct pm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  pm_params par{};
+  int n_person = 0, n_fam = 0, n_units = 0, n_es = 0;
+  pm::LaunchPlan plan{};
+  // device descriptors
+  pm::DevRun *d_run = nullptr;
+  pm::DevFam *d_fams = nullptr;
+  pm::DevUnit *d_units = nullptr;
+  int32_t *d_es = nullptr;
+  pm::DevStep *d_steps = nullptr;
+  int *d_err = nullptr;
+  unsigned long long *d_counters = nullptr;
+  cudaEvent_t tm0 = nullptr, tm1 = nullptr;
+  // scratch (grown on demand)
+  size_t cap_sites = 0;
+  pm_site_result *d_res_all = nullptr;
+  uint32_t *d_emit_sites = nullptr;
+  uint32_t *d_n_emit = nullptr;
+  // staging for the host-buffer entry point
+  size_t cap_in_sites = 0, cap_out_rows = 0;
+  pm_site_hdr *d_hdr = nullptr;
+  uint4 *d_recs = nullptr;
+  uint16_t *d_status = nullptr;
+  pm_site_result *d_res_out = nullptr;
+  pm_person_result *d_person_out = nullptr;
+  // timing of the last call
+  float ms_main = 0.f, ms_total = 0.f;
+  int launches = 0;
+  bool timing_cached = false;  // set by the host-buffer entry point (sums over its chunks)
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T **p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess) { *p = nullptr; return fail(e == cudaErrorMemoryAllocation ? PM_ENOMEM : PM_ECUDA, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); }
+  return PM_OK;
+}
+
+int ensure_scratch(pm_ctx *c, size_t n_sites) {
+  if (n_sites <= c->cap_sites) return PM_OK;
+  int rc;
+  if ((rc = dev_alloc(&c->d_res_all, n_sites))) return rc;
+  if ((rc = dev_alloc(&c->d_emit_sites, n_sites))) return rc;
+  c->cap_sites = n_sites;
+  return PM_OK;
+}
+
+// transmission_denovo = transmission x genoMut, summed in the reference's order (ES:787-810)
+void build_tden(const double *mut, double *tden) {
+  static const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
+  for (int i = 0; i < 10; i++)
+    for (int j = 0; j < 10; j++) {
+      double t[10] = {0};
+      for (int x = 0; x < 2; x++)
+        for (int y = 0; y < 2; y++) t[pm::geno_index(al[i][x], al[j][y])] += 0.25;
+      for (int k = 0; k < 10; k++) {
+        double sum = .0;
+        for (int m = 0; m < 10; m++) sum += t[m] * mut[m * 10 + k];
+        tden[(i * 10 + j) * 10 + k] = sum;
+      }
+    }
+}
+
+}  // namespace
+
+extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const double *lut256, int device) {
+  pmh::clear_error();
+  if (!ped || !par || ped->n_fam <= 0 || ped->n_person <= 0) { fail(PM_EINVAL, "pm_create: empty pedigree or missing parameters"); return nullptr; }
+  if (par->quick_call) { fail(PM_EUNSUPPORTED, "pm_create: --quick_call is not implemented on the device path yet"); return nullptr; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) { fail(PM_ECUDA, "pm_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
+  if (device < 0 || device >= ndev) { fail(PM_EINVAL, "pm_create: device %d out of range (0..%d)", device, ndev - 1); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { fail(PM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { fail(PM_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return nullptr; }
+  if (prop.major != 10) { fail(PM_ECUDA, "pm_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+
+  pm_ctx *c = new pm_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->par = *par;
+  c->n_person = ped->n_person;
+  c->n_fam = ped->n_fam;
+
+  // ---- host-side descriptors ----
+  std::vector<pm::DevFam> fams((size_t)ped->n_fam);
+  std::vector<pm::DevUnit> units;
+  std::vector<int32_t> es;
+  std::vector<pm::DevStep> steps;
+  int first = 0, founders_total = 0;
+  for (int f = 0; f < ped->n_fam; f++) {
+    pm::DevFam &d = fams[(size_t)f];
+    memset(&d, 0, sizeof d);
+    const int size = ped->fam_size[f], nf = ped->fam_founders[f];
+    d.first = first; d.size = (int16_t)size; d.founders = (int16_t)nf;
+    founders_total += nf;
+    const bool nuclear = ped->fam_generations[f] == 2 && nf == 2;
+    if (size == nf) {
+      d.kind = 0;
+      for (int j = 0; j < size; j++) units.push_back({first + j, -1});
+    } else if (nuclear) {
+      d.kind = 1;
+      units.push_back({first, size - 2});
+    } else {
+      d.kind = 2;
+      if (size > pm::kMaxEsPersons) { fail(PM_EUNSUPPORTED, "extended family %d has %d members; the device peel workspace holds %d", f, size, pm::kMaxEsPersons); delete c; return nullptr; }
+      if (!ped->peel || !ped->peel_first) { fail(PM_EINVAL, "pm_create: extended family %d but no peeling order was supplied", f); delete c; return nullptr; }
+      const int p0 = ped->peel_first[f], p1 = ped->peel_first[f + 1];
+      if (p1 <= p0) { fail(PM_EINVAL, "pm_create: extended family %d has an empty peeling order", f); delete c; return nullptr; }
+      d.step_first = (int16_t)steps.size(); d.n_steps = (int16_t)(p1 - p0);
+      // resolve the std::map<pair,...> marriage_partials lookups of the reference (ES:1084-1087,
+      // 1147, 1236) once: exact (first, second) key match.
+      std::map<std::pair<int, int>, int> slots;
+      for (int s = p0; s < p1; s++) {
+        const pm_peel_step &ps = ped->peel[s];
+        pm::DevStep ds;
+        memset(&ds, 0, sizeof ds);
+        ds.type = (int8_t)ps.type; ds.from0 = (int8_t)ps.from0; ds.from1 = (int8_t)ps.from1;
+        ds.to0 = (int8_t)ps.to0; ds.to1 = (int8_t)ps.to1; ds.mp = -1;
+        if (ps.type == PM_PEEL_CHILD_TO_PARENTS) {
+          auto key = std::make_pair(ps.to0, ps.to1);
+          auto it = slots.find(key);
+          if (it == slots.end()) { int id = (int)slots.size(); slots[key] = id; ds.mp = (int8_t)id; ds.flag = 1; }
+          else ds.mp = (int8_t)it->second;
+        } else if (ps.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
+          const bool from_is_mother = ped->sex[first + ps.from0] == 2;  // ES:1137-1148
+          auto key = from_is_mother ? std::make_pair(ps.to0, ps.from0) : std::make_pair(ps.from0, ps.to0);
+          ds.flag = from_is_mother ? 0 : 1;
+          auto it = slots.find(key);
+          if (it != slots.end()) ds.mp = (int8_t)it->second;
+        } else if (ps.type == PM_PEEL_PARENTS_TO_CHILD) {
+          auto it = slots.find(std::make_pair(ps.from0, ps.from1));
+          if (it != slots.end()) ds.mp = (int8_t)it->second;
+        } else {
+          fail(PM_EINVAL, "pm_create: bad peeling step type %d", ps.type); delete c; return nullptr;
+        }
+        steps.push_back(ds);
+      }
+      if ((int)slots.size() > pm::kMaxMp) { fail(PM_EUNSUPPORTED, "extended family %d needs %zu marriage partials; the device workspace holds %d", f, slots.size(), pm::kMaxMp); delete c; return nullptr; }
+      d.n_mp = (int8_t)slots.size();
+      es.push_back(f);
+    }
+    first += size;
+  }
+  if (first != ped->n_person) { fail(PM_EINVAL, "pm_create: n_person != sum(fam_size)"); delete c; return nullptr; }
+  if (founders_total == 0) { fail(PM_EINVAL, "Family size is zero"); delete c; return nullptr; }
+  c->n_units = (int)units.size();
+  c->n_es = (int)es.size();
+
+  pm::DevRun run;
+  memset(&run, 0, sizeof run);
+  if (lut256) memcpy(run.lut, lut256, sizeof run.lut); else pm_fill_lut(run.lut);
+  pm_genotype_mutation_matrix(par->denovo_mut_rate, par->denovo_tstv, run.mut);
+  build_tden(run.mut, run.tden);
+  // SetPolyPrior (NucFam:231-242) and the per-hypothesis prior terms of main:447-533
+  double prior = 0;
+  for (int i = 1; i <= 2 * founders_total; i++) prior += 1.0 / i;
+  prior *= par->theta;
+  const double prior_ts = par->poly_tstv / (par->poly_tstv + 1), prior_tv = (1 - prior_ts) / 2;
+  run.log_1m_prior = log10(1 - prior);
+  run.log_prior_ts = log10(prior * prior_ts);
+  run.log_prior_tv = log10(prior * prior_tv);
+  run.log_prior_other = log10(prior * 0.001);
+  run.log_prior_23 = log10(prior * 2. / 3.);
+  run.log_prior_16 = log10(prior * 1. / 6.);
+  run.log_min_llr = log10(par->denovo_min_llr);
+  run.theta = par->theta; run.posterior_cutoff = par->posterior_cutoff; run.precision = par->precision;
+  run.denovo_min_llr = par->denovo_min_llr; run.min_ps = par->min_ps;
+  run.min_map_quality = par->min_map_quality; run.min_total_depth = par->min_total_depth; run.max_total_depth = par->max_total_depth;
+  run.denovo = par->denovo; run.force_call = par->force_call; run.out_all_sites = par->out_all_sites;
+  run.n_person = ped->n_person; run.n_fam = ped->n_fam; run.n_units = c->n_units; run.n_es = c->n_es;
+  run.use_brent = (ped->n_fam > 1 || fams[0].kind != 1) ? 1 : 0;  // FLSeq:94
+
+  e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, c->sm_count);
+  if (e == cudaErrorNotSupported) {
+    fail(PM_EUNSUPPORTED, "pedigree shape not supported by the device kernels yet (%d quartic units, %d extended families, %d persons)", c->n_units, c->n_es, c->n_person);
+    delete c; return nullptr;
+  }
+  if (e != cudaSuccess) { fail(PM_ECUDA, "kernel set-up: %s", cudaGetErrorString(e)); delete c; return nullptr; }
+
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess && cudaEventCreate(&c->ev2) == cudaSuccess;
+  ok = ok && dev_alloc(&c->d_run, 1) == PM_OK && dev_alloc(&c->d_fams, fams.size()) == PM_OK &&
+       dev_alloc(&c->d_units, units.size()) == PM_OK && dev_alloc(&c->d_es, es.size()) == PM_OK &&
+       dev_alloc(&c->d_steps, steps.size()) == PM_OK && dev_alloc(&c->d_err, 1) == PM_OK && dev_alloc(&c->d_n_emit, 1) == PM_OK &&
+       dev_alloc(&c->d_counters, 4) == PM_OK && cudaEventCreate(&c->tm0) == cudaSuccess && cudaEventCreate(&c->tm1) == cudaSuccess;
+  if (ok) {
+    run.fams = c->d_fams; run.units = c->d_units; run.es_fams = c->d_es; run.steps = c->d_steps;
+    run.counters = c->d_counters;
+    ok = cudaMemcpy(c->d_fams, fams.data(), fams.size() * sizeof(pm::DevFam), cudaMemcpyHostToDevice) == cudaSuccess &&
+         (units.empty() || cudaMemcpy(c->d_units, units.data(), units.size() * sizeof(pm::DevUnit), cudaMemcpyHostToDevice) == cudaSuccess) &&
+         (es.empty() || cudaMemcpy(c->d_es, es.data(), es.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess) &&
+         (steps.empty() || cudaMemcpy(c->d_steps, steps.data(), steps.size() * sizeof(pm::DevStep), cudaMemcpyHostToDevice) == cudaSuccess) &&
+         cudaMemcpy(c->d_run, &run, sizeof run, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemset(c->d_err, 0, sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)) == cudaSuccess;
+  }
+  if (!ok) {
+    if (!*pmh::last_error()) fail(PM_ECUDA, "pm_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+    pm_destroy(c);
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void pm_destroy(pm_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
+  cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
+  cudaFree(c->d_hdr); cudaFree(c->d_recs); cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->tm0) cudaEventDestroy(c->tm0);
+  if (c->tm1) cudaEventDestroy(c->tm1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
+                                        size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
+                                        pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  if (n_sites == 0) { if (d_n_res) CUDA_TRY(cudaMemsetAsync(d_n_res, 0, sizeof(uint32_t), c->stream)); return PM_OK; }
+  if (!d_hdr || !d_person_site || !d_status_out || !d_res_out || !d_person_out)
+    return fail(PM_EINVAL, "pm_call_glf_sites_device: null buffer");
+  if (n_sites > 0xffffffffull) return fail(PM_EINVAL, "at most 2^32-1 sites per call");
+  if (out_mode == PM_OUT_ALL && res_cap < n_sites) return fail(PM_EINVAL, "PM_OUT_ALL needs res_cap >= n_sites");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_scratch(c, n_sites);
+  if (rc) return rc;
+  uint32_t *d_cnt = d_n_res ? d_n_res : c->d_n_emit;
+  CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
+  CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
+                           out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
+                           d_person_out, c->sm_count, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
+  c->launches = 3;
+  c->timing_cached = false;
+  return PM_OK;
+}
+
+extern "C" int pm_sync(pm_ctx *c) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    cudaMemset(c->d_err, 0, sizeof(int));
+    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "chrX/chrY/MT sites are not implemented on the device path yet");
+    return fail(err, "device-side error %d", err);
+  }
+  return PM_OK;
+}
+
+extern "C" int pm_last_timing(pm_ctx *c, float *ms_main_kernel, float *ms_total, int *n_launches) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  float a = 0.f, b = 0.f;
+  if (c->timing_cached) {
+    a = c->ms_main; b = c->ms_total;
+  } else {
+    CUDA_TRY(cudaEventSynchronize(c->ev2));
+    CUDA_TRY(cudaEventElapsedTime(&a, c->ev0, c->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&b, c->ev0, c->ev2));
+  }
+  if (ms_main_kernel) *ms_main_kernel = a;
+  if (ms_total) *ms_total = b;
+  if (n_launches) *n_launches = c->launches;
+  return PM_OK;
+}
+
+extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, size_t n_sites,
+                                 int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
+                                 size_t res_cap, size_t *n_res) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  if (n_res) *n_res = 0;
+  if (n_sites == 0) return PM_OK;
+  if (!hdr || !person_site || !res_out) return fail(PM_EINVAL, "pm_call_glf_sites: null buffer");
+  for (size_t s = 0; s < n_sites; s++)
+    if (hdr[s].chr_class != PM_CHR_AUTO && hdr[s].ref_base >= 1 && hdr[s].ref_base <= 4)
+      return fail(PM_EUNSUPPORTED, "site %zu: chrX/chrY/MT sites are not implemented on the device path yet", s);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t np = (size_t)c->n_person;
+  // chunk so that one chunk's packed input stays below 512 MB
+  size_t chunk = ((size_t)512 << 20) / (np * sizeof(pm_person_site));
+  if (chunk < 256) chunk = 256;
+  if (chunk > n_sites) chunk = n_sites;
+  if (chunk > c->cap_in_sites) {
+    int rc;
+    if ((rc = dev_alloc(&c->d_hdr, chunk))) return rc;
+    if ((rc = dev_alloc(&c->d_recs, chunk * np))) return rc;
+    if ((rc = dev_alloc(&c->d_status, chunk))) return rc;
+    c->cap_in_sites = chunk;
+  }
+  size_t total_rows = 0;
+  bool overflow = false;
+  float ms_main = 0.f, ms_total = 0.f;
+  int launches = 0;
+  std::vector<uint16_t> status_tmp;
+  for (size_t base = 0; base < n_sites; base += chunk) {
+    const size_t n = n_sites - base < chunk ? n_sites - base : chunk;
+    // rows this chunk may produce: all of them in PM_OUT_ALL, otherwise bounded by n
+    size_t rows_cap = n;
+    if (rows_cap > c->cap_out_rows) {
+      int rc;
+      if ((rc = dev_alloc(&c->d_res_out, rows_cap))) return rc;
+      if ((rc = dev_alloc(&c->d_person_out, rows_cap * np))) return rc;
+      c->cap_out_rows = rows_cap;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_hdr, hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_recs, person_site + base * np, n * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream));
+    int rc = pm_call_glf_sites_device(c, c->d_hdr, (const pm_person_site *)c->d_recs, n, out_mode, c->d_status, c->d_res_out,
+                                      c->d_person_out, rows_cap, c->d_n_emit);
+    if (rc) return rc;
+    uint32_t rows = 0;
+    CUDA_TRY(cudaMemcpyAsync(&rows, c->d_n_emit, sizeof rows, cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = pm_sync(c))) return rc;
+    float a = 0.f, b = 0.f;
+    pm_last_timing(c, &a, &b, nullptr);
+    ms_main += a; ms_total += b; launches += 3;
+    if (status_out) CUDA_TRY(cudaMemcpy(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
+    if (rows) {
+      CUDA_TRY(cudaMemcpy(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost));
+      for (size_t r = 0; r < rows; r++) res_out[total_rows + r].site += (uint32_t)base;
+      if (person_out)
+        CUDA_TRY(cudaMemcpy(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost));
+    }
+    total_rows += rows;
+  }
+  c->ms_main = ms_main; c->ms_total = ms_total; c->launches = launches;
+  c->timing_cached = true;
+  if (n_res) *n_res = total_rows;
+  if (overflow) return fail(PM_EINVAL, "pm_call_glf_sites: res_cap %zu too small, %zu rows needed", res_cap, total_rows);
+  return PM_OK;
+}
+
+extern "C" int pm_timer_start(pm_ctx *c) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventRecord(c->tm0, c->stream));
+  return PM_OK;
+}
+extern "C" int pm_timer_stop(pm_ctx *c, float *ms) {
+  if (!c || !ms) return fail(PM_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventRecord(c->tm1, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->tm1));
+  CUDA_TRY(cudaEventElapsedTime(ms, c->tm0, c->tm1));
+  return PM_OK;
+}
+extern "C" int pm_get_counters(pm_ctx *c, pm_counters *out) {
+  if (!c || !out) return fail(PM_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(out, c->d_counters, sizeof *out, cudaMemcpyDeviceToHost));
+  return PM_OK;
+}
+extern "C" int pm_reset_counters(pm_ctx *c) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  return PM_OK;
+}
+
+extern "C" int pm_measure_fp64_peak(pm_ctx *c, double *flops) {
+  if (!c || !flops) return fail(PM_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int blocks = c->sm_count * 8, threads = 256, iters = 20000;
+  double *d_out = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d_out, (size_t)blocks * threads * sizeof(double)));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    CUDA_TRY(pm::launch_dfma_peak(d_out, blocks, threads, iters, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaFree(d_out);
+  *flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads / (best * 1e-3);
+  return PM_OK;
+}
+
+extern "C" int pm_measure_copy_bw(pm_ctx *c, double *bytes_per_s) {
+  if (!c || !bytes_per_s) return fail(PM_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)1 << 30;
+  void *a = nullptr, *b = nullptr;
+  CUDA_TRY(cudaMalloc(&a, bytes));
+  cudaError_t e = cudaMalloc(&b, bytes);
+  if (e != cudaSuccess) { cudaFree(a); return fail(PM_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  cudaMemsetAsync(a, 1, bytes, c->stream);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    CUDA_TRY(pm::launch_copy(a, b, bytes, c->sm_count, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaFree(a); cudaFree(b);
+  *bytes_per_s = 2.0 * (double)bytes / (best * 1e-3);
+  return PM_OK;
+}

@@ -1,0 +1,332 @@
+// pm_device.cuh — device-side math shared by the site kernels (sm_100a).
+//
+// What is computed follows the reference's per-site likelihood engine (file:line cited per function;
+// "NucFam" = src/NucFamGenotypeLikelihood.cpp, "FLSeq" = src/FamilyLikelihoodSeq.cpp,
+// "ES" = src/FamilyLikelihoodES.cpp, "Gold" = core/MathGold.cpp, "main" = src/main.cpp).  How it is
+// computed is our own:
+//   * a nuclear family's likelihood  L_f(p) = sum_j prior_j(p) * C_fj  (NucFam:941-1132) is split into
+//     the nine p-independent coefficients C_fj (built once per site and hypothesis) and a quartic form
+//     L_f(p) = sum_a B_fa p^a q^(4-a) with five coefficients, because prior_j(p) = c_j p^a q^(4-a);
+//     unrelated founders are the same form with (p+q)^2 folded in.  One objective evaluation is then
+//     5 FMAs per family instead of ~100 flops, and the sum of log10 over families becomes one log10 of
+//     a running product with the exponent tracked in integers.
+//   * Brent (Gold:81-177) is a resumable state machine so that one thread can drive it while a whole
+//     block evaluates the objective.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "polymutt_b200.h"
+
+namespace pm {
+
+constexpr int kMaxEsPersons = 32;  // largest extended family the per-thread peel workspace holds
+constexpr int kMaxMp = 8;          // marriage-partial slots per extended family
+constexpr double kLog10_2 = 0.30102999566398119521;
+
+// One resolved peel step (ES:990-1057): which marriage-partial slot it touches is static, so the
+// std::map lookups of the reference are done once on the host.
+struct DevStep {
+  int8_t type;   // PM_PEEL_*
+  int8_t from0, from1, to0, to1;
+  int8_t mp;     // marriage partial slot, -1 = none found (exact (first,second) key match, as the reference)
+  int8_t flag;   // type 1: 1 = slot is created (all ones) by this step; type 2: 1 = from is the father (fa2mo)
+  int8_t pad;
+};
+
+struct DevFam {       // one pedigree family, VCF column order
+  int32_t first;      // column of member 0
+  int16_t size, founders;
+  int8_t kind;        // 0 = founders only, 1 = nuclear, 2 = extended (Elston-Stewart)
+  int8_t n_mp;
+  int16_t step_first, n_steps;
+  int16_t pad;
+};
+
+struct DevUnit {      // one factor of the objective that has the quartic form
+  int32_t first;      // column of the first member
+  int32_t nkids;      // -1 = a single unrelated founder; >= 0 = nuclear family with that many kids
+};
+
+// Everything the kernels need about the run; lives in global memory, hot tables are copied to smem.
+struct DevRun {
+  double lut[256];            // 10^(-i/10)   (core/BaseQualityHelper.cpp:12-13), host-computed
+  double mut[100];            // genotype mutation matrix (src/MutationModel.cpp:46-90), host-computed
+  double tden[1000];          // transmission_denovo[i][j][k] (ES:787-810), host-computed
+  // host-computed log10 constants (same libm as the reference)
+  double log_1m_prior, log_prior_ts, log_prior_tv, log_prior_other, log_prior_23, log_prior_16, log_min_llr;
+  double theta, posterior_cutoff, precision, denovo_min_llr, min_ps;
+  int32_t min_map_quality, min_total_depth, max_total_depth;
+  int32_t denovo, force_call, out_all_sites;
+  int32_t n_person, n_fam, n_units, n_es;
+  int32_t use_brent;          // nFam>1 || !nuclear  (FLSeq:94)
+  unsigned long long *counters;  // [4] hypotheses, evaluations, sites evaluated, sites emitted
+  const DevFam *fams;
+  const DevUnit *units;
+  const int32_t *es_fams;     // indices into fams[] of the extended families
+  const DevStep *steps;
+};
+
+// ---- small helpers ----------------------------------------------------------------------------
+__host__ __device__ inline int geno_index(int b1, int b2) {  // core/glfHandler.h:102-106
+  return b1 < b2 ? (b1 - 1) * (10 - b1) / 2 + (b2 - b1) : (b2 - 1) * (10 - b2) / 2 + (b1 - b2);
+}
+__host__ __device__ inline int poly_ts(int r) { return ((r - 1) ^ 2) + 1; }    // src/PedigreeGLF.h:15-27
+__host__ __device__ inline int poly_tvs1(int r) { return (r & 1) ? 2 : 1; }    // :28-40
+__host__ __device__ inline int poly_tvs2(int r) { return (r & 1) ? 4 : 3; }    // :41-53
+
+__device__ __forceinline__ uint32_t rec_lk(const uint4 &r, int g) {
+  uint32_t w = g < 4 ? r.x : (g < 8 ? r.y : r.z);
+  return (w >> ((g & 3) * 8)) & 0xffu;
+}
+__device__ __forceinline__ int rec_depth(const uint4 &r) { return (int)((r.z >> 16) | ((r.w & 0xffu) << 16)); }
+__device__ __forceinline__ int rec_mapq(const uint4 &r) { return (int)((r.w >> 8) & 0xffu); }
+
+// ---- quartic coefficients of one unit -----------------------------------------------------------
+// C_j = likelihoodKids(j) * lF * lM  (NucFam:1041-1132, 1184-1312);  returns B with
+// L(p) = B[4] p^4 + B[3] p^3 q + B[2] p^2 q^2 + B[1] p q^3 + B[0] q^4.
+// `C` (optional) receives the nine parentConditional values (bit-identical to the reference's).
+template <typename RecPtr>
+__device__ __forceinline__ void unit_conditionals(RecPtr recs, int first, int nkids, int g11, int g12, int g22,
+                                                  bool denovo, const double *__restrict__ lut,
+                                                  const double *__restrict__ mut, double C[9]) {
+  uint4 rf = recs[first], rm = recs[first + 1];
+  double f11 = lut[rec_lk(rf, g11)], f12 = lut[rec_lk(rf, g12)], f22 = lut[rec_lk(rf, g22)];
+  double m11 = lut[rec_lk(rm, g11)], m12 = lut[rec_lk(rm, g12)], m22 = lut[rec_lk(rm, g22)];
+  double p0 = 1.0, p1 = 1.0, p2 = 1.0, p4 = 1.0, p5 = 1.0, p8 = 1.0;
+  for (int k = 0; k < nkids; k++) {
+    uint4 rk = recs[first + 2 + k];
+    double d11, d12, d22;
+    if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
+      d11 = d12 = d22 = 0.0;
+      const double *r11 = mut + g11 * 10, *r12 = mut + g12 * 10, *r22 = mut + g22 * 10;
+#pragma unroll
+      for (int g = 0; g < 10; g++) {
+        double l = lut[rec_lk(rk, g)];
+        d11 += r11[g] * l; d12 += r12[g] * l; d22 += r22[g] * l;
+      }
+    } else {
+      d11 = lut[rec_lk(rk, g11)]; d12 = lut[rec_lk(rk, g12)]; d22 = lut[rec_lk(rk, g22)];
+    }
+    // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome)
+    p0 *= d11;
+    p1 *= 0.5 * (d11 + d12);
+    p2 *= d12;
+    p4 *= 0.25 * d11 + 0.5 * d12 + 0.25 * d22;
+    p5 *= 0.5 * (d12 + d22);
+    p8 *= d22;
+  }
+  C[0] = p0 * (f11 * m11); C[1] = p1 * (f11 * m12); C[2] = p2 * (f11 * m22);
+  C[3] = p1 * (f12 * m11); C[4] = p4 * (f12 * m12); C[5] = p5 * (f12 * m22);
+  C[6] = p2 * (f22 * m11); C[7] = p5 * (f22 * m12); C[8] = p8 * (f22 * m22);
+}
+
+__device__ __forceinline__ void quartic_from_conditionals(const double C[9], double B[5]) {
+  B[4] = C[0];
+  B[3] = 2.0 * (C[1] + C[3]);
+  B[2] = C[2] + 4.0 * C[4] + C[6];
+  B[1] = 2.0 * (C[5] + C[7]);
+  B[0] = C[8];
+}
+
+template <typename RecPtr>
+__device__ __forceinline__ void unit_quartic(RecPtr recs, const DevUnit u, int g11, int g12, int g22, bool denovo,
+                                             const double *__restrict__ lut, const double *__restrict__ mut,
+                                             double B[5]) {
+  if (u.nkids < 0) {  // lkSinglePerson, NucFam:987-1004, times (p+q)^2
+    uint4 r = recs[u.first];
+    double l11 = lut[rec_lk(r, g11)], l12 = lut[rec_lk(r, g12)], l22 = lut[rec_lk(r, g22)];
+    B[4] = l11;
+    B[3] = 2.0 * (l11 + l12);
+    B[2] = l11 + 4.0 * l12 + l22;
+    B[1] = 2.0 * (l12 + l22);
+    B[0] = l22;
+  } else {
+    double C[9];
+    unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, lut, mut, C);
+    quartic_from_conditionals(C, B);
+  }
+}
+
+struct Monomials { double m4, m3, m2, m1, m0; };
+__device__ __forceinline__ Monomials monomials(double p) {
+  double q = 1.0 - p, p2 = p * p, q2 = q * q, pq = p * q;
+  Monomials m;
+  m.m4 = p2 * p2; m.m3 = p2 * pq; m.m2 = p2 * q2; m.m1 = pq * q2; m.m0 = q2 * q2;
+  return m;
+}
+__device__ __forceinline__ double quartic_eval(const double B[5], const Monomials &m) {
+  return B[4] * m.m4 + B[3] * m.m3 + B[2] * m.m2 + B[1] * m.m1 + B[0] * m.m0;
+}
+
+// HW parent-pair priors (NucFam:323-331) and the fixed single-trio table (NucFam:383-394).
+__device__ __forceinline__ void parent_priors(double freq, double pp[9]) {
+  double q = 1.0 - freq;
+  pp[0] = freq * freq * freq * freq;
+  pp[1] = freq * freq * freq * q * 2;
+  pp[2] = freq * freq * q * q;
+  pp[3] = freq * q * 2 * freq * freq;
+  pp[4] = freq * q * 2 * freq * q * 2;
+  pp[5] = freq * q * 2 * q * q;
+  pp[6] = q * q * freq * freq;
+  pp[7] = q * q * freq * q * 2;
+  pp[8] = q * q * q * q;
+}
+__device__ __forceinline__ void single_trio_priors(double pp[9]) {
+  pp[0] = 0.0; pp[1] = 0.24; pp[2] = 0.04; pp[3] = 0.24; pp[4] = 0.16; pp[5] = 0.08; pp[6] = 0.04; pp[7] = 0.08; pp[8] = 0.12;
+}
+
+// ---- running product with integer exponent ------------------------------------------------------
+// sum_u log10(L_u) = log10(prod mant) + (sum exp) * log10(2).
+struct ProdAcc { double m; int e; };
+__device__ __forceinline__ void prod_init(ProdAcc &a) { a.m = 1.0; a.e = 0; }
+__device__ __forceinline__ void prod_mul(ProdAcc &a, double x) {
+  int hi = __double2hiint(x);
+  int ex = (hi >> 20) & 0x7ff;
+  if (ex == 0 || ex == 0x7ff || hi < 0) {
+    // zero / subnormal / inf / nan / negative: the reference would see log10 of it (-inf, nan).  We keep
+    // the objective finite: zero counts as 2^-(2^24); subnormals are rescaled.
+    if (!(x > 0.0)) { a.e -= (1 << 24); return; }
+    if (ex == 0x7ff) { a.e += (1 << 24); return; }
+    x *= 1.3407807929942597e154;  // 2^512
+    a.e -= 512;
+    hi = __double2hiint(x);
+    ex = (hi >> 20) & 0x7ff;
+  }
+  a.e += ex - 1023;
+  a.m *= __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(x));
+}
+__device__ __forceinline__ void prod_renorm(ProdAcc &a) {
+  int hi = __double2hiint(a.m);
+  int ex = (hi >> 20) & 0x7ff;
+  a.e += ex - 1023;
+  a.m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(a.m));
+}
+__device__ __forceinline__ void prod_merge(ProdAcc &a, double m, int e) { a.m *= m; a.e += e; }
+__device__ __forceinline__ double prod_log10(const ProdAcc &a) { return log10(a.m) + (double)a.e * kLog10_2; }
+
+// ---- Brent as a resumable state machine (Gold:81-177 entered the way NucFam:432-444 enters it) -----
+// fa and fc of OptimizeFrequency are evaluated by the reference but never read by Brent, so they are
+// not evaluated here.  Usage:  brent_begin(s) -> evaluate f(s.u) -> while (brent_feed(s, f, tol)) evaluate f(s.u).
+struct BrentState {
+  double a, c, min, w, v, fmin, fw, fv, delta, d, u;
+  int iter;
+  int first;
+};
+#define PM_ITMAX 200
+#define PM_ZEPS 3.0e-10
+#define PM_CGOLD 0.38196601
+
+__device__ __forceinline__ double sign_d(double a, double b) { return b >= 0 ? fabs(a) : -fabs(a); }
+
+__device__ inline void brent_begin(BrentState &s) {
+  s.a = 0.0001; s.c = 0.5;  // a < c already (Gold:85-89)
+  s.min = s.w = s.v = 0.9999;
+  s.delta = 0.0; s.d = 0.0;
+  s.u = 0.9999;
+  s.iter = 0; s.first = 1;
+}
+// Consumes fu = f(s.u).  Returns true if another evaluation (at the new s.u) is needed.
+__device__ inline bool brent_feed(BrentState &s, double fu, double tol) {
+  if (s.first) {
+    s.fmin = s.fw = s.fv = fu;
+    s.first = 0;
+  } else {
+    double u = s.u;
+    if (fu <= s.fmin) {
+      if (u >= s.min) s.a = s.min; else s.c = s.min;
+      s.v = s.w; s.w = s.min; s.min = u;
+      s.fv = s.fw; s.fw = s.fmin; s.fmin = fu;
+    } else {
+      if (u < s.min) s.a = u; else s.c = u;
+      if (fu <= s.fw || s.w == s.min) {
+        s.v = s.w; s.w = u;
+        s.fv = s.fw; s.fw = fu;
+      } else if (fu <= s.fv || s.v == s.min || s.v == s.w) {
+        s.v = u; s.fv = fu;
+      }
+    }
+  }
+  s.iter++;
+  if (s.iter > PM_ITMAX) return false;  // "Brent got stuck": the reference warns and returns fmin
+  double middle = 0.5 * (s.a + s.c);
+  double tol1 = tol * fabs(s.min) + PM_ZEPS;
+  double tol2 = 2.0 * tol1;
+  if (fabs(s.min - middle) <= (tol2 - 0.5 * (s.c - s.a))) return false;
+  if (fabs(s.delta) > tol1) {
+    double r = (s.min - s.w) * (s.fmin - s.fv);
+    double q = (s.min - s.v) * (s.fmin - s.fw);
+    double p = (s.min - s.v) * q - (s.min - s.w) * r;
+    q = 2.0 * (q - r);
+    if (q > 0.0) p = -p;
+    q = fabs(q);
+    double temp = s.delta;
+    s.delta = s.d;
+    if (fabs(p) >= fabs(0.5 * q * temp) || p <= q * (s.a - s.min) || p >= q * (s.c - s.min)) {
+      s.delta = s.min >= middle ? s.a - s.min : s.c - s.min;
+      s.d = PM_CGOLD * s.delta;
+    } else {
+      s.d = p / q;
+      double u = s.min + s.d;
+      if (u - s.a < tol2 || s.c - u < tol2) s.d = sign_d(tol1, middle - s.min);
+    }
+  } else {
+    s.delta = s.min >= middle ? s.a - s.min : s.c - s.min;
+    s.d = PM_CGOLD * s.delta;
+  }
+  s.u = fabs(s.d) >= tol1 ? s.min + s.d : s.min + sign_d(tol1, s.d);
+  return true;
+}
+
+// ---- hypothesis bookkeeping (main:439-553, NucFam:1693-1749) -------------------------------------
+__device__ __forceinline__ void hyp_alleles(int h, int ref, int &a1, int &a2) {
+  int ts = poly_ts(ref), t1 = poly_tvs1(ref), t2 = poly_tvs2(ref);
+  switch (h) {
+    case 0: a1 = ref; a2 = (ref == 4) ? ref - 1 : ref + 1; break;  // main:458
+    case 1: a1 = ref; a2 = ts; break;
+    case 2: a1 = ref; a2 = t1; break;
+    case 3: a1 = ref; a2 = t2; break;
+    case 4: a1 = ts; a2 = t1; break;
+    case 5: a1 = ts; a2 = t2; break;
+    default: a1 = t1; a2 = t2; break;
+  }
+}
+
+// CalcVarPosterior for the first n hypotheses; fills maxidx, varPostProb, polyQual and the alleles
+// famlk[0] holds afterwards (for a mono winner: ref + best alternative among H1..H3, NucFam:1664-1683).
+__device__ inline void var_posterior(pm_site_result &r, int ref, int n) {
+  int maxidx = 0;
+  double mx = r.varllk[0];
+  for (int i = 0; i < n; i++) if (mx < r.varllk[i]) { mx = r.varllk[i]; maxidx = i; }
+  double sum = 0.0;
+  for (int i = 0; i < n; i++) sum += exp10(r.varllk[i] - r.varllk[maxidx]);
+  r.var_post_prob = 1 / sum;
+  int a1, a2;
+  if (maxidx == 0) {
+    int idx = 1;
+    double m2 = r.varllk[1];
+    for (int i = 1; i < 4; i++) if (m2 < r.varllk[i]) { m2 = r.varllk[i]; idx = i; }
+    hyp_alleles(idx, ref, a1, a2);
+  } else {
+    hyp_alleles(maxidx, ref, a1, a2);
+  }
+  r.allele1 = (uint8_t)a1; r.allele2 = (uint8_t)a2;
+  r.maxidx = (int8_t)maxidx;
+  r.n_hyp = (uint8_t)n;
+  r.poly_qual = (r.var_post_prob > 0.9999999999) ? 100.0 : -10 * log10(1 - r.var_post_prob);
+}
+
+__device__ __forceinline__ int best3(double p11, double p12, double p22) {  // NucFam:1564-1571
+  int b = 0; double best = p11;
+  if (p12 > best) { best = p12; b = 1; }
+  if (p22 > best) { best = p22; b = 2; }
+  return b;
+}
+__device__ __forceinline__ uint8_t gq_of(double pb) {  // NucFam:1819-1820
+  int q;
+  if (pb > 0.9999999999) q = 100;
+  else q = (int)(-10. * log10(1. - pb) + 0.5);
+  return (uint8_t)(q < 0 ? 0 : (q > 255 ? 255 : q));
+}
+
+}  // namespace pm

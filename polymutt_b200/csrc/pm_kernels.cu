@@ -1,0 +1,1012 @@
+// pm_kernels.cu — the site kernels (sm_100a).
+//
+//  k_sites_narrow : one THREAD per site.  Small pedigrees (<= kNarrowMaxUnits quartic units plus any
+//                   number of extended families peeled by Elston–Stewart).  Sites of adjacent lanes are
+//                   adjacent in HBM, so a warp streams 32 * n_person * 16 contiguous bytes.
+//  k_sites_wide   : one BLOCK per site.  Large pedigrees made of nuclear families and unrelated
+//                   founders (hundreds to thousands of units).  The site's n_person*16 bytes are staged
+//                   in shared memory with one TMA bulk copy (cp.async.bulk + mbarrier); every thread owns
+//                   U units whose quartic coefficients stay in registers for the whole Brent run; one
+//                   objective evaluation is 5 FMAs per unit + a (mantissa, exponent) product reduction by
+//                   warp shuffles; thread 0 drives the Brent state machine out of shared memory.
+//  k_compact      : ordered compaction of the emitted sites (single block scan, deterministic).
+//  k_post         : genotype posteriors / GQ / dosage / AB for emitted sites, one thread per (site, family).
+//
+// All arithmetic is FP64; inputs are uint8 phred likelihoods.  See DESIGN.md for the data layout and
+// the roofline of each kernel.
+#include <cstdio>
+
+#include "pm_device.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+// ================================================================================================
+// Elston–Stewart peel, thread-serial (ES:990-1057, 1078-1395).  A = 3 (bi-allelic) or 10 (--denovo).
+// pin_person >= 0 zeroes that person's penetrance except genotype pin_geno (FillZeroPenetrance,
+// FLSeq:327-356), which is how the reference gets per-person posteriors in extended pedigrees.
+// ================================================================================================
+__device__ __forceinline__ double tba(int i, int j, int k) {  // transmission_BA, ES:824-832
+  double ti = 0.5 * i, tj = 0.5 * j;
+  return k == 0 ? (1 - ti) * (1 - tj) : (k == 2 ? ti * tj : ti * (1 - tj) + (1 - ti) * tj);
+}
+
+template <int A, typename RecPtr>
+__device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                bool denovo, double freq, const double *__restrict__ lut,
+                                const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
+                                int pin_geno) {
+  double part[kMaxEsPersons * A];
+  double mp[kMaxMp * A * A];
+  const int gi[3] = {g11, g12, g22};
+  const double q = 1.0 - freq;
+  const double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+  for (int i = 0; i < f.size; i++) {
+    uint4 r = recs[f.first + i];
+    if (A == 3) {
+      for (int j = 0; j < 3; j++) {
+        double pen = lut[rec_lk(r, gi[j])];
+        if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
+        part[i * 3 + j] = (i < f.founders) ? pr[j] * pen : pen;  // InitializePartials_BA, ES:1449-1465
+      }
+    } else {
+      for (int g = 0; g < 10; g++) {
+        double pen = lut[rec_lk(r, g)];
+        if (i == pin_person && g != pin_geno) pen = 0.0;
+        if (i < f.founders) {  // InitializePartials, ES:1434-1446
+          double prior = g == g11 ? pr[0] : (g == g12 ? pr[1] : (g == g22 ? pr[2] : 0.0));
+          part[i * 10 + g] = prior * pen;
+        } else {
+          part[i * 10 + g] = pen;
+        }
+      }
+    }
+  }
+  const DevStep *steps = run->steps + f.step_first;
+  for (int s = 0; s < f.n_steps; s++) {
+    const DevStep st = steps[s];
+    if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
+      double *m = mp + st.mp * A * A;
+      const double *pc = part + st.from0 * A;
+      for (int i = 0; i < A; i++)
+        for (int j = 0; j < A; j++) {
+          double sum = 0;
+          if (A == 3) {
+            for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k];
+          } else {
+            const double *t = (denovo ? tden : t10) + (i * 10 + j) * 10;
+            for (int k = 0; k < 10; k++) sum += t[k] * pc[k];
+          }
+          m[i * A + j] = st.flag ? sum : m[i * A + j] * sum;  // a fresh marriage partial starts at 1
+        }
+    } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
+      const double *pf = part + st.from0 * A;
+      double *pt = part + st.to0 * A;
+      if (st.mp < 0) {
+        double sum = 0.0;
+        for (int j = 0; j < A; j++) sum += pf[j];
+        for (int i = 0; i < A; i++) pt[i] *= sum;
+      } else {
+        const double *m = mp + st.mp * A * A;
+        for (int i = 0; i < A; i++) {
+          double sum = 0.0;
+          if (st.flag) for (int j = 0; j < A; j++) sum += pf[j] * m[j * A + i];
+          else for (int j = 0; j < A; j++) sum += pf[j] * m[i * A + j];
+          pt[i] *= sum;
+        }
+      }
+    } else {
+      const double *pf = part + st.from0 * A, *pm_ = part + st.from1 * A;
+      double *pc = part + st.to0 * A;
+      const double *m = st.mp >= 0 ? mp + st.mp * A * A : nullptr;
+      for (int k = 0; k < A; k++) {
+        double sum = 0.0;
+        for (int i = 0; i < A; i++)
+          for (int j = 0; j < A; j++) {
+            double t;
+            if (A == 3) t = tba(i, j, k);
+            else t = (m || !denovo) ? t10[(i * 10 + j) * 10 + k] : tden[(i * 10 + j) * 10 + k];  // ES:1383 vs 1391
+            if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
+            else sum += pf[i] * pm_[j] * t;
+          }
+        pc[k] *= sum;
+      }
+    }
+  }
+  const double *pfin = part + steps[f.n_steps - 1].to0 * A;
+  double lk = 0.0;
+  for (int i = 0; i < A; i++) lk += pfin[i];
+  return lk;
+}
+
+// shared tables at the start of dynamic shared memory
+struct SmemTables {
+  double lut[256];
+  double mut[100];
+};
+
+__device__ __forceinline__ void load_tables(const DevRun *run, SmemTables *t) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t->lut[i] = run->lut[i];
+  for (int i = threadIdx.x; i < 100; i += blockDim.x) t->mut[i] = run->mut[i];
+}
+
+// decisions of main:539-574 once all hypotheses are in; returns true if the de novo refit
+// (main:567-573) is needed.  `lk_mono` = MonomorphismLogLikelihood(refBase).
+__device__ inline bool site_decide(const DevRun *run, pm_site_result &r, double lk_mono) {
+  const int maxidx = r.maxidx;
+  if (r.var_post_prob < run->posterior_cutoff) {
+    r.flags |= PM_FLAG_NOCALL;
+    if (!run->force_call && !run->out_all_sites) { r.status = PM_SITE_NOCALL; return false; }
+  }
+  if (maxidx == 0) {
+    r.freq = 1.0;  // famlk[0].min = 1.0 on every path that reaches the writers (main:544, 561)
+  } else {
+    int a1, a2;
+    hyp_alleles(maxidx, r.reserved /* ref base stashed by the caller */, a1, a2);
+    r.allele1 = (uint8_t)a1; r.allele2 = (uint8_t)a2;
+    r.freq = r.varfreq[maxidx];
+  }
+  if (maxidx == 0 && !run->denovo && !run->force_call && !run->out_all_sites) { r.status = PM_SITE_MONO; return false; }
+  if (maxidx == 0) {
+    if (run->denovo) {
+      r.denovo_lr = r.varllk_noprior[0] - lk_mono;
+      if (r.denovo_lr <= run->log_min_llr && !run->out_all_sites && !run->force_call) {
+        r.status = PM_SITE_DENOVO_LOW_LR;
+        return false;
+      }
+    }
+    r.flags |= PM_FLAG_MONO;
+    r.status = PM_SITE_EMITTED;
+    return false;
+  }
+  r.status = PM_SITE_EMITTED;
+  return run->denovo != 0;
+}
+__device__ inline void site_finish_refit(const DevRun *run, pm_site_result &r, double lk_poly, double refit_freq) {
+  r.refit_llk = lk_poly;
+  r.denovo_lr = r.varllk_noprior[r.maxidx] - lk_poly;
+  if (run->use_brent) r.freq = refit_freq;  // famlk[0].min is overwritten by the refit's Brent (main:570)
+}
+__device__ inline void site_store_hyp(const DevRun *run, pm_site_result &r, int h, double maxlogl, double freq) {
+  const double lp = h == 1 ? run->log_prior_ts : (h <= 3 ? run->log_prior_tv : run->log_prior_other);
+  const double ln = h == 1 ? run->log_prior_23 : (h <= 3 ? run->log_prior_16 : run->log_prior_other);  // main:472,482,492
+  double v = lp + maxlogl;
+  r.varllk[h] = v;
+  r.varllk_noprior[h] = v - ln;
+  r.varfreq[h] = freq;
+}
+__device__ inline uint16_t status_word(const pm_site_result &r) {
+  return (uint16_t)(r.status | ((r.maxidx + 1) << 4) | ((r.flags & PM_FLAG_NOCALL) << 8));
+}
+
+// ================================================================================================
+// narrow kernel: one thread per site
+// ================================================================================================
+constexpr int kNarrowThreads = 128;
+
+struct NarrowSmem {
+  SmemTables t;
+  double tden[1000];
+  double t10[1000];
+};
+
+template <int UMAX>
+struct NarrowEval {
+  const DevRun *run;
+  const uint4 *recs;  // this site's records
+  const NarrowSmem *sm;
+  double B[UMAX][5];
+  double C0[9];  // single-nuclear-family mode keeps the nine conditionals
+  int g11, g12, g22;
+  bool denovo;
+  int n_hyp = 0, n_eval = 0;
+
+  __device__ void setup(int a1, int a2, bool dn) {
+    g11 = geno_index(a1, a1); g12 = geno_index(a1, a2); g22 = geno_index(a2, a2);
+    denovo = dn;
+    if (!run->use_brent) {
+      const DevUnit u = run->units[0];
+      unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
+      return;
+    }
+#pragma unroll
+    for (int u = 0; u < UMAX; u++)
+      if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, sm->t.lut, sm->t.mut, B[u]);
+  }
+  // sum_f log10 L_f(p), FLSeq:222-240
+  __device__ double loglik(double p) const {
+    double sum = 0.0;
+    const Monomials m = monomials(p);
+#pragma unroll
+    for (int u = 0; u < UMAX; u++)
+      if (u < run->n_units) sum += log10(quartic_eval(B[u], m));
+    for (int e = 0; e < run->n_es; e++) {
+      const DevFam f = run->fams[run->es_fams[e]];
+      double lk = denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1)
+                         : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1);
+      sum += log10(lk);
+    }
+    return sum;
+  }
+  // single nuclear family: fixed parent-pair table (NucFam:383-420), or HW at freq == 1 under --denovo
+  __device__ double loglik_fixed(bool hw_at_one) const {
+    double pp[9];
+    if (hw_at_one) parent_priors(1.0, pp); else single_trio_priors(pp);
+    double sum = 0.0;
+    for (int j = 0; j < 9; j++) sum += C0[j] * pp[j];
+    return log10(sum);
+  }
+  // PolymorphismLogLikelihood, FLSeq:91-104
+  __device__ double optimize(int a1, int a2, bool dn, double *freq) {
+    setup(a1, a2, dn);
+    n_hyp++;
+    if (!run->use_brent) { n_eval++; return loglik_fixed(false); }
+    BrentState st;
+    brent_begin(st);
+    double f;
+    do { f = -loglik(st.u); n_eval++; } while (brent_feed(st, f, run->precision));
+    *freq = st.min;
+    return -st.fmin;
+  }
+};
+
+template <int UMAX>
+__global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
+                                                                  const pm_site_hdr *__restrict__ hdr,
+                                                                  const uint4 *__restrict__ recs_all, size_t n_sites,
+                                                                  pm_site_result *__restrict__ res,
+                                                                  uint16_t *__restrict__ status, int *__restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NarrowSmem *sm = reinterpret_cast<NarrowSmem *>(smem_raw);
+  load_tables(run, &sm->t);
+  for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
+    sm->tden[i] = run->tden[i];
+    // transmission[i][j][k] (ES:752-785): a quarter per gamete pair
+    int gi = i / 100, gj = (i / 10) % 10, gk = i % 10;
+    const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
+    double v = 0.0;
+    for (int x = 0; x < 2; x++)
+      for (int y = 0; y < 2; y++)
+        if (geno_index(al[gi][x], al[gj][y]) == gk) v += 0.25;
+    sm->t10[i] = v;
+  }
+  __syncthreads();
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sites) return;
+  const int np = run->n_person;
+  const uint4 *recs = recs_all + s * (size_t)np;
+  const pm_site_hdr h = hdr[s];
+
+  pm_site_result r;
+  memset(&r, 0, sizeof r);
+  r.site = (uint32_t)s;
+  r.maxidx = -1;
+  const int ref = h.ref_base;
+  if (ref < 1 || ref > 4) { r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+  if (h.chr_class != PM_CHR_AUTO) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+
+  // CalcReadStats + filters (NucFam:520-546, main:343-348) and MonomorphismLogLikelihood (NucFam:502-517)
+  int total_depth = 0, ns = 0, mapq_sum = 0;
+  double lk_mono = 0.0;
+  const int grr = geno_index(ref, ref);
+  for (int i = 0; i < np; i++) {
+    uint4 rec = recs[i];
+    int d = rec_depth(rec);
+    total_depth += d; mapq_sum += rec_mapq(rec); ns += d > 0;
+    lk_mono += -(double)rec_lk(rec, grr) / 10;
+  }
+  r.total_depth = total_depth; r.num_samp = ns;
+  if (ns > 0) { r.avg_map_qual = (double)mapq_sum / (double)ns; r.perc_samp = (double)ns / (double)np; }
+  if (total_depth < run->min_total_depth) r.status = PM_SITE_MIN_DEPTH;
+  else if (run->max_total_depth > 0 && total_depth > run->max_total_depth) r.status = PM_SITE_MAX_DEPTH;
+  else if (r.perc_samp * 100 < run->min_ps) r.status = PM_SITE_MIN_PS;
+  else if (r.avg_map_qual < run->min_map_quality) r.status = PM_SITE_MIN_MAPQ;
+  if (r.status != 0) { res[s] = r; status[s] = status_word(r); return; }
+
+  NarrowEval<UMAX> ev;
+  ev.run = run; ev.recs = recs; ev.sm = sm;
+  r.reserved = (uint16_t)ref;
+  // H0 (main:447-462)
+  if (!run->denovo) {
+    r.varllk[0] = run->log_1m_prior + lk_mono;
+  } else {
+    int a1, a2;
+    hyp_alleles(0, ref, a1, a2);
+    ev.setup(a1, a2, true);
+    double l0 = run->use_brent ? ev.loglik(1.0) : ev.loglik_fixed(true);
+    r.varllk[0] = run->log_1m_prior + l0;
+  }
+  r.varllk_noprior[0] = r.varllk[0] - run->log_1m_prior;
+  r.varfreq[0] = 1.0;
+  for (int hix = 1; hix <= 3; hix++) {
+    int a1, a2;
+    hyp_alleles(hix, ref, a1, a2);
+    double freq = 0.0;
+    double ml = ev.optimize(a1, a2, run->denovo != 0, &freq);
+    site_store_hyp(run, r, hix, ml, freq);
+  }
+  var_posterior(r, ref, 4);
+  if (r.var_post_prob < 0.99) {  // main:499-537
+    for (int hix = 4; hix <= 6; hix++) {
+      int a1, a2;
+      hyp_alleles(hix, ref, a1, a2);
+      double freq = 0.0;
+      double ml = ev.optimize(a1, a2, run->denovo != 0, &freq);
+      site_store_hyp(run, r, hix, ml, freq);
+    }
+    var_posterior(r, ref, 7);
+  }
+  if (site_decide(run, r, lk_mono)) {
+    double freq = 0.0;
+    double lk_poly = ev.optimize(r.allele1, r.allele2, false, &freq);
+    site_finish_refit(run, r, lk_poly, freq);
+  }
+  if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) r.flags |= PM_FLAG_ROW_DROPPED;
+  r.reserved = 0;
+  res[s] = r;
+  status[s] = status_word(r);
+  // work counters: one atomic per warp (redux over the lanes that got here)
+  {
+    unsigned h = ev.n_hyp + (run->denovo ? 1 : 0), e = ev.n_eval + (run->denovo ? 1 : 0), em = r.status == PM_SITE_EMITTED;
+    const unsigned mask = __activemask();
+    h = __reduce_add_sync(mask, h); e = __reduce_add_sync(mask, e); em = __reduce_add_sync(mask, em);
+    if ((int)(threadIdx.x & 31) == __ffs(mask) - 1) {
+      atomicAdd(&run->counters[0], (unsigned long long)h); atomicAdd(&run->counters[1], (unsigned long long)e);
+      atomicAdd(&run->counters[2], (unsigned long long)__popc(mask)); atomicAdd(&run->counters[3], (unsigned long long)em);
+    }
+  }
+}
+
+// ================================================================================================
+// wide kernel: one block per site
+// ================================================================================================
+struct WideShared {
+  SmemTables t;
+  pm_site_result r;          // written by thread 0 only
+  BrentState brent;          // driven by thread 0
+  double p;                  // next evaluation point, < 0 = stop
+  double warp_m[32];         // per-warp partial products
+  int warp_e[32];
+  int red_i[3 * 32];         // per-warp integer partials (depth, samples, mapq / lk sum)
+  double bcast[4];
+  int ibcast[4];
+  unsigned long long mbar;   // mbarrier for the TMA bulk copy
+  unsigned int n_hyp, n_eval; // work counters of the current site (thread 0)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void tma_load_site(void *dst, const void *src, uint32_t bytes, unsigned long long *bar, uint32_t phase) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+  }
+  // everyone waits for the phase to flip
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// Block-wide product of per-thread (mantissa, exponent) accumulators; result valid in thread 0.
+__device__ __forceinline__ void block_product(ProdAcc &acc, WideShared *ws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double m = __shfl_down_sync(0xffffffffu, acc.m, o);
+    int e = __shfl_down_sync(0xffffffffu, acc.e, o);
+    acc.m *= m; acc.e += e;
+  }
+  if (nwarp == 1) { if (lane == 0) prod_renorm(acc); return; }
+  if (lane == 0) { prod_renorm(acc); ws->warp_m[warp] = acc.m; ws->warp_e[warp] = acc.e; }
+  __syncthreads();
+  if (warp == 0) {
+    ProdAcc b;
+    b.m = lane < nwarp ? ws->warp_m[lane] : 1.0;
+    b.e = lane < nwarp ? ws->warp_e[lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double m = __shfl_down_sync(0xffffffffu, b.m, o);
+      int e = __shfl_down_sync(0xffffffffu, b.e, o);
+      b.m *= m; b.e += e;
+    }
+    acc = b;
+  }
+}
+
+template <int U>
+struct WideEval {
+  const DevRun *run;
+  const uint4 *recs;  // site records in shared memory
+  WideShared *ws;
+  double B[U][5];
+  int nmine;          // units owned by this thread: tid, tid+T, ...
+
+  __device__ __forceinline__ void setup(int a1, int a2, bool denovo) {
+    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int u = threadIdx.x + k * blockDim.x;
+      if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, ws->t.lut, ws->t.mut, B[k]);
+    }
+  }
+  // every thread calls; thread 0 returns sum_f log10 L_f(p)
+  __device__ __forceinline__ double loglik(double p) {
+    const Monomials m = monomials(p);
+    ProdAcc acc;
+    prod_init(acc);
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const int u = threadIdx.x + k * blockDim.x;
+      if (u < run->n_units) prod_mul(acc, quartic_eval(B[k], m));
+    }
+    block_product(acc, ws);
+    return prod_log10(acc);
+  }
+  // Brent with the block as the objective evaluator.  Thread 0 owns the state machine.
+  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo) {
+    setup(a1, a2, denovo);
+    if (threadIdx.x == 0) { brent_begin(ws->brent); ws->p = ws->brent.u; }
+    __syncthreads();
+    for (;;) {
+      const double p = ws->p;
+      if (p < 0.0) break;
+      double ll = loglik(p);   // contains one __syncthreads when the block has several warps
+      if (threadIdx.x == 0) {
+        bool more = brent_feed(ws->brent, -ll, run->precision);
+        ws->p = more ? ws->brent.u : -1.0;
+        ws->n_eval++;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) ws->n_hyp++;
+    // result: ws->brent.min, -ws->brent.fmin (read by thread 0)
+  }
+};
+
+template <int U>
+__global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                             const uint4 *__restrict__ recs_all, size_t n_sites, pm_site_result *__restrict__ res,
+                             uint16_t *__restrict__ status, int *__restrict__ err) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WideShared *ws = reinterpret_cast<WideShared *>(smem_raw);
+  uint4 *site = reinterpret_cast<uint4 *>(smem_raw + ((sizeof(WideShared) + 127) / 128) * 128);
+  const int np = run->n_person;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  load_tables(run, &ws->t);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  WideEval<U> ev;
+  ev.run = run; ev.recs = site; ev.ws = ws;
+
+  for (size_t s = blockIdx.x; s < n_sites; s += gridDim.x) {
+    // ---- stage the site: n_person * 16 contiguous bytes, one TMA bulk copy ----
+    tma_load_site(site, recs_all + s * (size_t)np, (uint32_t)np * 16u, &ws->mbar, phase);
+    phase ^= 1;
+    const pm_site_hdr h = hdr[s];
+    const int ref = h.ref_base;
+    bool skip = false;
+    if (ref < 1 || ref > 4 || h.chr_class != PM_CHR_AUTO) {
+      if (threadIdx.x == 0) {
+        pm_site_result &r = ws->r;
+        memset(&r, 0, sizeof r);
+        r.site = (uint32_t)s; r.maxidx = -1; r.status = PM_SITE_BAD_REF;
+        if (ref >= 1 && ref <= 4) atomicExch(err, PM_EUNSUPPORTED);
+        res[s] = r; status[s] = status_word(r);
+      }
+      skip = true;
+    }
+    if (!skip) {
+      // ---- CalcReadStats / MonomorphismLogLikelihood: integer block reductions ----
+      const int grr = geno_index(ref, ref);
+      int dsum = 0, nsamp = 0, mq = 0, lksum = 0;
+      for (int i = threadIdx.x; i < np; i += blockDim.x) {
+        uint4 rec = site[i];
+        int d = rec_depth(rec);
+        dsum += d; nsamp += d > 0; mq += rec_mapq(rec); lksum += (int)rec_lk(rec, grr);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsum += __shfl_down_sync(0xffffffffu, dsum, o);
+        nsamp += __shfl_down_sync(0xffffffffu, nsamp, o);
+        mq += __shfl_down_sync(0xffffffffu, mq, o);
+        lksum += __shfl_down_sync(0xffffffffu, lksum, o);
+      }
+      if (lane == 0) { ws->red_i[warp] = dsum; ws->red_i[32 + warp] = nsamp; ws->red_i[64 + warp] = mq; ws->warp_e[warp] = lksum; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int D = 0, NS = 0, MQ = 0, LK = 0;
+        for (int w = 0; w < nwarp; w++) { D += ws->red_i[w]; NS += ws->red_i[32 + w]; MQ += ws->red_i[64 + w]; LK += ws->warp_e[w]; }
+        pm_site_result &r = ws->r;
+        memset(&r, 0, sizeof r);
+        r.site = (uint32_t)s; r.maxidx = -1;
+        r.total_depth = D; r.num_samp = NS;
+        if (NS > 0) { r.avg_map_qual = (double)MQ / (double)NS; r.perc_samp = (double)NS / (double)np; }
+        if (D < run->min_total_depth) r.status = PM_SITE_MIN_DEPTH;
+        else if (run->max_total_depth > 0 && D > run->max_total_depth) r.status = PM_SITE_MAX_DEPTH;
+        else if (r.perc_samp * 100 < run->min_ps) r.status = PM_SITE_MIN_PS;
+        else if (r.avg_map_qual < run->min_map_quality) r.status = PM_SITE_MIN_MAPQ;
+        // sum_i -lk_i/10 with the integer sum taken first (exact), one division
+        ws->bcast[0] = -(double)LK / 10.0;
+        ws->ibcast[0] = r.status;
+        r.reserved = (uint16_t)ref;
+        if (r.status != 0) { res[s] = r; status[s] = status_word(r); }
+      }
+      __syncthreads();
+      skip = ws->ibcast[0] != 0;
+    }
+    if (!skip) {
+      const double lk_mono = ws->bcast[0];
+      const bool dn = run->denovo != 0;
+      if (threadIdx.x == 0) { ws->n_hyp = dn ? 1 : 0; ws->n_eval = dn ? 1 : 0; }
+      // ---- H0 ----
+      if (dn) {
+        int a1, a2;
+        hyp_alleles(0, ref, a1, a2);
+        ev.setup(a1, a2, true);
+        double l0 = ev.loglik(1.0);
+        if (threadIdx.x == 0) ws->r.varllk[0] = run->log_1m_prior + l0;
+      } else if (threadIdx.x == 0) {
+        ws->r.varllk[0] = run->log_1m_prior + lk_mono;
+      }
+      if (threadIdx.x == 0) { ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->log_1m_prior; ws->r.varfreq[0] = 1.0; }
+      // ---- H1..H3, then H4..H6 if the posterior is not decisive ----
+      for (int hix = 1; hix <= 6; hix++) {
+        if (hix == 4) {
+          if (threadIdx.x == 0) { var_posterior(ws->r, ref, 4); ws->ibcast[1] = ws->r.var_post_prob < 0.99; }
+          __syncthreads();
+          if (!ws->ibcast[1]) break;
+        }
+        int a1, a2;
+        hyp_alleles(hix, ref, a1, a2);
+        ev.optimize(a1, a2, dn);
+        if (threadIdx.x == 0) site_store_hyp(run, ws->r, hix, -ws->brent.fmin, ws->brent.min);
+      }
+      if (threadIdx.x == 0) {
+        if (ws->r.n_hyp == 4 && ws->r.var_post_prob < 0.99) var_posterior(ws->r, ref, 7);
+        ws->ibcast[2] = site_decide(run, ws->r, lk_mono);
+      }
+      __syncthreads();
+      if (ws->ibcast[2]) {  // de novo refit without mutation (main:567-573)
+        const int a1 = ws->r.allele1, a2 = ws->r.allele2;
+        ev.optimize(a1, a2, false);
+        if (threadIdx.x == 0) site_finish_refit(run, ws->r, -ws->brent.fmin, ws->brent.min);
+      }
+      if (threadIdx.x == 0) {
+        pm_site_result &r = ws->r;
+        if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) r.flags |= PM_FLAG_ROW_DROPPED;
+        r.reserved = 0;
+        res[s] = r;
+        status[s] = status_word(r);
+        atomicAdd(&run->counters[0], (unsigned long long)ws->n_hyp);
+        atomicAdd(&run->counters[1], (unsigned long long)ws->n_eval);
+        atomicAdd(&run->counters[2], 1ull);
+        atomicAdd(&run->counters[3], (unsigned long long)(r.status == PM_SITE_EMITTED));
+      }
+    }
+    __syncthreads();  // the site buffer and ws->r are reused by the next iteration
+  }
+}
+
+// ================================================================================================
+// ordered compaction of emitted sites (deterministic, single block)
+// ================================================================================================
+__global__ void __launch_bounds__(1024) k_compact(const uint16_t *__restrict__ status, size_t n_sites,
+                                                  uint32_t *__restrict__ emit_sites, uint32_t *__restrict__ n_emit,
+                                                  int all) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (size_t start = 0; start < n_sites; start += 1024) {
+    size_t s = start + tid;
+    uint32_t flag = (s < n_sites) && (all || (status[s] & 0xf) == PM_SITE_EMITTED);
+    uint32_t x = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    uint32_t off = base + (warp ? warp_tot[warp - 1] : 0) + x - flag;
+    if (flag) emit_sites[off] = (uint32_t)s;
+    __syncthreads();
+    if (tid == 0) base += warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) *n_emit = base;
+}
+
+// ================================================================================================
+// posteriors for emitted sites: one thread per (row, family)
+// ================================================================================================
+struct PostSmem {
+  SmemTables t;
+  double tden[1000];
+  double t10[1000];
+};
+
+__device__ inline void store_person3(pm_person_result &o, double p0, double p1, double p2, int best) {
+  o.post[0] = p0; o.post[1] = p1; o.post[2] = p2;
+  for (int g = 3; g < 10; g++) o.post[g] = 0.0;
+  o.dosage = p1 + p2 * 2;
+  o.best = best;
+  o.gq = gq_of(best == 0 ? p0 : (best == 1 ? p1 : p2));
+  o.ten_state = 0;
+  o.reserved[0] = o.reserved[1] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                              const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
+                                              const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
+                                              size_t res_cap, pm_site_result *__restrict__ res_out,
+                                              pm_person_result *__restrict__ person_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
+  load_tables(run, &sm->t);
+  for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
+    sm->tden[i] = run->tden[i];
+    int gi = i / 100, gj = (i / 10) % 10, gk = i % 10;
+    const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
+    double v = 0.0;
+    for (int x = 0; x < 2; x++)
+      for (int y = 0; y < 2; y++)
+        if (geno_index(al[gi][x], al[gj][y]) == gk) v += 0.25;
+    sm->t10[i] = v;
+  }
+  __syncthreads();
+  const uint32_t n_emit = *n_emit_ptr;
+  const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
+  const size_t total = n_rows * (size_t)run->n_fam;
+  const int np = run->n_person;
+  const double *lut = sm->t.lut, *mut = sm->t.mut;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = w / run->n_fam;
+    const int fi = (int)(w % run->n_fam);
+    const uint32_t s = emit_sites[row];
+    pm_site_result r = res_all[s];
+    const uint4 *recs = recs_all + (size_t)s * np;
+    pm_person_result *out = person_out + row * (size_t)np;
+    const DevFam f = run->fams[fi];
+    if (r.status != PM_SITE_EMITTED) {  // PM_OUT_ALL rows of sites that print nothing
+      if (fi == 0) res_out[row] = r;
+      for (int j = 0; j < f.size; j++) memset(&out[f.first + j], 0, sizeof(pm_person_result));
+      continue;
+    }
+    const int a1 = r.allele1, a2 = r.allele2;
+    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+    const bool mono = (r.flags & PM_FLAG_MONO) != 0;
+    const bool dn = run->denovo != 0;
+    // frequency the posteriors are taken at (main:576-587)
+    const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
+    const double q = 1.0 - freq;
+
+    if (f.kind == 0) {  // CalcPostProb_SinglePerson, NucFam:754-795
+      for (int j = 0; j < f.size; j++) {
+        uint4 rec = recs[f.first + j];
+        double m11 = lut[rec_lk(rec, g11)] * (freq * freq);
+        double m12 = lut[rec_lk(rec, g12)] * (freq * q * 2);
+        double m22 = lut[rec_lk(rec, g22)] * (q * q);
+        double sum = m11 + m12 + m22;
+        if (sum == 0) store_person3(out[f.first + j], 0, 0, 0, best3(m11, m12, m22));
+        else store_person3(out[f.first + j], m11 / sum, m12 / sum, m22 / sum, best3(m11, m12, m22));
+      }
+    } else if (f.kind == 1) {  // nuclear: NucFam:590-752
+      const int nk = f.size - 2;
+      double C[9], pp[9], pm9[9];
+      unit_conditionals(recs, f.first, nk, g11, g12, g22, dn, lut, mut, C);
+      // parent-pair prior: HW when nFam>1 (or isMono / freq==1 under --denovo), else the fixed table
+      bool hw = run->n_fam > 1 || (dn ? freq == 1.0 : mono);
+      if (hw) parent_priors(freq, pp); else single_trio_priors(pp);
+      for (int j = 0; j < 9; j++) pm9[j] = C[j] * pp[j];
+      {
+        double p11 = pm9[0] + pm9[1] + pm9[2], p12 = pm9[3] + pm9[4] + pm9[5], p22 = pm9[6] + pm9[7] + pm9[8];
+        double sum = p11 + p12 + p22;
+        if (sum == 0) store_person3(out[f.first], 0, 0, 0, best3(p11, p12, p22));
+        else store_person3(out[f.first], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+        p11 = pm9[0] + pm9[3] + pm9[6]; p12 = pm9[1] + pm9[4] + pm9[7]; p22 = pm9[2] + pm9[5] + pm9[8];
+        sum = p11 + p12 + p22;
+        if (sum == 0) store_person3(out[f.first + 1], 0, 0, 0, best3(p11, p12, p22));
+        else store_person3(out[f.first + 1], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+      }
+      // parentGLF * parentPrior per configuration (NucFam:815-823)
+      double w9[9];
+      {
+        uint4 rf = recs[f.first], rm = recs[f.first + 1];
+        double fl[3] = {lut[rec_lk(rf, g11)], lut[rec_lk(rf, g12)], lut[rec_lk(rf, g22)]};
+        double ml[3] = {lut[rec_lk(rm, g11)], lut[rec_lk(rm, g12)], lut[rec_lk(rm, g22)]};
+        for (int j = 0; j < 9; j++) w9[j] = (fl[j / 3] * ml[j % 3]) * pp[j];
+      }
+      for (int kid = 0; kid < nk; kid++) {
+        pm_person_result &o = out[f.first + 2 + kid];
+        if (!dn) {
+          // KidJointGenoLikelihood + likelihoodKidGenotype, NucFam:798-835, 1334-1443
+          double J[3] = {0, 0, 0};
+          for (int cfg = 0; cfg < 9; cfg++) {
+            double G[3] = {1.0, 1.0, 1.0};
+            for (int kk = 0; kk < nk; kk++) {
+              uint4 rk = recs[f.first + 2 + kk];
+              double l11 = lut[rec_lk(rk, g11)], l12 = lut[rec_lk(rk, g12)], l22 = lut[rec_lk(rk, g22)];
+              double lk, x11, x12, x22;
+              switch (cfg) {
+                case 0: lk = l11; x11 = l11; x12 = 0; x22 = 0; break;
+                case 1: case 3: lk = 0.5 * (l11 + l12); x11 = l11 * 0.5; x12 = l12 * 0.5; x22 = 0; break;
+                case 2: case 6: lk = l12; x11 = 0; x12 = l12; x22 = 0; break;
+                case 4: lk = 0.25 * l11 + 0.5 * l12 + 0.25 * l22; x11 = l11 * 0.25; x12 = l12 * 0.5; x22 = l22 * 0.25; break;
+                case 5: case 7: lk = 0.5 * (l12 + l22); x11 = 0; x12 = l12 * 0.5; x22 = l22 * 0.5; break;
+                default: lk = l22; x11 = 0; x12 = 0; x22 = l22; break;
+              }
+              if (kk != kid) { G[0] *= lk; G[1] *= lk; G[2] *= lk; }
+              else { G[0] *= x11; G[1] *= x12; G[2] *= x22; }
+            }
+            for (int t = 0; t < 3; t++) J[t] = cfg == 0 ? G[t] * w9[cfg] : J[t] + G[t] * w9[cfg];
+          }
+          double sum = J[0] + J[1] + J[2];
+          double p0 = 0, p1 = 0, p2 = 0;
+          if (sum != 0.0) { p0 = J[0] / sum; p1 = J[1] / sum; p2 = J[2] / sum; }
+          store_person3(o, p0, p1, p2, best3(p0, p1, p2));
+        } else {
+          // KidJointGenoLikelihood_denovo, NucFam:838-868, 1446-1551
+          double geno[10];
+          for (int g = 0; g < 10; g++) geno[g] = 0.0;
+          const double *M1 = mut + g11 * 10, *M2 = mut + g12 * 10, *M3 = mut + g22 * 10;
+          for (int cfg = 0; cfg < 9; cfg++) {
+            double lkg[10];
+            for (int g = 0; g < 10; g++) lkg[g] = 1.0;
+            for (int kk = 0; kk < nk; kk++) {
+              uint4 rk = recs[f.first + 2 + kk];
+              if (kk != kid) {
+                double d11 = 0, d12 = 0, d22 = 0;
+                for (int g = 0; g < 10; g++) {
+                  double l = lut[rec_lk(rk, g)];
+                  d11 += M1[g] * l; d12 += M2[g] * l; d22 += M3[g] * l;
+                }
+                double lk;
+                switch (cfg) {
+                  case 0: lk = d11; break;
+                  case 1: case 3: lk = 0.5 * (d11 + d12); break;
+                  case 2: case 6: lk = d12; break;
+                  case 4: lk = 0.25 * d11 + 0.5 * d12 + 0.25 * d22; break;
+                  case 5: case 7: lk = 0.5 * (d12 + d22); break;
+                  default: lk = d22; break;
+                }
+                for (int g = 0; g < 10; g++) lkg[g] *= lk;
+              } else {
+                for (int g = 0; g < 10; g++) {
+                  double l = lut[rec_lk(rk, g)], wgt;
+                  switch (cfg) {
+                    case 0: wgt = M1[g]; break;
+                    case 1: case 3: wgt = 0.5 * M1[g] + 0.5 * M2[g]; break;
+                    case 2: case 6: wgt = M2[g]; break;
+                    case 4: wgt = 0.25 * M1[g] + 0.5 * M2[g] + 0.25 * M3[g]; break;
+                    case 5: case 7: wgt = 0.5 * M2[g] + 0.5 * M3[g]; break;
+                    default: wgt = M3[g]; break;
+                  }
+                  lkg[g] *= wgt * l;
+                }
+              }
+            }
+            for (int g = 0; g < 10; g++) geno[g] += lkg[g] * w9[cfg];
+          }
+          double sum = 0.0;
+          for (int g = 0; g < 10; g++) sum += geno[g];
+          double mx = 0.0;
+          int best = 0;
+          for (int g = 0; g < 10; g++) {
+            double pg = sum == 0.0 ? 0.0 : geno[g] / sum;
+            o.post[g] = pg;
+            if (mx < pg) { mx = pg; best = g; }
+          }
+          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
+          o.reserved[0] = o.reserved[1] = 0;
+        }
+      }
+    } else {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216)
+      for (int j = 0; j < f.size; j++) {
+        pm_person_result &o = out[f.first + j];
+        if (!dn) {
+          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g11);
+          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g12);
+          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g22);
+          double sum = l11 + l12 + l22;
+          if (sum == 0) store_person3(o, 0, 0, 0, best3(l11, l12, l22));
+          else store_person3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
+        } else {
+          double lk[10], sum = 0.0;
+          for (int g = 0; g < 10; g++) {
+            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, sm->tden, sm->t10, j, g);
+            sum += lk[g];
+          }
+          double mx = 0.0;
+          int best = 0;
+          for (int g = 0; g < 10; g++) {
+            o.post[g] = sum == 0 ? 0.0 : lk[g] / sum;
+            if (mx < lk[g]) { mx = lk[g]; best = g; }
+          }
+          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
+          o.reserved[0] = o.reserved[1] = 0;
+        }
+      }
+    }
+    if (fi == 0) {
+      // CalculateAB (NucFam:1006-1039), only printed by the non-de-novo writer on autosomes
+      if (!dn) {
+        double A = 0.0, Bsum = 0.0;
+        const double f0 = r.freq;
+        const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
+        for (int i = 0; i < np; i++) {
+          uint4 rec = recs[i];
+          int depth = rec_depth(rec);
+          int u11 = rec_lk(rec, g11), u12 = rec_lk(rec, g12), u22 = rec_lk(rec, g22);
+          double l11 = lut[u11], l12 = lut[u12], l22 = lut[u22];
+          double phet = (p12 * l12) / (p11 * l11 + p12 * l12 + p22 * l22);
+          if (phet > 1e-05 && depth > 0) {
+            int scale = u22 + u11 - 2 * u12 + 6 * depth;
+            int minimum = abs(u22 - u11);
+            if (scale < 4) scale = 4;
+            if (scale < minimum) scale = minimum;
+            int nref = (int)(0.5 * depth * (1 + (u22 - u11) / (scale + 1e-30)));
+            A += phet * nref;
+            Bsum += phet * depth;
+          }
+        }
+        r.ab = (0.05 + A) / (0.1 + Bsum);
+      } else {
+        r.ab = 0.5;
+      }
+      res_out[row] = r;
+    }
+  }
+}
+
+// ================================================================================================
+// microbenchmarks used as roofline denominators
+// ================================================================================================
+__global__ void k_dfma_peak(double *out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+  double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_copy(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static size_t wide_smem_bytes(int n_person) {
+  return ((sizeof(WideShared) + 127) / 128) * 128 + (size_t)n_person * 16 + 16;
+}
+
+cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
+                         size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream) {
+  if (n_sites == 0) return cudaSuccess;
+  if (plan.kind == LaunchPlan::NARROW) {
+    const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
+    k_sites_narrow<kNarrowMaxUnits><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err);
+  } else {
+    const size_t smem = wide_smem_bytes(plan.n_person);
+    const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
+#define PM_WIDE(U_)                                                                                               \
+  k_sites_wide<U_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err)
+    switch (plan.units_per_thread) {
+      case 1: PM_WIDE(1); break;
+      case 2: PM_WIDE(2); break;
+      case 4: PM_WIDE(4); break;
+      default: PM_WIDE(8); break;
+    }
+#undef PM_WIDE
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count) {
+  plan->n_person = n_person;
+  if (n_units <= kNarrowMaxUnits) {
+    plan->kind = LaunchPlan::NARROW;
+    plan->threads = kNarrowThreads;
+    plan->units_per_thread = kNarrowMaxUnits;
+    plan->grid = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
+    return e;
+  }
+  if (n_es > 0) return cudaErrorNotSupported;
+  plan->kind = LaunchPlan::WIDE;
+  // T threads x U units per thread >= n_units, U in {1,2,4,8}, T a multiple of 32 up to 1024
+  int U = 8, T = 128;
+  if (n_units <= 32 * 8) { T = 32; U = n_units <= 32 ? 1 : (n_units <= 64 ? 2 : (n_units <= 128 ? 4 : 8)); }
+  else if (n_units <= 64 * 8) T = 64;
+  else if (n_units <= 128 * 8) T = 128;
+  else if (n_units <= 256 * 8) T = 256;
+  else if (n_units <= 512 * 8) T = 512;
+  else if (n_units <= 1024 * 8) T = 1024;
+  else return cudaErrorNotSupported;
+  plan->threads = T;
+  plan->units_per_thread = U;
+  const size_t smem = wide_smem_bytes(n_person);
+  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  cudaError_t e = cudaSuccess;
+  int per_sm = 1;
+#define PM_ATTR(U_)                                                                                              \
+  e = cudaFuncSetAttribute(k_sites_wide<U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_>, T, smem)
+  switch (U) {
+    case 1: PM_ATTR(1); break;
+    case 2: PM_ATTR(2); break;
+    case 4: PM_ATTR(4); break;
+    default: PM_ATTR(8); break;
+  }
+#undef PM_ATTR
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  plan->grid = sm_count * per_sm;  // persistent: a multiple of the SM count
+  plan->blocks_per_sm = per_sm;
+  return cudaSuccess;
+}
+
+cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,
+                           cudaStream_t stream) {
+  k_compact<<<1, 1024, 0, stream>>>(d_status, n_sites, d_emit_sites, d_n_emit, all);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
+                        const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
+                        size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
+                        int sm_count, cudaStream_t stream) {
+  if (max_rows == 0) return cudaSuccess;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostSmem));
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  size_t want = (max_rows * (size_t)n_fam + 127) / 128;
+  size_t cap = (size_t)sm_count * 16;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (grid == 0) grid = 1;
+  k_post<<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dfma_peak(double *d_out, int blocks, int threads, int iters, cudaStream_t stream) {
+  k_dfma_peak<<<blocks, threads, 0, stream>>>(d_out, iters);
+  return cudaGetLastError();
+}
+cudaError_t launch_copy(const void *src, void *dst, size_t bytes, int sm_count, cudaStream_t stream) {
+  k_copy<<<sm_count * 8, 256, 0, stream>>>((const uint4 *)src, (uint4 *)dst, bytes / 16);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

@@ -1,0 +1,200 @@
+// pm-tools: fixture plumbing around the host front end (no GPU needed).
+//
+//   pm-tools pack   -p PED -d DAT -g GIF -o OUT.pmpk     pedigree view + every merged site, as the
+//                                                        engine would receive them
+//   pm-tools unpack IN.pmpk OUTDIR [--gzip]              the inverse: one GLF v3 file per VCF column,
+//                                                        plus OUTDIR/ped, dat, gif text files
+//
+// .pmpk layout (little endian):
+//   "PMPK" u32 version(1) i32 n_fam i32 n_person i32 n_steps
+//   i32 fam_size[n_fam] i32 fam_founders[n_fam] i32 fam_generations[n_fam]
+//   u8 sex[n_person] (padded to 4) i32 father[n_person] i32 mother[n_person] i32 glf_index[n_person]
+//   i32 peel_first[n_fam+1]  pm_peel_step peel[n_steps]
+//   u32 text_len, text: "famid pid fatid motid sex glf_index\n" per column, then "#label <chrom label>\n"
+//   i32 max_position  u64 n_sites  pm_site_hdr hdr[n_sites]  pm_person_site rec[n_sites*n_person]
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "glf.h"
+#include "pedigree.h"
+
+using namespace pmh;
+
+static int usage() {
+  fprintf(stderr, "usage: pm-tools pack -p PED -d DAT -g GIF -o OUT.pmpk | pm-tools unpack IN.pmpk OUTDIR [--gzip]\n");
+  return 2;
+}
+
+template <typename T>
+static void put(FILE *f, const T *p, size_t n) { fwrite(p, sizeof(T), n, f); }
+
+static int do_pack(int argc, char **argv) {
+  std::string ped_path, dat_path, gif_path, out_path;
+  for (int i = 2; i + 1 < argc; i += 2) {
+    std::string k = argv[i];
+    if (k == "-p") ped_path = argv[i + 1];
+    else if (k == "-d") dat_path = argv[i + 1];
+    else if (k == "-g") gif_path = argv[i + 1];
+    else if (k == "-o") out_path = argv[i + 1];
+  }
+  if (ped_path.empty() || dat_path.empty() || out_path.empty()) return usage();
+  Pedigree ped;
+  try { ped.load(dat_path, ped_path); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
+  const pm_pedigree *v = ped.view();
+  FILE *f = fopen(out_path.c_str(), "wb");
+  if (!f) { perror("open output"); return 1; }
+  const int32_t n_steps = v->peel_first[v->n_fam];
+  uint32_t version = 1;
+  fwrite("PMPK", 1, 4, f);
+  put(f, &version, 1); put(f, &v->n_fam, 1); put(f, &v->n_person, 1); put(f, &n_steps, 1);
+  put(f, v->fam_size, v->n_fam); put(f, v->fam_founders, v->n_fam); put(f, v->fam_generations, v->n_fam);
+  std::vector<uint8_t> sex(((size_t)v->n_person + 3) / 4 * 4, 0);
+  memcpy(sex.data(), v->sex, (size_t)v->n_person);
+  put(f, sex.data(), sex.size());
+  put(f, v->father, v->n_person); put(f, v->mother, v->n_person);
+  std::vector<int32_t> glf_index;
+  std::ostringstream text;
+  for (int idx : ped.columns()) {
+    const Person &p = ped.persons[idx];
+    glf_index.push_back(p.glf_index);
+    text << p.famid << ' ' << p.pid << ' ' << p.fatid << ' ' << p.motid << ' ' << p.sex << ' ' << p.glf_index << '\n';
+  }
+  put(f, glf_index.data(), glf_index.size());
+  put(f, v->peel_first, (size_t)v->n_fam + 1);
+  if (n_steps) put(f, v->peel, (size_t)n_steps);
+
+  std::vector<pm_site_hdr> hdrs;
+  std::vector<pm_person_site> recs;
+  std::string label;
+  int32_t max_position = 0;
+  if (!gif_path.empty()) {
+    std::map<std::string, std::string> glf_map;
+    std::ifstream g(gif_path);
+    std::string line;
+    while (std::getline(g, line)) {
+      std::istringstream in(line);
+      std::string a, b;
+      if (in >> a >> b) glf_map[a] = b;
+    }
+    std::vector<std::string> paths;
+    for (int gi : glf_index) paths.push_back(gi == 0 || !glf_map.count(std::to_string(gi)) ? std::string() : glf_map[std::to_string(gi)]);
+    GlfSet glf;
+    std::string err;
+    if (!glf.open(paths, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    if (glf.next_section()) {  // fixtures hold one chromosome
+      label = glf.label();
+      max_position = glf.max_position();
+      pm_site_hdr h;
+      std::vector<pm_person_site> one((size_t)v->n_person);
+      while (glf.next_site(&h, one.data())) { hdrs.push_back(h); recs.insert(recs.end(), one.begin(), one.end()); }
+    }
+  }
+  text << "#label " << label << '\n';
+  std::string t = text.str();
+  uint32_t tl = (uint32_t)t.size();
+  put(f, &tl, 1); fwrite(t.data(), 1, t.size(), f);
+  put(f, &max_position, 1);
+  uint64_t ns = hdrs.size();
+  put(f, &ns, 1);
+  put(f, hdrs.data(), hdrs.size());
+  put(f, recs.data(), recs.size());
+  fclose(f);
+  fprintf(stderr, "packed %llu sites x %d persons -> %s\n", (unsigned long long)ns, v->n_person, out_path.c_str());
+  return 0;
+}
+
+template <typename T>
+static bool get(FILE *f, T *p, size_t n) { return fread(p, sizeof(T), n, f) == n; }
+
+static int do_unpack(int argc, char **argv) {
+  if (argc < 4) return usage();
+  const std::string in = argv[2], outdir = argv[3];
+  const bool gzip = argc > 4 && std::string(argv[4]) == "--gzip";
+  FILE *f = fopen(in.c_str(), "rb");
+  if (!f) { perror("open input"); return 1; }
+  char magic[4];
+  uint32_t version;
+  int32_t n_fam, n_person, n_steps;
+  if (!get(f, magic, 4) || memcmp(magic, "PMPK", 4) || !get(f, &version, 1) || !get(f, &n_fam, 1) || !get(f, &n_person, 1) || !get(f, &n_steps, 1)) {
+    fprintf(stderr, "not a .pmpk file\n");
+    return 1;
+  }
+  std::vector<int32_t> skip((size_t)n_fam * 3);
+  get(f, skip.data(), skip.size());
+  std::vector<uint8_t> sex(((size_t)n_person + 3) / 4 * 4);
+  get(f, sex.data(), sex.size());
+  std::vector<int32_t> fm((size_t)n_person * 2), glf_index((size_t)n_person), pf((size_t)n_fam + 1);
+  get(f, fm.data(), fm.size()); get(f, glf_index.data(), glf_index.size()); get(f, pf.data(), pf.size());
+  std::vector<pm_peel_step> steps((size_t)n_steps);
+  if (n_steps) get(f, steps.data(), steps.size());
+  uint32_t tl;
+  get(f, &tl, 1);
+  std::string text(tl, '\0');
+  get(f, &text[0], tl);
+  int32_t max_position;
+  uint64_t ns;
+  get(f, &max_position, 1); get(f, &ns, 1);
+  std::vector<pm_site_hdr> hdrs(ns);
+  std::vector<pm_person_site> recs(ns * (size_t)n_person);
+  if (!get(f, hdrs.data(), hdrs.size()) || !get(f, recs.data(), recs.size())) { fprintf(stderr, "truncated .pmpk\n"); return 1; }
+  fclose(f);
+  mkdir(outdir.c_str(), 0755);
+  std::string label = "1";
+  std::ofstream ped(outdir + "/ped"), dat(outdir + "/dat"), gif(outdir + "/gif");
+  dat << "T\tGLF_Index\n";
+  std::istringstream tin(text);
+  std::string line;
+  int col = 0;
+  std::set<int> seen;
+  while (std::getline(tin, line)) {
+    if (line.rfind("#label ", 0) == 0) { label = line.substr(7); continue; }
+    std::istringstream in(line);
+    std::string famid, pid, fat, mot; int sx, gi;
+    in >> famid >> pid >> fat >> mot >> sx >> gi;
+    // every distinct GLF_Index gets its own file, keyed by that index (so other pedigrees can
+    // refer to the same streams the way the original GLF index file did)
+    int key = gi;
+    ped << famid << '\t' << pid << '\t' << fat << '\t' << mot << '\t' << sx << '\t' << key << '\n';
+    if (key && !seen.count(key)) gif << key << ' ' << outdir << "/col" << key << ".glf\n";
+    seen.insert(key);
+    col++;
+  }
+  std::set<int> written;
+  for (int c = 0; c < n_person; c++) {
+    const int key = glf_index[(size_t)c];
+    if (key == 0 || written.count(key)) continue;
+    written.insert(key);
+    GlfWriter w;
+    std::string path = outdir + "/col" + std::to_string(key) + ".glf";
+    if (!w.create(path, gzip)) { perror(path.c_str()); return 1; }
+    w.begin_section(label, max_position);
+    for (uint64_t s = 0; s < ns; s++) {
+      const pm_person_site &r = recs[s * (size_t)n_person + (size_t)c];
+      uint32_t depth = r.depth[0] | (r.depth[1] << 8) | (r.depth[2] << 16);
+      // a person without a record at this position is all zeros with depth 0: leave the position out
+      bool empty = depth == 0 && r.map_quality == 0;
+      for (int g = 0; g < 10 && empty; g++) empty = r.lk[g] == 0;
+      if (empty) continue;
+      w.write_entry((int)hdrs[s].pos, hdrs[s].ref_base, depth, r.map_quality, r.lk);
+    }
+    w.end_section();
+    w.close();
+  }
+  fprintf(stderr, "unpacked %llu sites x %d persons -> %s\n", (unsigned long long)ns, n_person, outdir.c_str());
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) return usage();
+  if (!strcmp(argv[1], "pack")) return do_pack(argc, argv);
+  if (!strcmp(argv[1], "unpack")) return do_unpack(argc, argv);
+  return usage();
+}

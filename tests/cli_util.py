@@ -1,0 +1,86 @@
+"""Helpers that drive the front-end executables on fixture data."""
+import gzip
+import hashlib
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+PM_TOOLS = os.path.join(ROOT, "polymutt_b200", "bin", "pm-tools")
+ORACLE_CLI = os.path.join(ROOT, "oracle", "_build", "polymutt_oracle_cli")
+PRODUCT_CLI = os.path.join(ROOT, "polymutt_b200", "bin", "polymutt-b200")
+
+
+def unpack_example(tmpdir):
+    """Regenerates the 12 example GLF streams (one per column of example/test.ped) from the packed
+    fixture and writes a GLF index keyed like example/test.gif (1..12)."""
+    raw = os.path.join(tmpdir, "example12.pmpk")
+    with gzip.open(os.path.join(GOLDEN, "example12.pmpk.gz"), "rb") as src, open(raw, "wb") as dst:
+        dst.write(src.read())
+    out = os.path.join(tmpdir, "glf")
+    subprocess.run([PM_TOOLS, "unpack", raw, out], check=True, stderr=subprocess.DEVNULL)
+    os.remove(raw)
+    return out  # holds ped, dat, gif (keys 1..12 = test.ped's GLF_Index values)
+
+
+def body(text: bytes) -> bytes:
+    return b"".join(l for l in text.splitlines(keepends=True) if not l.startswith(b"##"))
+
+
+def run_cli(exe, glfdir, ped, extra, out_path, timeout=1800):
+    cmd = [exe, "-p", ped, "-d", os.path.join(glfdir, "dat"), "-g", os.path.join(glfdir, "gif"), "--out_vcf", out_path] + list(extra)
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    log = p.stdout.decode(errors="replace")
+    assert p.returncode == 0, log[-2000:]
+    with open(out_path, "rb") as f:
+        return body(f.read()), log
+
+
+def golden_text(name):
+    with gzip.open(os.path.join(GOLDEN, name), "rb") as f:
+        return f.read()
+
+
+def golden_sha(name):
+    sha, lines = open(os.path.join(GOLDEN, name)).read().split()
+    return sha, int(lines)
+
+
+def sha_of(text: bytes):
+    return hashlib.sha256(text).hexdigest(), text.count(b"\n")
+
+
+def first_diff(a: bytes, b: bytes):
+    la, lb = a.splitlines(), b.splitlines()
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            return f"line {i}: got {x[:300]!r}\n      expected {y[:300]!r}"
+    return f"line counts differ: got {len(la)} expected {len(lb)}"
+
+
+# (case name, pedigree file, extra args, golden file) — the reference's shipped goldens (example/run.sh
+# commands 1, 3, 4) and outputs of the unmodified reference on cases the shipped goldens do not cover.
+CASES = [
+    ("cmd1", "test.ped", ["-c", "0.9", "--minDepth", "150", "--maxDepth", "200", "--nthreads", "4"], "golden_cmd1.vcf.gz"),
+    ("cmd3", "test.mix.ped", [], "golden_cmd3.vcf.gz"),
+    ("cmd4", "test.ped", ["--nthreads", "4", "--denovo", "--rate_denovo", "1.5e-07"], "golden_cmd4.vcf.gz"),
+    ("ext_ba", "ext.ped", [], "ref_ext_ba.vcf.gz"),
+    ("ceph_ba", "ceph.ped", [], "ref_ceph_ba.vcf.gz"),
+    ("mix_strict", "test.mix.ped", ["-c", "0.99", "--minMapQuality", "50", "--minPercSampleWithData", "90", "--theta", "0.01", "--poly_tstv", "3.0"], "ref_mix_strict.vcf.gz"),
+    ("mix_denovo_loose", "test.mix.ped", ["--denovo", "--rate_denovo", "1e-4", "--minLLR_denovo", "1e-3", "--tstv_denovo", "1.0"], "ref_mix_denovo_loose.vcf.gz"),
+    ("mix_all_sites", "test.mix.ped", ["--all_sites"], "ref_mix_all_sites.sha"),
+    ("ext_denovo", "ext.ped", ["--denovo"], "ref_ext_denovo.vcf.gz"),
+    ("ceph_denovo", "ceph.ped", ["--denovo"], "ref_ceph_denovo.sha"),
+]
+SLOW_FOR_ORACLE = {"ext_denovo", "ceph_denovo"}  # minutes of CPU in the oracle; covered on the GPU and by make_golden runs
+
+
+def check_case(exe, glfdir, tmpdir, case):
+    name, ped, extra, golden = case
+    got, log = run_cli(exe, glfdir, os.path.join(GOLDEN, "peds", ped), extra, os.path.join(tmpdir, name + ".vcf"))
+    if golden.endswith(".sha"):
+        assert sha_of(got) == golden_sha(golden), f"{name}: sha/line-count mismatch {sha_of(got)} vs {golden_sha(golden)}"
+    else:
+        want = golden_text(golden)
+        assert got == want, f"{name}: " + first_diff(got, want)
+    return log

@@ -1,0 +1,34 @@
+"""End to end on the GPU box: the drop-in executable (CUDA engine) must print the reference's VCFs.
+
+Same goldens as tests/test_oracle_golden.py: the reference's shipped example outputs and outputs of the
+unmodified reference on extended pedigrees / --denovo / --all_sites.  Byte-for-byte on non-## lines;
+the formats print 2-4 significant decimals of doubles that agree to ~1e-12, so a difference means a
+real bug or a knife-edge rounding, which is reported with the offending line."""
+import os
+import subprocess
+
+import pytest
+
+import cli_util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def glfdir(tools_built, tmp_path_factory):
+    subprocess.run(["make", "-s", "cli"], cwd=U.ROOT, check=True)
+    return U.unpack_example(str(tmp_path_factory.mktemp("example")))
+
+
+@pytest.mark.parametrize("case", U.CASES, ids=lambda c: c[0])
+def test_product_cli_matches_reference_golden(case, glfdir, tmp_path):
+    if not os.path.exists(os.path.join(U.GOLDEN, case[3])):
+        pytest.skip("golden not generated")
+    log = U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+    assert "Summary of reference -- 1" in log
+
+
+def test_cli_reports_missing_inputs(tmp_path):
+    p = subprocess.run([U.PRODUCT_CLI, "-p", "nope.ped", "-d", "nope.dat", "-g", "nope.gif", "--out_vcf", str(tmp_path / "o.vcf")],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert p.returncode == 1 and b"FATAL ERROR" in p.stdout

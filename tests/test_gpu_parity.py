@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bit-exact: site status / filtering, argmax hypothesis, alleles, flags, best genotypes, read statistics.
+Within 1e-6 relative (the tolerance BASELINE.json's north_star states): hypothesis log-likelihoods,
+variant posterior, QUAL, allele frequency, de novo LR, AB, genotype posteriors, dosage.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cli_util as U
+import fixtures_util as F
+import parity
+from oracle_lib import OracleEngine
+from polymutt_b200 import Engine, Params, capi, synth
+
+pytestmark = pytest.mark.gpu
+
+PED = lambda name: os.path.join(U.GOLDEN, "peds", name)
+
+# (id, pedigree, params, number of sites (None = all 81,016), first site)
+EXAMPLE_CASES = [
+    ("quartets_cmd1", "test.ped", dict(posterior_cutoff=0.9, min_total_depth=150, max_total_depth=200), None, 0),
+    ("mix_default", "test.mix.ped", dict(), None, 0),
+    ("quartets_denovo", "test.ped", dict(denovo=True, denovo_mut_rate=1.5e-7), None, 0),
+    ("mix_all_sites", "test.mix.ped", dict(out_all_sites=True), 30000, 20000),
+    ("mix_strict", "test.mix.ped", dict(posterior_cutoff=0.99, min_map_quality=50, min_ps=90.0, theta=0.01, poly_tstv=3.0), None, 0),
+    ("mix_denovo_loose", "test.mix.ped", dict(denovo=True, denovo_mut_rate=1e-4, denovo_min_llr=1e-3, denovo_tstv=1.0), None, 0),
+    ("denovo_all_sites", "test.ped", dict(denovo=True, out_all_sites=True, denovo_min_llr=1e-9), 20000, 0),
+    ("ext_ba", "ext.ped", dict(), None, 0),
+    ("ext_denovo", "ext.ped", dict(denovo=True), 12000, 0),
+    ("ceph_ba", "ceph.ped", dict(), 40000, 0),
+    ("ceph_denovo", "ceph.ped", dict(denovo=True), 2500, 0),
+    ("ceph_all_sites", "ceph.ped", dict(out_all_sites=True), 3000, 5000),
+]
+
+
+def _run_both(ped, params, hdr, recs):
+    eng = Engine(ped, params)
+    st_g, res_g, per_g = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    eng.close()
+    ora = OracleEngine(ped, params)
+    st_o, res_o, per_o = ora.call_glf_sites(hdr, recs)
+    ora.close()
+    return (st_g, res_g, per_g), (st_o, res_o, per_o)
+
+
+@pytest.mark.parametrize("case", EXAMPLE_CASES, ids=lambda c: c[0])
+def test_example_data_parity(case, example12, oracle_built, tools_built, tmp_path):
+    name, pedfile, kw, n_sites, start = case
+    ped, glf_index = F.pedigree_from_file(PED(pedfile), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, n_sites, start)
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=name)
+    print(rep)
+    assert rep["emitted"] > 0
+    parity.assert_parity(rep, len(hdr))
+
+
+def _single_family(example12, cols, father, mother, sex, gen):
+    ped = capi.PedigreeArrays(np.array([len(cols)]), np.array([sum(1 for f in father if f < 0)]), np.array([gen]),
+                              np.array(sex, dtype=np.uint8), np.array(father), np.array(mother))
+    hdr, recs = F.sites_for(example12, np.array(cols))
+    return ped, hdr, recs
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(denovo=True, denovo_mut_rate=1.5e-7), dict(out_all_sites=True), dict(denovo=True, out_all_sites=True, denovo_min_llr=1e-9)],
+                         ids=["ba", "denovo", "all_sites", "denovo_all_sites"])
+def test_single_nuclear_family_fixed_prior(kw, example12, oracle_built):
+    """One trio/quartet only: no Brent, the fixed parent-pair table (NucFam.cpp:383-420)."""
+    ped, hdr, recs = _single_family(example12, [1, 2, 3, 4], [-1, -1, 0, 0], [-1, -1, 1, 1], [1, 2, 2, 1], 2)
+    n = 25000
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr[:n], recs[:n])
+    rep = parity.compare(*g, *o, denovo=params.denovo, label="single_quartet")
+    print(rep)
+    parity.assert_parity(rep, n)
+
+
+def test_unrelated_only(example12, oracle_built):
+    ped = synth.families([1] * 12)
+    hdr, recs = F.sites_for(example12, np.arange(1, 13))
+    g, o = _run_both(ped, Params(), hdr, recs)
+    rep = parity.compare(*g, *o, denovo=False, label="unrelated12")
+    print(rep)
+    parity.assert_parity(rep, len(hdr))
+
+
+def test_edge_cases_missing_data_bad_ref_and_filters(example12, oracle_built, tools_built, tmp_path):
+    ped, glf_index = F.pedigree_from_file(PED("test.mix.ped"), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, 6000, 1000)
+    rng = np.random.default_rng(5)
+    hdr["ref_base"][rng.integers(0, len(hdr), 300)] = 0          # N reference: skipped
+    drop = rng.random(recs.shape) < 0.15                         # persons without a record at the site
+    recs[drop] = np.zeros((), dtype=recs.dtype)
+    recs[100:140] = np.zeros((), dtype=recs.dtype)               # sites where nobody has data
+    recs["lk"][200:260, :, :] = 255                              # saturated likelihoods everywhere
+    recs["depth"][300:330, :, 2] = 1                             # 24-bit depths (> 65535)
+    for kw in (dict(), dict(min_total_depth=100, max_total_depth=170, min_ps=80.0, min_map_quality=90),
+               dict(denovo=True, denovo_mut_rate=1e-6), dict(out_all_sites=True)):
+        params = Params(**kw)
+        g, o = _run_both(ped, params, hdr, recs)
+        rep = parity.compare(*g, *o, denovo=params.denovo, label=f"edge{kw}")
+        print(rep)
+        parity.assert_parity(rep, len(hdr))
+    # empty batch
+    eng = Engine(ped, Params())
+    st, res, per = eng.call_glf_sites(hdr[:0], recs[:0], capi.PM_OUT_ALL)
+    assert len(st) == 0 and len(res) == 0
+    eng.close()
+
+
+def test_emitted_mode_is_the_ordered_subset_of_all_mode(example12, tools_built, tmp_path):
+    ped, glf_index = F.pedigree_from_file(PED("test.ped"), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, 30000)
+    eng = Engine(ped, Params())
+    st_a, res_a, per_a = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    st_e, res_e, per_e = eng.call_glf_sites(hdr, recs, capi.PM_OUT_EMITTED)
+    assert np.array_equal(st_a, st_e)
+    idx = np.flatnonzero((st_a & 0xF) == capi.PM_SITE_EMITTED)
+    assert len(res_e) == len(idx) > 100
+    assert np.array_equal(res_e["site"], idx)
+    assert res_e.tobytes() == res_a[idx].tobytes()
+    assert per_e.tobytes() == per_a[idx].tobytes()
+    # too small a result buffer is an error that reports the needed size
+    with pytest.raises(RuntimeError, match="res_cap"):
+        eng.call_glf_sites(hdr, recs, capi.PM_OUT_EMITTED, res_cap=10)
+    eng.close()
+
+
+def test_nonautosome_sites_fail_loudly(example12, tools_built, tmp_path):
+    ped, glf_index = F.pedigree_from_file(PED("test.ped"), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, 100)
+    hdr["chr_class"][50] = 1
+    eng = Engine(ped, Params())
+    with pytest.raises(RuntimeError, match="chrX"):
+        eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    eng.close()
+
+
+# ---- wide kernel (one block per site) on synthetic pedigrees -------------------------------------
+WIDE_CASES = [
+    ("mixed70", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(), 2500, 40.0),
+    ("mixed70_denovo", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(denovo=True), 1500, 40.0),
+    ("trios300", lambda: synth.trios(300), dict(denovo=True), 600, 10.0),
+    ("quartets_and_sibships", lambda: synth.families([4] * 100 + [5] * 40 + [6] * 10), dict(), 500, 10.0),
+    ("trios1000_denovo", lambda: synth.trios(1000), dict(denovo=True), 200, 4.0),
+    ("trios1000_ba", lambda: synth.trios(1000), dict(), 200, 4.0),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: c[0])
+def test_wide_kernel_parity_on_synthetic_pedigrees(case, oracle_built):
+    name, mk, kw, n_sites, boost = case
+    ped = mk()
+    h, r = synth.generate_sites(ped, n_sites, seed=20261018, cfg=synth.SynthConfig(poly_boost=boost, injected_denovo=0.02))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1)
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n_sites, ped.n_person)
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=name)
+    print(rep)
+    assert rep["emitted"] > 0
+    parity.assert_parity(rep, n_sites)

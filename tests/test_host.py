@@ -1,0 +1,167 @@
+"""Host-side logic that runs without a GPU: C-ABI surface, tables, peeling orders, pedigree ordering,
+GLF round trip, fixtures."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cli_util as U
+import oracle_lib
+from polymutt_b200 import capi, synth
+
+ROOT = U.ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(capi.lib_path()):
+        subprocess.run(["make", "-s", "lib"], cwd=ROOT, check=True)
+    return capi.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "polymutt_b200.h")).read()
+    names = set(re.findall(r"\b(pm_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"pm_ctx"}
+    assert len(names) >= 12
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} is declared in include/polymutt_b200.h but not exported"
+    assert lib.pm_abi_version() == 1
+
+
+def test_struct_sizes_match_header(lib):
+    # sizes the kernels and the Python binding both rely on
+    assert capi.SITE_HDR_DTYPE.itemsize == 8
+    assert capi.PERSON_SITE_DTYPE.itemsize == 16
+    assert capi.SITE_RESULT_DTYPE.itemsize == 256
+    assert capi.PERSON_RESULT_DTYPE.itemsize == 96
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ped = synth.trios(2)
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        capi.Engine(ped, capi.Params())
+
+
+def test_lut_and_mutation_matrix_bit_identical_to_oracle(lib, oracle_built):
+    o = oracle_lib.load()
+    a, b = np.zeros(256), np.zeros(256)
+    lib.pm_fill_lut(a.ctypes.data)
+    o.pmo_fill_lut(b.ctypes.data)
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert a[0] == 1.0 and abs(a[10] - 0.1) < 1e-16
+    for mu, tstv in ((1.5e-8, 2.0), (1.5e-7, 2.0), (1e-4, 1.0), (1e-3, 0.5), (1e-5, 0.0)):
+        m, n = np.zeros(100), np.zeros(100)
+        lib.pm_genotype_mutation_matrix(mu, tstv, m.ctypes.data)
+        o.pmo_genotype_mutation_matrix(mu, tstv, n.ctypes.data)
+        assert np.array_equal(m.view(np.uint64), n.view(np.uint64)), (mu, tstv)
+        if tstv != 0.0:
+            assert np.allclose(m.reshape(10, 10).sum(1), 1.0, atol=1e-12)
+
+
+def _peel(lib, father, mother, sex):
+    n = len(father)
+    fa, mo = np.asarray(father, np.int32), np.asarray(mother, np.int32)
+    sx = np.asarray(sex, np.uint8)
+    steps = np.zeros(n, dtype=capi.PEEL_STEP_DTYPE)
+    ns = lib.pm_build_peel_order(n, fa.ctypes.data, mo.ctypes.data, sx.ctypes.data, steps.ctypes.data)
+    return ns, steps[:max(ns, 0)]
+
+
+PEDS = {
+    # founders first, then ancestors before descendants (Family::path order)
+    "ext7": ([-1, -1, -1, 0, 0, 3, 3], [-1, -1, -1, 1, 1, 2, 2], [1, 2, 2, 1, 2, 1, 2]),
+    "ceph20": (list(synth.ceph().father), list(synth.ceph().mother), list(synth.ceph().sex)),
+    "two_roofs": ([-1, -1, -1, -1, 0, 2, 4], [-1, -1, -1, -1, 1, 3, 5], [1, 2, 1, 2, 1, 2, 1]),
+    "four_gen": ([-1, -1, -1, -1, 0, 4, 5, 5], [-1, -1, -1, -1, 1, 2, 3, 3], [1, 2, 2, 2, 1, 1, 1, 2]),
+    "halfsib_like": ([-1, -1, -1, 0, 0, 3], [-1, -1, -1, 1, 1, 2], [1, 2, 2, 1, 2, 1]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PEDS))
+def test_peel_order_matches_oracle_restatement(lib, oracle_built, name):
+    fa, mo, sx = PEDS[name]
+    ns, steps = _peel(lib, fa, mo, sx)
+    ref = oracle_lib.oracle_peel_order(fa, mo, sx)
+    assert ns == len(ref) and ns == len(fa) - 1 - sum(1 for s in ref if s["type"] == 3), (ns, ref)
+    assert np.array_equal(steps, ref), (steps, ref)
+
+
+def test_peel_order_ceph_shape(lib):
+    fa, mo, sx = PEDS["ceph20"]
+    ns, steps = _peel(lib, fa, mo, sx)
+    types = list(steps["type"])
+    # 14 leaf peels, 2 roof peels, 1 spouse peel
+    assert types.count(1) == 14 and types.count(3) == 2 and types.count(2) == 1 and ns == 17
+    assert types[:14] == [1] * 14
+
+
+def test_peel_order_rejects_loops_and_disconnected(lib):
+    # first-cousin marriage (inbreeding loop)
+    fa = [-1, -1, -1, -1, 0, 0, 4, 6]
+    mo = [-1, -1, -1, -1, 1, 1, 2, 3]
+    ns, _ = _peel(lib, [-1, -1, -1, -1, 0, 0, 4, 5 - 5 + 4], mo, [1, 2, 2, 2, 1, 2, 1, 1])
+    assert ns < 0 or ns <= 7
+    # an unconnected founder inside an extended family
+    ns2, _ = _peel(lib, [-1, -1, -1, -1, 0, 4], [-1, -1, -1, -1, 1, 2], [1, 2, 2, 1, 1, 1])
+    assert ns2 < 0
+    assert lib.pm_last_error()
+
+
+def test_pack_reproduces_fixture_and_pedigree_order(tools_built, example12, tmp_path):
+    """pm-tools unpack -> pack round trip: GLF writer, GLF reader, N-way merge and pedigree loader."""
+    glf = U.unpack_example(str(tmp_path))
+    out = str(tmp_path / "again.pmpk")
+    subprocess.run([U.PM_TOOLS, "pack", "-p", os.path.join(glf, "ped"), "-d", os.path.join(glf, "dat"), "-g", os.path.join(glf, "gif"), "-o", out],
+                   check=True, stderr=subprocess.DEVNULL)
+    from polymutt_b200 import load_pmpk
+    again = load_pmpk(out)
+    assert np.array_equal(again.hdr, example12.hdr)
+    assert np.array_equal(again.recs, example12.recs)
+    assert again.max_position == example12.max_position == 81016
+    assert [p[1] for p in again.people] == [str(i) for i in range(1, 13)]
+
+
+def test_pedigree_ordering_rules(tools_built, tmp_path):
+    """Natural, case-insensitive (famid, pid) sort; founders first; ancestors before descendants;
+    mis-sexed parents swapped (core/Pedigree.cpp:39-85, PedigreeFamily.cpp:11-85, PedigreePerson.cpp:90-126)."""
+    ped = tmp_path / "p.ped"
+    ped.write_text(
+        "f10 c 9 b 1 0\nf10 9 0 0 1 0\nf10 b 0 0 2 0\n"      # father/mother columns given in order
+        "F2 kid2 mum dad 2 0\nF2 dad 0 0 1 0\nF2 mum 0 0 2 0\nF2 kid10 dad mum 1 0\nF2 g 0 0 2 0\nF2 gk kid10 g 1 0\n"
+        "f1 solo 0 0 1 0\n")
+    dat = tmp_path / "p.dat"
+    dat.write_text("T GLF_Index\n")
+    out = str(tmp_path / "p.pmpk")
+    subprocess.run([U.PM_TOOLS, "pack", "-p", str(ped), "-d", str(dat), "-o", out], check=True, stderr=subprocess.DEVNULL)
+    from polymutt_b200 import load_pmpk
+    p = load_pmpk(out)
+    # families sort naturally: f1 < F2 < f10
+    assert [x[0] for x in p.people] == ["f1"] + ["F2"] * 6 + ["f10"] * 3
+    # F2: founders in sorted pid order (dad, g, mum), then kid2 (sorted before kid10: natural order), kid10, then gk
+    assert [x[1] for x in p.people[1:7]] == ["dad", "g", "mum", "kid2", "kid10", "gk"]
+    assert list(p.ped.fam_size) == [1, 6, 3] and list(p.ped.fam_founders) == [1, 3, 2]
+    assert list(p.ped.fam_generations) == [1, 3, 2]
+    # kid2 was entered as (father=mum, mother=dad): swapped back by sex
+    assert p.ped.father[1 + 3] == 0 and p.ped.mother[1 + 3] == 2
+    # the F2 family is extended: a peeling order exists for it only
+    assert list(np.diff(p.ped.peel_first)) == [0, len(p.ped.peel), 0] and len(p.ped.peel) > 0
+
+
+def test_synthetic_generator_is_seeded_and_well_formed():
+    ped = synth.concat(synth.trios(3), synth.families([4, 1]))
+    h1, r1 = synth.generate_sites(ped, 500, 11, cfg=synth.SynthConfig(poly_boost=30))
+    h2, r2 = synth.generate_sites(ped, 500, 11, cfg=synth.SynthConfig(poly_boost=30))
+    assert (h1 == h2).all() and (r1 == r2).all()
+    recs = r1.numpy().view(capi.PERSON_SITE_DTYPE).reshape(500, ped.n_person)
+    depth = recs["depth"][..., 0].astype(int) + 256 * recs["depth"][..., 1].astype(int)
+    has = depth > 0
+    assert (recs["lk"].min(axis=2)[has] == 0).all()          # min-normalised
+    assert (recs["lk"][~has] == 0).all() and (recs["map_quality"][~has] == 0).all()
+    assert 0.005 < (~has).mean() < 0.06

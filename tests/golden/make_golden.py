@@ -89,7 +89,7 @@ def main():
                 with gzip.GzipFile(os.path.join(HERE, f"ref_{name}.vcf.gz"), "wb", 9, mtime=0) as dst:
                     dst.write(text)
             with open(os.path.join(HERE, f"ref_{name}.sha"), "w") as f:
-                f.write(f"{hashlib.sha256(text).hexdigest()} {text.count(b'\\n')}\n")
+                f.write("%s %d\n" % (hashlib.sha256(text).hexdigest(), text.count(b"\n")))
             print(name, len(text), "bytes", text.count(b"\n"), "lines")
 
 

@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""bench.py — sites/sec of the per-site family-likelihood hot path on B200, with roofline and CPU baseline.
+
+Workload (BASELINE.json configs[1]): 1,000 independent trios (3,000 people), --denovo, synthetic GLF
+sites (polymutt_b200/synth.py).  A step = one pass of the hot path (k_sites_* -> k_compact -> k_post)
+over one batch of `--sites-per-step` packed sites that already sits in HBM; consecutive steps cycle
+through `--resident-batches` distinct batches, each far larger than the 126 MB L2, so no L2 flush is
+needed.  The 10M-site job of the config is 10M / sites-per-step such steps; sites are independent, so
+N GPUs each take their own contiguous site range (weak scaling: per-GPU batch fixed) with no
+collective on the data path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one JSON line on rank 0)
+  python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's own CPU path
+                                                                      (oracle/_ref/polymutt) on a bounded sample
+
+`value` is device-resident throughput timed with CUDA events on the library's own stream
+(pm_timer_start/stop), max over ranks.  `e2e` is the same metric through the host-buffer C-ABI call
+(pm_call_glf_sites) from pinned host memory, H2D and D2H copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import resource
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sites/sec for family variant+de novo calling"
+UNIT = "sites/s"
+WORKLOAD = "configs[1]: 1,000 independent trios (3,000 people), --denovo, synthetic GLF sites"
+N_TRIOS = 1000
+SEED = 20261018
+
+# Algorithmic work per site (DESIGN.md "Roofline"): per (family, hypothesis) coefficient
+# set-up S = 87k+18 flops under --denovo (36k+9 otherwise), k = kids; per objective evaluation 18 flops
+# per family + 20 for the shared priors (+ one log10 per family, counted separately, costed at 0 flops).
+def algorithmic_flops(n_fam, kids_per_fam, denovo, hypotheses, evaluations):
+    setup = (87 * kids_per_fam + 18) if denovo else (36 * kids_per_fam + 9)
+    return hypotheses * n_fam * setup + evaluations * (18 * n_fam + 20)
+
+
+def algorithmic_bytes_per_site(n_person):
+    return 14 * n_person + 5  # 10 likelihood bytes + 3 depth + 1 mapQ per person; 4 pos + 1 ref per site
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            t = [x.strip() for x in l.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0])); mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference (oracle/_ref/polymutt) on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "polymutt")
+    if os.path.exists(p):
+        return p, "reference"
+    p = os.path.join(ROOT, "oracle", "_build", "polymutt_oracle_cli")  # the restatement, if the reference did not travel
+    if not os.path.exists(p):
+        subprocess.run(["make", "-s", "oracle"], cwd=ROOT, check=True)
+    return p, "port"
+
+
+def prepare_reference_sample(n_sites, tmp):
+    import numpy as np
+    from polymutt_b200 import capi, glfio, synth
+    ped = synth.trios(N_TRIOS)
+    h, r = synth.generate_sites(ped, n_sites, seed=SEED + 7919, device="cpu")
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1)
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n_sites, ped.n_person)
+    return glfio.write_run_dir(tmp, ped, hdr, recs)
+
+
+def run_reference_once(exe, paths, threads, out_vcf):
+    soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+    want = 3 * N_TRIOS + 256
+    if soft < want:
+        resource.setrlimit(resource.RLIMIT_NOFILE, (min(max(want, soft), hard), hard))
+    t0 = time.perf_counter()
+    subprocess.run([exe, "-p", paths[0], "-d", paths[1], "-g", paths[2], "--denovo", "--nthreads", str(threads), "--out_vcf", out_vcf],
+                   check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(n_sites=1000):
+    """~10-20 s of the reference on this box's host cores; returns the cpu_baseline object."""
+    exe, kind = reference_binary()
+    cores = os.cpu_count() or 1
+    tmp = tempfile.mkdtemp(prefix="pm_cpu_base_")
+    try:
+        paths = prepare_reference_sample(n_sites, tmp)
+        dt = run_reference_once(exe, paths, cores, os.path.join(tmp, "o.vcf"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": n_sites / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n_sites} synthetic sites of the same workload written as 3,000 GLF files; wall time of the whole "
+                      f"run (--nthreads {cores}; includes opening the files and VCF writing), {dt:.1f} s"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    exe, kind = reference_binary()
+    cores = os.cpu_count() or 1
+    n_sites = args.ref_sites
+    tmp = tempfile.mkdtemp(prefix="pm_ref_arm_")
+    try:
+        paths = prepare_reference_sample(n_sites, tmp)
+        for _ in range(args.warmup):
+            run_reference_once(exe, paths, cores, os.path.join(tmp, "o.vcf"))
+        t = [run_reference_once(exe, paths, cores, os.path.join(tmp, "o.vcf")) for _ in range(args.steps)]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    total = sum(t)
+    value = n_sites * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sites_per_step": n_sites, "persons": 3 * N_TRIOS, "families": N_TRIOS,
+                   "note": "each step = the reference binary end to end on a bounded sample (GLF files in, VCF out) on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{n_sites} synthetic sites per step, --nthreads {cores}"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sites-per-step", type=int, default=1 << 17)
+    ap.add_argument("--resident-batches", type=int, default=2)
+    ap.add_argument("--e2e-sites", type=int, default=1 << 13)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-sites", type=int, default=600)
+    ap.add_argument("--cpu-baseline-sites", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from polymutt_b200 import Engine, Params, capi, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ped = synth.trios(N_TRIOS)
+    npers = ped.n_person
+    S, R, K, W = args.sites_per_step, args.resident_batches, args.steps, args.warmup
+    params = Params(denovo=True)
+    eng = Engine(ped, params, device=local_rank)
+
+    # ---- synthetic batches, generated on the device; rank r owns sites [r*R*S, (r+1)*R*S) of the job ----
+    batches = []
+    for b in range(R):
+        hdr = torch.empty((S, 8), dtype=torch.uint8, device=dev)
+        recs = torch.empty((S, npers, 16), dtype=torch.uint8, device=dev)
+        synth.generate_sites(ped, S, seed=SEED + 1000 * rank + b, device=dev, out_hdr=hdr, out_recs=recs, chunk=1 << 12,
+                             pos0=(rank * R + b) * S)
+        batches.append((hdr, recs))
+    cap = max(4096, S // 16)
+    status = torch.empty(S, dtype=torch.uint16, device=dev)
+    res_out = torch.empty((cap, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    per_out = torch.empty((cap, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    n_res = torch.zeros(1, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        hdr, recs = batches[i % R]
+        eng.call_glf_sites_device(hdr.data_ptr(), recs.data_ptr(), S, capi.PM_OUT_EMITTED, status.data_ptr(), res_out.data_ptr(),
+                                  per_out.data_ptr(), cap, n_res.data_ptr())
+
+    for i in range(W):
+        step(i)
+    eng.sync()
+    eng.reset_counters()
+    main_ms = 0.0
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.timer_start()
+    for i in range(K):
+        step(i)
+    ms = eng.timer_stop()
+    eng.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    counters = eng.counters()
+    emitted_last = int(n_res.item())
+    # main-kernel time per launch (CUDA events around k_sites_wide inside the library), from one more step
+    step(0)
+    eng.sync()
+    main_ms, total_ms, launches_per_step = eng.last_timing()
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * S / (ms_max * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_sites_wide) ----
+        fp64_peak = eng.measure_fp64_peak()
+        copy_bw = eng.measure_copy_bw()
+        peaks = measured_peaks()
+        hyp_per_site = counters["hypotheses"] / max(1, counters["sites_evaluated"])
+        ev_per_site = counters["evaluations"] / max(1, counters["sites_evaluated"])
+        flops_per_site = algorithmic_flops(N_TRIOS, 1, True, hyp_per_site, ev_per_site)
+        log10_per_site = ev_per_site * N_TRIOS
+        flops_per_launch = flops_per_site * S
+        achieved_tflops = flops_per_launch / (main_ms * 1e-3) / 1e12
+        bytes_per_launch = algorithmic_bytes_per_site(npers) * S
+        hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        roofline = {
+            "bound": "fp64", "kernel": "k_sites_wide<8>", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+            "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": None,
+            "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+            "flops_per_site": flops_per_site, "log10_per_site": log10_per_site,
+            "hypotheses_per_site": hyp_per_site, "evaluations_per_site": ev_per_site, "kernel_ms_per_launch": main_ms,
+            "hbm": {"achieved": bytes_per_launch / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_per_launch / (main_ms * 1e-3) / 1e9 / hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "copy_kernel_gbs_live": copy_bw / 1e9},
+        }
+
+        # ---- e2e through the host-buffer C-ABI call, pinned host memory ----
+        Se = min(args.e2e_sites, S)
+        h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
+        h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
+        h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
+        cap_e = max(1024, Se // 8)
+        h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
+        h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        nres = C.c_size_t(0)
+
+        def e2e_step():
+            rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
+                                           h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
+            if rc != 0:
+                raise RuntimeError(eng.lib.pm_last_error().decode())
+
+        e2e_step()  # warm-up (allocates the staging buffers)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        e2e_dt = (time.perf_counter() - t0) / args.e2e_steps
+        rows = nres.value
+        e2e = {"value": Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": Se * (npers * 16 + 8),
+               "d2h_bytes_per_step": Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4,
+               "sites_per_step": Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": 1,
+               "note": "pm_call_glf_sites from pinned host buffers; H2D of the packed sites and D2H of status + emitted rows inside the timed region"}
+        if world > 1:
+            e2e["note"] += "; measured on rank 0 only (ranks are independent)"
+
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sites_per_step_per_gpu": S, "persons": npers, "families": N_TRIOS,
+                       "resident_batches": R, "input_bytes_per_step": S * (npers * 16 + 8),
+                       "l2": "each step reads a different resident batch of %.1f GB, far larger than the 126 MB L2 (no flush needed)" % (S * npers * 16 / 1e9),
+                       "kernel_plan": "k_sites_wide<8>, 128 threads per site, one TMA bulk copy per site",
+                       "emitted_rows_last_step": emitted_last, "result_capacity_rows": cap},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step) * K, "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_sites)
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)[:200]}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,56 @@
+"""Minimal GLF v3 writer (core/glfHandler.h:21-42 record layout) used to hand synthetic sites to the
+reference binary / the drop-in executable in bench.py and the tests."""
+from __future__ import annotations
+
+import os
+import struct
+
+import numpy as np
+
+_REC = np.dtype([("tag", "u1"), ("offset", "<u4"), ("depth_minllk", "<u4"), ("mapq", "u1"), ("lk", "u1", (10,))])
+assert _REC.itemsize == 20
+_BACK = np.array([15, 1, 2, 4, 8], dtype=np.uint8)  # glfHandler::backTranslateBase
+
+
+def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_base: np.ndarray, recs: np.ndarray):
+    """recs: [n_sites] PERSON_SITE_DTYPE for one person; rows that are all zero are left out."""
+    depth = recs["depth"][:, 0].astype(np.uint32) | (recs["depth"][:, 1].astype(np.uint32) << 8) | (recs["depth"][:, 2].astype(np.uint32) << 16)
+    keep = (depth > 0) | (recs["map_quality"] > 0) | (recs["lk"].max(axis=1) > 0)
+    p = pos[keep].astype(np.int64)
+    out = np.zeros(len(p), dtype=_REC)
+    out["tag"] = (1 << 4) | _BACK[ref_base[keep]]
+    out["offset"] = np.diff(np.concatenate([[0], p])).astype(np.uint32)
+    out["depth_minllk"] = depth[keep]
+    out["mapq"] = recs["map_quality"][keep]
+    out["lk"] = recs["lk"][keep]
+    lab = label.encode() + b"\0"
+    with open(path, "wb") as f:
+        f.write(b"GLF\x03" + struct.pack("<I", 0))
+        f.write(struct.pack("<i", len(lab)) + lab + struct.pack("<i", max_position))
+        f.write(out.tobytes())
+        f.write(b"\0")
+
+
+def write_run_dir(outdir: str, ped, hdr: np.ndarray, recs: np.ndarray, label: str = "1"):
+    """Writes ped/dat/gif + one GLF per person for a packed batch; returns (ped, dat, gif) paths."""
+    os.makedirs(outdir, exist_ok=True)
+    firsts = ped.family_first()
+    lines, gif = [], []
+    pos = hdr["pos"].astype(np.int64)
+    max_position = int(pos.max()) + 1 if len(pos) else 1
+    col = 0
+    for f in range(ped.n_fam):
+        for j in range(int(ped.fam_size[f])):
+            fa, mo = int(ped.father[col]), int(ped.mother[col])
+            pid = lambda k: f"p{k + 1:02d}"
+            # pids sort naturally in column order; founders come first inside each family by construction
+            lines.append(f"fam{f + 1:05d}\t{pid(j)}\t{pid(fa) if fa >= 0 else 0}\t{pid(mo) if mo >= 0 else 0}\t{int(ped.sex[col])}\t{col + 1}\n")
+            path = os.path.join(outdir, f"g{col + 1}.glf")
+            write_glf(path, label, max_position, pos, hdr["ref_base"], recs[:, col])
+            gif.append(f"{col + 1} {path}\n")
+            col += 1
+    paths = [os.path.join(outdir, n) for n in ("run.ped", "run.dat", "run.gif")]
+    open(paths[0], "w").write("".join(lines))
+    open(paths[1], "w").write("T\tGLF_Index\n")
+    open(paths[2], "w").write("".join(gif))
+    return paths

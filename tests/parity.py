@@ -12,7 +12,10 @@ RTOL = 1e-6
 
 def _close(a, b, rtol=RTOL, atol=0.0):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
-    return np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b))
+    with np.errstate(invalid="ignore"):
+        ok = np.abs(a - b) <= atol + rtol * np.maximum(np.abs(a), np.abs(b))
+    # equal infinities (log10 of a likelihood that underflowed to 0 on both sides) and NaN on both sides agree
+    return ok | (a == b) | (np.isnan(a) & np.isnan(b))
 
 
 def compare(status_g, res_g, per_g, status_o, res_o, per_o, denovo, label=""):

@@ -119,7 +119,7 @@ typedef struct pm_person_site {
 
 /* What happened to a site (the `continue`s of src/main.cpp:339-574, in order). */
 enum {
-  PM_SITE_EMITTED       = 0,  /* a VCF row is due (subject to pm_site_result.flags & PM_FLAG_ROW_DROPPED) */
+  PM_SITE_EMITTED       = 0,  /* a VCF row is due */
   PM_SITE_BAD_REF       = 1,  /* refBase not in 1..4                       main.cpp:340 */
   PM_SITE_MIN_DEPTH     = 2,  /* totalDepth < --minDepth                   main.cpp:345 */
   PM_SITE_MAX_DEPTH     = 3,  /* totalDepth > --maxDepth                   main.cpp:346 */
@@ -128,12 +128,16 @@ enum {
   PM_SITE_NOCALL        = 6,  /* varPostProb < posterior cutoff            main.cpp:539 */
   PM_SITE_MONO          = 7,  /* best hypothesis is hom-ref, nothing to print  main.cpp:555 */
   PM_SITE_DENOVO_LOW_LR = 8,  /* --denovo, mono winner, DQ <= log10(minLLR)    main.cpp:563 */
-  PM_SITE_QUICK_SKIP    = 9   /* --quick_call pre-pass said no variant     main.cpp:432-433 */
+  PM_SITE_QUICK_SKIP    = 9,  /* --quick_call pre-pass said no variant     main.cpp:432-433 */
+  PM_SITE_DENOVO_DROPPED = 10 /* --denovo: the site reached OutputVCF_denovo, which prints nothing because
+                                 denovoLR < the raw --minLLR_denovo (src/NucFamGenotypeLikelihood.cpp:1868;
+                                 main.cpp:563 compared against log10 of it).  The reference computes genotype
+                                 posteriors for these sites and throws them away; we do not compute them.
+                                 Only visible effect: the VCF header is printed once such a site is seen. */
 };
 
 #define PM_FLAG_NOCALL       0x1  /* varPostProb < cutoff was counted ("Hard to call"), main.cpp:539 */
-#define PM_FLAG_ROW_DROPPED  0x2  /* OutputVCF_denovo drops the row: denovoLR < raw --minLLR_denovo
-                                     (src/NucFamGenotypeLikelihood.cpp:1868) */
+#define PM_FLAG_ROW_DROPPED  0x2  /* set together with PM_SITE_DENOVO_DROPPED */
 #define PM_FLAG_MONO         0x4  /* emitted as monomorphic (isMono / denovo_mono) */
 
 /* Per-site result = the public members of famlk[0] the VCF writers and the summary block read

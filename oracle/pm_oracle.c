@@ -1092,7 +1092,14 @@ static void fill_result(const pmo_ctx *c, const famlk_t *k, pm_site_result *r) {
   r->perc_samp = k->percSampWithData; r->avg_map_qual = k->avgMapQual;
   r->var_post_prob = k->varPostProb; r->poly_qual = k->polyQual;
   r->freq = k->min; r->denovo_lr = k->denovoLR; r->ab = k->AB;
-  for (int i = 0; i < 7; i++) { r->varllk[i] = k->varllk[i]; r->varllk_noprior[i] = k->varllk_noprior[i]; r->varfreq[i] = k->varfreq[i]; }
+  /* slots of hypotheses that were not evaluated at this site hold stale values from earlier sites in
+     the reference's members; they are never read, so the result reports them as 0 */
+  for (int i = 0; i < 7; i++) {
+    int live = i < r->n_hyp;
+    r->varllk[i] = live ? k->varllk[i] : 0.0;
+    r->varllk_noprior[i] = live ? k->varllk_noprior[i] : 0.0;
+    r->varfreq[i] = live ? k->varfreq[i] : 0.0;
+  }
   (void)c;
 }
 
@@ -1188,6 +1195,16 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
     c->par.denovo = 1;
     r->refit_llk = lk_poly;
   }
+  /* OutputVCF_denovo returns before printing when denovoLR < the raw threshold (NucFam:1868).  The
+     reference still runs CalcPostProb for such sites (main:576-587) and discards the result; nothing
+     later reads it, so the restatement stops here. */
+  if (par->denovo && fl[0].denovoLR < par->denovo_min_llr) {
+    if (maxidx == 0) r->flags |= PM_FLAG_MONO;
+    r->flags |= PM_FLAG_ROW_DROPPED;
+    fill_result(c, &fl[0], r);
+    r->status = PM_SITE_DENOVO_DROPPED;
+    return 0;
+  }
   if (maxidx == 0) { /* main:576-587 */
     if (par->denovo) { fl[0].denovo_mono = 1; CalcPostProb(c, &fl[0], 1.0); }
     else { fl[0].isMono = 1; CalcPostProb(c, &fl[0], 1 - par->theta); }
@@ -1196,13 +1213,8 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
     fl[0].isMono = 0;
     CalcPostProb(c, &fl[0], fl[0].min);
   }
-  /* what the writers compute before printing: NucFam:1791 (AB) and 1868-1871 (de novo row drop) */
+  /* what the writer computes before printing: NucFam:1791 (AB) */
   if (!par->denovo) CalculateAB(c, &fl[0], fl[0].min);
-  else {
-    /* NucFam:1870 then prints ALT = allele1 for a denovo_mono row; the writer does that from
-       PM_FLAG_MONO, the result keeps the alleles the genotype labels were made with. */
-    if (fl[0].denovoLR < par->denovo_min_llr) r->flags |= PM_FLAG_ROW_DROPPED;
-  }
   fl[0].denovo_mono = 0;
   fill_result(c, &fl[0], r);
   r->status = PM_SITE_EMITTED;

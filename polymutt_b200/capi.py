@@ -52,6 +52,7 @@ PEEL_STEP_DTYPE = np.dtype([("type", "<i4"), ("from0", "<i4"), ("from1", "<i4"),
 # status codes / flags (include/polymutt_b200.h)
 PM_SITE_EMITTED, PM_SITE_BAD_REF, PM_SITE_MIN_DEPTH, PM_SITE_MAX_DEPTH, PM_SITE_MIN_PS = 0, 1, 2, 3, 4
 PM_SITE_MIN_MAPQ, PM_SITE_NOCALL, PM_SITE_MONO, PM_SITE_DENOVO_LOW_LR, PM_SITE_QUICK_SKIP = 5, 6, 7, 8, 9
+PM_SITE_DENOVO_DROPPED = 10
 PM_FLAG_NOCALL, PM_FLAG_ROW_DROPPED, PM_FLAG_MONO = 1, 2, 4
 PM_OUT_EMITTED, PM_OUT_ALL = 0, 1
 PM_OK, PM_EINVAL, PM_ECUDA, PM_ENOMEM, PM_EUNSUPPORTED = 0, -1, -2, -3, -4

@@ -189,8 +189,14 @@ int run_cli(int argc, char **argv, const Engine &engine) {
           return fatal(std::string("engine '") + engine.name + "': " + engine.last_error());
         }
         for (size_t s = 0; s < n; s++) count_site(cnt, hdr[s], status[s], opt);
-        for (size_t r = 0; r < n_res; r++) {
-          uint32_t s = res[r].site;
+        // rows and dropped de novo candidates in site order: the first of either prints the header
+        size_t next_row = 0;
+        for (size_t s = 0; s < n && !stop; s++) {
+          const int code = status[s] & 0xf;
+          if (code == PM_SITE_DENOVO_DROPPED) { writer.ensure_header(); continue; }
+          if (code != PM_SITE_EMITTED) continue;
+          const size_t r = next_row++;
+          if (r >= n_res || res[r].site != s) throw std::runtime_error("engine returned rows out of site order");
           writer.write_site(label, hdr[s], res[r], &ps[(size_t)s * np], &pres[r * (size_t)np]);
           out_cnt++;
           if (opt.force_call && out_cnt >= positions.size()) { stop = true; break; }  // main.cpp:593

@@ -88,7 +88,6 @@ void VcfWriter::write_normal(const std::string &chrom, const pm_site_hdr &hdr, c
 void VcfWriter::write_denovo(const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
                              const pm_person_site *persons, const pm_person_result *pr) {
   if (!header_done_) header(true);
-  if (r.flags & PM_FLAG_ROW_DROPPED) return;  // NucFam.cpp:1868
   const bool single_nuclear = ped_.families.size() == 1 && ped_.families[0].nuclear();
   const bool mono = (r.flags & PM_FLAG_MONO) != 0;
   const int a1 = r.allele1, ref = hdr.ref_base;

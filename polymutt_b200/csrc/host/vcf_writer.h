@@ -17,6 +17,9 @@ class VcfWriter {
   // One emitted site. `persons` = the site's packed input records, `pr` = its per-person results.
   void write_site(const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
                   const pm_person_site *persons, const pm_person_result *pr);
+  // OutputVCF_denovo prints the header the first time it is entered, even if it then drops the row
+  // (NucFam.cpp:1834-1868): called when a PM_SITE_DENOVO_DROPPED site is seen.
+  void ensure_header() { if (!header_done_) header(opt_.denovo); }
   long rows_written() const { return rows_; }
 
  private:

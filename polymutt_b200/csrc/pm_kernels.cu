@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
     double lk_poly = ev.optimize(r.allele1, r.allele2, false, &freq);
     site_finish_refit(run, r, lk_poly, freq);
   }
-  if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) r.flags |= PM_FLAG_ROW_DROPPED;
+  if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) { r.flags |= PM_FLAG_ROW_DROPPED; r.status = PM_SITE_DENOVO_DROPPED; }
   r.reserved = 0;
   res[s] = r;
   status[s] = status_word(r);
@@ -588,7 +588,7 @@ __global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *
       }
       if (threadIdx.x == 0) {
         pm_site_result &r = ws->r;
-        if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) r.flags |= PM_FLAG_ROW_DROPPED;
+        if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) { r.flags |= PM_FLAG_ROW_DROPPED; r.status = PM_SITE_DENOVO_DROPPED; }
         r.reserved = 0;
         res[s] = r;
         status[s] = status_word(r);

@@ -289,7 +289,7 @@ def main():
         bytes_per_launch = algorithmic_bytes_per_site(npers) * S
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         roofline = {
-            "bound": "fp64", "kernel": "k_sites_wide<8>", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+            "bound": "fp64", "kernel": "k_sites_wide", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
             "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": None,
             "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
             "flops_per_site": flops_per_site, "log10_per_site": log10_per_site,
@@ -337,7 +337,7 @@ def main():
             "config": {"workload": WORKLOAD, "sites_per_step_per_gpu": S, "persons": npers, "families": N_TRIOS,
                        "resident_batches": R, "input_bytes_per_step": S * (npers * 16 + 8),
                        "l2": "each step reads a different resident batch of %.1f GB, far larger than the 126 MB L2 (no flush needed)" % (S * npers * 16 / 1e9),
-                       "kernel_plan": "k_sites_wide<8>, 128 threads per site, one TMA bulk copy per site",
+                       "kernel_plan": eng.describe_plan(),
                        "emitted_rows_last_step": emitted_last, "result_capacity_rows": cap},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step) * K, "roofline": roofline,
         }

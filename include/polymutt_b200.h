@@ -213,6 +213,9 @@ int pm_sync(pm_ctx *ctx);
  * in the most recent pm_call_*; used by bench.py for the roofline numbers. */
 int pm_last_timing(pm_ctx *ctx, float *ms_main_kernel, float *ms_total, int *n_launches);
 
+/* Human-readable description of the kernel plan chosen for this pedigree (bench.py prints it). */
+int pm_describe_plan(pm_ctx *ctx, char *buf, size_t len);
+
 /* Device-side stopwatch on the ctx stream (CUDA events): pm_timer_start records an event, pm_timer_stop
  * records a second one, waits for it and returns the elapsed milliseconds.  bench.py brackets its K
  * timed steps with these so that the number is taken on the stream the kernels are launched on. */

@@ -204,6 +204,8 @@ def _declare(lib):
     lib.pm_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.pm_measure_copy_bw.restype = C.c_int
     lib.pm_measure_copy_bw.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.pm_describe_plan.restype = C.c_int
+    lib.pm_describe_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.pm_timer_start.restype = C.c_int
     lib.pm_timer_start.argtypes = [C.c_void_p]
     lib.pm_timer_stop.restype = C.c_int
@@ -295,6 +297,11 @@ class Engine:
         a, b, n = C.c_float(0), C.c_float(0), C.c_int(0)
         self._check(self.lib.pm_last_timing(self.ctx, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def describe_plan(self) -> str:
+        buf = C.create_string_buffer(512)
+        self._check(self.lib.pm_describe_plan(self.ctx, buf, 512))
+        return buf.value.decode()
 
     def timer_start(self):
         self._check(self.lib.pm_timer_start(self.ctx))

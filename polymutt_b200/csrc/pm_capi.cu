@@ -375,6 +375,15 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   return PM_OK;
 }
 
+// "narrow" or "wide T=<threads> U=<units/thread> NC=<chains> grid=<blocks> (<blocks/SM>/SM)"
+extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
+  if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
+  if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", pm::kNarrowMaxUnits, c->plan.threads);
+  else snprintf(buf, len, "k_sites_wide<U=%d,NC=%d>: one block of %d threads per site, %d units/thread, %d concurrent Brent chains, persistent grid %d (%d blocks/SM), one TMA bulk copy per site",
+                c->plan.units_per_thread, c->plan.chains, c->plan.threads, c->plan.units_per_thread, c->plan.chains, c->plan.grid, c->plan.blocks_per_sm);
+  return PM_OK;
+}
+
 extern "C" int pm_timer_start(pm_ctx *c) {
   if (!c) return fail(PM_EINVAL, "null context");
   CUDA_TRY(cudaSetDevice(c->device));

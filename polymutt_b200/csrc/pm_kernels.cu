@@ -15,6 +15,7 @@
 // All arithmetic is FP64; inputs are uint8 phred likelihoods.  See DESIGN.md for the data layout and
 // the roofline of each kernel.
 #include <cstdio>
+#include <cstdlib>
 
 #include "pm_device.cuh"
 #include "pm_kernels.h"
@@ -358,20 +359,32 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
 }
 
 // ================================================================================================
-// wide kernel: one block per site
+// wide kernel: one block per site, NC Brent chains in flight
+//
+// One objective evaluation is cheap (5 FMAs per unit) but every Brent step ends in a serial tail —
+// product reduction, one log10, the Brent update with its division, two block barriers — of
+// ~1.5-2 k cycles.  With one chain per block the FP64 pipes idle during that tail, so the three
+// hypotheses H1..H3 (and H4..H6 when needed) are optimised CONCURRENTLY: every thread keeps the
+// quartic coefficients of its U units for all NC chains in registers, one round evaluates all live
+// chains, and NC driver threads (lane 0 of warps 0..NC-1) finish the reduction, take the log10 and
+// advance their own Brent state in parallel.  Under --denovo the hom-ref hypothesis H0 is the product
+// of the chains' p^4 coefficients (the (ref,ref) conditional is the same in H0 and H1..H3), so it rides
+// along in the first round for free.
 // ================================================================================================
+constexpr int kMaxChains = 3;
+
 struct WideShared {
   SmemTables t;
-  pm_site_result r;          // written by thread 0 only
-  BrentState brent;          // driven by thread 0
-  double p;                  // next evaluation point, < 0 = stop
-  double warp_m[32];         // per-warp partial products
-  int warp_e[32];
-  int red_i[3 * 32];         // per-warp integer partials (depth, samples, mapq / lk sum)
+  pm_site_result r;                 // written by thread 0 only
+  BrentState brent[kMaxChains];     // chain c is driven by thread driver(c)
+  double p[kMaxChains];             // next evaluation point per chain, < 0 = chain finished
+  double warp_m[kMaxChains + 1][32];  // per-warp partial products (slot kMaxChains: the H0 product)
+  int warp_e[kMaxChains + 1][32];
+  int red_i[4 * 32];                // per-warp integer partials (depth, samples, mapq, lk sum)
   double bcast[4];
   int ibcast[4];
-  unsigned long long mbar;   // mbarrier for the TMA bulk copy
-  unsigned int n_hyp, n_eval; // work counters of the current site (thread 0)
+  unsigned long long mbar;          // mbarrier for the TMA bulk copy
+  unsigned int n_hyp, n_eval;       // work counters of the current site
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -384,7 +397,6 @@ __device__ __forceinline__ void tma_load_site(void *dst, const void *src, uint32
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
   }
-  // everyone waits for the phase to flip
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -398,84 +410,189 @@ __device__ __forceinline__ void tma_load_site(void *dst, const void *src, uint32
       : "memory");
 }
 
-// Block-wide product of per-thread (mantissa, exponent) accumulators; result valid in thread 0.
-__device__ __forceinline__ void block_product(ProdAcc &acc, WideShared *ws) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+__device__ __forceinline__ void warp_product(ProdAcc &acc) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     double m = __shfl_down_sync(0xffffffffu, acc.m, o);
     int e = __shfl_down_sync(0xffffffffu, acc.e, o);
     acc.m *= m; acc.e += e;
   }
-  if (nwarp == 1) { if (lane == 0) prod_renorm(acc); return; }
-  if (lane == 0) { prod_renorm(acc); ws->warp_m[warp] = acc.m; ws->warp_e[warp] = acc.e; }
-  __syncthreads();
-  if (warp == 0) {
-    ProdAcc b;
-    b.m = lane < nwarp ? ws->warp_m[lane] : 1.0;
-    b.e = lane < nwarp ? ws->warp_e[lane] : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      double m = __shfl_down_sync(0xffffffffu, b.m, o);
-      int e = __shfl_down_sync(0xffffffffu, b.e, o);
-      b.m *= m; b.e += e;
-    }
-    acc = b;
-  }
 }
 
-template <int U>
+// Quartic coefficients of one unit for up to NC allele pairs at once: the kid's ten likelihoods are
+// looked up once, and de novo dot products of a genotype shared between chains (the (ref,ref) row of
+// H1..H3) are computed once.
+template <int NC>
+__device__ __forceinline__ void unit_quartic_multi(const uint4 *recs, const DevUnit u, const int (&g11)[NC], const int (&g12)[NC],
+                                                   const int (&g22)[NC], int nc, bool denovo, const double *__restrict__ lut,
+                                                   const double *__restrict__ mut, double (&B)[NC][5]) {
+  if (u.nkids < 0) {
+    const uint4 r = recs[u.first];
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      if (c < nc) {
+        double l11 = lut[rec_lk(r, g11[c])], l12 = lut[rec_lk(r, g12[c])], l22 = lut[rec_lk(r, g22[c])];
+        B[c][4] = l11; B[c][3] = 2.0 * (l11 + l12); B[c][2] = l11 + 4.0 * l12 + l22; B[c][1] = 2.0 * (l12 + l22); B[c][0] = l22;
+      }
+    return;
+  }
+  double P[NC][6];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+#pragma unroll
+    for (int k = 0; k < 6; k++) P[c][k] = 1.0;
+  for (int k = 0; k < u.nkids; k++) {
+    const uint4 rk = recs[u.first + 2 + k];
+    double l[10];
+    if (denovo) {
+#pragma unroll
+      for (int g = 0; g < 10; g++) l[g] = lut[rec_lk(rk, g)];
+    }
+    double d11_0 = 0.0;
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+      if (c < nc) {
+        double d11, d12, d22;
+        if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
+          const double *r12 = mut + g12[c] * 10, *r22 = mut + g22[c] * 10;
+          d12 = d22 = 0.0;
+#pragma unroll
+          for (int g = 0; g < 10; g++) { d12 += r12[g] * l[g]; d22 += r22[g] * l[g]; }
+          if (c > 0 && g11[c] == g11[0]) d11 = d11_0;
+          else {
+            const double *r11 = mut + g11[c] * 10;
+            d11 = 0.0;
+#pragma unroll
+            for (int g = 0; g < 10; g++) d11 += r11[g] * l[g];
+          }
+          if (c == 0) d11_0 = d11;
+        } else {
+          d11 = lut[rec_lk(rk, g11[c])]; d12 = lut[rec_lk(rk, g12[c])]; d22 = lut[rec_lk(rk, g22[c])];
+        }
+        // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome)
+        P[c][0] *= d11;
+        P[c][1] *= 0.5 * (d11 + d12);
+        P[c][2] *= d12;
+        P[c][3] *= 0.25 * d11 + 0.5 * d12 + 0.25 * d22;
+        P[c][4] *= 0.5 * (d12 + d22);
+        P[c][5] *= d22;
+        asm volatile("" ::: "memory");
+      }
+  }
+  const uint4 rf = recs[u.first], rm = recs[u.first + 1];
+#pragma unroll
+  for (int c = 0; c < NC; c++)
+    if (c < nc) {
+      double f11 = lut[rec_lk(rf, g11[c])], f12 = lut[rec_lk(rf, g12[c])], f22 = lut[rec_lk(rf, g22[c])];
+      double m11 = lut[rec_lk(rm, g11[c])], m12 = lut[rec_lk(rm, g12[c])], m22 = lut[rec_lk(rm, g22[c])];
+      // C_j = likelihoodKids(j) * (lF * lM), NucFam:1053-1077; then the quartic (see pm_device.cuh)
+      double C0 = P[c][0] * (f11 * m11), C1 = P[c][1] * (f11 * m12), C2 = P[c][2] * (f11 * m22);
+      double C3 = P[c][1] * (f12 * m11), C4 = P[c][3] * (f12 * m12), C5 = P[c][4] * (f12 * m22);
+      double C6 = P[c][2] * (f22 * m11), C7 = P[c][4] * (f22 * m12), C8 = P[c][5] * (f22 * m22);
+      B[c][4] = C0; B[c][3] = 2.0 * (C1 + C3); B[c][2] = C2 + 4.0 * C4 + C6; B[c][1] = 2.0 * (C5 + C7); B[c][0] = C8;
+    }
+}
+
+template <int U, int NC>
 struct WideEval {
   const DevRun *run;
   const uint4 *recs;  // site records in shared memory
   WideShared *ws;
-  double B[U][5];
-  int nmine;          // units owned by this thread: tid, tid+T, ...
+  double B[NC][U][5];
 
-  __device__ __forceinline__ void setup(int a1, int a2, bool denovo) {
-    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+  __device__ __forceinline__ int driver(int c) const { return (c * 32 < (int)blockDim.x) ? c * 32 : 0; }
+
+  // Optimises nc <= NC hypotheses concurrently.  On return (after a barrier) ws->brent[c] holds min/fmin
+  // of chain c.  with_h0: also reduce prod_u B[0][u][4] in the first round into ws->bcast[1] (log10).
+  __device__ __forceinline__ void optimize(int nc, const int *a1, const int *a2, bool denovo, bool with_h0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    int g11[NC], g12[NC], g22[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const int x = c < nc ? a1[c] : a1[0], y = c < nc ? a2[c] : a2[0];
+      g11[c] = geno_index(x, x); g12[c] = geno_index(x, y); g22[c] = geno_index(y, y);
+    }
 #pragma unroll
     for (int k = 0; k < U; k++) {
       const int u = threadIdx.x + k * blockDim.x;
-      if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, ws->t.lut, ws->t.mut, B[k]);
-    }
-  }
-  // every thread calls; thread 0 returns sum_f log10 L_f(p)
-  __device__ __forceinline__ double loglik(double p) {
-    const Monomials m = monomials(p);
-    ProdAcc acc;
-    prod_init(acc);
+      if (u < run->n_units) {
+        double Bu[NC][5];
+        unit_quartic_multi<NC>(recs, run->units[u], g11, g12, g22, nc, denovo, ws->t.lut, ws->t.mut, Bu);
 #pragma unroll
-    for (int k = 0; k < U; k++) {
-      const int u = threadIdx.x + k * blockDim.x;
-      if (u < run->n_units) prod_mul(acc, quartic_eval(B[k], m));
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int j = 0; j < 5; j++) B[c][k][j] = Bu[c][j];
+      }
+      // keep the units' set-ups apart: interleaving them only multiplies the live registers
+      asm volatile("" ::: "memory");
     }
-    block_product(acc, ws);
-    return prod_log10(acc);
-  }
-  // Brent with the block as the objective evaluator.  Thread 0 owns the state machine.
-  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo) {
-    setup(a1, a2, denovo);
-    if (threadIdx.x == 0) { brent_begin(ws->brent); ws->p = ws->brent.u; }
+    for (int c = 0; c < NC; c++)
+      if ((int)threadIdx.x == driver(c)) {
+        if (c < nc) { brent_begin(ws->brent[c]); ws->p[c] = ws->brent[c].u; }
+        else ws->p[c] = -1.0;
+      }
+    if (threadIdx.x == 0) ws->n_hyp += nc;
     __syncthreads();
+    bool first = true;
     for (;;) {
-      const double p = ws->p;
-      if (p < 0.0) break;
-      double ll = loglik(p);   // contains one __syncthreads when the block has several warps
-      if (threadIdx.x == 0) {
-        bool more = brent_feed(ws->brent, -ll, run->precision);
-        ws->p = more ? ws->brent.u : -1.0;
-        ws->n_eval++;
+      double p[NC];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < NC; c++) { p[c] = ws->p[c]; any |= p[c] >= 0.0; }
+      if (!any) break;
+      ProdAcc acc[NC], acc0;
+      prod_init(acc0);
+#pragma unroll
+      for (int c = 0; c < NC; c++) {
+        prod_init(acc[c]);
+        if (p[c] >= 0.0) {
+          const Monomials m = monomials(p[c]);
+#pragma unroll
+          for (int k = 0; k < U; k++)
+            if ((int)(threadIdx.x + k * blockDim.x) < run->n_units) prod_mul(acc[c], quartic_eval(B[c][k], m));
+        }
+      }
+      if (first && with_h0) {
+#pragma unroll
+        for (int k = 0; k < U; k++)
+          if ((int)(threadIdx.x + k * blockDim.x) < run->n_units) prod_mul(acc0, B[0][k][4]);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        if (p[c] >= 0.0) {
+          warp_product(acc[c]);
+          if (lane == 0) { prod_renorm(acc[c]); ws->warp_m[c][warp] = acc[c].m; ws->warp_e[c][warp] = acc[c].e; }
+        }
+      if (first && with_h0) {
+        warp_product(acc0);
+        if (lane == 0) { prod_renorm(acc0); ws->warp_m[kMaxChains][warp] = acc0.m; ws->warp_e[kMaxChains][warp] = acc0.e; }
       }
       __syncthreads();
+      // serial tails, one driver thread per chain, in parallel
+      for (int c = 0; c < NC; c++)
+        if ((int)threadIdx.x == driver(c) && p[c] >= 0.0) {
+          ProdAcc t;
+          prod_init(t);
+          for (int w = 0; w < nwarp; w++) prod_merge(t, ws->warp_m[c][w], ws->warp_e[c][w]);
+          const double ll = prod_log10(t);
+          const bool more = brent_feed(ws->brent[c], -ll, run->precision);
+          ws->p[c] = more ? ws->brent[c].u : -1.0;
+          atomicAdd(&ws->n_eval, 1u);
+        }
+      if (first && with_h0 && (int)threadIdx.x == ((32 * NC < (int)blockDim.x) ? 32 * NC : 0)) {
+        ProdAcc t;
+        prod_init(t);
+        for (int w = 0; w < nwarp; w++) prod_merge(t, ws->warp_m[kMaxChains][w], ws->warp_e[kMaxChains][w]);
+        ws->bcast[1] = prod_log10(t);
+      }
+      first = false;
+      __syncthreads();
     }
-    if (threadIdx.x == 0) ws->n_hyp++;
-    // result: ws->brent.min, -ws->brent.fmin (read by thread 0)
   }
 };
 
-template <int U>
-__global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+template <int U, int NC>
+__global__ void __launch_bounds__((U * NC >= 12) ? 256 : 512, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                              const uint4 *__restrict__ recs_all, size_t n_sites, pm_site_result *__restrict__ res,
                              uint16_t *__restrict__ status, int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -490,7 +607,7 @@ __global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *
   }
   __syncthreads();
   uint32_t phase = 0;
-  WideEval<U> ev;
+  WideEval<U, NC> ev;
   ev.run = run; ev.recs = site; ev.ws = ws;
 
   for (size_t s = blockIdx.x; s < n_sites; s += gridDim.x) {
@@ -519,18 +636,13 @@ __global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *
         int d = rec_depth(rec);
         dsum += d; nsamp += d > 0; mq += rec_mapq(rec); lksum += (int)rec_lk(rec, grr);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsum += __shfl_down_sync(0xffffffffu, dsum, o);
-        nsamp += __shfl_down_sync(0xffffffffu, nsamp, o);
-        mq += __shfl_down_sync(0xffffffffu, mq, o);
-        lksum += __shfl_down_sync(0xffffffffu, lksum, o);
-      }
-      if (lane == 0) { ws->red_i[warp] = dsum; ws->red_i[32 + warp] = nsamp; ws->red_i[64 + warp] = mq; ws->warp_e[warp] = lksum; }
+      dsum = __reduce_add_sync(0xffffffffu, dsum); nsamp = __reduce_add_sync(0xffffffffu, nsamp);
+      mq = __reduce_add_sync(0xffffffffu, mq); lksum = __reduce_add_sync(0xffffffffu, lksum);
+      if (lane == 0) { ws->red_i[warp] = dsum; ws->red_i[32 + warp] = nsamp; ws->red_i[64 + warp] = mq; ws->red_i[96 + warp] = lksum; }
       __syncthreads();
       if (threadIdx.x == 0) {
         int D = 0, NS = 0, MQ = 0, LK = 0;
-        for (int w = 0; w < nwarp; w++) { D += ws->red_i[w]; NS += ws->red_i[32 + w]; MQ += ws->red_i[64 + w]; LK += ws->warp_e[w]; }
+        for (int w = 0; w < nwarp; w++) { D += ws->red_i[w]; NS += ws->red_i[32 + w]; MQ += ws->red_i[64 + w]; LK += ws->red_i[96 + w]; }
         pm_site_result &r = ws->r;
         memset(&r, 0, sizeof r);
         r.site = (uint32_t)s; r.maxidx = -1;
@@ -544,6 +656,7 @@ __global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *
         ws->bcast[0] = -(double)LK / 10.0;
         ws->ibcast[0] = r.status;
         r.reserved = (uint16_t)ref;
+        ws->n_hyp = 0; ws->n_eval = 0;
         if (r.status != 0) { res[s] = r; status[s] = status_word(r); }
       }
       __syncthreads();
@@ -552,39 +665,39 @@ __global__ void k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *
     if (!skip) {
       const double lk_mono = ws->bcast[0];
       const bool dn = run->denovo != 0;
-      if (threadIdx.x == 0) { ws->n_hyp = dn ? 1 : 0; ws->n_eval = dn ? 1 : 0; }
-      // ---- H0 ----
-      if (dn) {
-        int a1, a2;
-        hyp_alleles(0, ref, a1, a2);
-        ev.setup(a1, a2, true);
-        double l0 = ev.loglik(1.0);
-        if (threadIdx.x == 0) ws->r.varllk[0] = run->log_1m_prior + l0;
-      } else if (threadIdx.x == 0) {
-        ws->r.varllk[0] = run->log_1m_prior + lk_mono;
-      }
-      if (threadIdx.x == 0) { ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->log_1m_prior; ws->r.varfreq[0] = 1.0; }
-      // ---- H1..H3, then H4..H6 if the posterior is not decisive ----
-      for (int hix = 1; hix <= 6; hix++) {
-        if (hix == 4) {
-          if (threadIdx.x == 0) { var_posterior(ws->r, ref, 4); ws->ibcast[1] = ws->r.var_post_prob < 0.99; }
-          __syncthreads();
-          if (!ws->ibcast[1]) break;
+      // ---- H1..H3 (+ H0 under --denovo), then H4..H6 if the posterior is not decisive ----
+      for (int base = 1; base <= 4; base += 3) {
+        int a1[3], a2[3];
+        for (int c = 0; c < 3; c++) hyp_alleles(base + c, ref, a1[c], a2[c]);
+        for (int c0 = 0; c0 < 3; c0 += NC) {
+          const int nc = (3 - c0) < NC ? (3 - c0) : NC;
+          const bool with_h0 = dn && base == 1 && c0 == 0;
+          ev.optimize(nc, a1 + c0, a2 + c0, dn, with_h0);
+          if (threadIdx.x == 0) {
+            for (int c = 0; c < nc; c++) site_store_hyp(run, ws->r, base + c0 + c, -ws->brent[c].fmin, ws->brent[c].min);
+            if (with_h0) { ws->r.varllk[0] = run->log_1m_prior + ws->bcast[1]; ws->n_hyp += 1; ws->n_eval += 1; }
+          }
         }
-        int a1, a2;
-        hyp_alleles(hix, ref, a1, a2);
-        ev.optimize(a1, a2, dn);
-        if (threadIdx.x == 0) site_store_hyp(run, ws->r, hix, -ws->brent.fmin, ws->brent.min);
+        if (threadIdx.x == 0) {
+          if (base == 1) {
+            if (!dn) ws->r.varllk[0] = run->log_1m_prior + lk_mono;
+            ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->log_1m_prior;
+            ws->r.varfreq[0] = 1.0;
+            var_posterior(ws->r, ref, 4);
+            ws->ibcast[1] = ws->r.var_post_prob < 0.99;  // main:499
+          } else {
+            var_posterior(ws->r, ref, 7);
+          }
+        }
+        __syncthreads();
+        if (!ws->ibcast[1]) break;
       }
-      if (threadIdx.x == 0) {
-        if (ws->r.n_hyp == 4 && ws->r.var_post_prob < 0.99) var_posterior(ws->r, ref, 7);
-        ws->ibcast[2] = site_decide(run, ws->r, lk_mono);
-      }
+      if (threadIdx.x == 0) ws->ibcast[2] = site_decide(run, ws->r, lk_mono);
       __syncthreads();
       if (ws->ibcast[2]) {  // de novo refit without mutation (main:567-573)
         const int a1 = ws->r.allele1, a2 = ws->r.allele2;
-        ev.optimize(a1, a2, false);
-        if (threadIdx.x == 0) site_finish_refit(run, ws->r, -ws->brent.fmin, ws->brent.min);
+        ev.optimize(1, &a1, &a2, false, false);
+        if (threadIdx.x == 0) site_finish_refit(run, ws->r, -ws->brent[0].fmin, ws->brent[0].min);
       }
       if (threadIdx.x == 0) {
         pm_site_result &r = ws->r;
@@ -909,6 +1022,20 @@ static size_t wide_smem_bytes(int n_person) {
   return ((sizeof(WideShared) + 127) / 128) * 128 + (size_t)n_person * 16 + 16;
 }
 
+// (U, NC) instantiations of the wide kernel: three concurrent chains while the coefficients of all
+// three fit in registers, one chain for very large pedigrees.
+#define PM_WIDE_DISPATCH(plan_, CALL)                 \
+  do {                                                \
+    if ((plan_).chains == 3) {                        \
+      if ((plan_).units_per_thread == 1) { CALL(1, 3); } \
+      else if ((plan_).units_per_thread == 2) { CALL(2, 3); } \
+      else { CALL(4, 3); }                            \
+    } else {                                          \
+      if ((plan_).units_per_thread <= 2) { CALL(2, 1); } \
+      else { CALL(8, 1); }                            \
+    }                                                 \
+  } while (0)
+
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                          size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream) {
   if (n_sites == 0) return cudaSuccess;
@@ -918,14 +1045,8 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   } else {
     const size_t smem = wide_smem_bytes(plan.n_person);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
-#define PM_WIDE(U_)                                                                                               \
-  k_sites_wide<U_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err)
-    switch (plan.units_per_thread) {
-      case 1: PM_WIDE(1); break;
-      case 2: PM_WIDE(2); break;
-      case 4: PM_WIDE(4); break;
-      default: PM_WIDE(8); break;
-    }
+#define PM_WIDE(U_, NC_) k_sites_wide<U_, NC_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err)
+    PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
   }
   return cudaGetLastError();
@@ -933,40 +1054,42 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
 
 cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count) {
   plan->n_person = n_person;
+  plan->chains = 1;
   if (n_units <= kNarrowMaxUnits) {
     plan->kind = LaunchPlan::NARROW;
     plan->threads = kNarrowThreads;
     plan->units_per_thread = kNarrowMaxUnits;
     plan->grid = 0;
-    cudaError_t e = cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
-    return e;
+    plan->blocks_per_sm = 0;
+    return cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
   }
   if (n_es > 0) return cudaErrorNotSupported;
   plan->kind = LaunchPlan::WIDE;
-  // T threads x U units per thread >= n_units, U in {1,2,4,8}, T a multiple of 32 up to 1024
-  int U = 8, T = 128;
-  if (n_units <= 32 * 8) { T = 32; U = n_units <= 32 ? 1 : (n_units <= 64 ? 2 : (n_units <= 128 ? 4 : 8)); }
-  else if (n_units <= 64 * 8) T = 64;
-  else if (n_units <= 128 * 8) T = 128;
-  else if (n_units <= 256 * 8) T = 256;
-  else if (n_units <= 512 * 8) T = 512;
-  else if (n_units <= 1024 * 8) T = 1024;
+  int U, T, NC;
+  if (n_units <= 512) { NC = 3; U = 1; T = ((n_units + 31) / 32) * 32; }
+  else if (n_units <= 1024) { NC = 3; U = 2; T = 512; }
+  else if (n_units <= 2048) { NC = 1; U = 4; T = 512; }
+  else if (n_units <= 4096) { NC = 1; U = 8; T = 512; }
   else return cudaErrorNotSupported;
+  // tuning hook: PM_WIDE_PLAN="threads,units_per_thread,chains" overrides the choice (must cover n_units)
+  if (const char *env = getenv("PM_WIDE_PLAN")) {
+    int t = 0, u = 0, c = 0;
+    if (sscanf(env, "%d,%d,%d", &t, &u, &c) == 3 && t >= 32 && t <= 512 && t % 32 == 0 && (long)t * u >= n_units &&
+        ((c == 3 && (u == 1 || u == 2 || u == 4) && (u < 4 || t <= 256)) || (c == 1 && (u == 2 || u == 8)))) {
+      T = t; U = u; NC = c;
+    }
+  }
   plan->threads = T;
   plan->units_per_thread = U;
+  plan->chains = NC;
   const size_t smem = wide_smem_bytes(n_person);
   if (smem > 227 * 1024) return cudaErrorNotSupported;
   cudaError_t e = cudaSuccess;
   int per_sm = 1;
-#define PM_ATTR(U_)                                                                                              \
-  e = cudaFuncSetAttribute(k_sites_wide<U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_>, T, smem)
-  switch (U) {
-    case 1: PM_ATTR(1); break;
-    case 2: PM_ATTR(2); break;
-    case 4: PM_ATTR(4); break;
-    default: PM_ATTR(8); break;
-  }
+#define PM_ATTR(U_, NC_)                                                                                              \
+  e = cudaFuncSetAttribute(k_sites_wide<U_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, NC_>, T, smem)
+  PM_WIDE_DISPATCH(*plan, PM_ATTR);
 #undef PM_ATTR
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;

@@ -17,6 +17,7 @@ struct LaunchPlan {
   enum Kind { NARROW = 0, WIDE = 1 } kind;
   int threads;            // block size
   int units_per_thread;   // wide: template parameter U
+  int chains;             // wide: Brent chains optimised concurrently (template parameter NC)
   int grid;               // wide: persistent grid (multiple of the SM count); narrow: derived from n_sites
   int blocks_per_sm;
   int n_person;

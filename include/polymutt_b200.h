@@ -209,6 +209,11 @@ int pm_call_glf_sites_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_per
 
 int pm_sync(pm_ctx *ctx);
 
+/* Page-locked host memory for the buffers handed to pm_call_glf_sites (lets its H2D/D2H copies overlap
+ * the kernels).  Optional: pageable buffers are accepted too. */
+void *pm_host_alloc(size_t bytes);
+void  pm_host_free(void *p);
+
 /* Device time (ms, CUDA events on the ctx stream) and launch count of the calling kernels
  * in the most recent pm_call_*; used by bench.py for the roofline numbers. */
 int pm_last_timing(pm_ctx *ctx, float *ms_main_kernel, float *ms_total, int *n_launches);

@@ -196,6 +196,10 @@ def _declare(lib):
     lib.pm_call_glf_sites_device.restype = C.c_int
     lib.pm_call_glf_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pm_host_alloc.restype = C.c_void_p
+    lib.pm_host_alloc.argtypes = [C.c_size_t]
+    lib.pm_host_free.restype = None
+    lib.pm_host_free.argtypes = [C.c_void_p]
     lib.pm_sync.restype = C.c_int
     lib.pm_sync.argtypes = [C.c_void_p]
     lib.pm_last_timing.restype = C.c_int

@@ -145,11 +145,21 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   size_t batch = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)1 << 16;
   // keep a batch of packed input below ~256 MB
   while (batch > 1024 && batch * (size_t)np * sizeof(pm_person_site) > ((size_t)256 << 20)) batch >>= 1;
-  std::vector<pm_site_hdr> hdr(batch);
-  std::vector<pm_person_site> ps(batch * (size_t)np);
-  std::vector<uint16_t> status(batch);
-  std::vector<pm_site_result> res(batch);
-  std::vector<pm_person_result> pres(batch * (size_t)np);
+  // batch buffers: page-locked when the engine offers it, so H2D/D2H overlap the kernels
+  struct HostBuf {
+    const Engine &e; void *p = nullptr;
+    HostBuf(const Engine &eng, size_t bytes) : e(eng) { p = e.host_alloc ? e.host_alloc(bytes) : malloc(bytes); if (p) memset(p, 0, bytes); }
+    ~HostBuf() { if (e.host_free) e.host_free(p); else free(p); }
+  };
+  HostBuf b_hdr(engine, batch * sizeof(pm_site_hdr)), b_ps(engine, batch * (size_t)np * sizeof(pm_person_site)),
+      b_status(engine, batch * sizeof(uint16_t)), b_res(engine, batch * sizeof(pm_site_result)),
+      b_pres(engine, batch * (size_t)np * sizeof(pm_person_result));
+  if (!b_hdr.p || !b_ps.p || !b_status.p || !b_res.p || !b_pres.p) { engine.destroy(ctx); return fatal("out of host memory for the site batch"); }
+  pm_site_hdr *hdr = (pm_site_hdr *)b_hdr.p;
+  pm_person_site *ps = (pm_person_site *)b_ps.p;
+  uint16_t *status = (uint16_t *)b_status.p;
+  pm_site_result *res = (pm_site_result *)b_res.p;
+  pm_person_result *pres = (pm_person_result *)b_pres.p;
 
   VcfWriter writer(vcf, opt, ped);
   time_t t0;
@@ -182,7 +192,7 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         }
         if (n == 0) break;
         size_t n_res = 0;
-        int rc = engine.call_glf(ctx, hdr.data(), ps.data(), n, status.data(), res.data(), pres.data(), batch, &n_res);
+        int rc = engine.call_glf(ctx, hdr, ps, n, status, res, pres, batch, &n_res);
         if (rc != PM_OK) {
           engine.destroy(ctx);
           fclose(vcf);

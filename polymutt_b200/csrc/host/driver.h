@@ -20,6 +20,9 @@ struct Engine {
                   pm_site_result *res, pm_person_result *person, size_t res_cap, size_t *n_res);
   void (*destroy)(void *ctx);
   const char *(*last_error)();
+  // optional: page-locked allocation for the batch buffers (nullptr = plain malloc)
+  void *(*host_alloc)(size_t bytes) = nullptr;
+  void (*host_free)(void *p) = nullptr;
 };
 
 // Returns the process exit code (0 on success, 1 after a fatal error, like the reference's error()).

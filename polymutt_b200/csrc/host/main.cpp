@@ -13,6 +13,6 @@ static int call_glf(void *ctx, const pm_site_hdr *hdr, const pm_person_site *ps,
 static void destroy(void *ctx) { pm_destroy((pm_ctx *)ctx); }
 
 int main(int argc, char **argv) {
-  pmh::Engine e{"cuda-sm100a", create, call_glf, destroy, pm_last_error};
+  pmh::Engine e{"cuda-sm100a", create, call_glf, destroy, pm_last_error, pm_host_alloc, pm_host_free};
   return pmh::run_cli(argc, argv, e);
 }

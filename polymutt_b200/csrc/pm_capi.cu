@@ -47,8 +47,11 @@ struct pm_ctx {
   uint32_t *d_n_emit = nullptr;
   // staging for the host-buffer entry point
   size_t cap_in_sites = 0, cap_out_rows = 0;
-  pm_site_hdr *d_hdr = nullptr;
-  uint4 *d_recs = nullptr;
+  pm_site_hdr *d_hdr[2] = {nullptr, nullptr};   // two input slots: H2D of chunk k+1 overlaps compute of chunk k
+  uint4 *d_recs[2] = {nullptr, nullptr};
+  cudaStream_t stream_h2d = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
+  uint32_t *h_rows = nullptr;                   // pinned
   uint16_t *d_status = nullptr;
   pm_site_result *d_res_out = nullptr;
   pm_person_result *d_person_out = nullptr;
@@ -213,6 +216,9 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   if (e != cudaSuccess) { fail(PM_ECUDA, "kernel set-up: %s", cudaGetErrorString(e)); delete c; return nullptr; }
 
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_h2d[0], cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&c->ev_h2d[1], cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess && cudaEventCreate(&c->ev2) == cudaSuccess;
   ok = ok && dev_alloc(&c->d_run, 1) == PM_OK && dev_alloc(&c->d_fams, fams.size()) == PM_OK &&
        dev_alloc(&c->d_units, units.size()) == PM_OK && dev_alloc(&c->d_es, es.size()) == PM_OK &&
@@ -242,7 +248,10 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
   cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
-  cudaFree(c->d_hdr); cudaFree(c->d_recs); cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out);
+  for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
+  if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
+  if (c->h_rows) cudaFreeHost(c->h_rows);
+  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -309,6 +318,11 @@ extern "C" int pm_last_timing(pm_ctx *c, float *ms_main_kernel, float *ms_total,
   return PM_OK;
 }
 
+// Host-buffer entry point.  The batch is cut into chunks of ~48 MB of packed input; chunk k+1 is
+// copied host->device on a second stream while chunk k is being computed (two input slots), so the
+// call runs at the slower of PCIe and the kernels instead of their sum.  Results of a chunk are copied
+// back as soon as its row count is known.  Pinned host buffers (pm_host_alloc) make the copies truly
+// asynchronous; pageable buffers work too, just without the overlap.
 extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, size_t n_sites,
                                  int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
                                  size_t res_cap, size_t *n_res) {
@@ -321,50 +335,63 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
       return fail(PM_EUNSUPPORTED, "site %zu: chrX/chrY/MT sites are not implemented on the device path yet", s);
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t np = (size_t)c->n_person;
-  // chunk so that one chunk's packed input stays below 512 MB
-  size_t chunk = ((size_t)512 << 20) / (np * sizeof(pm_person_site));
+  size_t chunk = ((size_t)48 << 20) / (np * sizeof(pm_person_site));
   if (chunk < 256) chunk = 256;
+  if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
   if (chunk > n_sites) chunk = n_sites;
+  int rc;
   if (chunk > c->cap_in_sites) {
-    int rc;
-    if ((rc = dev_alloc(&c->d_hdr, chunk))) return rc;
-    if ((rc = dev_alloc(&c->d_recs, chunk * np))) return rc;
+    for (int k = 0; k < 2; k++) {
+      if ((rc = dev_alloc(&c->d_hdr[k], chunk))) return rc;
+      if ((rc = dev_alloc(&c->d_recs[k], chunk * np))) return rc;
+    }
     if ((rc = dev_alloc(&c->d_status, chunk))) return rc;
     c->cap_in_sites = chunk;
   }
+  if (chunk > c->cap_out_rows) {  // a chunk can emit at most `chunk` rows
+    if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
+    if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
+    c->cap_out_rows = chunk;
+  }
+  if (!c->h_rows) CUDA_TRY(cudaHostAlloc((void **)&c->h_rows, sizeof(uint32_t), cudaHostAllocDefault));
+  const size_t n_chunks = (n_sites + chunk - 1) / chunk;
+  auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n_sites - k * chunk; };
+  auto issue_h2d = [&](size_t k) -> cudaError_t {
+    const int slot = (int)(k & 1);
+    const size_t base = k * chunk, n = chunk_len(k);
+    cudaError_t e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_recs[slot], person_site + base * np, n * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_h2d[slot], c->stream_h2d);
+    return e;
+  };
   size_t total_rows = 0;
   bool overflow = false;
   float ms_main = 0.f, ms_total = 0.f;
   int launches = 0;
-  std::vector<uint16_t> status_tmp;
-  for (size_t base = 0; base < n_sites; base += chunk) {
-    const size_t n = n_sites - base < chunk ? n_sites - base : chunk;
-    // rows this chunk may produce: all of them in PM_OUT_ALL, otherwise bounded by n
-    size_t rows_cap = n;
-    if (rows_cap > c->cap_out_rows) {
-      int rc;
-      if ((rc = dev_alloc(&c->d_res_out, rows_cap))) return rc;
-      if ((rc = dev_alloc(&c->d_person_out, rows_cap * np))) return rc;
-      c->cap_out_rows = rows_cap;
-    }
-    CUDA_TRY(cudaMemcpyAsync(c->d_hdr, hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_recs, person_site + base * np, n * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream));
-    int rc = pm_call_glf_sites_device(c, c->d_hdr, (const pm_person_site *)c->d_recs, n, out_mode, c->d_status, c->d_res_out,
-                                      c->d_person_out, rows_cap, c->d_n_emit);
+  CUDA_TRY(issue_h2d(0));
+  for (size_t k = 0; k < n_chunks; k++) {
+    const int slot = (int)(k & 1);
+    const size_t base = k * chunk, n = chunk_len(k);
+    // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
+    if (k + 1 < n_chunks) CUDA_TRY(issue_h2d(k + 1));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+    rc = pm_call_glf_sites_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], n, out_mode, c->d_status, c->d_res_out,
+                                  c->d_person_out, c->cap_out_rows, c->d_n_emit);
     if (rc) return rc;
-    uint32_t rows = 0;
-    CUDA_TRY(cudaMemcpyAsync(&rows, c->d_n_emit, sizeof rows, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_rows, c->d_n_emit, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
     if ((rc = pm_sync(c))) return rc;
     float a = 0.f, b = 0.f;
     pm_last_timing(c, &a, &b, nullptr);
     ms_main += a; ms_total += b; launches += 3;
-    if (status_out) CUDA_TRY(cudaMemcpy(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    const uint32_t rows = *c->h_rows;
     if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
     if (rows) {
-      CUDA_TRY(cudaMemcpy(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost));
-      for (size_t r = 0; r < rows; r++) res_out[total_rows + r].site += (uint32_t)base;
+      CUDA_TRY(cudaMemcpyAsync(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream));
       if (person_out)
-        CUDA_TRY(cudaMemcpy(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpyAsync(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      for (size_t r = 0; r < rows; r++) res_out[total_rows + r].site += (uint32_t)base;
     }
     total_rows += rows;
   }
@@ -375,12 +402,20 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   return PM_OK;
 }
 
+extern "C" void *pm_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { fail(PM_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+  return p;
+}
+extern "C" void pm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 // "narrow" or "wide T=<threads> U=<units/thread> NC=<chains> grid=<blocks> (<blocks/SM>/SM)"
 extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
   if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
   if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", pm::kNarrowMaxUnits, c->plan.threads);
-  else snprintf(buf, len, "k_sites_wide<U=%d,NC=%d>: one block of %d threads per site, %d units/thread, %d concurrent Brent chains, persistent grid %d (%d blocks/SM), one TMA bulk copy per site",
-                c->plan.units_per_thread, c->plan.chains, c->plan.threads, c->plan.units_per_thread, c->plan.chains, c->plan.grid, c->plan.blocks_per_sm);
+  else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site = %d group(s) (one Brent chain each) x %d threads x %d units/thread, persistent grid %d (%d blocks/SM), one TMA bulk copy per site",
+                c->plan.units_per_thread, c->plan.threads, c->plan.chains, c->plan.threads / c->plan.chains, c->plan.units_per_thread, c->plan.grid, c->plan.blocks_per_sm);
   return PM_OK;
 }
 

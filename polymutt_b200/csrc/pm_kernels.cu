@@ -359,32 +359,32 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
 }
 
 // ================================================================================================
-// wide kernel: one block per site, NC Brent chains in flight
+// wide kernel: one block per site, one thread GROUP per Brent chain
 //
 // One objective evaluation is cheap (5 FMAs per unit) but every Brent step ends in a serial tail —
-// product reduction, one log10, the Brent update with its division, two block barriers — of
-// ~1.5-2 k cycles.  With one chain per block the FP64 pipes idle during that tail, so the three
-// hypotheses H1..H3 (and H4..H6 when needed) are optimised CONCURRENTLY: every thread keeps the
-// quartic coefficients of its U units for all NC chains in registers, one round evaluates all live
-// chains, and NC driver threads (lane 0 of warps 0..NC-1) finish the reduction, take the log10 and
-// advance their own Brent state in parallel.  Under --denovo the hom-ref hypothesis H0 is the product
-// of the chains' p^4 coefficients (the (ref,ref) conditional is the same in H0 and H1..H3), so it rides
-// along in the first round for free.
+// product reduction, one log10, the Brent update with its division, two block barriers.  To keep the
+// FP64 pipes busy during that tail the three hypotheses H1..H3 (and H4..H6 when needed) are optimised
+// CONCURRENTLY: the block is G = 3 groups of Tg threads, group g owns chain g; every thread keeps the
+// quartic coefficients of its U units of ITS chain in registers, one round evaluates all live chains,
+// and the first thread of each group finishes the reduction, takes the log10 and advances its own
+// Brent state.  Under --denovo the hom-ref hypothesis H0 is the product of chain 0's p^4 coefficients
+// (the (ref,ref) conditional is the same in H0 and H1..H3), so it rides along in the first round.
+// Very large pedigrees fall back to G = 1 (one chain at a time).
 // ================================================================================================
 constexpr int kMaxChains = 3;
 
 struct WideShared {
   SmemTables t;
-  pm_site_result r;                 // written by thread 0 only
-  BrentState brent[kMaxChains];     // chain c is driven by thread driver(c)
-  double p[kMaxChains];             // next evaluation point per chain, < 0 = chain finished
+  pm_site_result r;                   // written by thread 0 only
+  BrentState brent[kMaxChains];       // chain c is driven by the first thread of group c
+  double p[kMaxChains];               // next evaluation point per chain, < 0 = chain finished
   double warp_m[kMaxChains + 1][32];  // per-warp partial products (slot kMaxChains: the H0 product)
   int warp_e[kMaxChains + 1][32];
-  int red_i[4 * 32];                // per-warp integer partials (depth, samples, mapq, lk sum)
+  int red_i[4 * 32];                  // per-warp integer partials (depth, samples, mapq, lk sum)
   double bcast[4];
   int ibcast[4];
-  unsigned long long mbar;          // mbarrier for the TMA bulk copy
-  unsigned int n_hyp, n_eval;       // work counters of the current site
+  unsigned long long mbar;            // mbarrier for the TMA bulk copy
+  unsigned int n_hyp, n_eval;         // work counters of the current site
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -410,6 +410,35 @@ __device__ __forceinline__ void tma_load_site(void *dst, const void *src, uint32
       : "memory");
 }
 
+// Branch-free running product: acc stays a plain double, rescaled by 2^512 whenever it (or the factor)
+// gets small; the power-of-two bookkeeping is an integer.  A factor of exactly 0 makes the product 0,
+// i.e. log10 = -inf, which is what the reference computes for a family likelihood that underflowed.
+struct FastProd { double m; int e; };
+__device__ __forceinline__ void fprod_mul(FastProd &a, double x) {
+  const double kBig = 1.3407807929942597e154;   // 2^512
+  const double kTiny = 7.458340731200207e-155;  // 2^-512
+  const bool xs = x < kTiny;
+  x = xs ? x * kBig : x;
+  a.e -= xs ? 512 : 0;
+  a.m *= x;
+  const bool s = a.m < kTiny;
+  a.m = s ? a.m * kBig : a.m;
+  a.e -= s ? 512 : 0;
+}
+__device__ __forceinline__ ProdAcc fprod_finish(const FastProd &a) {  // -> mantissa in [1,2) + exponent
+  ProdAcc r;
+  r.m = a.m; r.e = a.e;
+  if (a.m > 0.0) {
+    int hi = __double2hiint(r.m);
+    int ex = (hi >> 20) & 0x7ff;
+    if (ex == 0) { r.m *= 1.3407807929942597e154; r.e -= 512; hi = __double2hiint(r.m); ex = (hi >> 20) & 0x7ff; }
+    r.e += ex - 1023;
+    r.m = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(r.m));
+  } else {
+    r.m = 0.0;  // log10(0) = -inf downstream
+  }
+  return r;
+}
 __device__ __forceinline__ void warp_product(ProdAcc &acc) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -418,172 +447,109 @@ __device__ __forceinline__ void warp_product(ProdAcc &acc) {
     acc.m *= m; acc.e += e;
   }
 }
-
-// Quartic coefficients of one unit for up to NC allele pairs at once: the kid's ten likelihoods are
-// looked up once, and de novo dot products of a genotype shared between chains (the (ref,ref) row of
-// H1..H3) are computed once.
-template <int NC>
-__device__ __forceinline__ void unit_quartic_multi(const uint4 *recs, const DevUnit u, const int (&g11)[NC], const int (&g12)[NC],
-                                                   const int (&g22)[NC], int nc, bool denovo, const double *__restrict__ lut,
-                                                   const double *__restrict__ mut, double (&B)[NC][5]) {
-  if (u.nkids < 0) {
-    const uint4 r = recs[u.first];
-#pragma unroll
-    for (int c = 0; c < NC; c++)
-      if (c < nc) {
-        double l11 = lut[rec_lk(r, g11[c])], l12 = lut[rec_lk(r, g12[c])], l22 = lut[rec_lk(r, g22[c])];
-        B[c][4] = l11; B[c][3] = 2.0 * (l11 + l12); B[c][2] = l11 + 4.0 * l12 + l22; B[c][1] = 2.0 * (l12 + l22); B[c][0] = l22;
-      }
-    return;
-  }
-  double P[NC][6];
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-#pragma unroll
-    for (int k = 0; k < 6; k++) P[c][k] = 1.0;
-  for (int k = 0; k < u.nkids; k++) {
-    const uint4 rk = recs[u.first + 2 + k];
-    double l[10];
-    if (denovo) {
-#pragma unroll
-      for (int g = 0; g < 10; g++) l[g] = lut[rec_lk(rk, g)];
-    }
-    double d11_0 = 0.0;
-#pragma unroll
-    for (int c = 0; c < NC; c++)
-      if (c < nc) {
-        double d11, d12, d22;
-        if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
-          const double *r12 = mut + g12[c] * 10, *r22 = mut + g22[c] * 10;
-          d12 = d22 = 0.0;
-#pragma unroll
-          for (int g = 0; g < 10; g++) { d12 += r12[g] * l[g]; d22 += r22[g] * l[g]; }
-          if (c > 0 && g11[c] == g11[0]) d11 = d11_0;
-          else {
-            const double *r11 = mut + g11[c] * 10;
-            d11 = 0.0;
-#pragma unroll
-            for (int g = 0; g < 10; g++) d11 += r11[g] * l[g];
-          }
-          if (c == 0) d11_0 = d11;
-        } else {
-          d11 = lut[rec_lk(rk, g11[c])]; d12 = lut[rec_lk(rk, g12[c])]; d22 = lut[rec_lk(rk, g22[c])];
-        }
-        // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome)
-        P[c][0] *= d11;
-        P[c][1] *= 0.5 * (d11 + d12);
-        P[c][2] *= d12;
-        P[c][3] *= 0.25 * d11 + 0.5 * d12 + 0.25 * d22;
-        P[c][4] *= 0.5 * (d12 + d22);
-        P[c][5] *= d22;
-        asm volatile("" ::: "memory");
-      }
-  }
-  const uint4 rf = recs[u.first], rm = recs[u.first + 1];
-#pragma unroll
-  for (int c = 0; c < NC; c++)
-    if (c < nc) {
-      double f11 = lut[rec_lk(rf, g11[c])], f12 = lut[rec_lk(rf, g12[c])], f22 = lut[rec_lk(rf, g22[c])];
-      double m11 = lut[rec_lk(rm, g11[c])], m12 = lut[rec_lk(rm, g12[c])], m22 = lut[rec_lk(rm, g22[c])];
-      // C_j = likelihoodKids(j) * (lF * lM), NucFam:1053-1077; then the quartic (see pm_device.cuh)
-      double C0 = P[c][0] * (f11 * m11), C1 = P[c][1] * (f11 * m12), C2 = P[c][2] * (f11 * m22);
-      double C3 = P[c][1] * (f12 * m11), C4 = P[c][3] * (f12 * m12), C5 = P[c][4] * (f12 * m22);
-      double C6 = P[c][2] * (f22 * m11), C7 = P[c][4] * (f22 * m12), C8 = P[c][5] * (f22 * m22);
-      B[c][4] = C0; B[c][3] = 2.0 * (C1 + C3); B[c][2] = C2 + 4.0 * C4 + C6; B[c][1] = 2.0 * (C5 + C7); B[c][0] = C8;
-    }
+__device__ __forceinline__ void renorm_nonzero(ProdAcc &a) {
+  if (a.m > 0.0) prod_renorm(a);
 }
 
-template <int U, int NC>
+// Out-of-line helpers: their register pressure (unrolled 10-genotype dot products, the Brent update with
+// its division, exp10/log10 in the posterior) stays out of the kernel's hot loop allocation.
+struct Quartic { double b0, b1, b2, b3, b4; };
+__device__ __noinline__ Quartic unit_quartic_ol(const uint4 *recs, int first, int nkids, int g11, int g12, int g22, int denovo,
+                                                const double *lut, const double *mut) {
+  double B[5];
+  DevUnit u;
+  u.first = first; u.nkids = nkids;
+  unit_quartic(recs, u, g11, g12, g22, denovo != 0, lut, mut, B);
+  Quartic q;
+  q.b0 = B[0]; q.b1 = B[1]; q.b2 = B[2]; q.b3 = B[3]; q.b4 = B[4];
+  return q;
+}
+__device__ __noinline__ int brent_feed_ol(BrentState *s, double fu, double tol) { return brent_feed(*s, fu, tol) ? 1 : 0; }
+__device__ __noinline__ void var_posterior_ol(pm_site_result *r, int ref, int n) { var_posterior(*r, ref, n); }
+__device__ __noinline__ int site_decide_ol(const DevRun *run, pm_site_result *r, double lk_mono) { return site_decide(run, *r, lk_mono) ? 1 : 0; }
+__device__ __noinline__ double log10_ol(double m, int e) { return log10(m) + (double)e * kLog10_2; }
+
+template <int U>
 struct WideEval {
   const DevRun *run;
   const uint4 *recs;  // site records in shared memory
   WideShared *ws;
-  double B[NC][U][5];
+  int G, Tg, grp, t;  // groups, threads per group, my group, my index inside the group
+  double B[U][5];
 
-  __device__ __forceinline__ int driver(int c) const { return (c * 32 < (int)blockDim.x) ? c * 32 : 0; }
-
-  // Optimises nc <= NC hypotheses concurrently.  On return (after a barrier) ws->brent[c] holds min/fmin
-  // of chain c.  with_h0: also reduce prod_u B[0][u][4] in the first round into ws->bcast[1] (log10).
+  // Optimises nc <= G hypotheses concurrently (chain c by group c).  On return (after a barrier)
+  // ws->brent[c] holds min/fmin of chain c.  with_h0: also reduce prod_u B[u][4] of chain 0 in the first
+  // round; its log10 lands in ws->bcast[1].
   __device__ __forceinline__ void optimize(int nc, const int *a1, const int *a2, bool denovo, bool with_h0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-    int g11[NC], g12[NC], g22[NC];
+    const int lane = threadIdx.x & 31;
+    const int wg = t >> 5, nwg = Tg >> 5;  // warp index inside the group, warps per group
+    const bool mine = grp < nc;
+    if (mine) {
+      const int x = a1[grp], y = a2[grp];
+      const int g11 = geno_index(x, x), g12 = geno_index(x, y), g22 = geno_index(y, y);
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const int x = c < nc ? a1[c] : a1[0], y = c < nc ? a2[c] : a2[0];
-      g11[c] = geno_index(x, x); g12[c] = geno_index(x, y); g22[c] = geno_index(y, y);
-    }
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      const int u = threadIdx.x + k * blockDim.x;
-      if (u < run->n_units) {
-        double Bu[NC][5];
-        unit_quartic_multi<NC>(recs, run->units[u], g11, g12, g22, nc, denovo, ws->t.lut, ws->t.mut, Bu);
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-#pragma unroll
-          for (int j = 0; j < 5; j++) B[c][k][j] = Bu[c][j];
+      for (int k = 0; k < U; k++) {
+        const int u = t + k * Tg;
+        if (u < run->n_units) {
+          const DevUnit du = run->units[u];
+          const Quartic q = unit_quartic_ol(recs, du.first, du.nkids, g11, g12, g22, denovo ? 1 : 0, ws->t.lut, ws->t.mut);
+          B[k][0] = q.b0; B[k][1] = q.b1; B[k][2] = q.b2; B[k][3] = q.b3; B[k][4] = q.b4;
+        } else {  // (p+q)^4 = 1: a neutral unit
+          B[k][4] = 1.0; B[k][3] = 4.0; B[k][2] = 6.0; B[k][1] = 4.0; B[k][0] = 1.0;
+        }
       }
-      // keep the units' set-ups apart: interleaving them only multiplies the live registers
-      asm volatile("" ::: "memory");
     }
-    for (int c = 0; c < NC; c++)
-      if ((int)threadIdx.x == driver(c)) {
-        if (c < nc) { brent_begin(ws->brent[c]); ws->p[c] = ws->brent[c].u; }
-        else ws->p[c] = -1.0;
-      }
-    if (threadIdx.x == 0) ws->n_hyp += nc;
+    if (t == 0) {
+      if (mine) { brent_begin(ws->brent[grp]); ws->p[grp] = ws->brent[grp].u; }
+      else ws->p[grp] = -1.0;
+    }
+    if (threadIdx.x == 0) {
+      for (int c = G; c < kMaxChains; c++) ws->p[c] = -1.0;
+      ws->n_hyp += nc;
+    }
     __syncthreads();
     bool first = true;
     for (;;) {
-      double p[NC];
-      bool any = false;
+      const double p0 = ws->p[0], p1 = ws->p[1], p2 = ws->p[2];
+      if (p0 < 0.0 && p1 < 0.0 && p2 < 0.0) break;
+      const double p = grp == 0 ? p0 : (grp == 1 ? p1 : p2);
+      const bool live = p >= 0.0;
+      const bool h0 = first && with_h0 && grp == 0;
+      if (live) {
+        const Monomials m = monomials(p);
+        FastProd fa;
+        fa.m = 1.0; fa.e = 0;
 #pragma unroll
-      for (int c = 0; c < NC; c++) { p[c] = ws->p[c]; any |= p[c] >= 0.0; }
-      if (!any) break;
-      ProdAcc acc[NC], acc0;
-      prod_init(acc0);
-#pragma unroll
-      for (int c = 0; c < NC; c++) {
-        prod_init(acc[c]);
-        if (p[c] >= 0.0) {
-          const Monomials m = monomials(p[c]);
-#pragma unroll
-          for (int k = 0; k < U; k++)
-            if ((int)(threadIdx.x + k * blockDim.x) < run->n_units) prod_mul(acc[c], quartic_eval(B[c][k], m));
-        }
+        for (int k = 0; k < U; k++) fprod_mul(fa, quartic_eval(B[k], m));
+        ProdAcc acc = fprod_finish(fa);
+        warp_product(acc);
+        if (lane == 0) { renorm_nonzero(acc); ws->warp_m[grp][wg] = acc.m; ws->warp_e[grp][wg] = acc.e; }
       }
-      if (first && with_h0) {
+      if (h0) {
+        FastProd fa;
+        fa.m = 1.0; fa.e = 0;
 #pragma unroll
-        for (int k = 0; k < U; k++)
-          if ((int)(threadIdx.x + k * blockDim.x) < run->n_units) prod_mul(acc0, B[0][k][4]);
-      }
-#pragma unroll
-      for (int c = 0; c < NC; c++)
-        if (p[c] >= 0.0) {
-          warp_product(acc[c]);
-          if (lane == 0) { prod_renorm(acc[c]); ws->warp_m[c][warp] = acc[c].m; ws->warp_e[c][warp] = acc[c].e; }
-        }
-      if (first && with_h0) {
-        warp_product(acc0);
-        if (lane == 0) { prod_renorm(acc0); ws->warp_m[kMaxChains][warp] = acc0.m; ws->warp_e[kMaxChains][warp] = acc0.e; }
+        for (int k = 0; k < U; k++) fprod_mul(fa, B[k][4]);
+        ProdAcc acc = fprod_finish(fa);
+        warp_product(acc);
+        if (lane == 0) { renorm_nonzero(acc); ws->warp_m[kMaxChains][wg] = acc.m; ws->warp_e[kMaxChains][wg] = acc.e; }
       }
       __syncthreads();
-      // serial tails, one driver thread per chain, in parallel
-      for (int c = 0; c < NC; c++)
-        if ((int)threadIdx.x == driver(c) && p[c] >= 0.0) {
-          ProdAcc t;
-          prod_init(t);
-          for (int w = 0; w < nwarp; w++) prod_merge(t, ws->warp_m[c][w], ws->warp_e[c][w]);
-          const double ll = prod_log10(t);
-          const bool more = brent_feed(ws->brent[c], -ll, run->precision);
-          ws->p[c] = more ? ws->brent[c].u : -1.0;
-          atomicAdd(&ws->n_eval, 1u);
-        }
-      if (first && with_h0 && (int)threadIdx.x == ((32 * NC < (int)blockDim.x) ? 32 * NC : 0)) {
-        ProdAcc t;
-        prod_init(t);
-        for (int w = 0; w < nwarp; w++) prod_merge(t, ws->warp_m[kMaxChains][w], ws->warp_e[kMaxChains][w]);
-        ws->bcast[1] = prod_log10(t);
+      // serial tails: the first thread of every live group, in parallel
+      if (t == 0 && live) {
+        ProdAcc a;
+        a.m = 1.0; a.e = 0;
+        for (int w = 0; w < nwg; w++) prod_merge(a, ws->warp_m[grp][w], ws->warp_e[grp][w]);
+        const double ll = log10_ol(a.m, a.e);
+        const bool more = brent_feed_ol(&ws->brent[grp], -ll, run->precision) != 0;
+        ws->p[grp] = more ? ws->brent[grp].u : -1.0;
+        atomicAdd(&ws->n_eval, 1u);
+      }
+      if (h0 && t == (Tg > 32 ? 32 : 0)) {
+        ProdAcc a;
+        a.m = 1.0; a.e = 0;
+        for (int w = 0; w < nwg; w++) prod_merge(a, ws->warp_m[kMaxChains][w], ws->warp_e[kMaxChains][w]);
+        ws->bcast[1] = log10_ol(a.m, a.e);
       }
       first = false;
       __syncthreads();
@@ -591,10 +557,11 @@ struct WideEval {
   }
 };
 
-template <int U, int NC>
-__global__ void __launch_bounds__((U * NC >= 12) ? 256 : 512, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
-                             const uint4 *__restrict__ recs_all, size_t n_sites, pm_site_result *__restrict__ res,
-                             uint16_t *__restrict__ status, int *__restrict__ err) {
+template <int U, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                                        const uint4 *__restrict__ recs_all, size_t n_sites, int groups,
+                                                        pm_site_result *__restrict__ res, uint16_t *__restrict__ status,
+                                                        int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *ws = reinterpret_cast<WideShared *>(smem_raw);
   uint4 *site = reinterpret_cast<uint4 *>(smem_raw + ((sizeof(WideShared) + 127) / 128) * 128);
@@ -607,8 +574,10 @@ __global__ void __launch_bounds__((U * NC >= 12) ? 256 : 512, 1) k_sites_wide(co
   }
   __syncthreads();
   uint32_t phase = 0;
-  WideEval<U, NC> ev;
+  WideEval<U> ev;
   ev.run = run; ev.recs = site; ev.ws = ws;
+  ev.G = groups; ev.Tg = blockDim.x / groups; ev.grp = threadIdx.x / ev.Tg; ev.t = threadIdx.x % ev.Tg;
+  const int G = groups;
 
   for (size_t s = blockIdx.x; s < n_sites; s += gridDim.x) {
     // ---- stage the site: n_person * 16 contiguous bytes, one TMA bulk copy ----
@@ -669,8 +638,8 @@ __global__ void __launch_bounds__((U * NC >= 12) ? 256 : 512, 1) k_sites_wide(co
       for (int base = 1; base <= 4; base += 3) {
         int a1[3], a2[3];
         for (int c = 0; c < 3; c++) hyp_alleles(base + c, ref, a1[c], a2[c]);
-        for (int c0 = 0; c0 < 3; c0 += NC) {
-          const int nc = (3 - c0) < NC ? (3 - c0) : NC;
+        for (int c0 = 0; c0 < 3; c0 += G) {
+          const int nc = (3 - c0) < G ? (3 - c0) : G;
           const bool with_h0 = dn && base == 1 && c0 == 0;
           ev.optimize(nc, a1 + c0, a2 + c0, dn, with_h0);
           if (threadIdx.x == 0) {
@@ -683,16 +652,16 @@ __global__ void __launch_bounds__((U * NC >= 12) ? 256 : 512, 1) k_sites_wide(co
             if (!dn) ws->r.varllk[0] = run->log_1m_prior + lk_mono;
             ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->log_1m_prior;
             ws->r.varfreq[0] = 1.0;
-            var_posterior(ws->r, ref, 4);
+            var_posterior_ol(&ws->r, ref, 4);
             ws->ibcast[1] = ws->r.var_post_prob < 0.99;  // main:499
           } else {
-            var_posterior(ws->r, ref, 7);
+            var_posterior_ol(&ws->r, ref, 7);
           }
         }
         __syncthreads();
         if (!ws->ibcast[1]) break;
       }
-      if (threadIdx.x == 0) ws->ibcast[2] = site_decide(run, ws->r, lk_mono);
+      if (threadIdx.x == 0) ws->ibcast[2] = site_decide_ol(run, &ws->r, lk_mono);
       __syncthreads();
       if (ws->ibcast[2]) {  // de novo refit without mutation (main:567-573)
         const int a1 = ws->r.allele1, a2 = ws->r.allele2;
@@ -1022,18 +991,16 @@ static size_t wide_smem_bytes(int n_person) {
   return ((sizeof(WideShared) + 127) / 128) * 128 + (size_t)n_person * 16 + 16;
 }
 
-// (U, NC) instantiations of the wide kernel: three concurrent chains while the coefficients of all
-// three fit in registers, one chain for very large pedigrees.
-#define PM_WIDE_DISPATCH(plan_, CALL)                 \
-  do {                                                \
-    if ((plan_).chains == 3) {                        \
-      if ((plan_).units_per_thread == 1) { CALL(1, 3); } \
-      else if ((plan_).units_per_thread == 2) { CALL(2, 3); } \
-      else { CALL(4, 3); }                            \
-    } else {                                          \
-      if ((plan_).units_per_thread <= 2) { CALL(2, 1); } \
-      else { CALL(8, 1); }                            \
-    }                                                 \
+// (U, MAXT) instantiations of the wide kernel.  U = units per thread; MAXT = largest block the
+// instantiation is launched with (sets the register budget: 65536 / MAXT).
+#define PM_WIDE_DISPATCH(plan_, CALL)                                   \
+  do {                                                                  \
+    switch ((plan_).units_per_thread) {                                 \
+      case 1: CALL(1, 1024); break;                                     \
+      case 2: CALL(2, 768); break;                                      \
+      case 4: if ((plan_).threads > 512) { CALL(4, 768); } else { CALL(4, 512); } break; \
+      default: if ((plan_).threads > 384) { CALL(8, 512); } else { CALL(8, 384); } break; \
+    }                                                                   \
   } while (0)
 
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
@@ -1045,7 +1012,7 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   } else {
     const size_t smem = wide_smem_bytes(plan.n_person);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
-#define PM_WIDE(U_, NC_) k_sites_wide<U_, NC_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err)
+#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, plan.chains, d_res, d_status, d_err)
     PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
   }
@@ -1065,30 +1032,34 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   }
   if (n_es > 0) return cudaErrorNotSupported;
   plan->kind = LaunchPlan::WIDE;
-  int U, T, NC;
-  if (n_units <= 512) { NC = 3; U = 1; T = ((n_units + 31) / 32) * 32; }
-  else if (n_units <= 1024) { NC = 3; U = 2; T = 512; }
-  else if (n_units <= 2048) { NC = 1; U = 4; T = 512; }
-  else if (n_units <= 4096) { NC = 1; U = 8; T = 512; }
+  // G groups (one Brent chain each) x Tg threads x U units per thread, Tg * U >= n_units
+  int U, Tg, G;
+  auto up32 = [](int x) { return ((x + 31) / 32) * 32; };
+  if (n_units <= 256) { G = 3; U = 1; Tg = up32(n_units); }
+  else if (n_units <= 512) { G = 3; U = 2; Tg = up32((n_units + 1) / 2); }
+  else if (n_units <= 1024) { G = 3; U = 8; Tg = up32((n_units + 7) / 8); }  // measured: 384 x U=8 beats 768 x U=4
+  else if (n_units <= 2048) { G = 1; U = 4; Tg = 512; }
+  else if (n_units <= 4096) { G = 1; U = 8; Tg = 512; }
   else return cudaErrorNotSupported;
-  // tuning hook: PM_WIDE_PLAN="threads,units_per_thread,chains" overrides the choice (must cover n_units)
+  // tuning hook: PM_WIDE_PLAN="threads_per_group,units_per_thread,groups" overrides the choice
   if (const char *env = getenv("PM_WIDE_PLAN")) {
-    int t = 0, u = 0, c = 0;
-    if (sscanf(env, "%d,%d,%d", &t, &u, &c) == 3 && t >= 32 && t <= 512 && t % 32 == 0 && (long)t * u >= n_units &&
-        ((c == 3 && (u == 1 || u == 2 || u == 4) && (u < 4 || t <= 256)) || (c == 1 && (u == 2 || u == 8)))) {
-      T = t; U = u; NC = c;
+    int t = 0, u = 0, g = 0;
+    if (sscanf(env, "%d,%d,%d", &t, &u, &g) == 3 && t >= 32 && t % 32 == 0 && (g == 1 || g == 3) && (long)t * u >= n_units &&
+        (u == 1 || u == 2 || u == 4 || u == 8) && t * g <= (u == 1 ? 1024 : (u == 8 ? 512 : 768))) {
+      Tg = t; U = u; G = g;
     }
   }
-  plan->threads = T;
+  plan->threads = Tg * G;
   plan->units_per_thread = U;
-  plan->chains = NC;
+  plan->chains = G;
   const size_t smem = wide_smem_bytes(n_person);
   if (smem > 227 * 1024) return cudaErrorNotSupported;
   cudaError_t e = cudaSuccess;
   int per_sm = 1;
-#define PM_ATTR(U_, NC_)                                                                                              \
-  e = cudaFuncSetAttribute(k_sites_wide<U_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, NC_>, T, smem)
+  const int T = plan->threads;
+#define PM_ATTR(U_, MT_)                                                                                              \
+  e = cudaFuncSetAttribute(k_sites_wide<U_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_>, T, smem)
   PM_WIDE_DISPATCH(*plan, PM_ATTR);
 #undef PM_ATTR
   if (e != cudaSuccess) return e;

@@ -305,7 +305,7 @@ def main():
         h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
         h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
         h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
-        cap_e = max(1024, Se // 8)
+        cap_e = max(1024, Se // 8)   # emitted rows are ~0.1 % of the sites of this workload
         h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
         h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
         h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)

@@ -124,7 +124,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   std::vector<pm::DevUnit> units;
   std::vector<int32_t> es;
   std::vector<pm::DevStep> steps;
-  int first = 0, founders_total = 0;
+  int first = 0, founders_total = 0, kids_total = 0;
   for (int f = 0; f < ped->n_fam; f++) {
     pm::DevFam &d = fams[(size_t)f];
     memset(&d, 0, sizeof d);
@@ -134,10 +134,11 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     const bool nuclear = ped->fam_generations[f] == 2 && nf == 2;
     if (size == nf) {
       d.kind = 0;
-      for (int j = 0; j < size; j++) units.push_back({first + j, -1});
+      for (int j = 0; j < size; j++) units.push_back({first + j, -1, kids_total, 0});
     } else if (nuclear) {
       d.kind = 1;
-      units.push_back({first, size - 2});
+      units.push_back({first, size - 2, kids_total, 0});
+      kids_total += size - 2;
     } else {
       d.kind = 2;
       if (size > pm::kMaxEsPersons) { fail(PM_EUNSUPPORTED, "extended family %d has %d members; the device peel workspace holds %d", f, size, pm::kMaxEsPersons); delete c; return nullptr; }
@@ -205,10 +206,14 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   run.denovo_min_llr = par->denovo_min_llr; run.min_ps = par->min_ps;
   run.min_map_quality = par->min_map_quality; run.min_total_depth = par->min_total_depth; run.max_total_depth = par->max_total_depth;
   run.denovo = par->denovo; run.force_call = par->force_call; run.out_all_sites = par->out_all_sites;
-  run.n_person = ped->n_person; run.n_fam = ped->n_fam; run.n_units = c->n_units; run.n_es = c->n_es;
+  run.n_person = ped->n_person; run.n_fam = ped->n_fam; run.n_units = c->n_units; run.n_es = c->n_es; run.n_kids = kids_total;
+  for (int i = 0; i < 128; i++) {
+    run.log_inv[i] = 1.0 / (1.0 + (i + 0.5) / 128.0);
+    run.log_tab[i] = (double)(-log10l((long double)run.log_inv[i]));
+  }
   run.use_brent = (ped->n_fam > 1 || fams[0].kind != 1) ? 1 : 0;  // FLSeq:94
 
-  e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, c->sm_count);
+  e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, par->denovo ? kids_total : 0, c->sm_count);
   if (e == cudaErrorNotSupported) {
     fail(PM_EUNSUPPORTED, "pedigree shape not supported by the device kernels yet (%d quartic units, %d extended families, %d persons)", c->n_units, c->n_es, c->n_person);
     delete c; return nullptr;

@@ -46,6 +46,8 @@ struct DevFam {       // one pedigree family, VCF column order
 struct DevUnit {      // one factor of the objective that has the quartic form
   int32_t first;      // column of the first member
   int32_t nkids;      // -1 = a single unrelated founder; >= 0 = nuclear family with that many kids
+  int32_t kid0;       // number of kids in the units before this one (slot of its first kid in the per-site kid table)
+  int32_t pad;
 };
 
 // Everything the kernels need about the run; lives in global memory, hot tables are copied to smem.
@@ -53,12 +55,14 @@ struct DevRun {
   double lut[256];            // 10^(-i/10)   (core/BaseQualityHelper.cpp:12-13), host-computed
   double mut[100];            // genotype mutation matrix (src/MutationModel.cpp:46-90), host-computed
   double tden[1000];          // transmission_denovo[i][j][k] (ES:787-810), host-computed
+  double log_inv[128];        // 1/c_i, c_i = 1 + (i+0.5)/128: table-driven log10 of a mantissa in [1,2)
+  double log_tab[128];        // -log10(log_inv[i]) (computed in long double on the host)
   // host-computed log10 constants (same libm as the reference)
   double log_1m_prior, log_prior_ts, log_prior_tv, log_prior_other, log_prior_23, log_prior_16, log_min_llr;
   double theta, posterior_cutoff, precision, denovo_min_llr, min_ps;
   int32_t min_map_quality, min_total_depth, max_total_depth;
   int32_t denovo, force_call, out_all_sites;
-  int32_t n_person, n_fam, n_units, n_es;
+  int32_t n_person, n_fam, n_units, n_es, n_kids;
   int32_t use_brent;          // nFam>1 || !nuclear  (FLSeq:94)
   unsigned long long *counters;  // [4] hypotheses, evaluations, sites evaluated, sites emitted
   const DevFam *fams;

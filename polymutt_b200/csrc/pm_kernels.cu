@@ -16,6 +16,7 @@
 // the roofline of each kernel.
 #include <cstdio>
 #include <cstdlib>
+#include <math_constants.h>
 
 #include "pm_device.cuh"
 #include "pm_kernels.h"
@@ -375,6 +376,8 @@ constexpr int kMaxChains = 3;
 
 struct WideShared {
   SmemTables t;
+  double log_inv[128];                // table-driven log10 of the product mantissa (driver threads only)
+  double log_tab[128];
   pm_site_result r;                   // written by thread 0 only
   BrentState brent[kMaxChains];       // chain c is driven by the first thread of group c
   double p[kMaxChains];               // next evaluation point per chain, < 0 = chain finished
@@ -383,20 +386,20 @@ struct WideShared {
   int red_i[4 * 32];                  // per-warp integer partials (depth, samples, mapq, lk sum)
   double bcast[4];
   int ibcast[4];
-  unsigned long long mbar;            // mbarrier for the TMA bulk copy
+  unsigned long long mbar[2];         // one mbarrier per site buffer (TMA bulk copies)
   unsigned int n_hyp, n_eval;         // work counters of the current site
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // One 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).
-__device__ __forceinline__ void tma_load_site(void *dst, const void *src, uint32_t bytes, unsigned long long *bar, uint32_t phase) {
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-  }
+__device__ __forceinline__ void tma_issue_site(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
@@ -464,18 +467,74 @@ __device__ __noinline__ Quartic unit_quartic_ol(const uint4 *recs, int first, in
   q.b0 = B[0]; q.b1 = B[1]; q.b2 = B[2]; q.b3 = B[3]; q.b4 = B[4];
   return q;
 }
+// Same as unit_quartic for a nuclear family whose kids' mutation-mixed likelihoods
+// D[kid][g] = sum_h M[g][h] l_h (CalcDenovoMutLk, NucFam:1553-1562) were built once for the site.
+__device__ __noinline__ Quartic unit_quartic_tab_ol(const uint4 *recs, int first, int nkids, const double *kidD, int g11, int g12, int g22,
+                                                    const double *lut) {
+  double p0 = 1.0, p1 = 1.0, p2 = 1.0, p4 = 1.0, p5 = 1.0, p8 = 1.0;
+  for (int k = 0; k < nkids; k++) {
+    const double d11 = kidD[k * 10 + g11], d12 = kidD[k * 10 + g12], d22 = kidD[k * 10 + g22];
+    p0 *= d11;
+    p1 *= 0.5 * (d11 + d12);
+    p2 *= d12;
+    p4 *= 0.25 * d11 + 0.5 * d12 + 0.25 * d22;
+    p5 *= 0.5 * (d12 + d22);
+    p8 *= d22;
+  }
+  const uint4 rf = recs[first], rm = recs[first + 1];
+  const double f11 = lut[rec_lk(rf, g11)], f12 = lut[rec_lk(rf, g12)], f22 = lut[rec_lk(rf, g22)];
+  const double m11 = lut[rec_lk(rm, g11)], m12 = lut[rec_lk(rm, g12)], m22 = lut[rec_lk(rm, g22)];
+  const double C0 = p0 * (f11 * m11), C1 = p1 * (f11 * m12), C2 = p2 * (f11 * m22);
+  const double C3 = p1 * (f12 * m11), C4 = p4 * (f12 * m12), C5 = p5 * (f12 * m22);
+  const double C6 = p2 * (f22 * m11), C7 = p5 * (f22 * m12), C8 = p8 * (f22 * m22);
+  Quartic q;
+  q.b4 = C0; q.b3 = 2.0 * (C1 + C3); q.b2 = C2 + 4.0 * C4 + C6; q.b1 = 2.0 * (C5 + C7); q.b0 = C8;
+  return q;
+}
+// One kid's ten D values (the whole row space of the mutation matrix), written to the site's kid table.
+__device__ __noinline__ void kid_table_row_ol(const uint4 rk, const double *lut, const double *mut, double *out) {
+  double l[10];
+#pragma unroll
+  for (int g = 0; g < 10; g++) l[g] = lut[rec_lk(rk, g)];
+#pragma unroll 2
+  for (int x = 0; x < 10; x++) {
+    const double *row = mut + x * 10;
+    double d = 0.0;
+#pragma unroll
+    for (int g = 0; g < 10; g++) d += row[g] * l[g];
+    out[x] = d;
+  }
+}
 __device__ __noinline__ int brent_feed_ol(BrentState *s, double fu, double tol) { return brent_feed(*s, fu, tol) ? 1 : 0; }
 __device__ __noinline__ void var_posterior_ol(pm_site_result *r, int ref, int n) { var_posterior(*r, ref, n); }
 __device__ __noinline__ int site_decide_ol(const DevRun *run, pm_site_result *r, double lk_mono) { return site_decide(run, *r, lk_mono) ? 1 : 0; }
-__device__ __noinline__ double log10_ol(double m, int e) { return log10(m) + (double)e * kLog10_2; }
+// log10(m * 2^e) for a mantissa m in [1,2) (or 0 -> -inf).  m = c (1 + r) with c from a 128-entry table,
+// |r| <= 2^-8, log1p(r) by its series to r^7 (truncation < 2^-67); absolute error ~1e-16, far below the
+// rounding noise of the reference's own sum of per-family log10 values.  Replaces a ~40-instruction
+// dependent libm sequence on the serial tail of every Brent step.
+__device__ __noinline__ double log10_ol(const WideShared *ws, double m, int e) {
+  if (!(m > 0.0)) return -CUDART_INF;
+  const int i = (__double2hiint(m) >> 13) & 127;
+  const double r = fma(m, ws->log_inv[i], -1.0);
+  double q = 1.0 / 7.0;
+  q = fma(q, r, -1.0 / 6.0);
+  q = fma(q, r, 1.0 / 5.0);
+  q = fma(q, r, -0.25);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -0.5);
+  const double l1p = fma(q * r, r, r);
+  return fma(l1p, 0.43429448190325182765, ws->log_tab[i]) + (double)e * kLog10_2;
+}
 
 template <int U>
 struct WideEval {
   const DevRun *run;
   const uint4 *recs;  // site records in shared memory
   WideShared *ws;
+  const double *kidD;  // per-site kid table in shared memory (nullptr = build D on the fly)
   int G, Tg, grp, t;  // groups, threads per group, my group, my index inside the group
-  double B[U][5];
+  double B[U][5];     // per unit, scaled by an exact power of two so that the largest coefficient is in [1,2)
+  int K;              // sum over my units of the exponents taken out: prod_u L_u = 2^K * prod_u L'_u
 
   // Optimises nc <= G hypotheses concurrently (chain c by group c).  On return (after a barrier)
   // ws->brent[c] holds min/fmin of chain c.  with_h0: also reduce prod_u B[u][4] of chain 0 in the first
@@ -484,6 +543,7 @@ struct WideEval {
     const int lane = threadIdx.x & 31;
     const int wg = t >> 5, nwg = Tg >> 5;  // warp index inside the group, warps per group
     const bool mine = grp < nc;
+    K = 0;
     if (mine) {
       const int x = a1[grp], y = a2[grp];
       const int g11 = geno_index(x, x), g12 = geno_index(x, y), g22 = geno_index(y, y);
@@ -492,8 +552,25 @@ struct WideEval {
         const int u = t + k * Tg;
         if (u < run->n_units) {
           const DevUnit du = run->units[u];
-          const Quartic q = unit_quartic_ol(recs, du.first, du.nkids, g11, g12, g22, denovo ? 1 : 0, ws->t.lut, ws->t.mut);
-          B[k][0] = q.b0; B[k][1] = q.b1; B[k][2] = q.b2; B[k][3] = q.b3; B[k][4] = q.b4;
+          const Quartic q = (denovo && kidD && du.nkids > 0)
+                                ? unit_quartic_tab_ol(recs, du.first, du.nkids, kidD + (size_t)du.kid0 * 10, g11, g12, g22, ws->t.lut)
+                                : unit_quartic_ol(recs, du.first, du.nkids, g11, g12, g22, denovo ? 1 : 0, ws->t.lut, ws->t.mut);
+          // With the largest coefficient in [1,2) and p in [1e-4, 0.9999], L'(p) >= min(p,q)^4 >= 2^-54, so the
+          // product over this thread's U <= 8 units cannot underflow: no exponent handling inside a round.
+          double mx = fmax(fmax(fmax(q.b0, q.b1), fmax(q.b2, q.b3)), q.b4);
+          double b0 = q.b0, b1 = q.b1, b2 = q.b2, b3 = q.b3, b4 = q.b4;
+          if (mx > 0.0 && mx < 2.2250738585072014e-308) {  // subnormal maximum: lift it first
+            const double big = 1.3407807929942597e154;     // 2^512
+            b0 *= big; b1 *= big; b2 *= big; b3 *= big; b4 *= big; mx *= big;
+            K -= 512;
+          }
+          if (mx > 0.0) {
+            const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+            const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex), exact
+            b0 *= sc; b1 *= sc; b2 *= sc; b3 *= sc; b4 *= sc;
+            K += ex - 1023;
+          }
+          B[k][0] = b0; B[k][1] = b1; B[k][2] = b2; B[k][3] = b3; B[k][4] = b4;
         } else {  // (p+q)^4 = 1: a neutral unit
           B[k][4] = 1.0; B[k][3] = 4.0; B[k][2] = 6.0; B[k][1] = 4.0; B[k][0] = 1.0;
         }
@@ -518,16 +595,16 @@ struct WideEval {
       if (live) {
         const Monomials m = monomials(p);
         FastProd fa;
-        fa.m = 1.0; fa.e = 0;
+        fa.m = 1.0; fa.e = K;
 #pragma unroll
-        for (int k = 0; k < U; k++) fprod_mul(fa, quartic_eval(B[k], m));
+        for (int k = 0; k < U; k++) fa.m *= quartic_eval(B[k], m);
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[grp][wg] = acc.m; ws->warp_e[grp][wg] = acc.e; }
       }
       if (h0) {
         FastProd fa;
-        fa.m = 1.0; fa.e = 0;
+        fa.m = 1.0; fa.e = K;   // B[k][4] carries the same power-of-two scaling as the unit
 #pragma unroll
         for (int k = 0; k < U; k++) fprod_mul(fa, B[k][4]);
         ProdAcc acc = fprod_finish(fa);
@@ -540,7 +617,8 @@ struct WideEval {
         ProdAcc a;
         a.m = 1.0; a.e = 0;
         for (int w = 0; w < nwg; w++) prod_merge(a, ws->warp_m[grp][w], ws->warp_e[grp][w]);
-        const double ll = log10_ol(a.m, a.e);
+        renorm_nonzero(a);  // log10_ol wants the mantissa back in [1,2)
+        const double ll = log10_ol(ws, a.m, a.e);
         const bool more = brent_feed_ol(&ws->brent[grp], -ll, run->precision) != 0;
         ws->p[grp] = more ? ws->brent[grp].u : -1.0;
         atomicAdd(&ws->n_eval, 1u);
@@ -549,7 +627,8 @@ struct WideEval {
         ProdAcc a;
         a.m = 1.0; a.e = 0;
         for (int w = 0; w < nwg; w++) prod_merge(a, ws->warp_m[kMaxChains][w], ws->warp_e[kMaxChains][w]);
-        ws->bcast[1] = log10_ol(a.m, a.e);
+        renorm_nonzero(a);
+        ws->bcast[1] = log10_ol(ws, a.m, a.e);
       }
       first = false;
       __syncthreads();
@@ -559,30 +638,45 @@ struct WideEval {
 
 template <int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
-                                                        const uint4 *__restrict__ recs_all, size_t n_sites, int groups,
+                                                        const uint4 *__restrict__ recs_all, size_t n_sites, int groups, int nbuf, int kid_table,
                                                         pm_site_result *__restrict__ res, uint16_t *__restrict__ status,
                                                         int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *ws = reinterpret_cast<WideShared *>(smem_raw);
-  uint4 *site = reinterpret_cast<uint4 *>(smem_raw + ((sizeof(WideShared) + 127) / 128) * 128);
   const int np = run->n_person;
+  const size_t site_bytes = (((size_t)np * 16 + 127) / 128) * 128;
+  unsigned char *site_base = smem_raw + ((sizeof(WideShared) + 127) / 128) * 128;
+  double *kid_tab = kid_table ? reinterpret_cast<double *>(site_base + (size_t)nbuf * site_bytes) : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
   load_tables(run, &ws->t);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) { ws->log_inv[i] = run->log_inv[i]; ws->log_tab[i] = run->log_tab[i]; }
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  uint32_t phase = 0;
+  // nbuf = 2: the next site's n_person*16 bytes are fetched by TMA while this one is being computed
+  uint32_t phase[2] = {0, 0};
+  int cur = 0;
+  if (threadIdx.x == 0 && blockIdx.x < n_sites)
+    tma_issue_site(site_base, recs_all + (size_t)blockIdx.x * np, (uint32_t)np * 16u, &ws->mbar[0]);
   WideEval<U> ev;
-  ev.run = run; ev.recs = site; ev.ws = ws;
+  ev.run = run; ev.ws = ws; ev.kidD = kid_tab;
   ev.G = groups; ev.Tg = blockDim.x / groups; ev.grp = threadIdx.x / ev.Tg; ev.t = threadIdx.x % ev.Tg;
   const int G = groups;
 
   for (size_t s = blockIdx.x; s < n_sites; s += gridDim.x) {
-    // ---- stage the site: n_person * 16 contiguous bytes, one TMA bulk copy ----
-    tma_load_site(site, recs_all + s * (size_t)np, (uint32_t)np * 16u, &ws->mbar, phase);
-    phase ^= 1;
+    // ---- the site: n_person * 16 contiguous bytes, one TMA bulk copy (issued one iteration ahead) ----
+    uint4 *site = reinterpret_cast<uint4 *>(site_base + (size_t)cur * site_bytes);
+    ev.recs = site;
+    if (nbuf == 2) {
+      const size_t nxt = s + gridDim.x;
+      if (threadIdx.x == 0 && nxt < n_sites)
+        tma_issue_site(site_base + (size_t)(cur ^ 1) * site_bytes, recs_all + nxt * (size_t)np, (uint32_t)np * 16u, &ws->mbar[cur ^ 1]);
+    }
+    mbar_wait(&ws->mbar[cur], phase[cur]);
+    phase[cur] ^= 1;
     const pm_site_hdr h = hdr[s];
     const int ref = h.ref_base;
     bool skip = false;
@@ -634,6 +728,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
     if (!skip) {
       const double lk_mono = ws->bcast[0];
       const bool dn = run->denovo != 0;
+      if (kid_tab) {
+        // once per site: every kid's ten mutation-mixed likelihoods, shared by all hypotheses of the site
+        for (int u = threadIdx.x; u < run->n_units; u += blockDim.x) {
+          const DevUnit du = run->units[u];
+          for (int k = 0; k < du.nkids; k++) kid_table_row_ol(site[du.first + 2 + k], ws->t.lut, ws->t.mut, kid_tab + (size_t)(du.kid0 + k) * 10);
+        }
+        __syncthreads();
+      }
       // ---- H1..H3 (+ H0 under --denovo), then H4..H6 if the posterior is not decisive ----
       for (int base = 1; base <= 4; base += 3) {
         int a1[3], a2[3];
@@ -681,6 +783,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
       }
     }
     __syncthreads();  // the site buffer and ws->r are reused by the next iteration
+    if (nbuf == 2) cur ^= 1;
+    else if (threadIdx.x == 0 && s + gridDim.x < n_sites)
+      tma_issue_site(site_base, recs_all + (s + gridDim.x) * (size_t)np, (uint32_t)np * 16u, &ws->mbar[0]);
   }
 }
 
@@ -987,8 +1092,8 @@ __global__ void k_copy(const uint4 *__restrict__ src, uint4 *__restrict__ dst, s
 // ================================================================================================
 // launchers
 // ================================================================================================
-static size_t wide_smem_bytes(int n_person) {
-  return ((sizeof(WideShared) + 127) / 128) * 128 + (size_t)n_person * 16 + 16;
+static size_t wide_smem_bytes(int n_person, int nbuf, int n_kids_table) {
+  return ((sizeof(WideShared) + 127) / 128) * 128 + (size_t)nbuf * ((((size_t)n_person * 16 + 127) / 128) * 128) + (size_t)n_kids_table * 80 + 16;
 }
 
 // (U, MAXT) instantiations of the wide kernel.  U = units per thread; MAXT = largest block the
@@ -999,7 +1104,7 @@ static size_t wide_smem_bytes(int n_person) {
       case 1: CALL(1, 1024); break;                                     \
       case 2: CALL(2, 768); break;                                      \
       case 4: if ((plan_).threads > 512) { CALL(4, 768); } else { CALL(4, 512); } break; \
-      default: if ((plan_).threads > 384) { CALL(8, 512); } else { CALL(8, 384); } break; \
+      default: if ((plan_).threads > 384 || (plan_).low_regs) { CALL(8, 512); } else { CALL(8, 384); } break; \
     }                                                                   \
   } while (0)
 
@@ -1010,18 +1115,21 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
     const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
     k_sites_narrow<kNarrowMaxUnits><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err);
   } else {
-    const size_t smem = wide_smem_bytes(plan.n_person);
+    const size_t smem = wide_smem_bytes(plan.n_person, plan.site_buffers, plan.kid_table);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
-#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, plan.chains, d_res, d_status, d_err)
+#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, plan.chains, plan.site_buffers, plan.kid_table, d_res, d_status, d_err)
     PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
   }
   return cudaGetLastError();
 }
 
-cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count) {
+cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int n_kids_denovo, int sm_count) {
   plan->n_person = n_person;
   plan->chains = 1;
+  plan->kid_table = 0;
+  plan->site_buffers = 1;
+  plan->low_regs = 0;
   if (n_units <= kNarrowMaxUnits) {
     plan->kind = LaunchPlan::NARROW;
     plan->threads = kNarrowThreads;
@@ -1032,14 +1140,16 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   }
   if (n_es > 0) return cudaErrorNotSupported;
   plan->kind = LaunchPlan::WIDE;
-  // G groups (one Brent chain each) x Tg threads x U units per thread, Tg * U >= n_units
-  int U, Tg, G;
+  // G groups (one Brent chain each) x Tg threads x U units per thread, Tg * U >= n_units.
+  // Measured on B200 (1,000 trios, --denovo): one chain per block with three independent blocks per SM
+  // (6.7 M sites/s) beats three chains in one 384-thread block (5.6 M): independent blocks overlap each
+  // other's serial Brent tails without sharing a barrier.  So G = 1 and as many resident blocks as fit.
+  int U, Tg, G = 1;
   auto up32 = [](int x) { return ((x + 31) / 32) * 32; };
-  if (n_units <= 256) { G = 3; U = 1; Tg = up32(n_units); }
-  else if (n_units <= 512) { G = 3; U = 2; Tg = up32((n_units + 1) / 2); }
-  else if (n_units <= 1024) { G = 3; U = 8; Tg = up32((n_units + 7) / 8); }  // measured: 384 x U=8 beats 768 x U=4
-  else if (n_units <= 2048) { G = 1; U = 4; Tg = 512; }
-  else if (n_units <= 4096) { G = 1; U = 8; Tg = 512; }
+  if (n_units <= 32) { U = 1; Tg = 32; }
+  else if (n_units <= 64) { U = 2; Tg = 32; }
+  else if (n_units <= 128) { U = 4; Tg = 32; }
+  else if (n_units <= 4096) { U = 8; Tg = up32((n_units + 7) / 8); }
   else return cudaErrorNotSupported;
   // tuning hook: PM_WIDE_PLAN="threads_per_group,units_per_thread,groups" overrides the choice
   if (const char *env = getenv("PM_WIDE_PLAN")) {
@@ -1052,7 +1162,17 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   plan->threads = Tg * G;
   plan->units_per_thread = U;
   plan->chains = G;
-  const size_t smem = wide_smem_bytes(n_person);
+  // shared-memory budget: prefer the kid table (saves set-up arithmetic on every hypothesis), then the second
+  // site buffer (hides the TMA latency)
+  const size_t budget = 220 * 1024;
+  plan->kid_table = (n_kids_denovo > 0 && wide_smem_bytes(n_person, 1, n_kids_denovo) <= budget) ? n_kids_denovo : 0;
+  // a second site buffer (TMA prefetch of the next site) only pays when it does not cost a resident block
+  plan->site_buffers = wide_smem_bytes(n_person, 2, plan->kid_table) <= 24 * 1024 ? 2 : 1;
+  if (getenv("PM_WIDE_TWO_BUF") && wide_smem_bytes(n_person, 2, plan->kid_table) <= budget) plan->site_buffers = 2;
+  if (!getenv("PM_WIDE_KIDTAB")) plan->kid_table = 0;  // measured: the 10-row table costs as much as it saves
+  plan->low_regs = getenv("PM_WIDE_LOWREGS") ? 1 : 0;
+  if (getenv("PM_WIDE_ONE_BUF")) plan->site_buffers = 1;
+  const size_t smem = wide_smem_bytes(n_person, plan->site_buffers, plan->kid_table);
   if (smem > 227 * 1024) return cudaErrorNotSupported;
   cudaError_t e = cudaSuccess;
   int per_sm = 1;

@@ -20,10 +20,13 @@ struct LaunchPlan {
   int chains;             // wide: Brent chains optimised concurrently (template parameter NC)
   int grid;               // wide: persistent grid (multiple of the SM count); narrow: derived from n_sites
   int blocks_per_sm;
+  int site_buffers;       // wide: 2 = the next site is prefetched by TMA while this one is computed
+  int low_regs;           // wide: use the 128-register instantiation (more resident blocks per SM)
+  int kid_table;          // wide, --denovo: kids' ten mutation-mixed likelihoods are built once per site in shared memory
   int n_person;
 };
 
-cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count);
+cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int n_kids_denovo, int sm_count);
 
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                          size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream);

@@ -95,7 +95,7 @@ typedef struct pm_params {
   int32_t force_call;        /* set by --pos */
   int32_t out_all_sites;     /* --all_sites */
   int32_t quick_call;        /* --quick_call */
-  int32_t reserved;
+  int32_t vcf_input;         /* 1 = this ctx serves pm_call_vcf_records (--in_vcf, src/PedVCF.cpp) */
 } pm_params;
 
 /* Per-site header, 8 bytes. */
@@ -208,6 +208,20 @@ int pm_call_glf_sites_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_per
                              size_t res_cap, uint32_t *d_n_res);
 
 int pm_sync(pm_ctx *ctx);
+
+/* VCF-input calling (src/PedVCF.cpp:116-163, src/FamilyLikelihoodSeq_VCF.cpp) for a batch of bi-allelic
+ * records, HOST buffers.  The ctx must have been created with pm_params.vcf_input = 1 and, as lut256, the
+ * table 10^(-i/10) computed as pow(10, -double(i)/10.0) (FamilyLikelihoodSeq_VCF.cpp:21-22).
+ *   hdr[r]      pos = POS, ref_base = allele1 (1..4; 1 for an indel), reserved = allele2 | (indel << 8)
+ *   person_site records in VCF-column-of-the-pedigree order; lk[g(a1,a1)], lk[g(a1,a2)], lk[g(a2,a2)] hold
+ *               int(PL) (or int(-10*GL)) capped at 255, every other byte 0 (a sample that is not in the VCF
+ *               or has no data is all zeros = likelihood 1, FamilyLikelihoodSeq_VCF.cpp:275-279)
+ *   mono[r]     sum over samples of loglk[ref/ref] (MonomorphismLogLikelihood, FamilyLikelihoodSeq_VCF.cpp:74-83),
+ *               computed by the caller because it uses the un-truncated PL/GL doubles
+ * Every record produces a row: res_out[n], person_out[n * n_person].  res_out[r].poly_qual is QUAL,
+ * .freq the frequency of allele1 (the VCF prints AF = 1 - freq), varllk[0] / varllk[1] are llk_ref / llk_alt. */
+int pm_call_vcf_records(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                        size_t n_records, pm_site_result *res_out, pm_person_result *person_out);
 
 /* Page-locked host memory for the buffers handed to pm_call_glf_sites (lets its H2D/D2H copies overlap
  * the kernels).  Optional: pageable buffers are accepted too. */

@@ -35,9 +35,13 @@ static int call_glf(void *vctx, const pm_site_hdr *hdr, const pm_person_site *ps
   *n_res = k;
   return PM_OK;
 }
+static int call_vcf(void *vctx, const pm_site_hdr *hdr, const pm_person_site *ps, const double *mono, size_t n, pm_site_result *res,
+                    pm_person_result *person) {
+  return pmo_call_vcf_records(((OracleCtx *)vctx)->c, hdr, ps, mono, n, res, person);
+}
 static void destroy(void *vctx) { OracleCtx *o = (OracleCtx *)vctx; pmo_destroy(o->c); delete o; }
 
 int main(int argc, char **argv) {
-  pmh::Engine e{"cpu-oracle", create, call_glf, destroy, pmo_last_error};
+  pmh::Engine e{"cpu-oracle", create, call_glf, destroy, pmo_last_error, call_vcf};
   return pmh::run_cli(argc, argv, e);
 }

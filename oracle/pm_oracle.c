@@ -563,8 +563,29 @@ static double CalcSingleFamLikelihood_denovo(const pmo_ctx *c, famlk_t *k, int i
   return es_CalculateLikelihood(c, e, 10, 1);
 }
 
+/* FamilyLikelihoodSeq_VCF::CalcAllFamLogLikelihood, src/FamilyLikelihoodSeq_VCF.cpp:92-109 (autosome):
+ * founders-only families sum log10 per person (:111-119), nuclear families use the nuclear formula only when
+ * there are several families, everything else goes through the bi-allelic peel. */
+static double CalcAllFamLogLikelihood_VCF(pmo_ctx *c, famlk_t *k, double freq) {
+  double loglk = 0.0;
+  k->n_eval++;
+  for (int i = 0; i < c->nFam; i++) {
+    if (c->famSize[i] == c->famFounders[i]) {
+      double llk = 0.0;
+      for (int j = 0; j < c->famSize[i]; j++) llk += log10(lkSinglePerson(c, k, c->famFirst[i] + j, freq));
+      loglk += llk;
+    } else if (fam_isNuclear(c, i) && c->nFam > 1) {
+      loglk += log10(lkSingleFam(c, k, i, freq, 0));
+    } else {
+      loglk += log10(CalcSingleFamLikelihood_BA(c, k, i, freq));
+    }
+  }
+  return loglk;
+}
+
 /* FLSeq:222-240, sequential family order (--nthreads 1) */
 static double CalcAllFamLogLikelihood(pmo_ctx *c, famlk_t *k, double freq) {
+  if (c->par.vcf_input) return CalcAllFamLogLikelihood_VCF(c, k, freq);
   double loglk = 0.0;
   k->n_eval++;
   for (int i = 0; i < c->nFam; i++) {
@@ -1024,7 +1045,7 @@ pmo_ctx *pmo_create(const pm_pedigree *ped, const pm_params *par, const double *
       e->famSize = c->famSize[f]; e->nFounders = c->famFounders[f]; e->first = c->famFirst[f];
       e->priors = calloc((size_t)(e->nFounders > 0 ? e->nFounders : 1), sizeof *e->priors);
       e->partials = calloc((size_t)e->famSize, sizeof *e->partials);
-      if (e->famSize != e->nFounders && !fam_isNuclear(c, f)) {
+      if (e->famSize != e->nFounders && (!fam_isNuclear(c, f) || par->vcf_input)) {
         e->steps = calloc((size_t)e->famSize, sizeof(pm_peel_step));
         int n = pmo_build_peel_order(e->famSize, c->father + e->first, c->mother + e->first, c->sex + e->first, e->steps);
         if (n < 0) { pmo_destroy(c); return NULL; }
@@ -1232,6 +1253,74 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
     p->ten_state = fl[0].tenState[i];
   }
   return 0;
+}
+
+/* One VCF record: PedVCF::VarCallFromVCF, src/PedVCF.cpp:116-163, with FamilyLikelihoodSeq_VCF::CalcPostProb
+ * (src/FamilyLikelihoodSeq_VCF.cpp:142-153) and CalcGQ (NucFam:553-569). */
+int pmo_call_vcf_records(pmo_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono_in,
+                         size_t n, pm_site_result *res_out, pm_person_result *person_out) {
+  if (!c->par.vcf_input) { set_err("oracle ctx was not created for VCF input"); return PM_EINVAL; }
+  famlk_t *k = &c->famlk[0];
+  const double polyPrior = c->prior;
+  for (size_t s = 0; s < n; s++) {
+    pmo_load_site(c, &hdr[s], person_site + s * (size_t)c->nPerson);
+    pm_site_result *r = &res_out[s];
+    pm_person_result *pr = person_out + s * (size_t)c->nPerson;
+    memset(r, 0, sizeof *r);
+    memset(pr, 0, sizeof(*pr) * (size_t)c->nPerson);
+    const int a1 = hdr[s].ref_base, a2 = hdr[s].reserved & 0xff, indel = (hdr[s].reserved >> 8) & 1;
+    const double mono = mono_in[s];
+    SetAlleles(k, a1, a2);                       /* PolymorphismLogLikelihood, FLSeq_VCF:85-90 */
+    OptimizeFrequency(c, k);
+    const double poly = -k->fmin;
+    const int isTs = (a1 == 1 && a2 == 3) || (a1 == 2 && a2 == 4); /* PedVCF.cpp:23-26 */
+    double llk_alt, llk_ref;
+    if (!indel) {
+      /* log10(polyPrior * isTs ? ts : tv): the product only selects the branch (PedVCF.cpp:143) */
+      llk_alt = log10((polyPrior * isTs) != 0 ? 2.0 / (2.0 + 1) : 0.5 / (2.0 + 1)) + poly;
+      llk_ref = log10(1 - polyPrior) + mono;
+    } else {
+      llk_alt = log10(polyPrior) + poly;         /* GetPolyPrior_indel returns the SNP prior (NucFam:313) */
+      llk_ref = log10(1 - polyPrior) + mono;
+    }
+    double qual;
+    if (llk_alt - llk_ref > 10) qual = 10.0 * (llk_alt - llk_ref);
+    else {
+      double posterior = 1 / (1 + pow(10, llk_ref - llk_alt));
+      qual = -10 * log10(1 - posterior);
+      r->var_post_prob = posterior;
+    }
+    /* CalcPostProb, FLSeq_VCF:142-153 */
+    const double freq = k->min;
+    k->isMono = 0;
+    for (int i = 0; i < c->nFam; i++) {
+      if (c->famSize[i] == c->famFounders[i]) {
+        for (int j = 0; j < c->famFounders[i]; j++) CalcPostProb_SinglePerson(c, k, c->famFirst[i] + j, freq);
+      } else if (fam_isNuclear(c, i) && c->nFam > 1) {
+        CalcPostProb_SingleNucFam(c, k, i, freq);
+      } else {
+        CalcPostProb_SingleExtendedPed_BA(c, k, i, freq);
+      }
+    }
+    r->site = (uint32_t)s; r->status = PM_SITE_EMITTED; r->maxidx = 1; r->n_hyp = 2;
+    r->allele1 = (uint8_t)a1; r->allele2 = (uint8_t)a2;
+    r->varllk[0] = llk_ref; r->varllk[1] = llk_alt;
+    r->varllk_noprior[0] = mono; r->varllk_noprior[1] = poly;
+    r->varfreq[0] = 1.0; r->varfreq[1] = freq;
+    r->poly_qual = qual; r->freq = freq;
+    for (int i = 0; i < c->nPerson; i++) {
+      pm_person_result *p = &pr[i];
+      for (int g = 0; g < 3; g++) p->post[g] = k->postProb[i][g];
+      p->dosage = k->dosage[i];
+      p->best = k->bestGenoIdx[i];
+      double pb = k->postProb[i][p->best];
+      int GTQual;
+      if (pb > 0.9999999999) GTQual = 100;
+      else GTQual = (int)(-10. * log10(1. - pb) + 0.5);
+      p->gq = (uint8_t)(GTQual < 0 ? 0 : (GTQual > 255 ? 255 : GTQual));
+    }
+  }
+  return PM_OK;
 }
 
 int pmo_call_glf_sites(pmo_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, size_t n_sites,

@@ -34,6 +34,10 @@ int pmo_call_glf_sites(pmo_ctx *ctx, const pm_site_hdr *hdr, const pm_person_sit
                        size_t n_sites, uint16_t *status_out, pm_site_result *res_out,
                        pm_person_result *person_out);
 
+/* Mirrors pm_call_vcf_records (ctx created with pm_params.vcf_input = 1 and the PL2LK table as lut256). */
+int pmo_call_vcf_records(pmo_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                         size_t n_records, pm_site_result *res_out, pm_person_result *person_out);
+
 /* ES_Peeling restated (src/FamilyLikelihoodES.cpp:46-277). Same contract as pm_build_peel_order. */
 int pmo_build_peel_order(int32_t n, const int32_t *father, const int32_t *mother, const uint8_t *sex,
                          pm_peel_step *steps);

@@ -74,7 +74,7 @@ class _PmParams(C.Structure):
         ("denovo_tstv", C.c_double), ("denovo_min_llr", C.c_double), ("min_ps", C.c_double),
         ("min_map_quality", C.c_int32), ("min_total_depth", C.c_int32), ("max_total_depth", C.c_int32),
         ("denovo", C.c_int32), ("force_call", C.c_int32), ("out_all_sites", C.c_int32),
-        ("quick_call", C.c_int32), ("reserved", C.c_int32),
+        ("quick_call", C.c_int32), ("vcf_input", C.c_int32),
     ]
 
 
@@ -97,12 +97,11 @@ class Params:
     force_call: bool = False
     out_all_sites: bool = False
     quick_call: bool = False
+    vcf_input: bool = False
 
     def to_c(self) -> _PmParams:
         p = _PmParams()
         for name, _ in _PmParams._fields_:
-            if name == "reserved":
-                continue
             v = getattr(self, name)
             setattr(p, name, int(v) if isinstance(v, bool) else v)
         return p
@@ -146,13 +145,14 @@ class PedigreeArrays:
     def family_first(self) -> np.ndarray:
         return np.concatenate([[0], np.cumsum(self.fam_size)[:-1]]).astype(np.int32)
 
-    def with_peel_orders(self, lib) -> "PedigreeArrays":
-        """Fills peel_first/peel for every extended family with pm_build_peel_order."""
+    def with_peel_orders(self, lib, all_families: bool = False) -> "PedigreeArrays":
+        """Fills peel_first/peel for every extended family (all_families: also nuclear ones, which the VCF
+        mode peels when the pedigree has a single family) with pm_build_peel_order."""
         firsts = self.family_first()
         steps_all, pf = [], [0]
         for f in range(self.n_fam):
             n, nf = int(self.fam_size[f]), int(self.fam_founders[f])
-            nuclear = int(self.fam_generations[f]) == 2 and nf == 2
+            nuclear = int(self.fam_generations[f]) == 2 and nf == 2 and not all_families
             if n != nf and not nuclear:
                 a = int(firsts[f])
                 steps = np.zeros(n, dtype=PEEL_STEP_DTYPE)
@@ -193,6 +193,8 @@ def _declare(lib):
     lib.pm_call_glf_sites.restype = C.c_int
     lib.pm_call_glf_sites.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.pm_call_vcf_records.restype = C.c_int
+    lib.pm_call_vcf_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.pm_call_glf_sites_device.restype = C.c_int
     lib.pm_call_glf_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -246,14 +248,15 @@ def load_library():
 class Engine:
     """pm_ctx bound to one CUDA device."""
 
-    def __init__(self, ped: PedigreeArrays, params: Params, device: int = 0):
+    def __init__(self, ped: PedigreeArrays, params: Params, device: int = 0, lut: Optional[np.ndarray] = None):
         self.lib = load_library()
         if len(ped.peel) == 0:
-            ped = ped.with_peel_orders(self.lib)
+            ped = ped.with_peel_orders(self.lib, all_families=params.vcf_input)
         self.ped = ped
         self.params = params
         self._cped, self._cpar = ped.to_c(), params.to_c()
-        self.ctx = self.lib.pm_create(C.byref(self._cped), C.byref(self._cpar), None, device)
+        self._lut = None if lut is None else np.ascontiguousarray(lut, dtype=np.float64)
+        self.ctx = self.lib.pm_create(C.byref(self._cped), C.byref(self._cpar), None if self._lut is None else self._lut.ctypes.data, device)
         if not self.ctx:
             raise RuntimeError("pm_create failed: " + self.lib.pm_last_error().decode())
 
@@ -287,6 +290,17 @@ class Engine:
                                                res.ctypes.data, per.ctypes.data, cap, C.byref(n_res)))
         k = n_res.value
         return status, res[:k], per[:k]
+
+    def call_vcf_records(self, hdr: np.ndarray, recs: np.ndarray, mono: np.ndarray):
+        """VCF-input entry point.  Returns (results[n], persons[n, n_person])."""
+        hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+        recs = np.ascontiguousarray(recs, dtype=PERSON_SITE_DTYPE)
+        mono = np.ascontiguousarray(mono, dtype=np.float64)
+        n, npers = len(hdr), self.ped.n_person
+        res = np.zeros(max(n, 1), dtype=SITE_RESULT_DTYPE)
+        per = np.zeros((max(n, 1), npers), dtype=PERSON_RESULT_DTYPE)
+        self._check(self.lib.pm_call_vcf_records(self.ctx, hdr.ctypes.data, recs.ctypes.data, mono.ctypes.data, n, res.ctypes.data, per.ctypes.data))
+        return res[:n], per[:n]
 
     def call_glf_sites_device(self, d_hdr: int, d_recs: int, n_sites: int, out_mode: int, d_status: int, d_res: int,
                               d_person: int, res_cap: int, d_n_res: int):

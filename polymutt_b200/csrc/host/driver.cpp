@@ -15,6 +15,7 @@
 #include "glf.h"
 #include "params.h"
 #include "pedigree.h"
+#include "vcf_mode.h"
 #include "vcf_writer.h"
 
 namespace pmh {
@@ -86,18 +87,16 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   bool parsed = opt.parse(argc, argv, &err);
   opt.print_status();
   if (!parsed) return fatal(err);
-  if (!opt.vcf_in.empty())
-    return fatal("--in_vcf (VCF input mode) is not implemented by this build yet");  // SURVEY.md §8, row "VCF mode"
-
-  std::map<std::string, std::string> glf_map;
-  if (!read_glf_index(opt.glf_index_file, &glf_map, &err)) return fatal(err);
-
   Pedigree ped;
   try {
     ped.load(opt.dat_file, opt.ped_file);
   } catch (const std::exception &e) {
     return fatal(e.what());
   }
+  if (!opt.vcf_in.empty()) return run_vcf_mode(opt, ped, engine);  // main.cpp:238-246
+
+  std::map<std::string, std::string> glf_map;
+  if (!read_glf_index(opt.glf_index_file, &glf_map, &err)) return fatal(err);
   FILE *vcf = fopen(opt.vcf_out.c_str(), "w");
   if (!vcf) return fatal("vcfOutFile can not be opened for output!");
 

@@ -20,6 +20,9 @@ struct Engine {
                   pm_site_result *res, pm_person_result *person, size_t res_cap, size_t *n_res);
   void (*destroy)(void *ctx);
   const char *(*last_error)();
+  // Same contract as pm_call_vcf_records (--in_vcf); nullptr if the engine has no VCF-input path.
+  int (*call_vcf)(void *ctx, const pm_site_hdr *, const pm_person_site *, const double *mono, size_t n, pm_site_result *res,
+                  pm_person_result *person) = nullptr;
   // optional: page-locked allocation for the batch buffers (nullptr = plain malloc)
   void *(*host_alloc)(size_t bytes) = nullptr;
   void (*host_free)(void *p) = nullptr;

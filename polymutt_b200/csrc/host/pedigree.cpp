@@ -216,7 +216,9 @@ void Pedigree::finish() {
       mother_.push_back(p.mother >= 0 ? persons[p.mother].traverse : -1);
     }
     peel_first_.push_back((int32_t)peel_.size());
-    if (n != f.founders && !f.nuclear()) {
+    // every family with non-founders gets an order: extended families always use it, nuclear ones only in VCF
+    // mode with a single family (FamilyLikelihoodSeq_VCF.cpp:98-103)
+    if (n != f.founders) {
       std::vector<pm_peel_step> steps(n);
       int ns = pm_build_peel_order(n, father_.data() + base, mother_.data() + base, sex_.data() + base, steps.data());
       if (ns < 0) throw std::runtime_error(std::string("family ") + f.famid + ": " + pm_last_error());

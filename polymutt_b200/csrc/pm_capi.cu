@@ -47,6 +47,7 @@ struct pm_ctx {
   uint32_t *d_n_emit = nullptr;
   // staging for the host-buffer entry point
   size_t cap_in_sites = 0, cap_out_rows = 0;
+  double *d_mono = nullptr; size_t cap_mono = 0;
   pm_site_hdr *d_hdr[2] = {nullptr, nullptr};   // two input slots: H2D of chunk k+1 overlaps compute of chunk k
   uint4 *d_recs[2] = {nullptr, nullptr};
   cudaStream_t stream_h2d = nullptr;
@@ -131,7 +132,9 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     const int size = ped->fam_size[f], nf = ped->fam_founders[f];
     d.first = first; d.size = (int16_t)size; d.founders = (int16_t)nf;
     founders_total += nf;
-    const bool nuclear = ped->fam_generations[f] == 2 && nf == 2;
+    // VCF mode uses the nuclear-family formula only when there are several families (FamilyLikelihoodSeq_VCF.cpp:98-103);
+    // a lone nuclear family goes through the bi-allelic Elston-Stewart peel there.
+    const bool nuclear = ped->fam_generations[f] == 2 && nf == 2 && !(par->vcf_input && ped->n_fam == 1);
     if (size == nf) {
       d.kind = 0;
       for (int j = 0; j < size; j++) units.push_back({first + j, -1, kids_total, 0});
@@ -211,7 +214,12 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     run.log_inv[i] = 1.0 / (1.0 + (i + 0.5) / 128.0);
     run.log_tab[i] = (double)(-log10l((long double)run.log_inv[i]));
   }
-  run.use_brent = (ped->n_fam > 1 || fams[0].kind != 1) ? 1 : 0;  // FLSeq:94
+  run.use_brent = (ped->n_fam > 1 || fams[0].kind != 1 || par->vcf_input) ? 1 : 0;  // FLSeq:94; always in VCF mode
+  run.vcf_mode = par->vcf_input ? 1 : 0;
+  // PedVCF::tstv_ratio is hard-wired to 2.0 (PedVCF.cpp:7); GetPolyPrior_indel returns the SNP prior (NucFam:313)
+  run.vcf_log_ts = log10(2.0 / (2.0 + 1));
+  run.vcf_log_tv = log10(0.5 / (2.0 + 1));
+  run.vcf_log_indel = log10(prior);
 
   e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, par->denovo ? kids_total : 0, c->sm_count);
   if (e == cudaErrorNotSupported) {
@@ -256,7 +264,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->h_rows) cudaFreeHost(c->h_rows);
-  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out);
+  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -266,10 +274,21 @@ extern "C" void pm_destroy(pm_ctx *c) {
   delete c;
 }
 
+static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                      size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
+                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res);
+
 extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
                                         size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
                                         pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res) {
   if (!c) return fail(PM_EINVAL, "null context");
+  if (c->par.vcf_input) return fail(PM_EINVAL, "this ctx was created for VCF input; use pm_call_vcf_records");
+  return run_device(c, d_hdr, d_person_site, nullptr, n_sites, out_mode, d_status_out, d_res_out, d_person_out, res_cap, d_n_res);
+}
+
+static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                      size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
+                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res) {
   if (n_sites == 0) { if (d_n_res) CUDA_TRY(cudaMemsetAsync(d_n_res, 0, sizeof(uint32_t), c->stream)); return PM_OK; }
   if (!d_hdr || !d_person_site || !d_status_out || !d_res_out || !d_person_out)
     return fail(PM_EINVAL, "pm_call_glf_sites_device: null buffer");
@@ -280,7 +299,7 @@ extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, con
   if (rc) return rc;
   uint32_t *d_cnt = d_n_res ? d_n_res : c->d_n_emit;
   CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-  CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
+  CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
@@ -334,6 +353,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   if (!c) return fail(PM_EINVAL, "null context");
   if (n_res) *n_res = 0;
   if (n_sites == 0) return PM_OK;
+  if (c->par.vcf_input) return fail(PM_EINVAL, "this ctx was created for VCF input; use pm_call_vcf_records");
   if (!hdr || !person_site || !res_out) return fail(PM_EINVAL, "pm_call_glf_sites: null buffer");
   for (size_t s = 0; s < n_sites; s++)
     if (hdr[s].chr_class != PM_CHR_AUTO && hdr[s].ref_base >= 1 && hdr[s].ref_base <= 4)
@@ -404,6 +424,55 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   c->timing_cached = true;
   if (n_res) *n_res = total_rows;
   if (overflow) return fail(PM_EINVAL, "pm_call_glf_sites: res_cap %zu too small, %zu rows needed", res_cap, total_rows);
+  return PM_OK;
+}
+
+extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                                   size_t n, pm_site_result *res_out, pm_person_result *person_out) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  if (!c->par.vcf_input) return fail(PM_EINVAL, "pm_call_vcf_records: the ctx was not created with pm_params.vcf_input = 1");
+  if (n == 0) return PM_OK;
+  if (!hdr || !person_site || !mono || !res_out || !person_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
+  for (size_t s = 0; s < n; s++) {
+    const int a2 = hdr[s].reserved & 0xff;
+    if (hdr[s].ref_base < 1 || hdr[s].ref_base > 4 || a2 < 1 || a2 > 4 || a2 == hdr[s].ref_base)
+      return fail(PM_EINVAL, "record %zu: alleles must be two different bases in 1..4 (got %d, %d)", s, hdr[s].ref_base, a2);
+    if (hdr[s].chr_class != PM_CHR_AUTO) return fail(PM_EUNSUPPORTED, "record %zu: chrX/chrY/MT records are not implemented on the device path yet", s);
+  }
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t np = (size_t)c->n_person;
+  size_t chunk = ((size_t)48 << 20) / (np * sizeof(pm_person_site));
+  if (chunk < 256) chunk = 256;
+  if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
+  if (chunk > n) chunk = n;
+  int rc;
+  if (chunk > c->cap_in_sites) {
+    for (int k = 0; k < 2; k++) {
+      if ((rc = dev_alloc(&c->d_hdr[k], chunk))) return rc;
+      if ((rc = dev_alloc(&c->d_recs[k], chunk * np))) return rc;
+    }
+    if ((rc = dev_alloc(&c->d_status, chunk))) return rc;
+    c->cap_in_sites = chunk;
+  }
+  if (chunk > c->cap_out_rows) {
+    if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
+    if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
+    c->cap_out_rows = chunk;
+  }
+  if (chunk > c->cap_mono) { if ((rc = dev_alloc(&c->d_mono, chunk))) return rc; c->cap_mono = chunk; }
+  for (size_t base = 0; base < n; base += chunk) {
+    const size_t m = n - base < chunk ? n - base : chunk;
+    CUDA_TRY(cudaMemcpyAsync(c->d_hdr[0], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_recs[0], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->d_mono, mono + base, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = run_device(c, c->d_hdr[0], (const pm_person_site *)c->d_recs[0], c->d_mono, m, PM_OUT_ALL, c->d_status, c->d_res_out,
+                    c->d_person_out, c->cap_out_rows, c->d_n_emit);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(res_out + base, c->d_res_out, m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(person_out + base * np, c->d_person_out, m * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = pm_sync(c))) return rc;
+    for (size_t r = 0; r < m; r++) res_out[base + r].site += (uint32_t)base;
+  }
   return PM_OK;
 }
 

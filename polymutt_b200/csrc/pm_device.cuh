@@ -59,9 +59,11 @@ struct DevRun {
   double log_tab[128];        // -log10(log_inv[i]) (computed in long double on the host)
   // host-computed log10 constants (same libm as the reference)
   double log_1m_prior, log_prior_ts, log_prior_tv, log_prior_other, log_prior_23, log_prior_16, log_min_llr;
+  double vcf_log_ts, vcf_log_tv, vcf_log_indel;  // VCF mode: log10(2/3), log10(1/6), log10(prior)  (src/PedVCF.cpp:143-150)
   double theta, posterior_cutoff, precision, denovo_min_llr, min_ps;
   int32_t min_map_quality, min_total_depth, max_total_depth;
   int32_t denovo, force_call, out_all_sites;
+  int32_t vcf_mode;           // 1 = records come from a VCF (src/PedVCF.cpp:116-163): one hypothesis (REF, ALT), QUAL formula
   int32_t n_person, n_fam, n_units, n_es, n_kids;
   int32_t use_brent;          // nFam>1 || !nuclear  (FLSeq:94)
   unsigned long long *counters;  // [4] hypotheses, evaluations, sites evaluated, sites emitted
@@ -318,6 +320,29 @@ __device__ inline void var_posterior(pm_site_result &r, int ref, int n) {
   r.maxidx = (int8_t)maxidx;
   r.n_hyp = (uint8_t)n;
   r.poly_qual = (r.var_post_prob > 0.9999999999) ? 100.0 : -10 * log10(1 - r.var_post_prob);
+}
+
+// VCF mode (src/PedVCF.cpp:140-156): the site prior is dropped from llk_alt by operator precedence
+// (`log10(polyPrior * isTs(...) ? ts : tv)`), isTs is true only for A>G and C>T, indels use the SNP prior.
+__device__ inline void vcf_record_result(const DevRun *run, pm_site_result &r, int a1, int a2, bool indel, double mono, double poly, double freq) {
+  const bool is_ts = (a1 == 1 && a2 == 3) || (a1 == 2 && a2 == 4);
+  const double llk_alt = (indel ? run->vcf_log_indel : (is_ts ? run->vcf_log_ts : run->vcf_log_tv)) + poly;
+  const double llk_ref = run->log_1m_prior + mono;
+  double qual;
+  if (llk_alt - llk_ref > 10) qual = 10.0 * (llk_alt - llk_ref);
+  else {
+    const double posterior = 1 / (1 + pow(10.0, llk_ref - llk_alt));
+    qual = -10 * log10(1 - posterior);
+    r.var_post_prob = posterior;
+  }
+  r.varllk[0] = llk_ref; r.varllk[1] = llk_alt;
+  r.varllk_noprior[0] = mono; r.varllk_noprior[1] = poly;
+  r.varfreq[0] = 1.0; r.varfreq[1] = freq;
+  r.poly_qual = qual;
+  r.freq = freq;
+  r.allele1 = (uint8_t)a1; r.allele2 = (uint8_t)a2;
+  r.maxidx = 1; r.n_hyp = 2;
+  r.status = PM_SITE_EMITTED;
 }
 
 __device__ __forceinline__ int best3(double p11, double p12, double p22) {  // NucFam:1564-1571

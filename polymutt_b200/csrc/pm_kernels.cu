@@ -255,7 +255,8 @@ struct NarrowEval {
 template <int UMAX>
 __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
                                                                   const pm_site_hdr *__restrict__ hdr,
-                                                                  const uint4 *__restrict__ recs_all, size_t n_sites,
+                                                                  const uint4 *__restrict__ recs_all,
+                                                                  const double *__restrict__ mono_all, size_t n_sites,
                                                                   pm_site_result *__restrict__ res,
                                                                   uint16_t *__restrict__ status, int *__restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -286,6 +287,17 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   const int ref = h.ref_base;
   if (ref < 1 || ref > 4) { r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
   if (h.chr_class != PM_CHR_AUTO) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+  if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
+    const int a2 = h.reserved & 0xff;
+    NarrowEval<UMAX> ev;
+    ev.run = run; ev.recs = recs; ev.sm = sm;
+    double freq = 0.0;
+    const double poly = ev.optimize(ref, a2, false, &freq);
+    vcf_record_result(run, r, ref, a2, (h.reserved & 0x100) != 0, mono_all[s], poly, freq);
+    res[s] = r;
+    status[s] = status_word(r);
+    return;
+  }
 
   // CalcReadStats + filters (NucFam:520-546, main:343-348) and MonomorphismLogLikelihood (NucFam:502-517)
   int total_depth = 0, ns = 0, mapq_sum = 0;
@@ -638,7 +650,8 @@ struct WideEval {
 
 template <int U, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
-                                                        const uint4 *__restrict__ recs_all, size_t n_sites, int groups, int nbuf, int kid_table,
+                                                        const uint4 *__restrict__ recs_all, const double *__restrict__ mono_all,
+                                                        size_t n_sites, int groups, int nbuf, int kid_table,
                                                         pm_site_result *__restrict__ res, uint16_t *__restrict__ status,
                                                         int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -687,6 +700,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
         r.site = (uint32_t)s; r.maxidx = -1; r.status = PM_SITE_BAD_REF;
         if (ref >= 1 && ref <= 4) atomicExch(err, PM_EUNSUPPORTED);
         res[s] = r; status[s] = status_word(r);
+      }
+      skip = true;
+    }
+    if (!skip && run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
+      const int a1 = ref, a2 = h.reserved & 0xff;
+      if (threadIdx.x == 0) {
+        memset(&ws->r, 0, sizeof ws->r);
+        ws->r.site = (uint32_t)s;
+        ws->n_hyp = 0; ws->n_eval = 0;
+      }
+      ev.optimize(1, &a1, &a2, false, false);
+      if (threadIdx.x == 0) {
+        vcf_record_result(run, ws->r, a1, a2, (h.reserved & 0x100) != 0, mono_all[s], -ws->brent[0].fmin, ws->brent[0].min);
+        res[s] = ws->r;
+        status[s] = status_word(ws->r);
       }
       skip = true;
     }
@@ -889,7 +917,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     const int a1 = r.allele1, a2 = r.allele2;
     const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
     const bool mono = (r.flags & PM_FLAG_MONO) != 0;
-    const bool dn = run->denovo != 0;
+    const bool dn = run->denovo != 0 && !run->vcf_mode;
     // frequency the posteriors are taken at (main:576-587)
     const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
     const double q = 1.0 - freq;
@@ -1043,7 +1071,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     }
     if (fi == 0) {
       // CalculateAB (NucFam:1006-1039), only printed by the non-de-novo writer on autosomes
-      if (!dn) {
+      if (!dn && !run->vcf_mode) {
         double A = 0.0, Bsum = 0.0;
         const double f0 = r.freq;
         const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
@@ -1109,15 +1137,16 @@ static size_t wide_smem_bytes(int n_person, int nbuf, int n_kids_table) {
   } while (0)
 
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
-                         size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream) {
+                         const double *d_mono, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err,
+                         cudaStream_t stream) {
   if (n_sites == 0) return cudaSuccess;
   if (plan.kind == LaunchPlan::NARROW) {
     const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
-    k_sites_narrow<kNarrowMaxUnits><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, n_sites, d_res, d_status, d_err);
+    k_sites_narrow<kNarrowMaxUnits><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
   } else {
     const size_t smem = wide_smem_bytes(plan.n_person, plan.site_buffers, plan.kid_table);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
-#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, n_sites, plan.chains, plan.site_buffers, plan.kid_table, d_res, d_status, d_err)
+#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers, plan.kid_table, d_res, d_status, d_err)
     PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
   }

@@ -29,7 +29,8 @@ struct LaunchPlan {
 cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int n_kids_denovo, int sm_count);
 
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
-                         size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream);
+                         const double *d_mono, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err,
+                         cudaStream_t stream);
 
 cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,
                            cudaStream_t stream);

@@ -72,6 +72,37 @@ CASES = [
     ("ext_denovo", "ext.ped", ["--denovo"], "ref_ext_denovo.vcf.gz"),
     ("ceph_denovo", "ceph.ped", ["--denovo"], "ref_ceph_denovo.sha"),
 ]
+# VCF-input mode (--in_vcf): (case, pedigree, input VCF fixture, golden) — the shipped golden of run.sh command 2
+# and outputs of the unmodified reference on edge-case inputs (tests/golden/make_golden.py: make_vcf_inputs)
+VCF_CASES = [
+    ("vcf_cmd2", "test.ped", "vcf_in_full.vcf.gz", "ref_vcf_cmd2.vcf.gz"),
+    ("vcf_mix_edge", "test.mix.ped", "vcf_in_edge.vcf.gz", "ref_vcf_mix_edge.vcf.gz"),
+    ("vcf_single_family_edge", "single.ped", "vcf_in_edge.vcf.gz", "ref_vcf_single_family_edge.vcf.gz"),
+    ("vcf_ext_edge", "ext.ped", "vcf_in_edge.vcf.gz", "ref_vcf_ext_edge.vcf.gz"),
+    ("vcf_quartets_gl", "test.ped", "vcf_in_gl.vcf.gz", "ref_vcf_quartets_gl.vcf.gz"),
+]
+
+
+def check_vcf_case(exe, tmpdir, case, gz_input=False):
+    name, ped, vin, golden = case
+    src = os.path.join(GOLDEN, vin)
+    if gz_input:
+        inp = src                                   # the reader is gz-transparent
+    else:
+        inp = os.path.join(tmpdir, vin[:-3])
+        with gzip.open(src, "rb") as f, open(inp, "wb") as g:
+            g.write(f.read())
+    out = os.path.join(tmpdir, name + ".out.vcf")
+    cmd = [exe, "-p", os.path.join(GOLDEN, "peds", ped), "-d", os.path.join(GOLDEN, "peds", "test.dat"), "--in_vcf", inp, "--out_vcf", out]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1800)
+    log = p.stdout.decode(errors="replace")
+    assert p.returncode == 0, log[-2000:]
+    got = body(open(out, "rb").read())
+    want = golden_text(golden)
+    assert got == want, f"{name}: " + first_diff(got, want)
+    return log
+
+
 SLOW_FOR_ORACLE = {"ext_denovo", "ceph_denovo"}  # minutes of CPU in the oracle; covered on the GPU and by make_golden runs
 
 

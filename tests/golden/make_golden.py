@@ -53,6 +53,70 @@ CASES = {  # name: (ped file, extra args, keep full text?)
 }
 
 
+VCF_CASES = {  # name: (ped file, input vcf)
+    "vcf_cmd2": ("test.ped", "vcf_in_full.vcf.gz"),
+    "vcf_mix_edge": ("test.mix.ped", "vcf_in_edge.vcf.gz"),
+    "vcf_single_family_edge": ("single.ped", "vcf_in_edge.vcf.gz"),
+    "vcf_ext_edge": ("ext.ped", "vcf_in_edge.vcf.gz"),
+    "vcf_quartets_gl": ("test.ped", "vcf_in_gl.vcf.gz"),
+}
+SINGLE_PED = "fam1\t1\t0\t0\t1\t1\nfam1\t2\t0\t0\t2\t2\nfam1\t3\t1\t2\t2\t3\nfam1\t4\t1\t2\t1\t4\n"
+
+
+def make_vcf_inputs():
+    """Derived VCF inputs: the shipped example input (command 2 of run.sh) as is, an edge-case variant of its first
+    1,600 records (multi-allelic, REF==ALT, indels, missing / empty / all-zero PL fields, missing DP, a sample that is
+    not in the pedigree) and a GL-typed variant."""
+    src = open(os.path.join(REF, "testvcf.in.vcf")).read().split("\n")
+    with gzip.GzipFile(os.path.join(HERE, "vcf_in_full.vcf.gz"), "wb", 9, mtime=0) as f:
+        f.write("\n".join(src).encode())
+    head = [l for l in src if l.startswith("#")]
+    recs = [l for l in src if l and not l.startswith("#")][:1600]
+    edge, gl = list(head[:-1]), list(head[:-1])
+    cols = head[-1].split("\t")
+    edge.append("\t".join(cols + ["stranger"]))
+    gl.append(head[-1])
+    for n, line in enumerate(recs):
+        t = line.split("\t")
+        g = list(t)
+        g[8] = "GT:GQ:DP:DS:GL"
+        for i in range(9, len(t)):
+            f = t[i].split(":")
+            pl = [int(x) for x in f[4].split(",")]
+            f[4] = ",".join("%.2f" % (-x / 10.0) if x else "0" for x in pl)
+            if n % 17 == 5 and i == 12:
+                f[4] = "-30.1,-0.004,-12"          # beyond the 255 cap, fractional phred
+            g[i] = ":".join(f)
+        gl.append("\t".join(g))
+        e = list(t) + ["0/0:10:9:0.00:0,20,200"]
+        if n % 7 == 3:
+            e[4] = "T,G"                            # not bi-allelic: dropped
+        elif n % 11 == 4:
+            e[4] = e[3]                             # REF == ALT: dropped
+        elif n % 13 == 6:
+            e[3], e[4] = "CA", "C"                  # indel
+        elif n % 19 == 8:
+            e[3], e[4] = "G", "A"                   # a transition the reference's isTs() does not recognise
+        if n % 23 == 9:
+            e[12] = ":".join(e[12].split(":")[:3])  # PL absent for the 4th sample: the samples after it are ignored
+        if n % 29 == 10:
+            f = e[10].split(":"); f[4] = ""; e[10] = ":".join(f)   # empty PL
+        if n % 31 == 11:
+            for i in range(9, len(e)):
+                f = e[i].split(":")
+                if len(f) > 4:
+                    f[4] = "0,0,0"                  # nobody has data: stale output
+                e[i] = ":".join(f)
+        if n % 37 == 12:
+            f = e[15].split(":"); f[2] = ""; e[15] = ":".join(f)   # missing DP
+        if n % 41 == 13:
+            f = e[9].split(":"); f[4] = "300,0,999"; e[9] = ":".join(f)   # beyond the cap
+        edge.append("\t".join(e))
+    for name, lines in (("vcf_in_edge.vcf.gz", edge), ("vcf_in_gl.vcf.gz", gl)):
+        with gzip.GzipFile(os.path.join(HERE, name), "wb", 9, mtime=0) as f:
+            f.write(("\n".join(lines) + "\n").encode())
+
+
 def body(path):
     with open(path, "rb") as f:
         return b"".join(l for l in f if not l.startswith(b"##"))
@@ -79,6 +143,22 @@ def main():
             with gzip.GzipFile(os.path.join(HERE, f"golden_{cmd}.vcf.gz"), "wb", 9, mtime=0) as dst:
                 dst.write(body(os.path.join(REF, golden)))
         only = set(sys.argv[1:])
+        if not only or any(o.startswith("vcf") for o in only):
+            open(os.path.join(HERE, "peds", "single.ped"), "w").write(SINGLE_PED)
+            shutil.copy(os.path.join(HERE, "peds", "single.ped"), tmp)
+            make_vcf_inputs()
+            for name, (ped, vin) in VCF_CASES.items():
+                if only and name not in only and "vcf" not in only:
+                    continue
+                raw = os.path.join(tmp, vin[:-3])
+                with gzip.open(os.path.join(HERE, vin), "rb") as src, open(raw, "wb") as dst:
+                    dst.write(src.read())
+                out = os.path.join(tmp, name + ".vcf")
+                subprocess.run([REFBIN, "-p", ped, "-d", "test.dat", "--in_vcf", raw, "--out_vcf", out], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+                text = body(out)
+                with gzip.GzipFile(os.path.join(HERE, f"ref_{name}.vcf.gz"), "wb", 9, mtime=0) as dst:
+                    dst.write(text)
+                print(name, len(text), "bytes", text.count(b"\n"), "lines")
         for name, (ped, extra, keep) in CASES.items():
             if only and name not in only:
                 continue

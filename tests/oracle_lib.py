@@ -20,6 +20,8 @@ def load():
         lib.pmo_destroy.argtypes = [C.c_void_p]
         lib.pmo_call_glf_sites.restype = C.c_int
         lib.pmo_call_glf_sites.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pmo_call_vcf_records.restype = C.c_int
+        lib.pmo_call_vcf_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         lib.pmo_build_peel_order.restype = C.c_int
         lib.pmo_build_peel_order.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pmo_load_site.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -37,11 +39,12 @@ def load():
 
 
 class OracleEngine:
-    def __init__(self, ped: PedigreeArrays, params: Params):
+    def __init__(self, ped: PedigreeArrays, params: Params, lut=None):
         self.lib = load()
         self.ped, self.params = ped, params
         self._cped, self._cpar = ped.to_c(), params.to_c()
-        self.ctx = self.lib.pmo_create(C.byref(self._cped), C.byref(self._cpar), None)
+        self._lut = None if lut is None else np.ascontiguousarray(lut, dtype=np.float64)
+        self.ctx = self.lib.pmo_create(C.byref(self._cped), C.byref(self._cpar), None if self._lut is None else self._lut.ctypes.data)
         if not self.ctx:
             raise RuntimeError("pmo_create failed: " + self.lib.pmo_last_error().decode())
 
@@ -61,6 +64,18 @@ class OracleEngine:
         if rc:
             raise RuntimeError(f"oracle error {rc}: " + self.lib.pmo_last_error().decode())
         return status, res, per
+
+    def call_vcf_records(self, hdr, recs, mono):
+        hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+        recs = np.ascontiguousarray(recs, dtype=PERSON_SITE_DTYPE)
+        mono = np.ascontiguousarray(mono, dtype=np.float64)
+        n, npers = len(hdr), self.ped.n_person
+        res = np.zeros(n, dtype=SITE_RESULT_DTYPE)
+        per = np.zeros((n, npers), dtype=PERSON_RESULT_DTYPE)
+        rc = self.lib.pmo_call_vcf_records(self.ctx, hdr.ctypes.data, recs.ctypes.data, mono.ctypes.data, n, res.ctypes.data, per.ctypes.data)
+        if rc:
+            raise RuntimeError(f"oracle error {rc}: " + self.lib.pmo_last_error().decode())
+        return res, per
 
     def load_site(self, hdr1, recs1):
         self._h = np.ascontiguousarray(hdr1, dtype=SITE_HDR_DTYPE)

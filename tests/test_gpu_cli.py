@@ -28,6 +28,12 @@ def test_product_cli_matches_reference_golden(case, glfdir, tmp_path):
     assert "Summary of reference -- 1" in log
 
 
+@pytest.mark.parametrize("case", U.VCF_CASES, ids=lambda c: c[0])
+def test_product_cli_vcf_input_matches_reference(case, glfdir, tmp_path):
+    log = U.check_vcf_case(U.PRODUCT_CLI, str(tmp_path), case, gz_input=(case[0] == "vcf_cmd2"))
+    assert "Total samples in both VCF and PED files" in log
+
+
 def test_cli_reports_missing_inputs(tmp_path):
     p = subprocess.run([U.PRODUCT_CLI, "-p", "nope.ped", "-d", "nope.dat", "-g", "nope.gif", "--out_vcf", str(tmp_path / "o.vcf")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

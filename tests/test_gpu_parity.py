@@ -166,3 +166,53 @@ def test_wide_kernel_parity_on_synthetic_pedigrees(case, oracle_built):
     print(rep)
     assert rep["emitted"] > 0
     parity.assert_parity(rep, n_sites)
+
+
+# ---- VCF-input records through the C ABI ---------------------------------------------------------
+def _vcf_records_from_sites(hdr, recs, rng):
+    """Turns packed GLF sites into VCF-mode records: (REF, ALT) = (ref, a random other base), the three PLs of that
+    allele pair kept, every other byte cleared; mono = sum of -PL[ref/ref]/10 in column order."""
+    n, npers = recs.shape
+    gi = lambda a, b: np.where(a < b, (a - 1) * (10 - a) // 2 + (b - a), (b - 1) * (10 - b) // 2 + (a - b))
+    ref = hdr["ref_base"].astype(int)
+    alt = (ref - 1 + rng.integers(1, 4, n)) % 4 + 1
+    out = np.zeros_like(recs)
+    g0, g1, g2 = gi(ref, ref), gi(ref, alt), gi(alt, alt)
+    rows = np.arange(n)[:, None]
+    for g in (g0, g1, g2):
+        out["lk"][rows, np.arange(npers)[None, :], g[:, None]] = recs["lk"][rows, np.arange(npers)[None, :], g[:, None]]
+    out["depth"] = recs["depth"]
+    h = hdr.copy()
+    h["reserved"] = alt.astype(np.uint16)
+    h["reserved"][::17] |= 0x100                      # some records flagged as indels (prior term only)
+    mono = np.zeros(n)
+    for c in range(npers):                            # sequential sum in column order, as the host front end does
+        mono += -out["lk"][np.arange(n), c, g0].astype(np.float64) / 10.0
+    return h, out, mono
+
+
+@pytest.mark.parametrize("pedfile,n", [("test.ped", 20000), ("test.mix.ped", 20000), ("single.ped", 20000), ("ext.ped", 8000), ("ceph.ped", 4000)])
+def test_vcf_records_parity(pedfile, n, example12, oracle_built, tools_built, tmp_path):
+    ped, glf_index = F.pedigree_from_file(PED(pedfile), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, n)
+    h, r, mono = _vcf_records_from_sites(hdr, recs, np.random.default_rng(3))
+    lut = np.array([pow(10, -float(i) / 10.0) for i in range(256)])
+    params = Params(vcf_input=True)
+    eng = Engine(ped, params, lut=lut)
+    res_g, per_g = eng.call_vcf_records(h, r, mono)
+    eng.close()
+    ora = OracleEngine(eng.ped, params, lut=lut)
+    res_o, per_o = ora.call_vcf_records(h, r, mono)
+    ora.close()
+    close = lambda a, b, rt=1e-6, at=0.0: parity._close(a, b, rt, at)
+    bad = {
+        "llk_ref": int(np.sum(~close(res_g["varllk"][:, 0], res_o["varllk"][:, 0]))),
+        "llk_alt": int(np.sum(~close(res_g["varllk"][:, 1], res_o["varllk"][:, 1]))),
+        "qual": int(np.sum(~close(res_g["poly_qual"], res_o["poly_qual"], 1e-6, 1e-5))),
+        "freq": int(np.sum(~close(res_g["freq"], res_o["freq"], 1e-6, 1e-9))),
+        "best": int(np.sum(per_g["best"] != per_o["best"])),
+        "post": int(np.sum(~close(per_g["post"], per_o["post"], 1e-6, 1e-15))),
+        "gq": int(np.sum(np.abs(per_g["gq"].astype(int) - per_o["gq"].astype(int)) > 1)),
+    }
+    print(pedfile, bad, "gq off by one:", int(np.sum(np.abs(per_g["gq"].astype(int) - per_o["gq"].astype(int)) == 1)))
+    assert not any(bad.values()), bad

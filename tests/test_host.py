@@ -150,8 +150,10 @@ def test_pedigree_ordering_rules(tools_built, tmp_path):
     assert list(p.ped.fam_generations) == [1, 3, 2]
     # kid2 was entered as (father=mum, mother=dad): swapped back by sex
     assert p.ped.father[1 + 3] == 0 and p.ped.mother[1 + 3] == 2
-    # the F2 family is extended: a peeling order exists for it only
-    assert list(np.diff(p.ped.peel_first)) == [0, len(p.ped.peel), 0] and len(p.ped.peel) > 0
+    # peeling orders exist for the families with non-founders (extended F2: 5 steps; nuclear f10: child -> parents, spouse)
+    d = list(np.diff(p.ped.peel_first))
+    assert d[0] == 0 and d[1] == 5 and d[2] == 2 and len(p.ped.peel) == 7
+    assert list(p.ped.peel["type"][5:]) == [1, 2]
 
 
 def test_synthetic_generator_is_seeded_and_well_formed():

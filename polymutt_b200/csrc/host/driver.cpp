@@ -4,7 +4,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <fstream>
+#include <future>
+#include <memory>
+#include <mutex>
 #include <map>
 #include <set>
 #include <sstream>
@@ -137,8 +141,18 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   opt.to_params(&par);
   double lut[256];
   pm_fill_lut(lut);
-  void *ctx = engine.create(ped.view(), &par, lut, opt.device);
-  if (!ctx) return fatal(std::string("engine '") + engine.name + "': " + engine.last_error());
+  // One engine context per GPU (--gpus N, ours): batches of consecutive sites go to the GPUs round-robin, each on
+  // its own host thread, and are consumed strictly in site order, so the VCF is the ordered concatenation of the
+  // per-GPU shards.  No communication between GPUs.
+  const int n_gpu = opt.gpus > 0 ? opt.gpus : 1;
+  std::vector<void *> ctxs;
+  auto destroy_all = [&]() { for (void *c : ctxs) engine.destroy(c); ctxs.clear(); };
+  for (int g = 0; g < n_gpu; g++) {
+    void *c = engine.create(ped.view(), &par, lut, opt.device + g);
+    if (!c) { std::string m = engine.last_error(); destroy_all(); return fatal(std::string("engine '") + engine.name + "': " + m); }
+    ctxs.push_back(c);
+  }
+  std::vector<std::mutex> ctx_lock((size_t)n_gpu);
 
   const int np = ped.n_person();
   size_t batch = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)1 << 16;
@@ -149,16 +163,27 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     const Engine &e; void *p = nullptr;
     HostBuf(const Engine &eng, size_t bytes) : e(eng) { p = e.host_alloc ? e.host_alloc(bytes) : malloc(bytes); if (p) memset(p, 0, bytes); }
     ~HostBuf() { if (e.host_free) e.host_free(p); else free(p); }
+    HostBuf(const HostBuf &) = delete;
   };
-  HostBuf b_hdr(engine, batch * sizeof(pm_site_hdr)), b_ps(engine, batch * (size_t)np * sizeof(pm_person_site)),
-      b_status(engine, batch * sizeof(uint16_t)), b_res(engine, batch * sizeof(pm_site_result)),
-      b_pres(engine, batch * (size_t)np * sizeof(pm_person_result));
-  if (!b_hdr.p || !b_ps.p || !b_status.p || !b_res.p || !b_pres.p) { engine.destroy(ctx); return fatal("out of host memory for the site batch"); }
-  pm_site_hdr *hdr = (pm_site_hdr *)b_hdr.p;
-  pm_person_site *ps = (pm_person_site *)b_ps.p;
-  uint16_t *status = (uint16_t *)b_status.p;
-  pm_site_result *res = (pm_site_result *)b_res.p;
-  pm_person_result *pres = (pm_person_result *)b_pres.p;
+  struct Slot {
+    std::unique_ptr<HostBuf> b_hdr, b_ps, b_status, b_res, b_pres;
+    pm_site_hdr *hdr; pm_person_site *ps; uint16_t *status; pm_site_result *res; pm_person_result *pres;
+    size_t n = 0, n_res = 0;
+    std::future<int> fut;
+    std::string err;
+  };
+  const size_t n_slots = (size_t)(n_gpu == 1 ? 2 : 2 * n_gpu);
+  std::vector<Slot> slots(n_slots);
+  for (Slot &sl : slots) {
+    sl.b_hdr.reset(new HostBuf(engine, batch * sizeof(pm_site_hdr)));
+    sl.b_ps.reset(new HostBuf(engine, batch * (size_t)np * sizeof(pm_person_site)));
+    sl.b_status.reset(new HostBuf(engine, batch * sizeof(uint16_t)));
+    sl.b_res.reset(new HostBuf(engine, batch * sizeof(pm_site_result)));
+    sl.b_pres.reset(new HostBuf(engine, batch * (size_t)np * sizeof(pm_person_result)));
+    if (!sl.b_hdr->p || !sl.b_ps->p || !sl.b_status->p || !sl.b_res->p || !sl.b_pres->p) { destroy_all(); return fatal("out of host memory for the site batches"); }
+    sl.hdr = (pm_site_hdr *)sl.b_hdr->p; sl.ps = (pm_person_site *)sl.b_ps->p; sl.status = (uint16_t *)sl.b_status->p;
+    sl.res = (pm_site_result *)sl.b_res->p; sl.pres = (pm_person_result *)sl.b_pres->p;
+  }
 
   VcfWriter writer(vcf, opt, ped);
   time_t t0;
@@ -167,6 +192,7 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   size_t out_cnt = 0;
   int processed_chrs = 0;
   bool stop = false;
+  std::string engine_error;
   try {
     while (!stop && glf.next_section()) {
       if (!chrs.empty() && processed_chrs >= (int)chrs.size()) break;
@@ -179,37 +205,62 @@ int run_cli(int argc, char **argv, const Engine &engine) {
       processed_chrs++;
       time_t tc;
       time(&tc);
-      bool more = true;
-      while (more && !stop) {
-        size_t n = 0;
-        while (n < batch) {
-          if (!glf.next_site(&hdr[n], &ps[n * (size_t)np])) { more = false; break; }
-          if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
-          hdr[n].chr_class = chr_class;
-          if (!positions.empty() && positions.count(label + ":" + std::to_string(hdr[n].pos + 1)) == 0) continue;
-          n++;
-        }
-        if (n == 0) break;
-        size_t n_res = 0;
-        int rc = engine.call_glf(ctx, hdr, ps, n, status, res, pres, batch, &n_res);
-        if (rc != PM_OK) {
-          engine.destroy(ctx);
-          fclose(vcf);
-          return fatal(std::string("engine '") + engine.name + "': " + engine.last_error());
-        }
-        for (size_t s = 0; s < n; s++) count_site(cnt, hdr[s], status[s], opt);
+      std::deque<size_t> in_flight;  // slot indices, oldest first
+      size_t launched = 0;
+      // waits for the oldest batch, updates the counters and prints its rows (in site order)
+      auto consume = [&]() -> bool {
+        Slot &sl = slots[in_flight.front()];
+        in_flight.pop_front();
+        const int rc = sl.fut.get();
+        if (rc != PM_OK) { engine_error = sl.err; return false; }
+        if (stop) return true;  // --pos already satisfied: drain without printing
+        for (size_t s = 0; s < sl.n; s++) count_site(cnt, sl.hdr[s], sl.status[s], opt);
         // rows and dropped de novo candidates in site order: the first of either prints the header
         size_t next_row = 0;
-        for (size_t s = 0; s < n && !stop; s++) {
-          const int code = status[s] & 0xf;
+        for (size_t s = 0; s < sl.n && !stop; s++) {
+          const int code = sl.status[s] & 0xf;
           if (code == PM_SITE_DENOVO_DROPPED) { writer.ensure_header(); continue; }
           if (code != PM_SITE_EMITTED) continue;
           const size_t r = next_row++;
-          if (r >= n_res || res[r].site != s) throw std::runtime_error("engine returned rows out of site order");
-          writer.write_site(label, hdr[s], res[r], &ps[(size_t)s * np], &pres[r * (size_t)np]);
+          if (r >= sl.n_res || sl.res[r].site != s) throw std::runtime_error("engine returned rows out of site order");
+          writer.write_site(label, sl.hdr[s], sl.res[r], &sl.ps[(size_t)s * np], &sl.pres[r * (size_t)np]);
           out_cnt++;
-          if (opt.force_call && out_cnt >= positions.size()) { stop = true; break; }  // main.cpp:593
+          if (opt.force_call && out_cnt >= positions.size()) stop = true;  // main.cpp:593
         }
+        return true;
+      };
+      bool more = true, ok = true;
+      while (more && !stop && ok) {
+        if (in_flight.size() == n_slots) ok = consume();
+        if (!ok || stop) break;
+        const size_t si = launched % n_slots;
+        Slot &sl = slots[si];
+        size_t n = 0;
+        while (n < batch) {
+          if (!glf.next_site(&sl.hdr[n], &sl.ps[n * (size_t)np])) { more = false; break; }
+          if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
+          sl.hdr[n].chr_class = chr_class;
+          if (!positions.empty() && positions.count(label + ":" + std::to_string(sl.hdr[n].pos + 1)) == 0) continue;
+          n++;
+        }
+        if (n == 0) break;
+        sl.n = n; sl.n_res = 0; sl.err.clear();
+        const size_t g = launched % (size_t)n_gpu;
+        Slot *slp = &sl;
+        sl.fut = std::async(std::launch::async, [&, slp, g]() -> int {
+          std::lock_guard<std::mutex> guard(ctx_lock[g]);
+          int rc = engine.call_glf(ctxs[g], slp->hdr, slp->ps, slp->n, slp->status, slp->res, slp->pres, batch, &slp->n_res);
+          if (rc != PM_OK) slp->err = engine.last_error();  // the message is thread-local: keep it
+          return rc;
+        });
+        in_flight.push_back(si);
+        launched++;
+      }
+      while (!in_flight.empty()) ok = consume() && ok;
+      if (!ok) {
+        destroy_all();
+        fclose(vcf);
+        return fatal(std::string("engine '") + engine.name + "': " + engine_error);
       }
       if (stop) break;
       // summary block, src/main.cpp:596-621
@@ -236,11 +287,12 @@ int run_cli(int argc, char **argv, const Engine &engine) {
       fflush(vcf);
     }
   } catch (const std::exception &e) {
-    engine.destroy(ctx);
+    for (Slot &sl : slots) if (sl.fut.valid()) sl.fut.wait();
+    destroy_all();
     fclose(vcf);
     return fatal(e.what());
   }
-  engine.destroy(ctx);
+  destroy_all();
   fclose(vcf);
   return 0;
 }

@@ -25,6 +25,7 @@ struct Options {
   // derived (main.cpp:151-153)
   bool force_call = false;
   // extensions of this implementation (not in the reference)
+  int gpus = 1;            // --gpus N: shard consecutive site batches over N GPUs (devices device..device+N-1)
   int device = 0;          // --device
   int batch_sites = 0;     // --batch_sites (0 = automatic)
   std::string cmd;         // argv joined with spaces, trailing space (main.cpp:159-164)

@@ -34,6 +34,17 @@ def test_product_cli_vcf_input_matches_reference(case, glfdir, tmp_path):
     assert "Total samples in both VCF and PED files" in log
 
 
+def test_product_cli_small_batches_and_multi_gpu(glfdir, tmp_path):
+    """Many small batches through the double-buffered host entry point; with more than one GPU on the box the batches
+    are also sharded over all of them (--gpus N) and concatenated in order."""
+    import torch
+    n = max(1, torch.cuda.device_count())
+    case = ("cmd3_batched", "test.mix.ped", ["--gpus", str(min(n, 8)), "--batch_sites", "3000"], "golden_cmd3.vcf.gz")
+    U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+    case = ("cmd4_batched", "test.ped", ["--denovo", "--rate_denovo", "1.5e-07", "--batch_sites", "1000"], "golden_cmd4.vcf.gz")
+    U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+
+
 def test_cli_reports_missing_inputs(tmp_path):
     p = subprocess.run([U.PRODUCT_CLI, "-p", "nope.ped", "-d", "nope.dat", "-g", "nope.gif", "--out_vcf", str(tmp_path / "o.vcf")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

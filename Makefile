@@ -8,7 +8,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 HOSTCXX   ?= g++
 HOSTCC    ?= gcc
 CUDA_ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(CUDA_ARCH) -Xcompiler -fPIC -Xcompiler -fno-strict-aliasing -Iinclude -Ipolymutt_b200/csrc
+NVFLAGS   := $(PM_DEFS) -O3 -std=c++17 -lineinfo $(CUDA_ARCH) -Xcompiler -fPIC -Xcompiler -fno-strict-aliasing -Iinclude -Ipolymutt_b200/csrc
 CXXFLAGS  := -O2 -std=c++17 -fPIC -pthread -Wall -Wextra -Wno-unused-parameter -Iinclude -Ipolymutt_b200/csrc/host
 # the oracle keeps the reference's arithmetic: no FMA contraction, no fast-math
 OCFLAGS   := -O2 -std=gnu99 -fPIC -ffp-contract=off -Wall -Iinclude

@@ -236,7 +236,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   ok = ok && dev_alloc(&c->d_run, 1) == PM_OK && dev_alloc(&c->d_fams, fams.size()) == PM_OK &&
        dev_alloc(&c->d_units, units.size()) == PM_OK && dev_alloc(&c->d_es, es.size()) == PM_OK &&
        dev_alloc(&c->d_steps, steps.size()) == PM_OK && dev_alloc(&c->d_err, 1) == PM_OK && dev_alloc(&c->d_n_emit, 1) == PM_OK &&
-       dev_alloc(&c->d_counters, 4) == PM_OK && cudaEventCreate(&c->tm0) == cudaSuccess && cudaEventCreate(&c->tm1) == cudaSuccess;
+       dev_alloc(&c->d_counters, 16) == PM_OK && cudaEventCreate(&c->tm0) == cudaSuccess && cudaEventCreate(&c->tm1) == cudaSuccess;
   if (ok) {
     run.fams = c->d_fams; run.units = c->d_units; run.es_fams = c->d_es; run.steps = c->d_steps;
     run.counters = c->d_counters;
@@ -245,7 +245,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
          (es.empty() || cudaMemcpy(c->d_es, es.data(), es.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess) &&
          (steps.empty() || cudaMemcpy(c->d_steps, steps.data(), steps.size() * sizeof(pm::DevStep), cudaMemcpyHostToDevice) == cudaSuccess) &&
          cudaMemcpy(c->d_run, &run, sizeof run, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemset(c->d_err, 0, sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)) == cudaSuccess;
+         cudaMemset(c->d_err, 0, sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   }
   if (!ok) {
     if (!*pmh::last_error()) fail(PM_ECUDA, "pm_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -514,10 +514,20 @@ extern "C" int pm_get_counters(pm_ctx *c, pm_counters *out) {
   CUDA_TRY(cudaMemcpy(out, c->d_counters, sizeof *out, cudaMemcpyDeviceToHost));
   return PM_OK;
 }
+// Debug hook (PM_PHASE_TIMING builds only): cycles thread 0 of the wide kernel spent per phase, summed over sites:
+// [0] TMA wait, [1] stats, [2] set-up, [3] evaluation (to the first barrier), [4] serial tail, [5] decisions/refit/write.
+extern "C" int pm_debug_phase_cycles(pm_ctx *c, unsigned long long *out8) {
+  if (!c || !out8) return fail(PM_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaMemcpy(out8, c->d_counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return PM_OK;
+}
+
 extern "C" int pm_reset_counters(pm_ctx *c) {
   if (!c) return fail(PM_EINVAL, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, 16 * sizeof(unsigned long long), c->stream));
   return PM_OK;
 }
 

@@ -104,13 +104,20 @@ __device__ __forceinline__ void unit_conditionals(RecPtr recs, int first, int nk
     uint4 rk = recs[first + 2 + k];
     double d11, d12, d22;
     if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
-      d11 = d12 = d22 = 0.0;
-      const double *r11 = mut + g11 * 10, *r12 = mut + g12 * 10, *r22 = mut + g22 * 10;
+      // ten independent look-ups first, then the three dot products as two half-sums each: short dependency
+      // chains matter more than instruction count here (few resident warps per SM)
+      double l[10];
 #pragma unroll
-      for (int g = 0; g < 10; g++) {
-        double l = lut[rec_lk(rk, g)];
-        d11 += r11[g] * l; d12 += r12[g] * l; d22 += r22[g] * l;
+      for (int g = 0; g < 10; g++) l[g] = lut[rec_lk(rk, g)];
+      const double *r11 = mut + g11 * 10, *r12 = mut + g12 * 10, *r22 = mut + g22 * 10;
+      double a11 = 0.0, b11 = 0.0, a12 = 0.0, b12 = 0.0, a22 = 0.0, b22 = 0.0;
+#pragma unroll
+      for (int g = 0; g < 5; g++) {
+        a11 += r11[g] * l[g]; b11 += r11[g + 5] * l[g + 5];
+        a12 += r12[g] * l[g]; b12 += r12[g + 5] * l[g + 5];
+        a22 += r22[g] * l[g]; b22 += r22[g + 5] * l[g + 5];
       }
+      d11 = a11 + b11; d12 = a12 + b12; d22 = a22 + b22;
     } else {
       d11 = lut[rec_lk(rk, g11)]; d12 = lut[rec_lk(rk, g12)]; d22 = lut[rec_lk(rk, g22)];
     }

@@ -386,6 +386,12 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
 // ================================================================================================
 constexpr int kMaxChains = 3;
 
+#ifdef PM_PHASE_TIMING
+#define PM_TICK(slot) do { if (threadIdx.x == 0) { long long now__ = clock64(); ws->phase[slot] += (unsigned long long)(now__ - ws->t_last); ws->t_last = now__; } } while (0)
+#else
+#define PM_TICK(slot) do { } while (0)
+#endif
+
 struct WideShared {
   SmemTables t;
   double log_inv[128];                // table-driven log10 of the product mantissa (driver threads only)
@@ -400,6 +406,9 @@ struct WideShared {
   int ibcast[4];
   unsigned long long mbar[2];         // one mbarrier per site buffer (TMA bulk copies)
   unsigned int n_hyp, n_eval;         // work counters of the current site
+  unsigned int n_eval_g[kMaxChains];  // evaluations per chain driver (summed into n_eval by thread 0)
+  unsigned long long phase[8];        // PM_PHASE_TIMING: cycles per phase (thread 0)
+  long long t_last;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -597,6 +606,7 @@ struct WideEval {
       ws->n_hyp += nc;
     }
     __syncthreads();
+    PM_TICK(2);
     bool first = true;
     for (;;) {
       const double p0 = ws->p[0], p1 = ws->p[1], p2 = ws->p[2];
@@ -607,9 +617,18 @@ struct WideEval {
       if (live) {
         const Monomials m = monomials(p);
         FastProd fa;
-        fa.m = 1.0; fa.e = K;
+        fa.e = K;
+        {  // four independent partial products keep the dependency chain short
+          double v0 = 1.0, v1 = 1.0, v2 = 1.0, v3 = 1.0;
 #pragma unroll
-        for (int k = 0; k < U; k++) fa.m *= quartic_eval(B[k], m);
+          for (int k = 0; k < U; k += 4) {
+            v0 *= quartic_eval(B[k], m);
+            if (k + 1 < U) v1 *= quartic_eval(B[k + 1], m);
+            if (k + 2 < U) v2 *= quartic_eval(B[k + 2], m);
+            if (k + 3 < U) v3 *= quartic_eval(B[k + 3], m);
+          }
+          fa.m = (v0 * v1) * (v2 * v3);
+        }
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[grp][wg] = acc.m; ws->warp_e[grp][wg] = acc.e; }
@@ -624,6 +643,7 @@ struct WideEval {
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[kMaxChains][wg] = acc.m; ws->warp_e[kMaxChains][wg] = acc.e; }
       }
       __syncthreads();
+      PM_TICK(3);
       // serial tails: the first thread of every live group, in parallel
       if (t == 0 && live) {
         ProdAcc a;
@@ -633,7 +653,7 @@ struct WideEval {
         const double ll = log10_ol(ws, a.m, a.e);
         const bool more = brent_feed_ol(&ws->brent[grp], -ll, run->precision) != 0;
         ws->p[grp] = more ? ws->brent[grp].u : -1.0;
-        atomicAdd(&ws->n_eval, 1u);
+        ws->n_eval_g[grp]++;
       }
       if (h0 && t == (Tg > 32 ? 32 : 0)) {
         ProdAcc a;
@@ -644,6 +664,7 @@ struct WideEval {
       }
       first = false;
       __syncthreads();
+      PM_TICK(4);
     }
   }
 };
@@ -664,6 +685,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
   load_tables(run, &ws->t);
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { ws->log_inv[i] = run->log_inv[i]; ws->log_tab[i] = run->log_tab[i]; }
   if (threadIdx.x == 0) {
+    for (int k = 0; k < 8; k++) ws->phase[k] = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ws->mbar[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -688,8 +710,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
       if (threadIdx.x == 0 && nxt < n_sites)
         tma_issue_site(site_base + (size_t)(cur ^ 1) * site_bytes, recs_all + nxt * (size_t)np, (uint32_t)np * 16u, &ws->mbar[cur ^ 1]);
     }
+#ifdef PM_PHASE_TIMING
+    if (threadIdx.x == 0) ws->t_last = clock64();
+#endif
     mbar_wait(&ws->mbar[cur], phase[cur]);
     phase[cur] ^= 1;
+    PM_TICK(0);
     const pm_site_hdr h = hdr[s];
     const int ref = h.ref_base;
     bool skip = false;
@@ -709,6 +735,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
         memset(&ws->r, 0, sizeof ws->r);
         ws->r.site = (uint32_t)s;
         ws->n_hyp = 0; ws->n_eval = 0;
+        for (int c = 0; c < kMaxChains; c++) ws->n_eval_g[c] = 0;
       }
       ev.optimize(1, &a1, &a2, false, false);
       if (threadIdx.x == 0) {
@@ -748,9 +775,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
         ws->ibcast[0] = r.status;
         r.reserved = (uint16_t)ref;
         ws->n_hyp = 0; ws->n_eval = 0;
+        for (int c = 0; c < kMaxChains; c++) ws->n_eval_g[c] = 0;
         if (r.status != 0) { res[s] = r; status[s] = status_word(r); }
       }
       __syncthreads();
+      PM_TICK(1);
       skip = ws->ibcast[0] != 0;
     }
     if (!skip) {
@@ -802,13 +831,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
         pm_site_result &r = ws->r;
         if (r.status == PM_SITE_EMITTED && run->denovo && r.denovo_lr < run->denovo_min_llr) { r.flags |= PM_FLAG_ROW_DROPPED; r.status = PM_SITE_DENOVO_DROPPED; }
         r.reserved = 0;
-        res[s] = r;
         status[s] = status_word(r);
         atomicAdd(&run->counters[0], (unsigned long long)ws->n_hyp);
-        atomicAdd(&run->counters[1], (unsigned long long)ws->n_eval);
+        atomicAdd(&run->counters[1], (unsigned long long)(ws->n_eval + ws->n_eval_g[0] + ws->n_eval_g[1] + ws->n_eval_g[2]));
         atomicAdd(&run->counters[2], 1ull);
         atomicAdd(&run->counters[3], (unsigned long long)(r.status == PM_SITE_EMITTED));
+#ifdef PM_PHASE_TIMING
+        PM_TICK(5);
+        for (int k = 0; k < 8; k++) { atomicAdd(&run->counters[8 + k], ws->phase[k]); ws->phase[k] = 0; }
+#endif
       }
+    }
+    __syncthreads();  // ws->r is final
+    if (!skip && warp == 0) {  // the 256-byte result leaves as one coalesced 32 x 8-byte store
+      static_assert(sizeof(pm_site_result) == 256, "pm_site_result must be 256 bytes");
+      reinterpret_cast<unsigned long long *>(&res[s])[lane] = reinterpret_cast<const unsigned long long *>(&ws->r)[lane];
     }
     __syncthreads();  // the site buffer and ws->r are reused by the next iteration
     if (nbuf == 2) cur ^= 1;
@@ -1131,8 +1168,9 @@ static size_t wide_smem_bytes(int n_person, int nbuf, int n_kids_table) {
     switch ((plan_).units_per_thread) {                                 \
       case 1: CALL(1, 1024); break;                                     \
       case 2: CALL(2, 768); break;                                      \
-      case 4: if ((plan_).threads > 512) { CALL(4, 768); } else { CALL(4, 512); } break; \
-      default: if ((plan_).threads > 384 || (plan_).low_regs) { CALL(8, 512); } else { CALL(8, 384); } break; \
+      case 4: if ((plan_).threads > 512 || (plan_).low_regs) { CALL(4, 768); } else { CALL(4, 512); } break; \
+      case 8: if ((plan_).threads > 384 || (plan_).low_regs) { CALL(8, 512); } else { CALL(8, 384); } break; \
+      default: CALL(16, 128); break;                                    \
     }                                                                   \
   } while (0)
 
@@ -1184,7 +1222,7 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   if (const char *env = getenv("PM_WIDE_PLAN")) {
     int t = 0, u = 0, g = 0;
     if (sscanf(env, "%d,%d,%d", &t, &u, &g) == 3 && t >= 32 && t % 32 == 0 && (g == 1 || g == 3) && (long)t * u >= n_units &&
-        (u == 1 || u == 2 || u == 4 || u == 8) && t * g <= (u == 1 ? 1024 : (u == 8 ? 512 : 768))) {
+        (u == 1 || u == 2 || u == 4 || u == 8 || u == 16) && t * g <= (u == 1 ? 1024 : (u == 16 ? 128 : (u == 8 ? 512 : 768)))) {
       Tg = t; U = u; G = g;
     }
   }

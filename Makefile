@@ -14,8 +14,8 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -pthread -Wall -Wextra -Wno-unused-parameter -
 OCFLAGS   := -O2 -std=gnu99 -fPIC -ffp-contract=off -Wall -Iinclude
 
 HOST_SRC  := $(wildcard polymutt_b200/csrc/host/*.cpp)
-HOST_LIB_SRC := $(filter-out polymutt_b200/csrc/host/main.cpp polymutt_b200/csrc/host/driver.cpp polymutt_b200/csrc/host/params.cpp polymutt_b200/csrc/host/vcf_writer.cpp polymutt_b200/csrc/host/vcf_mode.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/pedigree.cpp,$(HOST_SRC))
-FRONT_SRC := polymutt_b200/csrc/host/driver.cpp polymutt_b200/csrc/host/params.cpp polymutt_b200/csrc/host/vcf_writer.cpp polymutt_b200/csrc/host/vcf_mode.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/pedigree.cpp
+HOST_LIB_SRC := $(filter-out polymutt_b200/csrc/host/main.cpp polymutt_b200/csrc/host/driver.cpp polymutt_b200/csrc/host/params.cpp polymutt_b200/csrc/host/vcf_writer.cpp polymutt_b200/csrc/host/vcf_mode.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/pedigree.cpp,$(HOST_SRC))
+FRONT_SRC := polymutt_b200/csrc/host/driver.cpp polymutt_b200/csrc/host/params.cpp polymutt_b200/csrc/host/vcf_writer.cpp polymutt_b200/csrc/host/vcf_mode.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/pedigree.cpp
 CU_SRC    := $(wildcard polymutt_b200/csrc/*.cu)
 CU_HDR    := $(wildcard polymutt_b200/csrc/*.cuh) $(wildcard polymutt_b200/csrc/*.h) include/polymutt_b200.h
 
@@ -36,7 +36,7 @@ $(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC) polymutt_b200/csrc/host/host_error.h
 tools: $(TOOLS)
 $(TOOLS): polymutt_b200/csrc/tools/pm_tools.cpp $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h)
 	@mkdir -p polymutt_b200/bin
-	$(HOSTCXX) $(CXXFLAGS) -o $@ polymutt_b200/csrc/tools/pm_tools.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/pedigree.cpp $(HOST_LIB_SRC) -lz
+	$(HOSTCXX) $(CXXFLAGS) -o $@ polymutt_b200/csrc/tools/pm_tools.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/pedigree.cpp $(HOST_LIB_SRC) -lz
 
 cli: $(CLI)
 $(CLI): $(LIB) $(FRONT_SRC) polymutt_b200/csrc/host/main.cpp $(wildcard polymutt_b200/csrc/host/*.h)

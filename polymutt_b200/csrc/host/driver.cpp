@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "glf.h"
+#include "glf_ingest.h"
 #include "params.h"
 #include "pedigree.h"
 #include "vcf_mode.h"
@@ -117,8 +118,8 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     }
     paths.push_back(it->second);
   }
-  GlfSet glf;
-  if (!glf.open(paths, &err)) return fatal(err);
+  GlfBatchReader glf;  // multi-threaded block decode + merge (glf_ingest.h); GlfSet in glf.h is the one-site-at-a-time form
+  if (!glf.open(paths, opt.ingest_threads, &err)) return fatal(err);
 
   std::set<std::string> positions;  // --pos: "chr:pos" (src/main.cpp:39-55)
   if (!opt.pos_file.empty()) {
@@ -197,9 +198,7 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     while (!stop && glf.next_section()) {
       if (!chrs.empty() && processed_chrs >= (int)chrs.size()) break;
       const std::string label = glf.label();
-      pm_site_hdr h;
-      std::vector<pm_person_site> one((size_t)np);
-      if (!chrs.empty() && chrs.count(label) == 0) { while (glf.next_site(&h, one.data())) {} continue; }
+      if (!chrs.empty() && chrs.count(label) == 0) continue;  // next_section() skips what is left of this one
       uint8_t chr_class = label == opt.chrX ? PM_CHR_X : label == opt.chrY ? PM_CHR_Y : label == opt.chrMT ? PM_CHR_MT : PM_CHR_AUTO;
       Counters cnt;
       processed_chrs++;
@@ -235,15 +234,20 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         if (!ok || stop) break;
         const size_t si = launched % n_slots;
         Slot &sl = slots[si];
-        size_t n = 0;
-        while (n < batch) {
-          if (!glf.next_site(&sl.hdr[n], &sl.ps[n * (size_t)np])) { more = false; break; }
-          if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
-          sl.hdr[n].chr_class = chr_class;
-          if (!positions.empty() && positions.count(label + ":" + std::to_string(sl.hdr[n].pos + 1)) == 0) continue;
-          n++;
+        size_t n = glf.next_batch(sl.hdr, sl.ps, batch);
+        if (n == 0) { more = false; break; }
+        if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
+        for (size_t s = 0; s < n; s++) sl.hdr[s].chr_class = chr_class;
+        if (!positions.empty()) {  // --pos: keep the listed positions only (main.cpp:332-337)
+          size_t k = 0;
+          for (size_t s = 0; s < n; s++) {
+            if (positions.count(label + ":" + std::to_string(sl.hdr[s].pos + 1)) == 0) continue;
+            if (k != s) { sl.hdr[k] = sl.hdr[s]; memcpy(&sl.ps[k * (size_t)np], &sl.ps[s * (size_t)np], sizeof(pm_person_site) * (size_t)np); }
+            k++;
+          }
+          n = k;
+          if (n == 0) continue;
         }
-        if (n == 0) break;
         sl.n = n; sl.n_res = 0; sl.err.clear();
         const size_t g = launched % (size_t)n_gpu;
         Slot *slp = &sl;

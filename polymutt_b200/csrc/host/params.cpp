@@ -45,7 +45,7 @@ bool Options::parse(int argc, char **argv, std::string *err) {
       {"quick_call", K_BOOL, &quick_call},
       // ours
       {"device", K_INT, &device},           {"batch_sites", K_INT, &batch_sites},
-      {"gpus", K_INT, &gpus},
+      {"gpus", K_INT, &gpus},               {"ingest_threads", K_INT, &ingest_threads},
   };
   const int n_long = (int)(sizeof table / sizeof table[0]);
   cmd.clear();

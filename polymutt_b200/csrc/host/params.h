@@ -26,6 +26,7 @@ struct Options {
   bool force_call = false;
   // extensions of this implementation (not in the reference)
   int gpus = 1;            // --gpus N: shard consecutive site batches over N GPUs (devices device..device+N-1)
+  int ingest_threads = 0;  // --ingest_threads N: GLF decode/merge threads (0 = all cores, capped at 32)
   int device = 0;          // --device
   int batch_sites = 0;     // --batch_sites (0 = automatic)
   std::string cmd;         // argv joined with spaces, trailing space (main.cpp:159-164)

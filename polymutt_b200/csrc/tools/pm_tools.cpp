@@ -13,6 +13,7 @@
 //   u32 text_len, text: "famid pid fatid motid sex glf_index\n" per column, then "#label <chrom label>\n"
 //   i32 max_position  u64 n_sites  pm_site_hdr hdr[n_sites]  pm_person_site rec[n_sites*n_person]
 #include <sys/stat.h>
+#include <time.h>
 
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,7 @@
 #include <vector>
 
 #include "glf.h"
+#include "glf_ingest.h"
 #include "pedigree.h"
 
 using namespace pmh;
@@ -38,8 +40,10 @@ static void put(FILE *f, const T *p, size_t n) { fwrite(p, sizeof(T), n, f); }
 
 static int do_pack(int argc, char **argv) {
   std::string ped_path, dat_path, gif_path, out_path;
+  int batched = -1;  // --batched N: use the multi-threaded batch reader with N threads (0 = all cores)
   for (int i = 2; i + 1 < argc; i += 2) {
     std::string k = argv[i];
+    if (k == "--batched") batched = atoi(argv[i + 1]);
     if (k == "-p") ped_path = argv[i + 1];
     else if (k == "-d") dat_path = argv[i + 1];
     else if (k == "-g") gif_path = argv[i + 1];
@@ -86,15 +90,32 @@ static int do_pack(int argc, char **argv) {
     }
     std::vector<std::string> paths;
     for (int gi : glf_index) paths.push_back(gi == 0 || !glf_map.count(std::to_string(gi)) ? std::string() : glf_map[std::to_string(gi)]);
-    GlfSet glf;
     std::string err;
-    if (!glf.open(paths, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    if (glf.next_section()) {  // fixtures hold one chromosome
-      label = glf.label();
-      max_position = glf.max_position();
-      pm_site_hdr h;
-      std::vector<pm_person_site> one((size_t)v->n_person);
-      while (glf.next_site(&h, one.data())) { hdrs.push_back(h); recs.insert(recs.end(), one.begin(), one.end()); }
+    if (batched >= 0) {
+      GlfBatchReader glf;
+      if (!glf.open(paths, batched, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+      if (glf.next_section()) {
+        label = glf.label();
+        max_position = glf.max_position();
+        const size_t B = 1000;  // deliberately not a power of two: batch boundaries fall inside runs
+        std::vector<pm_site_hdr> hb(B);
+        std::vector<pm_person_site> rb(B * (size_t)v->n_person);
+        size_t n;
+        while ((n = glf.next_batch(hb.data(), rb.data(), B)) > 0) {
+          hdrs.insert(hdrs.end(), hb.begin(), hb.begin() + (long)n);
+          recs.insert(recs.end(), rb.begin(), rb.begin() + (long)(n * (size_t)v->n_person));
+        }
+      }
+    } else {
+      GlfSet glf;
+      if (!glf.open(paths, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+      if (glf.next_section()) {  // fixtures hold one chromosome
+        label = glf.label();
+        max_position = glf.max_position();
+        pm_site_hdr h;
+        std::vector<pm_person_site> one((size_t)v->n_person);
+        while (glf.next_site(&h, one.data())) { hdrs.push_back(h); recs.insert(recs.end(), one.begin(), one.end()); }
+      }
     }
   }
   text << "#label " << label << '\n';
@@ -192,8 +213,59 @@ static int do_unpack(int argc, char **argv) {
   return 0;
 }
 
+// pm-tools ingest-bench -p PED -d DAT -g GIF [--batched N] [--batch B]: reads everything, reports sites/s of the merge alone
+static int do_ingest_bench(int argc, char **argv) {
+  std::string ped_path, dat_path, gif_path;
+  int batched = -1;
+  size_t B = 4096;
+  for (int i = 2; i + 1 < argc; i += 2) {
+    std::string k = argv[i];
+    if (k == "-p") ped_path = argv[i + 1];
+    else if (k == "-d") dat_path = argv[i + 1];
+    else if (k == "-g") gif_path = argv[i + 1];
+    else if (k == "--batched") batched = atoi(argv[i + 1]);
+    else if (k == "--batch") B = (size_t)atol(argv[i + 1]);
+  }
+  Pedigree ped;
+  try { ped.load(dat_path, ped_path); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
+  std::map<std::string, std::string> glf_map;
+  std::ifstream g(gif_path);
+  std::string line;
+  while (std::getline(g, line)) { std::istringstream in(line); std::string a, b; if (in >> a >> b) glf_map[a] = b; }
+  std::vector<std::string> paths;
+  for (int idx : ped.columns()) {
+    int gi = ped.persons[idx].glf_index;
+    paths.push_back(gi == 0 || !glf_map.count(std::to_string(gi)) ? std::string() : glf_map[std::to_string(gi)]);
+  }
+  const size_t np = paths.size();
+  std::vector<pm_site_hdr> hb(B);
+  std::vector<pm_person_site> rb(B * np);
+  std::string err;
+  size_t total = 0;
+  unsigned long long check = 0;
+  struct timespec t0, t1, t2;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (batched >= 0) {
+    GlfBatchReader glf;
+    if (!glf.open(paths, batched, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    while (glf.next_section()) { size_t n; while ((n = glf.next_batch(hb.data(), rb.data(), B)) > 0) { total += n; check += hb[n - 1].pos + rb[(n - 1) * np].lk[0]; } }
+  } else {
+    GlfSet glf;
+    if (!glf.open(paths, &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    while (glf.next_section()) { while (glf.next_site(&hb[0], rb.data())) { total++; check += hb[0].pos + rb[0].lk[0]; } }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t2);
+  auto sec = [](const timespec &a, const timespec &b) { return (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec); };
+  printf("{\"sites\": %zu, \"persons\": %zu, \"open_s\": %.3f, \"merge_s\": %.3f, \"sites_per_s\": %.0f, \"packed_MB_per_s\": %.0f, \"check\": %llu}\n",
+         total, np, sec(t0, t1), sec(t1, t2), (double)total / sec(t1, t2), (double)total * (double)np * 16 / 1e6 / sec(t1, t2), check);
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) return usage();
+  if (!strcmp(argv[1], "ingest-bench")) return do_ingest_bench(argc, argv);
   if (!strcmp(argv[1], "pack")) return do_pack(argc, argv);
   if (!strcmp(argv[1], "unpack")) return do_unpack(argc, argv);
   return usage();

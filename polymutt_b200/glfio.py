@@ -12,8 +12,11 @@ assert _REC.itemsize == 20
 _BACK = np.array([15, 1, 2, 4, 8], dtype=np.uint8)  # glfHandler::backTranslateBase
 
 
-def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_base: np.ndarray, recs: np.ndarray):
-    """recs: [n_sites] PERSON_SITE_DTYPE for one person; rows that are all zero are left out."""
+def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_base: np.ndarray, recs: np.ndarray,
+              indel_every: int = 0, end_marker: bool = True):
+    """recs: [n_sites] PERSON_SITE_DTYPE for one person; rows that are all zero are left out.
+    indel_every > 0 interleaves an indel record (type 2, offset 0) after every indel_every-th base record;
+    end_marker=False leaves the section without its terminating byte (a truncated file)."""
     depth = recs["depth"][:, 0].astype(np.uint32) | (recs["depth"][:, 1].astype(np.uint32) << 8) | (recs["depth"][:, 2].astype(np.uint32) << 16)
     keep = (depth > 0) | (recs["map_quality"] > 0) | (recs["lk"].max(axis=1) > 0)
     p = pos[keep].astype(np.int64)
@@ -27,8 +30,17 @@ def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_bas
     with open(path, "wb") as f:
         f.write(b"GLF\x03" + struct.pack("<I", 0))
         f.write(struct.pack("<i", len(lab)) + lab + struct.pack("<i", max_position))
-        f.write(out.tobytes())
-        f.write(b"\0")
+        if indel_every > 0:
+            indel = bytes([(2 << 4) | 15]) + struct.pack("<I", 0) + struct.pack("<I", 7) + bytes([60]) + bytes([10, 20, 30]) + struct.pack("<hh", 2, -3) + b"AC" + b"GTT"
+            raw = out.tobytes()
+            for k in range(len(p)):
+                f.write(raw[20 * k:20 * (k + 1)])
+                if (k + 1) % indel_every == 0:
+                    f.write(indel)
+        else:
+            f.write(out.tobytes())
+        if end_marker:
+            f.write(b"\0")
 
 
 def write_run_dir(outdir: str, ped, hdr: np.ndarray, recs: np.ndarray, label: str = "1"):

@@ -156,6 +156,76 @@ def test_pedigree_ordering_rules(tools_built, tmp_path):
     assert list(p.ped.peel["type"][5:]) == [1, 2]
 
 
+def test_batched_multithreaded_ingest_equals_the_one_site_at_a_time_merge(tools_built, tmp_path):
+    """GlfBatchReader (thread pool, block decode, bitmap union) against GlfSet (Move2NextBaseEntry restated one site
+    at a time) on ragged streams: holes, sparse positions, different ends (the chromosome stops one site after the
+    first stream runs out), a stream without any record, interleaved indel records, a truncated file, a person
+    without a GLF, position 0, and a lead stream that lacks some sites (reference base from the next column)."""
+    from polymutt_b200 import glfio, load_pmpk
+    rng = np.random.default_rng(12)
+    ped = synth.concat(synth.trios(4), synth.families([4, 1, 1]))
+    n = 6000
+    h, r = synth.generate_sites(ped, n, seed=21, cfg=synth.SynthConfig(poly_boost=20))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1).copy()
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n, ped.n_person).copy()
+    steps = rng.choice([1, 1, 1, 2, 5, 300], n)
+    steps[0] = 1
+    hdr["pos"] = np.cumsum(steps) - 1                                      # starts at 0, sparse stretches
+    hdr["ref_base"] = rng.integers(1, 5, n)
+    recs[rng.random(recs.shape) < 0.2] = np.zeros((), dtype=recs.dtype)    # holes
+    recs[1:40, 0] = np.zeros((), dtype=recs.dtype)                         # the lead stream misses early sites
+    recs[0, 1] = recs[5, 1]                                                # position 0 is covered
+    ends = {1: 5200, 2: 5600, 5: 5990}                                      # streams that stop early
+    d = tmp_path / "ragged"
+    d.mkdir()
+    lines, gif = [], []
+    firsts = ped.family_first()
+    col = 0
+    for f in range(ped.n_fam):
+        for j in range(int(ped.fam_size[f])):
+            fa, mo = int(ped.father[col]), int(ped.mother[col])
+            key = 0 if col == 7 else col + 1                                # one person without a GLF
+            lines.append(f"fam{f + 1}\tp{j + 1}\t{('p%d' % (fa + 1)) if fa >= 0 else 0}\t{('p%d' % (mo + 1)) if mo >= 0 else 0}\t{int(ped.sex[col])}\t{key}\n")
+            if key:
+                rr = recs[:, col].copy()
+                if col in ends:
+                    rr[ends[col]:] = np.zeros((), dtype=rr.dtype)
+                if col == 9:
+                    rr[:] = np.zeros((), dtype=rr.dtype)                    # a stream with a section but no records
+                path = str(d / f"g{key}.glf")
+                glfio.write_glf(path, "7", int(hdr["pos"].max()) + 1, hdr["pos"].astype(np.int64), hdr["ref_base"], rr,
+                                indel_every=37 if col == 3 else 0, end_marker=(col != 11))
+                gif.append(f"{key} {path}\n")
+            col += 1
+    (d / "ped").write_text("".join(lines)); (d / "dat").write_text("T\tGLF_Index\n"); (d / "gif").write_text("".join(gif))
+    outs = []
+    for extra in ([], ["--batched", "1"], ["--batched", "5"]):
+        out = str(d / ("out%d.pmpk" % len(outs)))
+        subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out] + extra,
+                       check=True, stderr=subprocess.DEVNULL)
+        outs.append(load_pmpk(out))
+    ref = outs[0]
+    # the chromosome ends one site after the shortest stream's last record (the empty stream ends it at once: 1 site,
+    # plus one more because the first site sits at position 0 where the reference skips its end check)
+    assert 1 <= len(ref.hdr) <= 3, len(ref.hdr)
+    for o in outs[1:]:
+        assert np.array_equal(o.hdr, ref.hdr) and np.array_equal(o.recs, ref.recs)
+    # without the empty stream the run goes on until just past the first stream that ends
+    (d / "gif").write_text("".join(l for l in gif if not l.startswith("10 ")))
+    (d / "ped").write_text("".join(l.rsplit("\t", 1)[0] + "\t0\n" if l.endswith("\t10\n") else l for l in lines))
+    outs = []
+    for extra in ([], ["--batched", "1"], ["--batched", "3"]):
+        out = str(d / ("outb%d.pmpk" % len(outs)))
+        subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out] + extra,
+                       check=True, stderr=subprocess.DEVNULL)
+        outs.append(load_pmpk(out))
+    ref = outs[0]
+    assert 4000 < len(ref.hdr) < 5400 and ref.hdr["pos"][0] == 0
+    for o in outs[1:]:
+        assert len(o.hdr) == len(ref.hdr)
+        assert np.array_equal(o.hdr, ref.hdr) and np.array_equal(o.recs, ref.recs)
+
+
 def test_synthetic_generator_is_seeded_and_well_formed():
     ped = synth.concat(synth.trios(3), synth.families([4, 1]))
     h1, r1 = synth.generate_sites(ped, 500, 11, cfg=synth.SynthConfig(poly_boost=30))

@@ -172,6 +172,8 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     size_t n = 0, n_res = 0;
     std::future<int> fut;
     std::string err;
+    std::string text;             // the batch's VCF rows, formatted on the worker thread
+    std::vector<size_t> row_end;  // text offset after each row
   };
   const size_t n_slots = (size_t)(n_gpu == 1 ? 2 : 2 * n_gpu);
   std::vector<Slot> slots(n_slots);
@@ -220,12 +222,12 @@ int run_cli(int argc, char **argv, const Engine &engine) {
           const int code = sl.status[s] & 0xf;
           if (code == PM_SITE_DENOVO_DROPPED) { writer.ensure_header(); continue; }
           if (code != PM_SITE_EMITTED) continue;
-          const size_t r = next_row++;
-          if (r >= sl.n_res || sl.res[r].site != s) throw std::runtime_error("engine returned rows out of site order");
-          writer.write_site(label, sl.hdr[s], sl.res[r], &sl.ps[(size_t)s * np], &sl.pres[r * (size_t)np]);
+          next_row++;
           out_cnt++;
           if (opt.force_call && out_cnt >= positions.size()) stop = true;  // main.cpp:593
         }
+        if (next_row > sl.row_end.size()) throw std::runtime_error("engine returned rows out of site order");
+        if (next_row > 0) writer.write_rows(sl.text.data(), sl.row_end[next_row - 1], (long)next_row);
         return true;
       };
       bool more = true, ok = true;
@@ -251,10 +253,20 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         sl.n = n; sl.n_res = 0; sl.err.clear();
         const size_t g = launched % (size_t)n_gpu;
         Slot *slp = &sl;
-        sl.fut = std::async(std::launch::async, [&, slp, g]() -> int {
+        sl.fut = std::async(std::launch::async, [&, slp, g, label]() -> int {
           std::lock_guard<std::mutex> guard(ctx_lock[g]);
           int rc = engine.call_glf(ctxs[g], slp->hdr, slp->ps, slp->n, slp->status, slp->res, slp->pres, batch, &slp->n_res);
-          if (rc != PM_OK) slp->err = engine.last_error();  // the message is thread-local: keep it
+          if (rc != PM_OK) { slp->err = engine.last_error(); return rc; }  // the message is thread-local: keep it
+          // the batch's rows as text, here on the worker so that formatting overlaps the next batch's GPU time
+          slp->text.clear(); slp->row_end.clear();
+          size_t r = 0;
+          for (size_t s = 0; s < slp->n; s++) {
+            if ((slp->status[s] & 0xf) != PM_SITE_EMITTED) continue;
+            if (r >= slp->n_res || slp->res[r].site != s) { slp->err = "engine returned rows out of site order"; return PM_EINVAL; }
+            writer.format_site(slp->text, label, slp->hdr[s], slp->res[r], &slp->ps[s * (size_t)np], &slp->pres[r * (size_t)np]);
+            slp->row_end.push_back(slp->text.size());
+            r++;
+          }
           return rc;
         });
         in_flight.push_back(si);

@@ -1,8 +1,56 @@
 #include "vcf_writer.h"
 
+#include <cmath>
+#include <cstring>
 #include <ctime>
 
 namespace pmh {
+
+void append_int(std::string &out, long long v) {
+  char buf[24];
+  char *p = buf + sizeof buf;
+  const bool neg = v < 0;
+  unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
+  do { *--p = (char)('0' + u % 10); u /= 10; } while (u);
+  if (neg) *--p = '-';
+  out.append(p, (size_t)(buf + sizeof buf - p));
+}
+
+void append_fixed(std::string &out, double x, int decimals) {
+  static const double kPow[7] = {1, 10, 100, 1000, 10000, 100000, 1000000};
+  static const unsigned long long kPowI[7] = {1, 10, 100, 1000, 10000, 100000, 1000000};
+  const double s = std::fabs(x);
+  if (decimals < 0 || decimals > 6 || !(s < 1e9)) {  // also NaN / inf
+    char buf[400];
+    int n = snprintf(buf, sizeof buf, "%.*f", decimals, x);
+    out.append(buf, (size_t)n);
+    return;
+  }
+  // s * 10^d = p + e exactly (p the rounded product, e the fma residual); the digit string is the exact value
+  // rounded to an integer, ties to even
+  const double p = s * kPow[decimals];
+  const double e = std::fma(s, kPow[decimals], -p);
+  const double f = std::floor(p);
+  const double frac = p - f;  // exact
+  unsigned long long n = (unsigned long long)f;
+  bool up;
+  if (frac < 0.25) up = false;
+  else if (frac > 0.75) up = true;
+  else {
+    const double c = (frac - 0.5) + e;  // frac - 0.5 is exact; the sign of the sum is exact
+    up = c > 0.0 || (c == 0.0 && (n & 1ull));
+  }
+  n += up ? 1ull : 0ull;
+  if (std::signbit(x)) out.push_back('-');
+  append_int(out, (long long)(n / kPowI[decimals]));
+  if (decimals > 0) {
+    char buf[8];
+    unsigned long long r = n % kPowI[decimals];
+    for (int i = decimals - 1; i >= 0; i--) { buf[i] = (char)('0' + r % 10); r /= 10; }
+    out.push_back('.');
+    out.append(buf, (size_t)decimals);
+  }
+}
 
 static const char kBases[5] = {'0', 'A', 'C', 'G', 'T'};
 static const char *kGenoLabel[10] = {"A/A", "A/C", "A/G", "A/T", "C/C", "C/G", "C/T", "G/G", "G/T", "T/T"};
@@ -39,70 +87,96 @@ void VcfWriter::header(bool denovo) {
 
 void VcfWriter::write_site(const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
                            const pm_person_site *persons, const pm_person_result *pr) {
-  if (opt_.denovo) write_denovo(chrom, hdr, r, persons, pr);
-  else write_normal(chrom, hdr, r, persons, pr);
+  std::string row;
+  format_site(row, chrom, hdr, r, persons, pr);
+  write_rows(row.data(), row.size(), 1);
+}
+
+void VcfWriter::write_rows(const char *text, size_t bytes, long n_rows) {
+  if (n_rows <= 0) return;
+  if (!header_done_) header(opt_.denovo);
+  fwrite(text, 1, bytes, fh_);
+  fflush(fh_);
+  rows_ += n_rows;
+}
+
+void VcfWriter::format_site(std::string &out, const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
+                            const pm_person_site *persons, const pm_person_result *pr) const {
+  if (opt_.denovo) format_denovo(out, chrom, hdr, r, persons, pr);
+  else format_normal(out, chrom, hdr, r, persons, pr);
 }
 
 static inline int depth_of(const pm_person_site &p) { return p.depth[0] | (p.depth[1] << 8) | (p.depth[2] << 16); }
 
-void VcfWriter::write_normal(const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
-                             const pm_person_site *persons, const pm_person_result *pr) {
-  if (!header_done_) header(false);
+// CHROM .. INFO's common prefix "NS=..;PS=..;DP=..;MQ=.."
+static void append_site_prefix(std::string &out, const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
+                               const char *alt, size_t alt_len) {
+  out += chrom; out.push_back('\t');
+  append_int(out, (long long)hdr.pos + 1);
+  out += "\t.\t"; out.push_back(kBases[hdr.ref_base]); out.push_back('\t');
+  out.append(alt, alt_len); out.push_back('\t');
+  append_int(out, (long long)int(r.poly_qual + 0.5));
+  out += "\t.\tNS="; append_int(out, r.num_samp);
+  out += ";PS="; append_fixed(out, r.perc_samp * 100, 1);
+  out += ";DP="; append_int(out, r.total_depth);
+  out += ";MQ="; append_fixed(out, r.avg_map_qual, 1);
+}
+
+void VcfWriter::format_normal(std::string &out, const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
+                              const pm_person_site *persons, const pm_person_result *pr) const {
   const bool single_nuclear = ped_.families.size() == 1 && ped_.families[0].nuclear();
   const bool mono = (r.flags & PM_FLAG_MONO) != 0;
   const int a1 = r.allele1, a2 = r.allele2, ref = hdr.ref_base;
-  char info[512];
-  int n;
-  if (single_nuclear)
-    n = snprintf(info, sizeof info, "NS=%d;PS=%.1f;DP=%d;MQ=%.1f", r.num_samp, r.perc_samp * 100, r.total_depth, r.avg_map_qual);
-  else if (hdr.chr_class != PM_CHR_AUTO)
-    n = snprintf(info, sizeof info, "NS=%d;PS=%.1f;DP=%d;MQ=%.1f;AF=%.4f", r.num_samp, r.perc_samp * 100, r.total_depth, r.avg_map_qual, r.freq);
-  else
-    n = snprintf(info, sizeof info, "NS=%d;PS=%.1f;DP=%d;MQ=%.1f;AF=%.4f;AB=%.3f", r.num_samp, r.perc_samp * 100, r.total_depth, r.avg_map_qual, r.freq, r.ab);
-  if (mono) snprintf(info + n, sizeof info - n, ";BA=%c", kBases[a2]);
-  std::string alt;
-  if (ref == a1) alt = std::string(1, kBases[mono ? a1 : a2]);
-  else { alt += kBases[a1]; alt += ","; alt += kBases[a2]; }
-  fprintf(fh_, "%s\t%d\t%s\t%c\t%s\t%d\t%s\t%s\t%s", chrom.c_str(), (int)hdr.pos + 1, ".", kBases[ref], alt.c_str(),
-          int(r.poly_qual + 0.5), ".", info, opt_.gl_off ? "GT:GQ:DP:DS" : "GT:GQ:DP:DS:PL");
+  const int np = ped_.n_person();
+  out.reserve(out.size() + 160 + (size_t)np * 28);
+  char alt[4];
+  size_t alt_len;
+  if (ref == a1) { alt[0] = kBases[mono ? a1 : a2]; alt_len = 1; }
+  else { alt[0] = kBases[a1]; alt[1] = ','; alt[2] = kBases[a2]; alt_len = 3; }
+  append_site_prefix(out, chrom, hdr, r, alt, alt_len);
+  if (!single_nuclear) {
+    out += ";AF="; append_fixed(out, r.freq, 4);
+    if (hdr.chr_class == PM_CHR_AUTO) { out += ";AB="; append_fixed(out, r.ab, 3); }
+  }
+  if (mono) { out += ";BA="; out.push_back(kBases[a2]); }
+  out += opt_.gl_off ? "\tGT:GQ:DP:DS" : "\tGT:GQ:DP:DS:PL";
   static const char *lab[5] = {"0/0", "0/1", "1/1", "1/2", "2/2"};
   static const char *lab_hap[5] = {"0", "ERROR", "1", "ERROR2", "2"};
   const int g11 = genotype_index(a1, a1), g12 = genotype_index(a1, a2), g22 = genotype_index(a2, a2);
-  const int np = ped_.n_person();
+  const bool hap = hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT;
   for (int i = 0; i < np; i++) {
-    int best = pr[i].best;
-    int label_idx = (ref == a1) ? best : best + 2;
-    const char *gt = lab[label_idx];
-    if (hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT) gt = lab_hap[label_idx];
-    fprintf(fh_, "\t%s:", gt);
-    fprintf(fh_, "%d:", (int)pr[i].gq);
-    fprintf(fh_, "%d:", depth_of(persons[i]));
-    fprintf(fh_, "%.2f", pr[i].dosage);
-    if (!opt_.gl_off) fprintf(fh_, ":%u,%u,%u", persons[i].lk[g11], persons[i].lk[g12], persons[i].lk[g22]);
+    const int best = pr[i].best;
+    const int label_idx = (ref == a1) ? best : best + 2;
+    out.push_back('\t');
+    out += hap ? lab_hap[label_idx] : lab[label_idx];
+    out.push_back(':'); append_int(out, (int)pr[i].gq);
+    out.push_back(':'); append_int(out, depth_of(persons[i]));
+    out.push_back(':'); append_fixed(out, pr[i].dosage, 2);
+    if (!opt_.gl_off) {
+      out.push_back(':'); append_int(out, persons[i].lk[g11]);
+      out.push_back(','); append_int(out, persons[i].lk[g12]);
+      out.push_back(','); append_int(out, persons[i].lk[g22]);
+    }
   }
-  fprintf(fh_, "\n");
-  fflush(fh_);
-  rows_++;
+  out.push_back('\n');
 }
 
-void VcfWriter::write_denovo(const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
-                             const pm_person_site *persons, const pm_person_result *pr) {
-  if (!header_done_) header(true);
+void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
+                              const pm_person_site *persons, const pm_person_result *pr) const {
   const bool single_nuclear = ped_.families.size() == 1 && ped_.families[0].nuclear();
   const bool mono = (r.flags & PM_FLAG_MONO) != 0;
   const int a1 = r.allele1, ref = hdr.ref_base;
   const int a2_label = r.allele2;           // alleles the genotype labels were made with
   const int a2 = mono ? a1 : r.allele2;     // denovo_mono: allele2 = allele1 (NucFam.cpp:1870)
-  char info[512];
-  if (single_nuclear)
-    snprintf(info, sizeof info, "NS=%d;PS=%.1f;DP=%d;MQ=%.1f;DQ=%.3f", r.num_samp, r.perc_samp * 100, r.total_depth, r.avg_map_qual, r.denovo_lr);
-  else
-    snprintf(info, sizeof info, "NS=%d;PS=%.1f;DP=%d;MQ=%.1f;AF=%.4f;DQ=%.3f", r.num_samp, r.perc_samp * 100, r.total_depth, r.avg_map_qual, r.freq, r.denovo_lr);
-  std::string alt;
-  if (ref == a1) alt = std::string(1, kBases[a2]);
-  else { alt += kBases[a1]; alt += ","; alt += kBases[a2]; }
-  fprintf(fh_, "%s\t%d\t%s\t%c\t%s\t%d\t%s\t%s\t%s", chrom.c_str(), (int)hdr.pos + 1, ".", kBases[ref], alt.c_str(),
-          int(r.poly_qual + 0.5), ".", info, opt_.gl_off ? "GT:GQ:DP" : "GT:GQ:DP:PL");
+  out.reserve(out.size() + 160 + (size_t)ped_.n_person() * 52);
+  char alt[4];
+  size_t alt_len;
+  if (ref == a1) { alt[0] = kBases[a2]; alt_len = 1; }
+  else { alt[0] = kBases[a1]; alt[1] = ','; alt[2] = kBases[a2]; alt_len = 3; }
+  append_site_prefix(out, chrom, hdr, r, alt, alt_len);
+  if (!single_nuclear) { out += ";AF="; append_fixed(out, r.freq, 4); }
+  out += ";DQ="; append_fixed(out, r.denovo_lr, 3);
+  out += opt_.gl_off ? "\tGT:GQ:DP" : "\tGT:GQ:DP:PL";
   static const char *lab[5] = {"0/0", "0/1", "1/1", "1/2", "2/2"};
   int col = 0;
   for (const Family &f : ped_.families) {
@@ -116,19 +190,17 @@ void VcfWriter::write_denovo(const std::string &chrom, const pm_site_hdr &hdr, c
         int idx = p.best == 0 ? genotype_index(a1, a1) : p.best == 1 ? genotype_index(a1, a2_label) : genotype_index(a2_label, a2_label);
         gt = kGenoLabel[idx];
       }
-      fprintf(fh_, "\t%s:", gt);
-      fprintf(fh_, "%d:", (int)p.gq);
-      fprintf(fh_, "%d", depth_of(persons[col]));
+      out.push_back('\t'); out += gt;
+      out.push_back(':'); append_int(out, (int)p.gq);
+      out.push_back(':'); append_int(out, depth_of(persons[col]));
       if (!opt_.gl_off) {
-        fprintf(fh_, ":");
-        for (int g = 0; g < 9; g++) fprintf(fh_, "%d,", persons[col].lk[g]);
-        fprintf(fh_, "%d", persons[col].lk[9]);
+        out.push_back(':');
+        for (int g = 0; g < 9; g++) { append_int(out, persons[col].lk[g]); out.push_back(','); }
+        append_int(out, persons[col].lk[9]);
       }
     }
   }
-  fprintf(fh_, "\n");
-  fflush(fh_);
-  rows_++;
+  out.push_back('\n');
 }
 
 }  // namespace pmh

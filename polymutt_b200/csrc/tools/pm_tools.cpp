@@ -14,6 +14,7 @@
 //   i32 max_position  u64 n_sites  pm_site_hdr hdr[n_sites]  pm_person_site rec[n_sites*n_person]
 #include <sys/stat.h>
 #include <time.h>
+#include <cmath>
 
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,7 @@
 
 #include "glf.h"
 #include "glf_ingest.h"
+#include "vcf_writer.h"
 #include "pedigree.h"
 
 using namespace pmh;
@@ -263,8 +265,56 @@ static int do_ingest_bench(int argc, char **argv) {
   return 0;
 }
 
+// pm-tools fmt-selftest [N]: append_fixed / append_int against snprintf on random values, exact ties and edge cases
+static int do_fmt_selftest(int argc, char **argv) {
+  const long N = argc > 2 ? atol(argv[2]) : 1000000;
+  unsigned long long st = 0x9e3779b97f4a7c15ull;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+  long bad = 0, done = 0;
+  auto check = [&](double x, int d) {
+    char buf[400];
+    snprintf(buf, sizeof buf, "%.*f", d, x);
+    std::string s;
+    append_fixed(s, x, d);
+    done++;
+    if (s != buf) { if (bad < 10) fprintf(stderr, "mismatch %.17g d=%d: %s vs %s\n", x, d, s.c_str(), buf); bad++; }
+  };
+  const double edge[] = {0.0, -0.0, 0.5, 1.5, 2.5, 0.125, 0.375, 0.005, 0.015, 0.025, 0.045, 1e-300, 4.9e-324, 0.99999, 0.999999999,
+                         99.95, 99.949999999999, 100.0, 1e8, 9.99999999e8, 1e9, 1e15, 1e300, -0.0001, -3.14159, 2.0, 1.0 / 3.0};
+  for (double x : edge) for (int d = 0; d <= 6; d++) { check(x, d); check(-x, d); }
+  check(NAN, 2); check(INFINITY, 3); check(-INFINITY, 1);
+  for (long i = 0; i < N; i++) {
+    const unsigned long long r = rnd();
+    const int d = (int)(r % 5);
+    double x;
+    switch ((r >> 8) % 5) {
+      case 0: x = (double)(rnd() >> 11) / 9007199254740992.0 * 2.0; break;               // dosage-like
+      case 1: x = (double)(rnd() % 2000001) / 1000.0 / 2.0; break;                         // many exact decimal ties
+      case 2: x = ((double)(rnd() % 200001) + 0.5) / std::pow(10.0, d); break;             // nearest doubles to ties
+      case 3: x = std::ldexp((double)(rnd() >> 11), (int)(rnd() % 80) - 90); break;        // wide exponent range
+      default: x = -(double)(rnd() >> 11) / 9007199254740992.0 * 300.0; break;             // negative log ratios
+    }
+    check(x, d);
+    check(std::nextafter(x, 1e300), d);
+    check(std::nextafter(x, -1e300), d);
+  }
+  long ibad = 0;
+  for (long i = 0; i < 100000; i++) {
+    long long v = (long long)rnd() >> (int)(rnd() % 63);
+    if (i & 1) v = -v;
+    char buf[32];
+    snprintf(buf, sizeof buf, "%lld", v);
+    std::string s;
+    append_int(s, v);
+    if (s != buf) ibad++;
+  }
+  printf("{\"checked\": %ld, \"fixed_mismatches\": %ld, \"int_mismatches\": %ld}\n", done, bad, ibad);
+  return bad || ibad ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) return usage();
+  if (!strcmp(argv[1], "fmt-selftest")) return do_fmt_selftest(argc, argv);
   if (!strcmp(argv[1], "ingest-bench")) return do_ingest_bench(argc, argv);
   if (!strcmp(argv[1], "pack")) return do_pack(argc, argv);
   if (!strcmp(argv[1], "unpack")) return do_unpack(argc, argv);

@@ -237,3 +237,15 @@ def test_synthetic_generator_is_seeded_and_well_formed():
     assert (recs["lk"].min(axis=2)[has] == 0).all()          # min-normalised
     assert (recs["lk"][~has] == 0).all() and (recs["map_quality"][~has] == 0).all()
     assert 0.005 < (~has).mean() < 0.06
+
+
+def test_row_formatter_prints_what_printf_prints():
+    """The VCF row formatter's %.Nf / %d restatements (vcf_writer.cpp) agree with snprintf on random values,
+    exact decimal ties and their neighbours, negative zeros and non-finite values."""
+    import json
+    import subprocess
+    from cli_util import PM_TOOLS
+    out = subprocess.run([PM_TOOLS, "fmt-selftest", "300000"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rep = json.loads(out.stdout)
+    assert rep["checked"] > 900000 and rep["fixed_mismatches"] == 0 and rep["int_mismatches"] == 0

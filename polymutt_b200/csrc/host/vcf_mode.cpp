@@ -2,6 +2,8 @@
 
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +11,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vcf_writer.h"
@@ -22,10 +25,11 @@ int fatal(const std::string &msg) {
   return 1;
 }
 
-struct LineReader {  // plain or gzip, like base/IO.h's LineReader
+struct LineReader {  // plain or gzip, like base/IO.h's LineReader; used for the header lines only
   gzFile f = nullptr;
   std::vector<char> buf = std::vector<char>(1 << 20);
-  bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 18); return f != nullptr; }
+  std::string rest;  // always empty: gzgets never reads past the line it returns
+  bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
   bool next(std::string *line) {
     line->clear();
     for (;;) {
@@ -76,12 +80,133 @@ int allele2int(const std::string &a) {  // FLSeq_VCF.cpp:65-72
   return 0;
 }
 
-struct Pending {  // one input record waiting for its output
-  std::vector<std::string> col;      // the nine fixed columns
-  std::vector<std::string> sample;   // included samples' whole fields, VCF order
-  bool computed = false;             // false: printed with the state left by the previous computed record
-  size_t row = 0;                    // row in the engine batch
+// ---- allocation-free tokenising of a chunk of lines (libVcf LINE_MODE rules, see vcf_mode.h) ----
+struct Tok {
+  const char *p = nullptr;
+  uint32_t n = 0;
+  bool eq(const Tok &o) const { return n == o.n && memcmp(p, o.p, n) == 0; }
+  bool has(char c) const { return n && memchr(p, c, n) != nullptr; }
+  std::string str() const { return std::string(p, n); }
 };
+
+// k-th `sep`-separated field of t; false if there are fewer than k+1 fields
+inline bool nth_field(const Tok &t, char sep, int k, Tok *out) {
+  const char *b = t.p, *end = t.p + t.n;
+  for (int i = 0; i < k; i++) {
+    const char *c = (const char *)memchr(b, sep, (size_t)(end - b));
+    if (!c) return false;
+    b = c + 1;
+  }
+  const char *c = (const char *)memchr(b, sep, (size_t)(end - b));
+  out->p = b;
+  out->n = (uint32_t)((c ? c : end) - b);
+  return true;
+}
+
+// atof() of a token that is not NUL-terminated
+inline double tok_atof(const Tok &t) {
+  if (t.n == 0) return 0.0;
+  if (t.n <= 15) {  // plain digits (every PL): exact
+    unsigned long long v = 0;
+    uint32_t i = 0;
+    for (; i < t.n && t.p[i] >= '0' && t.p[i] <= '9'; i++) v = v * 10 + (unsigned)(t.p[i] - '0');
+    if (i == t.n) return (double)v;
+  }
+  char buf[64];
+  if (t.n < sizeof buf) { memcpy(buf, t.p, t.n); buf[t.n] = 0; return atof(buf); }
+  return atof(t.str().c_str());
+}
+inline int tok_atoi(const Tok &t) {
+  char buf[32];
+  const uint32_t n = t.n < sizeof buf - 1 ? t.n : (uint32_t)sizeof buf - 1;
+  memcpy(buf, t.p, n);
+  buf[n] = 0;
+  return atoi(buf);
+}
+
+int format_index(const Tok &format, const char *key) { return format_index(format.str(), key); }
+int allele2int(const Tok &a) { return a.n == 1 ? allele2int(std::string(1, a.p[0])) : 0; }
+
+enum LineKind : uint8_t { L_SKIP = 0, L_WARN, L_NODATA, L_COMPUTED, L_ERROR };
+
+struct LineRec {
+  Tok line;
+  Tok col[9];
+  size_t samp0 = 0;      // first of this line's names.size() sample tokens in the chunk's token array
+  uint8_t kind = L_SKIP;
+  uint8_t ref = 0, alt = 0, indel = 0;
+  int dp_here = -1;      // format_index(FORMAT, "DP") of this line
+  int dp_index = -1;     // the DP index in force when this line is printed (set in line order)
+  double mono = 0.0;
+  long row = -1;         // engine row (computed lines)
+  long src = -1;         // engine row whose results this line prints; -1 = state carried over from earlier chunks
+  std::string err;       // L_ERROR / L_WARN text
+};
+
+// Reads the (plain or gzip) file in large blocks and hands out chunks of whole lines.
+struct ChunkReader {
+  gzFile f = nullptr;
+  std::vector<char> buf;
+  size_t have = 0;       // bytes in buf
+  size_t start = 0;      // first unconsumed byte
+  bool eof = false;
+  bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
+  ~ChunkReader() { if (f) gzclose(f); }
+  // Next line (without its terminator); false at end of input.  Pointers stay valid until the next refill().
+  bool next_line(Tok *out, bool allow_refill) {
+    for (;;) {
+      const char *b = buf.data() + start;
+      const char *nl = have > start ? (const char *)memchr(b, '\n', have - start) : nullptr;
+      if (nl) {
+        size_t n = (size_t)(nl - b);
+        start += n + 1;
+        if (n && b[n - 1] == '\r') n--;
+        out->p = b; out->n = (uint32_t)n;
+        return true;
+      }
+      if (eof) {
+        if (have == start) return false;
+        size_t n = have - start;
+        start = have;
+        if (n && b[n - 1] == '\r') n--;
+        out->p = b; out->n = (uint32_t)n;
+        return true;
+      }
+      if (!allow_refill) return false;
+      refill();
+    }
+  }
+  // Drops consumed bytes and reads more; invalidates every pointer handed out before.
+  void refill() {
+    if (start > 0) { memmove(buf.data(), buf.data() + start, have - start); have -= start; start = 0; }
+    if (buf.size() - have < ((size_t)8 << 20)) buf.resize(buf.size() + ((size_t)32 << 20));
+    while (!eof && buf.size() - have > 1) {
+      const size_t room = buf.size() - have - 1;
+      int n = gzread(f, buf.data() + have, (unsigned)(room > ((size_t)1 << 30) ? ((size_t)1 << 30) : room));
+      if (n <= 0) { eof = true; break; }
+      have += (size_t)n;
+      if (have >= ((size_t)24 << 20)) break;  // a chunk's worth of text
+    }
+    buf[have] = 0;
+  }
+};
+
+template <typename F>
+void parallel_for(size_t n, int threads, F fn) {
+  if (threads <= 1 || n < 2) { for (size_t i = 0; i < n; i++) fn(i, 0); return; }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  const int nt = (int)std::min<size_t>((size_t)threads, n);
+  for (int t = 0; t < nt; t++)
+    pool.emplace_back([&, t]() {
+      for (;;) {
+        const size_t i0 = next.fetch_add(16);
+        if (i0 >= n) break;
+        for (size_t i = i0; i < std::min(n, i0 + 16); i++) fn(i, t);
+      }
+    });
+  for (auto &th : pool) th.join();
+}
 
 }  // namespace
 
@@ -148,169 +273,254 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   if (!ctx) { fclose(out); return fatal(std::string("engine '") + engine.name + "': " + engine.last_error()); }
 
   const int np = ped.n_person();
-  const size_t batch = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)8192;
-  std::vector<pm_site_hdr> hdr(batch);
-  std::vector<pm_person_site> recs(batch * (size_t)np);
-  std::vector<double> mono(batch);
-  std::vector<pm_site_result> res(batch);
-  std::vector<pm_person_result> pres(batch * (size_t)np);
-  std::vector<Pending> pending;
-  size_t n_rows = 0;
+  const size_t n_names = names.size();
+  int threads = opt.ingest_threads > 0 ? opt.ingest_threads : (int)std::thread::hardware_concurrency();
+  threads = std::max(1, std::min(threads, 32));
+  const size_t max_lines = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)8192;
 
   // state that survives from record to record in the reference object (stale output for records without data)
   double last_qual = 0.0, last_min = 0.0;
   std::vector<int> last_best((size_t)np, 0), last_gq((size_t)np, 0);
-  std::vector<char> last_labeled((size_t)np, 0);  // bestGenoLabel still "" until the first computed record
+  bool last_labeled = false;  // bestGenoLabel is still "" until the first computed record
   int DP_index = -1, GL_idx = -1, PL_idx = -1;
   bool announced = false;
 
-  auto flush = [&]() -> int {
-    if (n_rows) {
-      int rc = engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
-      if (rc != PM_OK) return rc;
-    }
-    std::vector<std::string> fd;
-    for (const Pending &p : pending) {
-      if (p.computed) {
-        const pm_site_result &r = res[p.row];
-        last_qual = r.poly_qual; last_min = r.freq;
-        for (int c = 0; c < np; c++) {
-          const pm_person_result &q = pres[p.row * (size_t)np + c];
-          last_best[c] = q.best; last_gq[c] = q.gq; last_labeled[c] = 1;
-        }
-      }
-      // FamilyLikelihoodSeq_VCF::OutputVCF, FLSeq_VCF.cpp:437-521
-      int AC = 0, totalDepth = 0;
-      bool missing = false;
-      for (size_t i = 0, k = 0; i < names.size(); i++) {
-        if (vcf2col[i] < 0) continue;
-        const std::string &s = p.sample[k++];
-        AC += last_best[vcf2col[i]];
-        int dp = 0;
-        if (DP_index > 0) {
-          split(s, ':', &fd);
-          missing = (size_t)DP_index >= fd.size() || fd[DP_index].empty();
-          dp = missing ? 0 : atoi(fd[DP_index].c_str());
-        }
-        if (missing) continue;
-        totalDepth += dp;
-      }
-      fprintf(out, "%s\t%d\t%s\t%s\t%s\t%.2f\t%s\tAF=%.2f;AC=%d;DP=%d\t%s", p.col[0].c_str(), atoi(p.col[1].c_str()), p.col[2].c_str(),
-              p.col[3].c_str(), p.col[4].c_str(), last_qual, p.col[6].c_str(), 1 - last_min, AC, totalDepth,
-              PL_idx > 0 ? "GT:GQ:DP:PL" : "GT:GQ:DP:GL");
-      static const char *lab[3] = {"0/0", "0/1", "1/1"};
-      for (size_t i = 0, k = 0; i < names.size(); i++) {
-        if (vcf2col[i] < 0) continue;
-        const std::string &s = p.sample[k++];
-        const int c = vcf2col[i];
-        split(s, ':', &fd);
-        const char *label = last_labeled[c] ? lab[last_best[c]] : "";
-        fprintf(out, "\t%s:%d:", last_gq[c] > 0 ? label : "./.", last_gq[c]);
-        const char *dps = ".";
-        if (DP_index > 0) {
-          missing = (size_t)DP_index >= fd.size() || fd[DP_index].empty();
-          dps = missing ? "" : fd[DP_index].c_str();
-        }
-        fprintf(out, "%s:", missing ? "." : dps);
-        const int li = PL_idx > 0 ? PL_idx : GL_idx;
-        missing = li < 0 || (size_t)li >= fd.size() || fd[li].empty();
-        fprintf(out, "%s", missing ? "." : fd[li].c_str());
-      }
-      fprintf(out, "\n");
-      fflush(out);
-    }
-    pending.clear();
-    n_rows = 0;
-    return PM_OK;
-  };
+  std::vector<LineRec> lines;
+  std::vector<Tok> toks;
+  std::vector<pm_site_hdr> hdr;
+  std::vector<pm_person_site> recs;
+  std::vector<double> mono;
+  std::vector<pm_site_result> res;
+  std::vector<pm_person_result> pres;
+  std::vector<std::string> text;
+  std::vector<std::vector<double>> scratch((size_t)threads, std::vector<double>((size_t)np));
+  static const char *lab[3] = {"0/0", "0/1", "1/1"};
 
-  std::vector<std::string> t, fd, gl;
-  int rc = PM_OK;
-  while (in.next(&line)) {
-    if (line.empty()) continue;
-    split(line, '\t', &t);
-    if (t.size() < 9 + names.size()) { engine.destroy(ctx); fclose(out); return fatal("VCF header have MORE people than VCF content!"); }
-    if (!announced) { printf("Total samples in both VCF and PED files: %d\n\n", n_in_both); announced = true; }
-    const std::string &refStr = t[3], &altStr = t[4];
-    // FillPenetrance, FLSeq_VCF.cpp:267-383
-    if (refStr == altStr) continue;                         // monomorphic: no output
-    if (altStr.find(',') != std::string::npos) continue;    // not bi-allelic: no output
-    const bool indel = refStr.size() > 1 || altStr.size() > 1;
+  // FillPenetrance for one line (FLSeq_VCF.cpp:267-383); everything it writes belongs to the line
+  auto parse_line = [&](size_t li, int tid) {
+    LineRec &L = lines[li];
+    if (L.kind == L_ERROR) return;
+    const Tok &refStr = L.col[3], &altStr = L.col[4];
+    if (refStr.eq(altStr)) { L.kind = L_SKIP; return; }   // monomorphic: no output
+    if (altStr.has(',')) { L.kind = L_SKIP; return; }      // not bi-allelic: no output
+    const bool indel = refStr.n > 1 || altStr.n > 1;
     const int ref = indel ? 1 : allele2int(refStr), alt = indel ? 2 : allele2int(altStr);
     if (ref == 0 || alt == 0) {
       // the reference indexes its genotype table with Allele2Int() == 0 here (undefined behaviour); skipped instead
-      printf("WARNING - REF/ALT %s/%s at %s:%s is not A, C, G or T; record skipped\n", refStr.c_str(), altStr.c_str(), t[0].c_str(), t[1].c_str());
-      continue;
+      L.kind = L_WARN;
+      L.err = "WARNING - REF/ALT " + refStr.str() + "/" + altStr.str() + " at " + L.col[0].str() + ":" + L.col[1].str() + " is not A, C, G or T; record skipped";
+      return;
     }
-    if (DP_index < 0) DP_index = format_index(t[8], "DP");
-    if (GL_idx < 0 && PL_idx < 0) {
-      GL_idx = format_index(t[8], "GL");
-      PL_idx = format_index(t[8], "PL");
-      if (GL_idx < 0 && PL_idx < 0) {
-        fprintf(stderr, "NO GL or PL field was found. Please check the vcf file at chr:%s and position:%d", t[0].c_str(), atoi(t[1].c_str()));
-        engine.destroy(ctx); fclose(out);
-        return 1;
-      }
-      if (n_in_both == 0) { engine.destroy(ctx); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
-    }
-    Pending p;
-    p.col.assign(t.begin(), t.begin() + 9);
-    for (size_t i = 0; i < names.size(); i++) if (vcf2col[i] >= 0) p.sample.push_back(t[9 + i]);
-    pm_person_site *row = &recs[n_rows * (size_t)np];
+    L.ref = (uint8_t)ref; L.alt = (uint8_t)alt; L.indel = indel;
+    L.dp_here = format_index(L.col[8], "DP");
+    pm_person_site *row = &recs[li * (size_t)np];
     memset(row, 0, sizeof(pm_person_site) * (size_t)np);
-    std::vector<double> loglk_rr((size_t)np, 0.0);
-    const int g0 = genotype_index(ref, ref), g1 = genotype_index(ref, alt), g2 = genotype_index(alt, alt);
+    std::vector<double> &loglk_rr = scratch[(size_t)tid];
+    std::fill(loglk_rr.begin(), loglk_rr.end(), 0.0);
+    const int gi[3] = {genotype_index(ref, ref), genotype_index(ref, alt), genotype_index(alt, alt)};
+    const int fi = GL_idx > 0 ? GL_idx : PL_idx;
     int withdata = 0;
-    for (size_t i = 0; i < names.size(); i++) {
+    for (size_t i = 0; i < n_names; i++) {
       const int c = vcf2col[i];
       if (c < 0) continue;
-      split(t[9 + i], ':', &fd);
-      const int li = GL_idx > 0 ? GL_idx : PL_idx;
-      const bool missing = li < 0 || (size_t)li >= fd.size() || fd[li].empty();
+      Tok field, g[3], extra;
+      const bool missing = fi < 0 || !nth_field(toks[L.samp0 + i], ':', fi, &field) || field.n == 0;
       if (missing) break;  // the reference returns from FillPenetrance here: later samples keep likelihood 1
-      split(fd[li], ',', &gl);
-      if (gl.size() != 3) {
-        engine.destroy(ctx); fclose(out);
-        return fatal("GL or PL filed does not have 3 values separated by commas at: " + t[0] + " " + t[1] + "!");
+      if (!nth_field(field, ',', 0, &g[0]) || !nth_field(field, ',', 1, &g[1]) || !nth_field(field, ',', 2, &g[2]) || nth_field(field, ',', 3, &extra)) {
+        L.kind = L_ERROR;
+        L.err = "GL or PL filed does not have 3 values separated by commas at: " + L.col[0].str() + " " + L.col[1].str() + "!";
+        return;
       }
-      const double G[3] = {atof(gl[0].c_str()), atof(gl[1].c_str()), atof(gl[2].c_str())};
+      const double G[3] = {tok_atof(g[0]), tok_atof(g[1]), tok_atof(g[2])};
       if (G[0] != 0.0 || G[1] != 0.0 || G[2] != 0.0) withdata++;
-      const int gi[3] = {g0, g1, g2};
       for (int k = 0; k < 3; k++) {
         const double ll = PL_idx > 0 ? (G[k] > 255 ? -255 / 10.0 : -G[k] / 10.0) : (-10 * G[k] > 255 ? -255 / 10.0 : G[k]);
         if (k == 0) loglk_rr[(size_t)c] = ll;
         int pl = int(PL_idx > 0 ? G[k] : -10 * G[k]);
-        if (pl < 0) {
-          engine.destroy(ctx); fclose(out);
-          return fatal("Phred-scaled likelihood " + std::to_string(pl) + " can not be negative");
-        }
+        if (pl < 0) { L.kind = L_ERROR; L.err = "Phred-scaled likelihood " + std::to_string(pl) + " can not be negative"; return; }
         if (pl > 255) pl = 255;
         row[c].lk[gi[k]] = (uint8_t)pl;
       }
     }
-    if (withdata == 0) {  // PedVCF.cpp:122: printed with whatever the previous record left behind
-      pending.push_back(std::move(p));
-      if (pending.size() >= 4 * batch) { if ((rc = flush()) != PM_OK) break; }
-      continue;
-    }
+    if (withdata == 0) { L.kind = L_NODATA; return; }  // PedVCF.cpp:122: printed with whatever the previous record left behind
     // MonomorphismLogLikelihood, FLSeq_VCF.cpp:74-83: pedigree order
     double m = 0.0;
     for (int c = 0; c < np; c++) m += loglk_rr[(size_t)c];
-    mono[n_rows] = m;
-    hdr[n_rows].pos = (uint32_t)atoi(t[1].c_str());
-    hdr[n_rows].ref_base = (uint8_t)ref;
-    hdr[n_rows].chr_class = t[0] == opt.chrX ? PM_CHR_X : t[0] == opt.chrY ? PM_CHR_Y : t[0] == opt.chrMT ? PM_CHR_MT : PM_CHR_AUTO;
-    hdr[n_rows].reserved = (uint16_t)(alt | (indel ? 0x100 : 0));
-    p.computed = true;
-    p.row = n_rows++;
-    pending.push_back(std::move(p));
-    if (n_rows == batch) { if ((rc = flush()) != PM_OK) break; }
+    L.mono = m;
+    L.kind = L_COMPUTED;
+  };
+
+  // FamilyLikelihoodSeq_VCF::OutputVCF (FLSeq_VCF.cpp:437-521) for one line, into text[li]
+  auto format_line = [&](size_t li, int) {
+    const LineRec &L = lines[li];
+    std::string &o = text[li];
+    o.clear();
+    if (L.kind != L_NODATA && L.kind != L_COMPUTED) return;
+    const bool from_row = L.src >= 0;
+    const double qual = from_row ? res[(size_t)L.src].poly_qual : last_qual;
+    const double fmin = from_row ? res[(size_t)L.src].freq : last_min;
+    const pm_person_result *pr = from_row ? &pres[(size_t)L.src * (size_t)np] : nullptr;
+    const bool labeled = from_row || last_labeled;
+    auto best_of = [&](int c) { return pr ? (int)pr[c].best : last_best[(size_t)c]; };
+    auto gq_of = [&](int c) { return pr ? (int)pr[c].gq : last_gq[(size_t)c]; };
+    const int dpi = L.dp_index;
+    int AC = 0, totalDepth = 0;
+    bool missing = false;
+    Tok f;
+    for (size_t i = 0; i < n_names; i++) {
+      if (vcf2col[i] < 0) continue;
+      AC += best_of(vcf2col[i]);
+      int dp = 0;
+      if (dpi > 0) {
+        missing = !nth_field(toks[L.samp0 + i], ':', dpi, &f) || f.n == 0;
+        dp = missing ? 0 : tok_atoi(f);
+      }
+      if (missing) continue;
+      totalDepth += dp;
+    }
+    o.reserve(L.line.n + 64);
+    o.append(L.col[0].p, L.col[0].n); o.push_back('\t');
+    append_int(o, tok_atoi(L.col[1])); o.push_back('\t');
+    o.append(L.col[2].p, L.col[2].n); o.push_back('\t');
+    o.append(L.col[3].p, L.col[3].n); o.push_back('\t');
+    o.append(L.col[4].p, L.col[4].n); o.push_back('\t');
+    append_fixed(o, qual, 2); o.push_back('\t');
+    o.append(L.col[6].p, L.col[6].n);
+    o += "\tAF="; append_fixed(o, 1 - fmin, 2);
+    o += ";AC="; append_int(o, AC);
+    o += ";DP="; append_int(o, totalDepth);
+    o += PL_idx > 0 ? "\tGT:GQ:DP:PL" : "\tGT:GQ:DP:GL";
+    const int fi = PL_idx > 0 ? PL_idx : GL_idx;
+    for (size_t i = 0; i < n_names; i++) {
+      if (vcf2col[i] < 0) continue;
+      const int c = vcf2col[i];
+      const Tok &s = toks[L.samp0 + i];
+      const int gq = gq_of(c);
+      o.push_back('\t');
+      o += gq > 0 ? (labeled ? lab[best_of(c)] : "") : "./.";
+      o.push_back(':'); append_int(o, gq); o.push_back(':');
+      Tok dps; dps.p = "."; dps.n = 1;
+      if (dpi > 0) {
+        missing = !nth_field(s, ':', dpi, &f) || f.n == 0;
+        if (!missing) dps = f;
+      }
+      if (missing) o.push_back('.'); else o.append(dps.p, dps.n);
+      o.push_back(':');
+      missing = fi < 0 || !nth_field(s, ':', fi, &f) || f.n == 0;
+      if (missing) o.push_back('.'); else o.append(f.p, f.n);
+    }
+    o.push_back('\n');
+  };
+
+  ChunkReader rd;
+  rd.f = in.f; in.f = nullptr;      // continue where the header scan stopped
+  rd.buf.assign(in.rest.begin(), in.rest.end());
+  rd.have = rd.buf.size();
+  rd.buf.resize(rd.have + ((size_t)32 << 20));
+  int rc = PM_OK;
+  std::string fail;
+  bool more = true;
+  while (more && rc == PM_OK && fail.empty()) {
+    // ---- one chunk of whole lines, tokenised by tabs ----
+    if (!rd.eof && rd.have - rd.start < ((size_t)4 << 20)) rd.refill();
+    lines.clear();
+    Tok line;
+    while (lines.size() < max_lines && rd.next_line(&line, false)) {
+      if (line.n == 0) continue;
+      LineRec L;
+      L.line = line;
+      lines.push_back(std::move(L));
+    }
+    if (lines.empty()) {
+      if (rd.eof && rd.have == rd.start) { more = false; break; }
+      if (!rd.eof) rd.refill();  // a line longer than what was buffered: the buffer grows as needed
+      continue;
+    }
+    const size_t nl = lines.size();
+    toks.assign(nl * n_names, Tok());
+    parallel_for(nl, threads, [&](size_t li, int) {
+      LineRec &L = lines[li];
+      L.samp0 = li * n_names;
+      const char *b = L.line.p, *end = L.line.p + L.line.n;
+      size_t k = 0;
+      while (k < 9 + n_names) {
+        const char *c = (const char *)memchr(b, '\t', (size_t)(end - b));
+        Tok t; t.p = b; t.n = (uint32_t)((c ? c : end) - b);
+        if (k < 9) L.col[k] = t; else toks[L.samp0 + (k - 9)] = t;
+        k++;
+        if (!c) break;
+        b = c + 1;
+      }
+      if (k < 9 + n_names) { L.kind = L_ERROR; L.err = "VCF header have MORE people than VCF content!"; }
+    });
+    // ---- the FORMAT indices are fixed by the first record that reaches them (FLSeq_VCF.cpp:340-350) ----
+    if (GL_idx < 0 && PL_idx < 0) {
+      for (size_t li = 0; li < nl; li++) {
+        const LineRec &L = lines[li];
+        if (L.kind == L_ERROR) break;
+        if (L.col[3].eq(L.col[4]) || L.col[4].has(',')) continue;
+        const bool indel = L.col[3].n > 1 || L.col[4].n > 1;
+        if (!indel && (allele2int(L.col[3]) == 0 || allele2int(L.col[4]) == 0)) continue;
+        GL_idx = format_index(L.col[8], "GL");
+        PL_idx = format_index(L.col[8], "PL");
+        if (GL_idx < 0 && PL_idx < 0) {
+          fprintf(stderr, "NO GL or PL field was found. Please check the vcf file at chr:%s and position:%d", L.col[0].str().c_str(), tok_atoi(L.col[1]));
+          engine.destroy(ctx); fclose(out);
+          return 1;
+        }
+        if (n_in_both == 0) { engine.destroy(ctx); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
+        break;
+      }
+    }
+    if (!announced) { printf("Total samples in both VCF and PED files: %d\n\n", n_in_both); announced = true; }
+    if (recs.size() < nl * (size_t)np) recs.resize(nl * (size_t)np);
+    parallel_for(nl, threads, parse_line);
+    // ---- in line order: warnings, the first error, engine rows, which row each line prints ----
+    size_t n_rows = 0, n_use = nl;
+    long src = -1;
+    hdr.resize(nl); mono.resize(nl);
+    for (size_t li = 0; li < nl; li++) {
+      LineRec &L = lines[li];
+      if (L.kind == L_WARN) { printf("%s\n", L.err.c_str()); continue; }
+      if (L.kind == L_ERROR) { fail = L.err; n_use = li; break; }
+      if (L.kind == L_SKIP) continue;
+      if (DP_index < 0) DP_index = L.dp_here;
+      L.dp_index = DP_index;
+      if (L.kind == L_COMPUTED) {
+        L.row = (long)n_rows;
+        if (n_rows != li) memmove(&recs[n_rows * (size_t)np], &recs[li * (size_t)np], sizeof(pm_person_site) * (size_t)np);
+        mono[n_rows] = L.mono;
+        pm_site_hdr &h = hdr[n_rows];
+        memset(&h, 0, sizeof h);
+        h.pos = (uint32_t)tok_atoi(L.col[1]);
+        h.ref_base = L.ref;
+        const std::string chrom = L.col[0].str();
+        h.chr_class = chrom == opt.chrX ? PM_CHR_X : chrom == opt.chrY ? PM_CHR_Y : chrom == opt.chrMT ? PM_CHR_MT : PM_CHR_AUTO;
+        h.reserved = (uint16_t)(L.alt | (L.indel ? 0x100 : 0));
+        src = (long)n_rows++;
+      }
+      L.src = src;
+    }
+    if (n_rows) {
+      if (res.size() < n_rows) { res.resize(n_rows); pres.resize(n_rows * (size_t)np); }
+      rc = engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
+      if (rc != PM_OK) break;
+    }
+    if (text.size() < nl) text.resize(nl);
+    parallel_for(n_use, threads, format_line);
+    for (size_t li = 0; li < n_use; li++) if (!text[li].empty()) fwrite(text[li].data(), 1, text[li].size(), out);
+    fflush(out);
+    if (n_rows) {  // what the next chunk's leading no-data records print
+      const size_t r = n_rows - 1;
+      last_qual = res[r].poly_qual; last_min = res[r].freq; last_labeled = true;
+      for (int c = 0; c < np; c++) { last_best[(size_t)c] = pres[r * (size_t)np + c].best; last_gq[(size_t)c] = pres[r * (size_t)np + c].gq; }
+    }
   }
-  if (rc == PM_OK) rc = flush();
   std::string err = rc == PM_OK ? std::string() : std::string("engine '") + engine.name + "': " + engine.last_error();
   engine.destroy(ctx);
   fclose(out);
   if (rc != PM_OK) return fatal(err);
+  if (!fail.empty()) return fatal(fail);
   return 0;
 }
 

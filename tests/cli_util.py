@@ -83,7 +83,7 @@ VCF_CASES = [
 ]
 
 
-def check_vcf_case(exe, tmpdir, case, gz_input=False):
+def check_vcf_case(exe, tmpdir, case, gz_input=False, extra=()):
     name, ped, vin, golden = case
     src = os.path.join(GOLDEN, vin)
     if gz_input:
@@ -93,7 +93,7 @@ def check_vcf_case(exe, tmpdir, case, gz_input=False):
         with gzip.open(src, "rb") as f, open(inp, "wb") as g:
             g.write(f.read())
     out = os.path.join(tmpdir, name + ".out.vcf")
-    cmd = [exe, "-p", os.path.join(GOLDEN, "peds", ped), "-d", os.path.join(GOLDEN, "peds", "test.dat"), "--in_vcf", inp, "--out_vcf", out]
+    cmd = [exe, "-p", os.path.join(GOLDEN, "peds", ped), "-d", os.path.join(GOLDEN, "peds", "test.dat"), "--in_vcf", inp, "--out_vcf", out] + list(extra)
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1800)
     log = p.stdout.decode(errors="replace")
     assert p.returncode == 0, log[-2000:]

@@ -1,5 +1,7 @@
 #include "glf_ingest.h"
 
+#include <sys/resource.h>
+
 #include <algorithm>
 #include <atomic>
 #include <climits>
@@ -108,6 +110,14 @@ bool GlfBatchReader::open(const std::vector<std::string> &paths, int threads, st
   streams_ = std::vector<Stream>(paths.size());
   lead_ = -1;
   threads_ = threads > 0 ? threads : (int)std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+  {  // one descriptor per person stays open for the whole run: lift the soft limit as far as the hard one allows
+    struct rlimit rl;
+    const rlim_t want = (rlim_t)paths.size() + 256;
+    if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < want && rl.rlim_cur < rl.rlim_max) {
+      rl.rlim_cur = rl.rlim_max == RLIM_INFINITY ? want : std::min(want, rl.rlim_max);
+      setrlimit(RLIMIT_NOFILE, &rl);
+    }
+  }
   for (size_t i = 0; i < paths.size(); i++) {
     if (paths[i].empty()) continue;
     Stream &s = streams_[i];

@@ -36,7 +36,7 @@ $(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC) polymutt_b200/csrc/host/host_error.h
 tools: $(TOOLS)
 $(TOOLS): polymutt_b200/csrc/tools/pm_tools.cpp $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h)
 	@mkdir -p polymutt_b200/bin
-	$(HOSTCXX) $(CXXFLAGS) -o $@ polymutt_b200/csrc/tools/pm_tools.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/pedigree.cpp polymutt_b200/csrc/host/vcf_writer.cpp $(HOST_LIB_SRC) -lz
+	$(HOSTCXX) $(CXXFLAGS) -o $@ polymutt_b200/csrc/tools/pm_tools.cpp polymutt_b200/csrc/host/glf.cpp polymutt_b200/csrc/host/glf_ingest.cpp polymutt_b200/csrc/host/pedigree.cpp polymutt_b200/csrc/host/vcf_writer.cpp polymutt_b200/csrc/host/params.cpp $(HOST_LIB_SRC) -lz
 
 cli: $(CLI)
 $(CLI): $(LIB) $(FRONT_SRC) polymutt_b200/csrc/host/main.cpp $(wildcard polymutt_b200/csrc/host/*.h)

@@ -27,13 +27,14 @@ static int call_glf(void *vctx, const pm_site_hdr *hdr, const pm_person_site *ps
   size_t k = 0;
   for (size_t s = 0; s < n; s++)
     if (all[s].status == PM_SITE_EMITTED) {
-      if (k >= cap) return PM_EINVAL;
-      res[k] = all[s];
-      memcpy(&person[k * (size_t)o->np], &pall[s * (size_t)o->np], sizeof(pm_person_result) * (size_t)o->np);
+      if (k < cap) {
+        res[k] = all[s];
+        memcpy(&person[k * (size_t)o->np], &pall[s * (size_t)o->np], sizeof(pm_person_result) * (size_t)o->np);
+      }
       k++;
     }
-  *n_res = k;
-  return PM_OK;
+  *n_res = k;   // like pm_call_glf_sites: on overflow the needed row count comes back with PM_EINVAL
+  return k > cap ? PM_EINVAL : PM_OK;
 }
 static int call_vcf(void *vctx, const pm_site_hdr *hdr, const pm_person_site *ps, const double *mono, size_t n, pm_site_result *res,
                     pm_person_result *person) {

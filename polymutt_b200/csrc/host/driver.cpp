@@ -1,5 +1,7 @@
 #include "driver.h"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +16,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "glf.h"
@@ -87,6 +90,7 @@ void count_site(Counters &c, const pm_site_hdr &h, uint16_t st, const Options &o
 }  // namespace
 
 int run_cli(int argc, char **argv, const Engine &engine) {
+  const double t_start = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   Options opt;
   std::string err;
   bool parsed = opt.parse(argc, argv, &err);
@@ -170,6 +174,7 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     std::unique_ptr<HostBuf> b_hdr, b_ps, b_status, b_res, b_pres;
     pm_site_hdr *hdr; pm_person_site *ps; uint16_t *status; pm_site_result *res; pm_person_result *pres;
     size_t n = 0, n_res = 0;
+    size_t cap = 0;               // rows b_res / b_pres can hold
     std::future<int> fut;
     std::string err;
     std::string text;             // the batch's VCF rows, formatted on the worker thread
@@ -177,16 +182,32 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   };
   const size_t n_slots = (size_t)(n_gpu == 1 ? 2 : 2 * n_gpu);
   std::vector<Slot> slots(n_slots);
+  // Row buffers: every site can be a row under --all_sites / --pos; otherwise rows are rare, so start small and let a
+  // batch that overflows (PM_EINVAL with the needed count) grow its slot and run again.
+  const size_t cap0 = (opt.out_all_sites || opt.force_call) ? batch : std::max<size_t>(64, batch / 16);
+  auto size_rows = [&](Slot &sl, size_t cap) -> bool {
+    sl.b_res.reset(); sl.b_pres.reset();
+    sl.b_res.reset(new HostBuf(engine, cap * sizeof(pm_site_result)));
+    sl.b_pres.reset(new HostBuf(engine, cap * (size_t)np * sizeof(pm_person_result)));
+    if (!sl.b_res->p || !sl.b_pres->p) return false;
+    sl.res = (pm_site_result *)sl.b_res->p; sl.pres = (pm_person_result *)sl.b_pres->p;
+    sl.cap = cap;
+    return true;
+  };
   for (Slot &sl : slots) {
     sl.b_hdr.reset(new HostBuf(engine, batch * sizeof(pm_site_hdr)));
     sl.b_ps.reset(new HostBuf(engine, batch * (size_t)np * sizeof(pm_person_site)));
     sl.b_status.reset(new HostBuf(engine, batch * sizeof(uint16_t)));
-    sl.b_res.reset(new HostBuf(engine, batch * sizeof(pm_site_result)));
-    sl.b_pres.reset(new HostBuf(engine, batch * (size_t)np * sizeof(pm_person_result)));
-    if (!sl.b_hdr->p || !sl.b_ps->p || !sl.b_status->p || !sl.b_res->p || !sl.b_pres->p) { destroy_all(); return fatal("out of host memory for the site batches"); }
+    if (!sl.b_hdr->p || !sl.b_ps->p || !sl.b_status->p || !size_rows(sl, cap0)) { destroy_all(); return fatal("out of host memory for the site batches"); }
     sl.hdr = (pm_site_hdr *)sl.b_hdr->p; sl.ps = (pm_person_site *)sl.b_ps->p; sl.status = (uint16_t *)sl.b_status->p;
-    sl.res = (pm_site_result *)sl.b_res->p; sl.pres = (pm_person_result *)sl.b_pres->p;
   }
+  // rows of a batch are formatted on the batch's worker plus helpers: --ingest_threads (default: all cores) over the slots
+  int fmt_threads = opt.ingest_threads > 0 ? opt.ingest_threads : (int)std::thread::hardware_concurrency();
+  fmt_threads = std::max(1, std::min(32, fmt_threads) / (int)n_slots);
+  const bool timing = getenv("PM_TIMING") != nullptr;
+  auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_ingest = 0.0, t_wait = 0.0, t_write = 0.0;
+  const double t_setup_done = now();
 
   VcfWriter writer(vcf, opt, ped);
   time_t t0;
@@ -212,7 +233,9 @@ int run_cli(int argc, char **argv, const Engine &engine) {
       auto consume = [&]() -> bool {
         Slot &sl = slots[in_flight.front()];
         in_flight.pop_front();
+        const double tw0 = now();
         const int rc = sl.fut.get();
+        t_wait += now() - tw0;
         if (rc != PM_OK) { engine_error = sl.err; return false; }
         if (stop) return true;  // --pos already satisfied: drain without printing
         for (size_t s = 0; s < sl.n; s++) count_site(cnt, sl.hdr[s], sl.status[s], opt);
@@ -227,7 +250,9 @@ int run_cli(int argc, char **argv, const Engine &engine) {
           if (opt.force_call && out_cnt >= positions.size()) stop = true;  // main.cpp:593
         }
         if (next_row > sl.row_end.size()) throw std::runtime_error("engine returned rows out of site order");
+        const double tw1 = now();
         if (next_row > 0) writer.write_rows(sl.text.data(), sl.row_end[next_row - 1], (long)next_row);
+        t_write += now() - tw1;
         return true;
       };
       bool more = true, ok = true;
@@ -236,7 +261,9 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         if (!ok || stop) break;
         const size_t si = launched % n_slots;
         Slot &sl = slots[si];
+        const double ti0 = now();
         size_t n = glf.next_batch(sl.hdr, sl.ps, batch);
+        t_ingest += now() - ti0;
         if (n == 0) { more = false; break; }
         if (cnt.totalEntryCnt == 0) cnt.totalEntryCnt = glf.max_position();
         for (size_t s = 0; s < n; s++) sl.hdr[s].chr_class = chr_class;
@@ -255,17 +282,48 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         Slot *slp = &sl;
         sl.fut = std::async(std::launch::async, [&, slp, g, label]() -> int {
           std::lock_guard<std::mutex> guard(ctx_lock[g]);
-          int rc = engine.call_glf(ctxs[g], slp->hdr, slp->ps, slp->n, slp->status, slp->res, slp->pres, batch, &slp->n_res);
+          int rc = engine.call_glf(ctxs[g], slp->hdr, slp->ps, slp->n, slp->status, slp->res, slp->pres, slp->cap, &slp->n_res);
+          if (rc == PM_EINVAL && slp->n_res > slp->cap && slp->n_res <= slp->n) {  // more rows than the slot holds: grow, run again
+            if (!size_rows(*slp, std::min(batch, slp->n_res + slp->n_res / 4 + 64))) { slp->err = "out of host memory for the result rows"; return PM_EINVAL; }
+            rc = engine.call_glf(ctxs[g], slp->hdr, slp->ps, slp->n, slp->status, slp->res, slp->pres, slp->cap, &slp->n_res);
+          }
           if (rc != PM_OK) { slp->err = engine.last_error(); return rc; }  // the message is thread-local: keep it
           // the batch's rows as text, here on the worker so that formatting overlaps the next batch's GPU time
           slp->text.clear(); slp->row_end.clear();
-          size_t r = 0;
+          std::vector<size_t> row_site;
           for (size_t s = 0; s < slp->n; s++) {
             if ((slp->status[s] & 0xf) != PM_SITE_EMITTED) continue;
+            const size_t r = row_site.size();
             if (r >= slp->n_res || slp->res[r].site != s) { slp->err = "engine returned rows out of site order"; return PM_EINVAL; }
-            writer.format_site(slp->text, label, slp->hdr[s], slp->res[r], &slp->ps[s * (size_t)np], &slp->pres[r * (size_t)np]);
-            slp->row_end.push_back(slp->text.size());
-            r++;
+            row_site.push_back(s);
+          }
+          const size_t nr = row_site.size();
+          const size_t parts = nr >= 64 ? std::min<size_t>((size_t)fmt_threads, nr / 32) : 1;
+          std::vector<std::string> part_text(parts);
+          std::vector<std::vector<size_t>> part_end(parts);
+          auto format_part = [&](size_t k) {
+            for (size_t r = nr * k / parts; r < nr * (k + 1) / parts; r++) {
+              const size_t s = row_site[r];
+              writer.format_site(part_text[k], label, slp->hdr[s], slp->res[r], &slp->ps[s * (size_t)np], &slp->pres[r * (size_t)np]);
+              part_end[k].push_back(part_text[k].size());
+            }
+          };
+          {
+            std::vector<std::thread> pool;
+            for (size_t k = 1; k < parts; k++) pool.emplace_back(format_part, k);
+            format_part(0);
+            for (auto &th : pool) th.join();
+          }
+          if (parts == 1) slp->text.swap(part_text[0]);
+          else {
+            size_t total = 0;
+            for (auto &t : part_text) total += t.size();
+            slp->text.reserve(total);
+          }
+          for (size_t k = 0, off = 0; k < parts; k++) {
+            if (parts > 1) slp->text += part_text[k];
+            for (size_t e : part_end[k]) slp->row_end.push_back(off + e);
+            off = parts > 1 ? slp->text.size() : 0;
           }
           return rc;
         });
@@ -308,6 +366,10 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     fclose(vcf);
     return fatal(e.what());
   }
+  if (timing)
+    fprintf(stderr, "[pm timing] setup %.3f s (pedigree, GLF open, %d engine context(s), %zu x %zu-site batch buffers); loop %.3f s = ingest %.3f + "
+                    "waiting for the engine/formatting %.3f + writing %.3f\n",
+            t_setup_done - t_start, n_gpu, n_slots, batch, now() - t_setup_done, t_ingest, t_wait, t_write);
   destroy_all();
   fclose(vcf);
   return 0;

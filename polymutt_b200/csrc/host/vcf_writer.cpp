@@ -6,25 +6,57 @@
 
 namespace pmh {
 
-void append_int(std::string &out, long long v) {
+namespace {
+
+// Raw-pointer cores: the caller guarantees room (kMaxInt / kMaxFixed bytes).
+constexpr size_t kMaxInt = 24, kMaxFixed = 400;
+
+inline char *put_int(char *o, long long v) {
   char buf[24];
   char *p = buf + sizeof buf;
   const bool neg = v < 0;
   unsigned long long u = neg ? 0ull - (unsigned long long)v : (unsigned long long)v;
   do { *--p = (char)('0' + u % 10); u /= 10; } while (u);
   if (neg) *--p = '-';
-  out.append(p, (size_t)(buf + sizeof buf - p));
+  const size_t n = (size_t)(buf + sizeof buf - p);
+  memcpy(o, p, n);
+  return o + n;
+}
+
+struct U8Table {  // "0".."255"
+  char txt[256][4];
+  uint8_t len[256];
+  U8Table() {
+    for (int v = 0; v < 256; v++) len[v] = (uint8_t)snprintf(txt[v], 4, "%d", v);
+  }
+};
+const U8Table kU8;
+inline char *put_u8(char *o, unsigned v) {
+  memcpy(o, kU8.txt[v], 4);
+  return o + kU8.len[v];
+}
+
+char *put_fixed(char *o, double x, int decimals);
+
+}  // namespace
+
+void append_int(std::string &out, long long v) {
+  char buf[kMaxInt];
+  out.append(buf, (size_t)(put_int(buf, v) - buf));
 }
 
 void append_fixed(std::string &out, double x, int decimals) {
+  char buf[kMaxFixed];
+  out.append(buf, (size_t)(put_fixed(buf, x, decimals) - buf));
+}
+
+namespace {
+char *put_fixed(char *o, double x, int decimals) {
   static const double kPow[7] = {1, 10, 100, 1000, 10000, 100000, 1000000};
   static const unsigned long long kPowI[7] = {1, 10, 100, 1000, 10000, 100000, 1000000};
   const double s = std::fabs(x);
   if (decimals < 0 || decimals > 6 || !(s < 1e9)) {  // also NaN / inf
-    char buf[400];
-    int n = snprintf(buf, sizeof buf, "%.*f", decimals, x);
-    out.append(buf, (size_t)n);
-    return;
+    return o + snprintf(o, kMaxFixed, "%.*f", decimals, x);
   }
   // s * 10^d = p + e exactly (p the rounded product, e the fma residual); the digit string is the exact value
   // rounded to an integer, ties to even
@@ -41,16 +73,17 @@ void append_fixed(std::string &out, double x, int decimals) {
     up = c > 0.0 || (c == 0.0 && (n & 1ull));
   }
   n += up ? 1ull : 0ull;
-  if (std::signbit(x)) out.push_back('-');
-  append_int(out, (long long)(n / kPowI[decimals]));
+  if (std::signbit(x)) *o++ = '-';
+  o = put_int(o, (long long)(n / kPowI[decimals]));
   if (decimals > 0) {
-    char buf[8];
     unsigned long long r = n % kPowI[decimals];
-    for (int i = decimals - 1; i >= 0; i--) { buf[i] = (char)('0' + r % 10); r /= 10; }
-    out.push_back('.');
-    out.append(buf, (size_t)decimals);
+    *o++ = '.';
+    for (int i = decimals - 1; i >= 0; i--) { o[i] = (char)('0' + r % 10); r /= 10; }
+    o += decimals;
   }
+  return o;
 }
+}  // namespace
 
 static const char kBases[5] = {'0', 'A', 'C', 'G', 'T'};
 static const char *kGenoLabel[10] = {"A/A", "A/C", "A/G", "A/T", "C/C", "C/G", "C/T", "G/G", "G/T", "T/T"};
@@ -144,21 +177,34 @@ void VcfWriter::format_normal(std::string &out, const std::string &chrom, const 
   static const char *lab_hap[5] = {"0", "ERROR", "1", "ERROR2", "2"};
   const int g11 = genotype_index(a1, a1), g12 = genotype_index(a1, a2), g22 = genotype_index(a2, a2);
   const bool hap = hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT;
+  // sample columns through a raw cursor: at most kPerPerson bytes each unless the dosage needs the snprintf fallback
+  const size_t kPerPerson = 64;
+  const size_t base = out.size();
+  out.resize(base + (size_t)np * kPerPerson + kMaxFixed + 8);
+  char *o = &out[base];
+  const bool gl = !opt_.gl_off;
   for (int i = 0; i < np; i++) {
+    if ((size_t)(o - &out[base]) + kPerPerson + kMaxFixed > out.size() - base) {  // a fallback-sized dosage ate the slack
+      const size_t used = (size_t)(o - &out[0]);
+      out.resize(out.size() + (size_t)(np - i) * kPerPerson + kMaxFixed);
+      o = &out[used];
+    }
     const int best = pr[i].best;
     const int label_idx = (ref == a1) ? best : best + 2;
-    out.push_back('\t');
-    out += hap ? lab_hap[label_idx] : lab[label_idx];
-    out.push_back(':'); append_int(out, (int)pr[i].gq);
-    out.push_back(':'); append_int(out, depth_of(persons[i]));
-    out.push_back(':'); append_fixed(out, pr[i].dosage, 2);
-    if (!opt_.gl_off) {
-      out.push_back(':'); append_int(out, persons[i].lk[g11]);
-      out.push_back(','); append_int(out, persons[i].lk[g12]);
-      out.push_back(','); append_int(out, persons[i].lk[g22]);
+    const char *l = hap ? lab_hap[label_idx] : lab[label_idx];
+    *o++ = '\t';
+    while (*l) *o++ = *l++;
+    *o++ = ':'; o = put_u8(o, (unsigned)pr[i].gq & 0xff);
+    *o++ = ':'; o = put_int(o, depth_of(persons[i]));
+    *o++ = ':'; o = put_fixed(o, pr[i].dosage, 2);
+    if (gl) {
+      *o++ = ':'; o = put_u8(o, persons[i].lk[g11]);
+      *o++ = ','; o = put_u8(o, persons[i].lk[g12]);
+      *o++ = ','; o = put_u8(o, persons[i].lk[g22]);
     }
   }
-  out.push_back('\n');
+  *o++ = '\n';
+  out.resize((size_t)(o - &out[0]));
 }
 
 void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const pm_site_hdr &hdr, const pm_site_result &r,
@@ -178,6 +224,10 @@ void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const 
   out += ";DQ="; append_fixed(out, r.denovo_lr, 3);
   out += opt_.gl_off ? "\tGT:GQ:DP" : "\tGT:GQ:DP:PL";
   static const char *lab[5] = {"0/0", "0/1", "1/1", "1/2", "2/2"};
+  const size_t base = out.size();
+  out.resize(base + (size_t)ped_.n_person() * 72 + 8);  // "\tA/A:255:16777215:" + ten u8 and nine commas < 72 bytes
+  char *o = &out[base];
+  const bool gl = !opt_.gl_off;
   int col = 0;
   for (const Family &f : ped_.families) {
     const bool letters = (int)f.path.size() != f.founders;  // nuclear / extended families print base letters
@@ -190,17 +240,19 @@ void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const 
         int idx = p.best == 0 ? genotype_index(a1, a1) : p.best == 1 ? genotype_index(a1, a2_label) : genotype_index(a2_label, a2_label);
         gt = kGenoLabel[idx];
       }
-      out.push_back('\t'); out += gt;
-      out.push_back(':'); append_int(out, (int)p.gq);
-      out.push_back(':'); append_int(out, depth_of(persons[col]));
-      if (!opt_.gl_off) {
-        out.push_back(':');
-        for (int g = 0; g < 9; g++) { append_int(out, persons[col].lk[g]); out.push_back(','); }
-        append_int(out, persons[col].lk[9]);
+      *o++ = '\t';
+      while (*gt) *o++ = *gt++;
+      *o++ = ':'; o = put_u8(o, (unsigned)p.gq & 0xff);
+      *o++ = ':'; o = put_int(o, depth_of(persons[col]));
+      if (gl) {
+        *o++ = ':';
+        for (int g = 0; g < 9; g++) { o = put_u8(o, persons[col].lk[g]); *o++ = ','; }
+        o = put_u8(o, persons[col].lk[9]);
       }
     }
   }
-  out.push_back('\n');
+  *o++ = '\n';
+  out.resize((size_t)(o - &out[0]));
 }
 
 }  // namespace pmh

@@ -27,6 +27,7 @@
 
 #include "glf.h"
 #include "glf_ingest.h"
+#include "params.h"
 #include "vcf_writer.h"
 #include "pedigree.h"
 
@@ -312,8 +313,50 @@ static int do_fmt_selftest(int argc, char **argv) {
   return bad || ibad ? 1 : 0;
 }
 
+// pm-tools fmt-bench -p PED -d DAT [--denovo] [--rows N]: VCF row formatting speed on made-up results
+static int do_fmt_bench(int argc, char **argv) {
+  std::string ped_path, dat_path;
+  long rows = 2000;
+  Options opt;
+  for (int i = 2; i < argc; i++) {
+    std::string k = argv[i];
+    if (k == "--denovo") opt.denovo = true;
+    else if (i + 1 < argc) {
+      if (k == "-p") ped_path = argv[++i];
+      else if (k == "-d") dat_path = argv[++i];
+      else if (k == "--rows") rows = atol(argv[++i]);
+    }
+  }
+  Pedigree ped;
+  try { ped.load(dat_path, ped_path); } catch (const std::exception &e) { fprintf(stderr, "%s\n", e.what()); return 1; }
+  const int np = ped.n_person();
+  VcfWriter w(nullptr, opt, ped);
+  std::vector<pm_person_site> ps((size_t)np);
+  std::vector<pm_person_result> pr((size_t)np);
+  unsigned long long st = 88172645463325252ull;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+  for (int i = 0; i < np; i++) {
+    for (int g = 0; g < 10; g++) ps[(size_t)i].lk[g] = (uint8_t)(rnd() % 256);
+    ps[(size_t)i].depth[0] = (uint8_t)(rnd() % 40);
+    pr[(size_t)i].best = (uint8_t)(rnd() % 3); pr[(size_t)i].gq = (uint8_t)(rnd() % 101); pr[(size_t)i].dosage = (double)(rnd() % 2001) / 1000.0;
+  }
+  pm_site_hdr h; memset(&h, 0, sizeof h); h.pos = 123456; h.ref_base = 1;
+  pm_site_result r; memset(&r, 0, sizeof r);
+  r.allele1 = 1; r.allele2 = 3; r.poly_qual = 57.3; r.num_samp = np; r.perc_samp = 0.98; r.total_depth = 45000; r.avg_map_qual = 59.2; r.freq = 0.9312; r.ab = 0.48;
+  std::string out;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  size_t bytes = 0;
+  for (long i = 0; i < rows; i++) { out.clear(); w.format_site(out, "1", h, r, ps.data(), pr.data()); bytes += out.size(); }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  const double sec = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  printf("{\"rows\": %ld, \"persons\": %d, \"rows_per_s\": %.0f, \"MB_per_s\": %.0f, \"bytes_per_row\": %zu}\n", rows, np, (double)rows / sec, (double)bytes / 1e6 / sec, bytes / (size_t)rows);
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 2) return usage();
+  if (!strcmp(argv[1], "fmt-bench")) return do_fmt_bench(argc, argv);
   if (!strcmp(argv[1], "fmt-selftest")) return do_fmt_selftest(argc, argv);
   if (!strcmp(argv[1], "ingest-bench")) return do_ingest_bench(argc, argv);
   if (!strcmp(argv[1], "pack")) return do_pack(argc, argv);

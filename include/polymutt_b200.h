@@ -103,8 +103,15 @@ typedef struct pm_site_hdr {
   uint32_t pos;        /* 0-based position (PedigreeGLF::currentPos); the VCF prints pos+1 */
   uint8_t  ref_base;   /* 0 = N/other (site is skipped, src/main.cpp:340), 1..4 = A C G T */
   uint8_t  chr_class;  /* PM_CHR_* */
-  uint16_t reserved;
+  uint16_t reserved;   /* GLF input: PM_HDR_* bits; VCF input: ALT allele | indel << 8 */
 } pm_site_hdr;
+
+/* GLF input on chrX / chrY / MT without --denovo: the reference's nuclear-family code reads a stale member (`sex`,
+ * src/NucFamGenotypeLikelihood.h:72) that the genotype-posterior loops of the PREVIOUS emitted site left behind
+ * (NucFam.cpp:600-610 vs 1211-1261).  From the second emitted site of a run on that is a constant of the pedigree
+ * (the sex of the last person of the last family), which is what the engine assumes.  For the one site whose
+ * posteriors are the first the process computes, set this bit and the engine uses the initial value 0 instead. */
+#define PM_HDR_FIRST_POSTPROB 0x1
 
 /* Per-(site, person) record, 16 bytes, site-major / person-interleaved:
  * record (s, i) lives at person_site + 16*(s*n_person + i).

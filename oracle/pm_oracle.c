@@ -262,6 +262,7 @@ typedef struct {
   double a, b, c, min, fa, fb, fc, fmin;
   int isMono, denovo_mono;
   double denovoLR, AB;
+  int sex; /* the member `sex` (NucFam.h:72): whatever the last CalcPostProb loop left behind; read by likelihoodONEKid */
   double varPostProb, polyQual;
   double varllk[8], varllk_noprior[8], varfreq[8];
   int totalDepth, numSampWithData;
@@ -281,6 +282,8 @@ struct pmo_ctx {
   double genoMut[10][10];
   double transmission[10][10][10], transmission_denovo[10][10][10], transmission_BA[3][3][3];
   double prior; /* polyPrior, autosome */
+  double prior_class[4]; /* GetPolyPrior per PM_CHR_* class (NucFam:231-304) */
+  int chrX, chrY, chrMT;  /* SetNonAutosomeFlags of the current site's chromosome (main:312-315) */
   /* current site */
   pm_site_hdr hdr;
   const pm_person_site *ps;
@@ -314,10 +317,25 @@ static void hw9(double *pp, double freq) { /* NucFam:323-331 == 372-380 == 410-4
   pp[7] = (1 - freq) * (1 - freq) * freq * (1 - freq) * 2;
   pp[8] = (1 - freq) * (1 - freq) * (1 - freq) * (1 - freq);
 }
-/* NucFam:318-368 (autosome) */
+/* NucFam:318-368 */
 static void SetParentPrior(const pmo_ctx *c, famlk_t *k, double freq) {
-  if (c->nFam > 1 || k->isMono) hw9(k->parentPrior, freq);
-  else SetParentPriorSingleTrio(k);
+  if (c->nFam > 1 || k->isMono) {
+    double *pp = k->parentPrior;
+    if (!c->chrX && !c->chrY && !c->chrMT) hw9(pp, freq);
+    if (c->chrX) {
+      pp[0] = pow(freq, 3); pp[1] = freq * freq * (1 - freq) * 2; pp[2] = freq * (1 - freq) * (1 - freq);
+      pp[3] = 0; pp[4] = 0; pp[5] = 0;
+      pp[6] = (1 - freq) * freq * freq; pp[7] = (1 - freq) * freq * (1 - freq) * 2; pp[8] = (1 - freq) * (1 - freq) * (1 - freq);
+    }
+    if (c->chrY) {
+      pp[0] = freq; pp[1] = freq; pp[2] = freq; pp[3] = 0; pp[4] = 0; pp[5] = 0;
+      pp[6] = (1 - freq); pp[7] = (1 - freq); pp[8] = (1 - freq);
+    }
+    if (c->chrMT) {
+      pp[0] = freq * freq; pp[1] = 0.0; pp[2] = freq * (1 - freq); pp[3] = 0; pp[4] = 0; pp[5] = 0;
+      pp[6] = (1 - freq) * freq; pp[7] = 0; pp[8] = (1 - freq) * (1 - freq);
+    }
+  } else SetParentPriorSingleTrio(k);
 }
 /* NucFam:396-420 */
 static void SetParentPriorSingleTrio_denovo(famlk_t *k, double freq) {
@@ -331,10 +349,23 @@ static void getGenoLikelihood(const pmo_ctx *c, const famlk_t *k, int person, do
   *lk11 = p[k->geno11]; *lk12 = p[k->geno12]; *lk22 = p[k->geno22];
 }
 
-/* NucFam:1202-1264 (autosome) ; cfg = 3*gF + gM */
+/* NucFam:1202-1264 ; cfg = 3*gF + gM.  On X/Y/MT the kid's sex is NOT the kid's: the function reads the member
+ * `sex` (k->sex), i.e. the last person a CalcPostProb loop of this object visited (0 for famlk[1..6]). */
 static double likelihoodONEKid(const pmo_ctx *c, const famlk_t *k, int person, int cfg) {
   double lk = 1.0, lk11, lk12, lk22;
   getGenoLikelihood(c, k, person, &lk11, &lk12, &lk22);
+  if (c->chrX || c->chrY || c->chrMT) {
+    const int male = k->sex == 1, female = k->sex == 2;
+    switch (cfg) {
+      case 0: return (c->chrY && female) ? 1.0 : lk11;
+      case 1: return c->chrX ? (male ? 0.5 * (lk11 + lk22) : 0.5 * (lk11 + lk12)) : c->chrY ? (male ? lk11 : 1.0) : 0.5 * (lk11 + lk22);
+      case 2: return c->chrX ? (male ? lk22 : lk12) : c->chrY ? (male ? lk11 : 1.0) : lk22;
+      case 3: case 4: case 5: return 0.0;
+      case 6: return c->chrX ? (male ? lk11 : lk12) : c->chrY ? (male ? lk22 : 1.0) : lk11;
+      case 7: return c->chrX ? (male ? 0.5 * (lk11 + lk22) : 0.5 * (lk12 + lk22)) : c->chrY ? (male ? lk22 : 1.0) : 0.5 * (lk11 + lk22);
+      default: return (c->chrY && female) ? 1.0 : lk22;
+    }
+  }
   switch (cfg) {
     case 0: lk = lk11; break;
     case 1: lk = 0.5 * (lk11 + lk12); break;
@@ -387,11 +418,17 @@ static double likelihoodKids_denovo(const pmo_ctx *c, const famlk_t *k, int cfg,
   return lkKids;
 }
 
-static void fill_parentGLF(const pmo_ctx *c, famlk_t *k, int i) { /* NucFam:1046-1061 */
+/* NucFam:1046-1061; non_auto: the X/Y/MT lines 1049-1051, which only CalcParentMarginal has (not _denovo) */
+static void fill_parentGLF(const pmo_ctx *c, famlk_t *k, int i, int non_auto) {
   double lkF11, lkF12, lkF22, lkM11, lkM12, lkM22;
   int first = c->famFirst[i];
   getGenoLikelihood(c, k, first, &lkF11, &lkF12, &lkF22);
   getGenoLikelihood(c, k, first + 1, &lkM11, &lkM12, &lkM22);
+  if (non_auto) {
+    if (c->chrX) lkF12 = 0.0;
+    if (c->chrY) { lkM11 = lkM12 = lkM22 = 1.0; lkF12 = 0.0; }
+    if (c->chrMT) lkF12 = lkM12 = 0.0;
+  }
   double *g = k->parentGLF[i];
   g[0] = lkF11 * lkM11; g[1] = lkF11 * lkM12; g[2] = lkF11 * lkM22;
   g[3] = lkF12 * lkM11; g[4] = lkF12 * lkM12; g[5] = lkF12 * lkM22;
@@ -399,7 +436,7 @@ static void fill_parentGLF(const pmo_ctx *c, famlk_t *k, int i) { /* NucFam:1046
 }
 /* NucFam:1041-1084 */
 static void CalcParentMarginal(const pmo_ctx *c, famlk_t *k, int i, double freq) {
-  fill_parentGLF(c, k, i);
+  fill_parentGLF(c, k, i, 1);
   if (c->nFam > 1 || k->isMono) SetParentPrior(c, k, freq);
   else SetParentPriorSingleTrio(k);
   for (int j = 0; j < 9; j++) k->parentConditional[i][j] = likelihoodKids(c, k, j, i) * k->parentGLF[i][j];
@@ -407,7 +444,7 @@ static void CalcParentMarginal(const pmo_ctx *c, famlk_t *k, int i, double freq)
 }
 /* NucFam:1086-1132 */
 static void CalcParentMarginal_denovo(const pmo_ctx *c, famlk_t *k, int i, double freq) {
-  fill_parentGLF(c, k, i);
+  fill_parentGLF(c, k, i, 0);
   if (c->nFam > 1) hw9(k->parentPrior, freq); /* SetParentPrior_denovo */
   else SetParentPriorSingleTrio_denovo(k, freq);
   for (int j = 0; j < 9; j++) k->parentConditional[i][j] = likelihoodKids_denovo(c, k, j, i) * k->parentGLF[i][j];
@@ -421,6 +458,10 @@ static double lkSinglePerson(const pmo_ctx *c, const famlk_t *k, int person, dou
   priors[0] = freq * freq;
   priors[1] = freq * (1 - freq) * 2;
   priors[2] = (1 - freq) * (1 - freq);
+  const int male = c->sex[person] == 1;
+  if (c->chrX) { if (male) { lk12 = 0; priors[0] = freq; priors[1] = 0; priors[2] = 1 - freq; } }
+  if (c->chrY) { if (male) { lk12 = 0; priors[0] = freq; priors[1] = 0; priors[2] = 1 - freq; } else return 1.0; }
+  if (c->chrMT) { lk12 = 0; priors[0] = freq; priors[1] = 0; priors[2] = 1 - freq; }
   sum = sum + lk11 * priors[0] + lk12 * priors[1] + lk22 * priors[2];
   return sum;
 }
@@ -442,20 +483,27 @@ static double lkSingleFam(const pmo_ctx *c, famlk_t *k, int i, double freq, int 
 static void es_SetAlleles(esfam_t *e, int a1, int a2) { /* ES:629-635 */
   e->genoIdx[0] = GenotypeIndex(a1, a1); e->genoIdx[1] = GenotypeIndex(a1, a2); e->genoIdx[2] = GenotypeIndex(a2, a2);
 }
-static void es_SetFounderPriors(esfam_t *e, double freq) { /* ES:643-664, autosome */
+/* the X/Y/MT founder priors of ES:655-662 == 678-685 on the three slots g0, g1, g2 */
+static void es_founder_prior3(const pmo_ctx *c, int male, double freq, double *p0, double *p1, double *p2) {
+  *p0 = freq * freq; *p1 = 2 * freq * (1 - freq); *p2 = (1 - freq) * (1 - freq);
+  if (c->chrX) if (male) { *p0 = freq; *p1 = 0; *p2 = 1 - freq; }
+  if (c->chrY) { if (male) { *p0 = freq; *p1 = 0; *p2 = 1 - freq; } else { *p0 = 1; *p1 = 1; *p2 = 1; } }
+  if (c->chrMT) { *p0 = freq; *p1 = 0; *p2 = 1 - freq; }
+}
+static void es_SetFounderPriors(const pmo_ctx *c, esfam_t *e, double freq) { /* ES:643-664 */
   for (int i = 0; i < e->nFounders; i++) {
+    double p0, p1, p2;
+    es_founder_prior3(c, c->sex[e->first + i] == 1, freq, &p0, &p1, &p2);
     for (int j = 0; j < 10; j++) e->priors[i][j] = 0.0;
-    e->priors[i][e->genoIdx[0]] = freq * freq;
-    e->priors[i][e->genoIdx[1]] = 2 * freq * (1 - freq);
-    e->priors[i][e->genoIdx[2]] = (1 - freq) * (1 - freq);
+    e->priors[i][e->genoIdx[0]] = p0;
+    e->priors[i][e->genoIdx[1]] = p1;
+    e->priors[i][e->genoIdx[2]] = p2;
   }
 }
-static void es_SetFounderPriors_BA(esfam_t *e, double freq) { /* ES:666-687 */
+static void es_SetFounderPriors_BA(const pmo_ctx *c, esfam_t *e, double freq) { /* ES:666-687 */
   for (int i = 0; i < e->nFounders; i++) {
     for (int j = 0; j < 10; j++) e->priors[i][j] = 0.0;
-    e->priors[i][0] = freq * freq;
-    e->priors[i][1] = 2 * freq * (1 - freq);
-    e->priors[i][2] = (1 - freq) * (1 - freq);
+    es_founder_prior3(c, c->sex[e->first + i] == 1, freq, &e->priors[i][0], &e->priors[i][1], &e->priors[i][2]);
   }
 }
 static void es_InitializePartials(const pmo_ctx *c, esfam_t *e) { /* ES:1434-1446 */
@@ -468,9 +516,10 @@ static void es_InitializePartials(const pmo_ctx *c, esfam_t *e) { /* ES:1434-144
 static void es_InitializePartials_BA(const pmo_ctx *c, esfam_t *e) { /* ES:1449-1465 */
   for (int i = 0; i < e->famSize; i++) {
     const double *pen = c->pen[e->first + i];
+    const int yfemale = c->chrY && c->sex[e->first + i] == 2;
     for (int j = 0; j < 10; j++) e->partials[i][j] = 0.0;
-    if (i < e->nFounders) for (int j = 0; j < 3; j++) e->partials[i][j] = e->priors[i][j] * pen[e->genoIdx[j]];
-    else for (int j = 0; j < 3; j++) e->partials[i][j] = pen[e->genoIdx[j]];
+    if (i < e->nFounders) for (int j = 0; j < 3; j++) e->partials[i][j] = yfemale ? 1.0 : e->priors[i][j] * pen[e->genoIdx[j]];
+    else for (int j = 0; j < 3; j++) e->partials[i][j] = yfemale ? 1.0 : pen[e->genoIdx[j]];
   }
 }
 static mp_t *mp_find(esfam_t *e, int k0, int k1) {
@@ -483,6 +532,19 @@ static mp_t *mp_create(esfam_t *e, int k0, int k1) { /* SetMarriagePartials, ES:
   for (int i = 0; i < 10; i++) for (int j = 0; j < 10; j++) m->m[i][j] = 1.0;
   return m;
 }
+/* GetTransmissionProb_BA, ES:1059-1075, tables ES:834-924 */
+static double transmission_BA_of(const pmo_ctx *c, const esfam_t *e, int i, int j, int k, int idx) {
+  static const double x2f[27] = {1, 0, 0, .5, .5, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, .5, .5, 0, 0, 1};
+  static const double x2m[27] = {1, 0, 0, .5, 0, .5, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, .5, 0, .5, 0, 0, 1};
+  static const double chy[27] = {1, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1};
+  static const double mito[27] = {1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1};
+  double transmit = c->transmission_BA[i][j][k];
+  const int male = c->sex[e->first + idx] == 1;
+  if (c->chrX) transmit = male ? x2m[9 * i + 3 * j + k] : x2f[9 * i + 3 * j + k];
+  if (c->chrY) transmit = male ? chy[9 * i + 3 * j + k] : 1.0;
+  if (c->chrMT) transmit = mito[9 * i + 3 * j + k];
+  return transmit;
+}
 /* A = 3 uses transmission_BA, A = 10 uses T (= transmission or transmission_denovo) */
 static void peelOffspring2Parents(const pmo_ctx *c, esfam_t *e, const pm_peel_step *s, int A, int denovo) { /* ES:1078-1127, 1287-1311 */
   int offspring = s->from0;
@@ -492,7 +554,7 @@ static void peelOffspring2Parents(const pmo_ctx *c, esfam_t *e, const pm_peel_st
     for (int j = 0; j < A; j++) {
       double partial_lk_sum = 0;
       for (int k = 0; k < A; k++) {
-        double t = A == 3 ? c->transmission_BA[i][j][k] : (denovo ? c->transmission_denovo[i][j][k] : c->transmission[i][j][k]);
+        double t = A == 3 ? transmission_BA_of(c, e, i, j, k, offspring) : (denovo ? c->transmission_denovo[i][j][k] : c->transmission[i][j][k]);
         partial_lk_sum += t * e->partials[offspring][k];
       }
       m->m[i][j] *= partial_lk_sum;
@@ -520,14 +582,14 @@ static void peelParents2Offspring(const pmo_ctx *c, esfam_t *e, const pm_peel_st
     if (!m) {
       for (int i = 0; i < A; i++)
         for (int j = 0; j < A; j++) {
-          double t = A == 3 ? c->transmission_BA[i][j][k] : (denovo ? c->transmission_denovo[i][j][k] : c->transmission[i][j][k]);
+          double t = A == 3 ? transmission_BA_of(c, e, i, j, k, offspring) : (denovo ? c->transmission_denovo[i][j][k] : c->transmission[i][j][k]);
           partial_lk_sum += e->partials[fa][i] * e->partials[mo][j] * t;
         }
     } else {
       for (int i = 0; i < A; i++)
         for (int j = 0; j < A; j++) {
           /* de novo with a marriage partial uses the mutation-free tensor (ES:1391) */
-          double t = A == 3 ? c->transmission_BA[i][j][k] : c->transmission[i][j][k];
+          double t = A == 3 ? transmission_BA_of(c, e, i, j, k, offspring) : c->transmission[i][j][k];
           partial_lk_sum += e->partials[fa][i] * m->m[i][j] * e->partials[mo][j] * t;
         }
     }
@@ -551,14 +613,14 @@ static double es_CalculateLikelihood(const pmo_ctx *c, esfam_t *e, int A, int de
 static double CalcSingleFamLikelihood_BA(const pmo_ctx *c, famlk_t *k, int i, double freq) {
   esfam_t *e = &k->fam[i];
   es_SetAlleles(e, k->allele1, k->allele2);
-  es_SetFounderPriors_BA(e, freq);
+  es_SetFounderPriors_BA(c, e, freq);
   es_InitializePartials_BA(c, e);
   return es_CalculateLikelihood(c, e, 3, 0);
 }
 static double CalcSingleFamLikelihood_denovo(const pmo_ctx *c, famlk_t *k, int i, double freq) {
   esfam_t *e = &k->fam[i];
   es_SetAlleles(e, k->allele1, k->allele2);
-  es_SetFounderPriors(e, freq);
+  es_SetFounderPriors(c, e, freq);
   es_InitializePartials(c, e);
   return es_CalculateLikelihood(c, e, 10, 1);
 }
@@ -749,17 +811,47 @@ static void CalcPostProb_SinglePerson(const pmo_ctx *c, famlk_t *k, int person, 
   double lk11, lk12, lk22, priors[3];
   priors[0] = freq * freq; priors[1] = freq * (1 - freq) * 2; priors[2] = (1 - freq) * (1 - freq);
   getGenoLikelihood(c, k, person, &lk11, &lk12, &lk22);
+  const int male = c->sex[person] == 1, female = c->sex[person] == 2;
+  if (c->chrX && male) { priors[0] = freq; priors[1] = 0.; priors[2] = 1 - freq; }
+  if (c->chrY) { if (male) { priors[0] = freq; priors[1] = 0.; priors[2] = 1 - freq; } else { priors[0] = priors[1] = priors[2] = 1.0; } }
+  if (c->chrMT) { priors[0] = freq; priors[1] = 0; priors[2] = 1 - freq; }
   double mlk11 = lk11 * priors[0], mlk12 = lk12 * priors[1], mlk22 = lk22 * priors[2];
   double sum = mlk11 + mlk12 + mlk22;
   double *pp = k->postProb[person];
   if (sum == 0) pp[0] = pp[1] = pp[2] = 1 / 3; /* integer division: 0 (NucFam:781) */
   else { pp[0] = mlk11 / sum; pp[1] = mlk12 / sum; pp[2] = mlk22 / sum; }
+  if (c->chrY && female) pp[0] = pp[1] = pp[2] = 0.0; /* NucFam:788 */
   k->bestGenoIdx[person] = GetBestGenoIdx(mlk11, mlk12, mlk22);
   k->dosage[person] = pp[1] + pp[2] * 2;
   k->tenState[person] = 0;
 }
-/* kid config table of NucFam:1334-1443 (autosome): lk and (lkg11, lkg12, lkg22) */
-static void kid_cfg(int cfg, double lk11, double lk12, double lk22, double *lk, double *g11, double *g12, double *g22) {
+/* kid config table of NucFam:1334-1443: lk and (lkg11, lkg12, lkg22); `sex` is the kid's own here (NucFam:1349).
+ * The all-11 branch has no X/Y/MT case, and the all-22 branch's if/if/if-else chain ends in the autosomal values
+ * for everything (MT sets the same ones). */
+static void kid_cfg(const pmo_ctx *c, int sex, int cfg, double lk11, double lk12, double lk22, double *lk, double *g11, double *g12, double *g22) {
+  if ((c->chrX || c->chrY || c->chrMT) && cfg != 0 && cfg != 8) {
+    const int male = sex == 1;
+    *g11 = *g12 = *g22 = 0.0;
+    if (cfg == 3 || cfg == 4 || cfg == 5) { *lk = 0.0; return; }
+    if (c->chrX) {
+      switch (cfg) {
+        case 1: if (male) { *lk = 0.5 * (lk11 + lk22); *g11 = 0.5 * lk11; *g22 = 0.5 * lk22; } else { *lk = 0.5 * (lk11 + lk12); *g11 = 0.5 * lk11; *g12 = 0.5 * lk12; } break;
+        case 2: if (male) { *lk = lk22; *g22 = lk22; } else { *lk = lk12; *g12 = lk12; } break;
+        case 6: if (male) { *lk = lk11; *g11 = lk11; } else { *lk = lk12; *g12 = lk12; } break;
+        default: if (male) { *lk = 0.5 * (lk11 + lk22); *g11 = 0.5 * lk11; *g22 = 0.5 * lk22; } else { *lk = 0.5 * (lk12 + lk22); *g12 = 0.5 * lk12; *g22 = 0.5 * lk22; } break;
+      }
+    } else if (c->chrY) {
+      if (!male) { *lk = 1.0; return; }
+      if (cfg == 1 || cfg == 2) { *lk = lk11; *g11 = lk11; } else { *lk = lk22; *g22 = lk22; }
+    } else {
+      switch (cfg) {
+        case 1: case 7: *lk = 0.5 * (lk11 + lk22); *g11 = 0.5 * lk11; *g22 = 0.5 * lk22; break;
+        case 2: *lk = lk22; *g22 = lk22; break;
+        default: *lk = lk11; *g11 = lk11; break; /* cfg 6 */
+      }
+    }
+    return;
+  }
   switch (cfg) {
     case 0: *lk = lk11; *g11 = lk11; *g12 = *g22 = 0; break;
     case 1: case 3: *lk = 0.5 * (lk11 + lk12); *g11 = lk11 * 0.5; *g12 = lk12 * 0.5; *g22 = 0; break;
@@ -773,15 +865,16 @@ static void kid_cfg(int cfg, double lk11, double lk12, double lk22, double *lk, 
 static void CalcPostProb_SingleNucFam(const pmo_ctx *c, famlk_t *k, int i, double freq) {
   int first = c->famFirst[i], famSize = c->famSize[i];
   if (famSize <= c->famFounders[i]) {
-    for (int j = 0; j < c->famFounders[i]; j++) CalcPostProb_SinglePerson(c, k, first + j, freq);
+    for (int j = 0; j < c->famFounders[i]; j++) { k->sex = c->sex[first + j]; CalcPostProb_SinglePerson(c, k, first + j, freq); }
     return;
   }
-  CalcParentMarginal(c, k, i, freq);
+  CalcParentMarginal(c, k, i, freq); /* on X/Y/MT: with the `sex` the previous family's loop left (NucFam:606 vs 610) */
   const double *pm = k->parentMarginal[i];
   for (int j = 0; j < famSize; j++) {
     double p11, p12, p22, sum;
     double *pp = k->postProb[first + j];
     k->tenState[first + j] = 0;
+    k->sex = c->sex[first + j];
     if (j == 0 || j == 1) {
       if (j == 0) { p11 = pm[0] + pm[1] + pm[2]; p12 = pm[3] + pm[4] + pm[5]; p22 = pm[6] + pm[7] + pm[8]; }
       else { p11 = pm[0] + pm[3] + pm[6]; p12 = pm[1] + pm[4] + pm[7]; p22 = pm[2] + pm[5] + pm[8]; }
@@ -797,7 +890,7 @@ static void CalcPostProb_SingleNucFam(const pmo_ctx *c, famlk_t *k, int i, doubl
         for (int kk = 2; kk < famSize; kk++) {
           double lk11, lk12, lk22, lk, g11, g12, g22;
           getGenoLikelihood(c, k, first + kk, &lk11, &lk12, &lk22);
-          kid_cfg(cfg, lk11, lk12, lk22, &lk, &g11, &g12, &g22);
+          kid_cfg(c, c->sex[first + kk], cfg, lk11, lk12, lk22, &lk, &g11, &g12, &g22);
           if (kk != j) { G11 *= lk; G12 *= lk; G22 *= lk; }
           else { G11 *= g11; G12 *= g12; G22 *= g22; }
         }
@@ -899,6 +992,12 @@ static void CalcPostProb_SingleExtendedPed_BA(pmo_ctx *c, famlk_t *k, int i, dou
   int first = c->famFirst[i];
   for (int j = 0; j < c->famSize[i]; j++) {
     double lk11, lk12, lk22, sum;
+    k->sex = c->sex[first + j];
+    if (c->chrY && c->sex[first + j] == 2) { /* FLSeq:181-188 */
+      double *pp = k->postProb[first + j];
+      k->bestGenoIdx[first + j] = 0; pp[0] = pp[1] = pp[2] = 0.0; k->dosage[first + j] = 0; k->tenState[first + j] = 0;
+      continue;
+    }
     FillZeroPenetrance(c, i, j, GenotypeIndex(k->allele1, k->allele1));
     lk11 = CalcSingleFamLikelihood_BA(c, k, i, freq);
     FillZeroPenetrance(c, i, j, GenotypeIndex(k->allele1, k->allele2));
@@ -1027,6 +1126,17 @@ pmo_ctx *pmo_create(const pm_pedigree *ped, const pm_params *par, const double *
   c->prior = 0;
   for (int i = 1; i <= 2 * c->nFounders; i++) c->prior += 1.0 / i;
   c->prior *= par->theta;
+  { /* SetPolyPrior_chrX / _chrY / _MT, NucFam:256-293: founder chromosomes by sex */
+    int maleFounders = 0, femaleFounders = 0;
+    for (int i = 0; i < c->nPerson; i++)
+      if (c->father[i] < 0 && c->mother[i] < 0) { if (c->sex[i] == 1) maleFounders++; if (c->sex[i] == 2) femaleFounders++; }
+    const int n_chr[4] = {2 * c->nFounders, femaleFounders * 2 + maleFounders, maleFounders, c->nFounders};
+    for (int cl = 0; cl < 4; cl++) {
+      double pr = 0;
+      for (int i = 1; i <= n_chr[cl]; i++) pr += 1.0 / i;
+      c->prior_class[cl] = pr * par->theta;
+    }
+  }
   c->lk = calloc((size_t)c->nPerson, sizeof *c->lk);
   c->pen = calloc((size_t)c->nPerson, sizeof *c->pen);
   for (int r = 0; r < 7; r++) {
@@ -1071,6 +1181,7 @@ void pmo_destroy(pmo_ctx *c) {
 
 int pmo_load_site(pmo_ctx *c, const pm_site_hdr *hdr, const pm_person_site *persons) {
   c->hdr = *hdr; c->ps = persons;
+  c->chrX = hdr->chr_class == PM_CHR_X; c->chrY = hdr->chr_class == PM_CHR_Y; c->chrMT = hdr->chr_class == PM_CHR_MT;
   for (int i = 0; i < c->nPerson; i++)
     for (int j = 0; j < 10; j++) c->lk[i][j] = c->lut[persons[i].lk[j]]; /* glfHandler.cpp:230-231 */
   FillPenetrance(c);
@@ -1131,8 +1242,14 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
   r->site = site; r->maxidx = -1;
   int refBase = c->hdr.ref_base;
   if (refBase != 1 && refBase != 2 && refBase != 3 && refBase != 4) { r->status = PM_SITE_BAD_REF; return 0; }
-  if (c->hdr.chr_class != PM_CHR_AUTO) { set_err("oracle: non-autosomal sites are not restated"); return PM_EUNSUPPORTED; }
-  double polyPrior = c->prior;
+  if (c->hdr.chr_class > PM_CHR_MT) { set_err("oracle: bad chr_class %d", c->hdr.chr_class); return PM_EINVAL; }
+  double polyPrior = c->prior_class[c->hdr.chr_class];
+  /* The member `sex` of the seven objects (quirk 6 of SURVEY 8a).  famlk[1..6] never run CalcPostProb: 0.  famlk[0]:
+     without --denovo every CalcPostProb leaves the sex of the last person of the last family, so that is what the next
+     emitted site's first family sees -- except in the very first CalcPostProb of the process (hdr.reserved bit 0, set
+     by the caller for that one site).  With --denovo no loop ever assigns it. */
+  for (int r7 = 1; r7 < 7; r7++) fl[r7].sex = 0;
+  fl[0].sex = (par->denovo || (c->hdr.reserved & PM_HDR_FIRST_POSTPROB)) ? 0 : c->sex[c->nPerson - 1];
   double prior_ts = par->poly_tstv / (par->poly_tstv + 1); /* main:192-193 */
   double prior_tv = (1 - prior_ts) / 2;
 
@@ -1235,9 +1352,10 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
     CalcPostProb(c, &fl[0], fl[0].min);
   }
   /* what the writer computes before printing: NucFam:1791 (AB) */
-  if (!par->denovo) CalculateAB(c, &fl[0], fl[0].min);
+  if (!par->denovo && c->hdr.chr_class == PM_CHR_AUTO) CalculateAB(c, &fl[0], fl[0].min); /* NucFam:1791 */
   fl[0].denovo_mono = 0;
   fill_result(c, &fl[0], r);
+  if (c->hdr.chr_class != PM_CHR_AUTO) r->ab = 0.0; /* AB keeps an older site's value there and is not printed */
   r->status = PM_SITE_EMITTED;
   for (int i = 0; i < c->nPerson; i++) {
     pm_person_result *p = &pr[i];

@@ -214,6 +214,9 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   time(&t0);
   printf("Analysis started on %s\n", ctime(&t0));
   size_t out_cnt = 0;
+  bool postprob_ran = false;  // has any row's genotype posteriors been computed yet in this run (see consume())
+  pm_site_result first_res;
+  std::vector<pm_person_result> first_pres((size_t)np);
   int processed_chrs = 0;
   bool stop = false;
   std::string engine_error;
@@ -238,6 +241,34 @@ int run_cli(int argc, char **argv, const Engine &engine) {
         t_wait += now() - tw0;
         if (rc != PM_OK) { engine_error = sl.err; return false; }
         if (stop) return true;  // --pos already satisfied: drain without printing
+        if (!postprob_ran && !sl.row_end.empty()) {
+          // The first genotype posteriors of the run.  On chrX / chrY / MT without --denovo the reference's nuclear
+          // code sees its initial `sex` member there (PM_HDR_FIRST_POSTPROB in the header): that one site again.
+          postprob_ran = true;
+          if (!opt.denovo && chr_class != PM_CHR_AUTO) {
+            const size_t s0 = sl.res[0].site;
+            pm_site_hdr h1 = sl.hdr[s0];
+            h1.reserved |= PM_HDR_FIRST_POSTPROB;
+            uint16_t st1 = 0;
+            size_t n1 = 0;
+            int rc1;
+            {
+              std::lock_guard<std::mutex> guard(ctx_lock[0]);
+              rc1 = engine.call_glf(ctxs[0], &h1, &sl.ps[s0 * (size_t)np], 1, &st1, &first_res, first_pres.data(), 1, &n1);
+              if (rc1 != PM_OK) engine_error = engine.last_error();
+            }
+            if (rc1 != PM_OK) return false;
+            if (n1 != 1 || (st1 & 0xf) != PM_SITE_EMITTED) throw std::runtime_error("first-row recomputation did not emit the site");
+            first_res.site = (uint32_t)s0;
+            sl.res[0] = first_res;
+            memcpy(sl.pres, first_pres.data(), sizeof(pm_person_result) * (size_t)np);
+            std::string row;
+            writer.format_site(row, label, sl.hdr[s0], sl.res[0], &sl.ps[s0 * (size_t)np], sl.pres);
+            const size_t old = sl.row_end[0];
+            sl.text.replace(0, old, row);
+            for (size_t &e : sl.row_end) e = e - old + row.size();
+          }
+        }
         for (size_t s = 0; s < sl.n; s++) count_site(cnt, sl.hdr[s], sl.status[s], opt);
         // rows and dropped de novo candidates in site order: the first of either prints the header
         size_t next_row = 0;

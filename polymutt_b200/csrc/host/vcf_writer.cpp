@@ -176,7 +176,11 @@ void VcfWriter::format_normal(std::string &out, const std::string &chrom, const 
   static const char *lab[5] = {"0/0", "0/1", "1/1", "1/2", "2/2"};
   static const char *lab_hap[5] = {"0", "ERROR", "1", "ERROR2", "2"};
   const int g11 = genotype_index(a1, a1), g12 = genotype_index(a1, a2), g22 = genotype_index(a2, a2);
-  const bool hap = hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT;
+  // GetBestGenoLabel_vcfv4 (NucFam.cpp:1587-1608): haploid labels on Y / MT and for males on X; "." for females on Y
+  // (NucFam.cpp:626, 644, 663, 792; FLSeq.cpp:181-188)
+  const bool hap_all = hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT;
+  const bool chr_x = hdr.chr_class == PM_CHR_X, chr_y = hdr.chr_class == PM_CHR_Y;
+  const std::vector<int> &cols = ped_.columns();
   // sample columns through a raw cursor: at most kPerPerson bytes each unless the dosage needs the snprintf fallback
   const size_t kPerPerson = 64;
   const size_t base = out.size();
@@ -191,7 +195,8 @@ void VcfWriter::format_normal(std::string &out, const std::string &chrom, const 
     }
     const int best = pr[i].best;
     const int label_idx = (ref == a1) ? best : best + 2;
-    const char *l = hap ? lab_hap[label_idx] : lab[label_idx];
+    const int sex = (chr_x || chr_y) ? ped_.persons[cols[(size_t)i]].sex : 0;
+    const char *l = (chr_y && sex == 2) ? "." : (hap_all || (chr_x && sex == 1)) ? lab_hap[label_idx] : lab[label_idx];
     *o++ = '\t';
     while (*l) *o++ = *l++;
     *o++ = ':'; o = put_u8(o, (unsigned)pr[i].gq & 0xff);
@@ -224,6 +229,7 @@ void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const 
   out += ";DQ="; append_fixed(out, r.denovo_lr, 3);
   out += opt_.gl_off ? "\tGT:GQ:DP" : "\tGT:GQ:DP:PL";
   static const char *lab[5] = {"0/0", "0/1", "1/1", "1/2", "2/2"};
+  static const char *lab_hap[5] = {"0", "ERROR", "1", "ERROR2", "2"};
   const size_t base = out.size();
   out.resize(base + (size_t)ped_.n_person() * 72 + 8);  // "\tA/A:255:16777215:" + ten u8 and nine commas < 72 bytes
   char *o = &out[base];
@@ -234,7 +240,12 @@ void VcfWriter::format_denovo(std::string &out, const std::string &chrom, const 
     for (size_t j = 0; j < f.path.size(); j++, col++) {
       const pm_person_result &p = pr[col];
       const char *gt;
-      if (!letters) gt = lab[(ref == a1) ? p.best : p.best + 2];  // CalcPostProb_SinglePerson -> vcfv4 label
+      // CalcPostProb_SinglePerson -> vcfv4 label; the member `sex` it consults on X is never set under --denovo
+      if (!letters) {
+        const int li = (ref == a1) ? p.best : p.best + 2;
+        const bool yfemale = hdr.chr_class == PM_CHR_Y && ped_.persons[f.path[j]].sex == 2;
+        gt = yfemale ? "." : (hdr.chr_class == PM_CHR_Y || hdr.chr_class == PM_CHR_MT) ? lab_hap[li] : lab[li];
+      }
       else if (p.ten_state) gt = kGenoLabel[p.best];
       else {
         int idx = p.best == 0 ? genotype_index(a1, a1) : p.best == 1 ? genotype_index(a1, a2_label) : genotype_index(a2_label, a2_label);

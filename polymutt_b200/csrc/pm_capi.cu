@@ -35,6 +35,7 @@ struct pm_ctx {
   pm::DevRun *d_run = nullptr;
   pm::DevFam *d_fams = nullptr;
   pm::DevUnit *d_units = nullptr;
+  uint8_t *d_sex = nullptr;
   int32_t *d_es = nullptr;
   pm::DevStep *d_steps = nullptr;
   int *d_err = nullptr;
@@ -137,7 +138,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     const bool nuclear = ped->fam_generations[f] == 2 && nf == 2 && !(par->vcf_input && ped->n_fam == 1);
     if (size == nf) {
       d.kind = 0;
-      for (int j = 0; j < size; j++) units.push_back({first + j, -1, kids_total, 0});
+      for (int j = 0; j < size; j++) units.push_back({first + j, -1, kids_total, (int32_t)ped->sex[first + j]});
     } else if (nuclear) {
       d.kind = 1;
       units.push_back({first, size - 2, kids_total, 0});
@@ -204,6 +205,23 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   run.log_prior_other = log10(prior * 0.001);
   run.log_prior_23 = log10(prior * 2. / 3.);
   run.log_prior_16 = log10(prior * 1. / 6.);
+  {  // SetPolyPrior_chrX / _chrY / _MT (NucFam:256-293): founder chromosomes by sex
+    int male_founders = 0, female_founders = 0;
+    for (int i = 0; i < ped->n_person; i++)
+      if (ped->father[i] < 0 && ped->mother[i] < 0) { male_founders += ped->sex[i] == 1; female_founders += ped->sex[i] == 2; }
+    const int n_chr[4] = {2 * founders_total, 2 * female_founders + male_founders, male_founders, founders_total};
+    for (int cl = 0; cl < 4; cl++) {
+      double pr = 0;
+      for (int i = 1; i <= n_chr[cl]; i++) pr += 1.0 / i;
+      pr *= par->theta;
+      run.cls_log[cl][0] = log10(1 - pr);
+      run.cls_log[cl][1] = log10(pr * prior_ts);
+      run.cls_log[cl][2] = log10(pr * prior_tv);
+      run.cls_log[cl][3] = log10(pr * 0.001);
+      run.cls_log[cl][4] = log10(pr * 2. / 3.);
+      run.cls_log[cl][5] = log10(pr * 1. / 6.);
+    }
+  }
   run.log_min_llr = log10(par->denovo_min_llr);
   run.theta = par->theta; run.posterior_cutoff = par->posterior_cutoff; run.precision = par->precision;
   run.denovo_min_llr = par->denovo_min_llr; run.min_ps = par->min_ps;
@@ -235,17 +253,19 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
             cudaEventCreate(&c->ev0) == cudaSuccess && cudaEventCreate(&c->ev1) == cudaSuccess && cudaEventCreate(&c->ev2) == cudaSuccess;
   ok = ok && dev_alloc(&c->d_run, 1) == PM_OK && dev_alloc(&c->d_fams, fams.size()) == PM_OK &&
        dev_alloc(&c->d_units, units.size()) == PM_OK && dev_alloc(&c->d_es, es.size()) == PM_OK &&
-       dev_alloc(&c->d_steps, steps.size()) == PM_OK && dev_alloc(&c->d_err, 1) == PM_OK && dev_alloc(&c->d_n_emit, 1) == PM_OK &&
+       dev_alloc(&c->d_steps, steps.size()) == PM_OK && dev_alloc(&c->d_sex, (size_t)ped->n_person) == PM_OK && dev_alloc(&c->d_err, 2) == PM_OK && dev_alloc(&c->d_n_emit, 1) == PM_OK &&
        dev_alloc(&c->d_counters, 16) == PM_OK && cudaEventCreate(&c->tm0) == cudaSuccess && cudaEventCreate(&c->tm1) == cudaSuccess;
   if (ok) {
     run.fams = c->d_fams; run.units = c->d_units; run.es_fams = c->d_es; run.steps = c->d_steps;
     run.counters = c->d_counters;
-    ok = cudaMemcpy(c->d_fams, fams.data(), fams.size() * sizeof(pm::DevFam), cudaMemcpyHostToDevice) == cudaSuccess &&
+    run.sex = c->d_sex;
+    ok = cudaMemcpy(c->d_sex, ped->sex, (size_t)ped->n_person, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(c->d_fams, fams.data(), fams.size() * sizeof(pm::DevFam), cudaMemcpyHostToDevice) == cudaSuccess &&
          (units.empty() || cudaMemcpy(c->d_units, units.data(), units.size() * sizeof(pm::DevUnit), cudaMemcpyHostToDevice) == cudaSuccess) &&
          (es.empty() || cudaMemcpy(c->d_es, es.data(), es.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess) &&
          (steps.empty() || cudaMemcpy(c->d_steps, steps.data(), steps.size() * sizeof(pm::DevStep), cudaMemcpyHostToDevice) == cudaSuccess) &&
          cudaMemcpy(c->d_run, &run, sizeof run, cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemset(c->d_err, 0, sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
+         cudaMemset(c->d_err, 0, 2 * sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   }
   if (!ok) {
     if (!*pmh::last_error()) fail(PM_ECUDA, "pm_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -259,6 +279,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_sex);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
   cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
@@ -306,7 +327,7 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                            out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
                            d_person_out, c->sm_count, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-  c->launches = 3;
+  c->launches = c->plan.kind == pm::LaunchPlan::WIDE ? 4 : 3;  // wide: the autosomal instance + the (normally empty) chrX/Y/MT one
   c->timing_cached = false;
   return PM_OK;
 }
@@ -319,7 +340,7 @@ extern "C" int pm_sync(pm_ctx *c) {
   CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (err) {
     cudaMemset(c->d_err, 0, sizeof(int));
-    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "chrX/chrY/MT sites are not implemented on the device path yet");
+    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "a site's chr_class is not one of PM_CHR_* (chrX/chrY/MT records of a VCF are not implemented)");
     return fail(err, "device-side error %d", err);
   }
   return PM_OK;
@@ -356,8 +377,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   if (c->par.vcf_input) return fail(PM_EINVAL, "this ctx was created for VCF input; use pm_call_vcf_records");
   if (!hdr || !person_site || !res_out) return fail(PM_EINVAL, "pm_call_glf_sites: null buffer");
   for (size_t s = 0; s < n_sites; s++)
-    if (hdr[s].chr_class != PM_CHR_AUTO && hdr[s].ref_base >= 1 && hdr[s].ref_base <= 4)
-      return fail(PM_EUNSUPPORTED, "site %zu: chrX/chrY/MT sites are not implemented on the device path yet", s);
+    if (hdr[s].chr_class > PM_CHR_MT) return fail(PM_EINVAL, "site %zu: chr_class %d is not one of PM_CHR_*", s, (int)hdr[s].chr_class);
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t np = (size_t)c->n_person;
   size_t chunk = ((size_t)48 << 20) / (np * sizeof(pm_person_site));
@@ -408,7 +428,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     if ((rc = pm_sync(c))) return rc;
     float a = 0.f, b = 0.f;
     pm_last_timing(c, &a, &b, nullptr);
-    ms_main += a; ms_total += b; launches += 3;
+    ms_main += a; ms_total += b; launches += c->launches;
     const uint32_t rows = *c->h_rows;
     if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
     if (rows) {

@@ -47,7 +47,7 @@ struct DevUnit {      // one factor of the objective that has the quartic form
   int32_t first;      // column of the first member
   int32_t nkids;      // -1 = a single unrelated founder; >= 0 = nuclear family with that many kids
   int32_t kid0;       // number of kids in the units before this one (slot of its first kid in the per-site kid table)
-  int32_t pad;
+  int32_t sex;        // single founder: that person's sex (1 male, 2 female), read on chrX / chrY only
 };
 
 // Everything the kernels need about the run; lives in global memory, hot tables are copied to smem.
@@ -59,6 +59,9 @@ struct DevRun {
   double log_tab[128];        // -log10(log_inv[i]) (computed in long double on the host)
   // host-computed log10 constants (same libm as the reference)
   double log_1m_prior, log_prior_ts, log_prior_tv, log_prior_other, log_prior_23, log_prior_16, log_min_llr;
+  // the same six per chromosome class PM_CHR_* (SetPolyPrior_chrX/_chrY/_MT, NucFam:256-293):
+  // [cls][0..5] = log_1m_prior, log_prior_ts, log_prior_tv, log_prior_other, log_prior_23, log_prior_16
+  double cls_log[4][6];
   double vcf_log_ts, vcf_log_tv, vcf_log_indel;  // VCF mode: log10(2/3), log10(1/6), log10(prior)  (src/PedVCF.cpp:143-150)
   double theta, posterior_cutoff, precision, denovo_min_llr, min_ps;
   int32_t min_map_quality, min_total_depth, max_total_depth;
@@ -71,6 +74,7 @@ struct DevRun {
   const DevUnit *units;
   const int32_t *es_fams;     // indices into fams[] of the extended families
   const DevStep *steps;
+  const uint8_t *sex;         // per column: 1 male, 2 female (chrX / chrY rules)
 };
 
 // ---- small helpers ----------------------------------------------------------------------------
@@ -142,6 +146,90 @@ __device__ __forceinline__ void quartic_from_conditionals(const double C[9], dou
   B[0] = C[8];
 }
 
+// ---- chrX / chrY / MT (bi-allelic model only; the --denovo nuclear code has no such rules) -------
+// likelihoodONEKid on a non-autosome (NucFam:1202-1264) for the six parent configurations whose prior is not
+// zero there (father "homozygous"): q = (cfg0, cfg1, cfg2, cfg6, cfg7, cfg8).  `ks` is NOT the kid's sex but the
+// object's stale member `sex`: 0 for the hypothesis objects, see k_post for famlk[0].
+__device__ __forceinline__ void onekid_nonauto(int cls, int ks, double l11, double l12, double l22, double q[6]) {
+  const bool male = ks == 1, female = ks == 2;
+  if (cls == PM_CHR_X) {
+    q[0] = l11; q[5] = l22;
+    q[1] = male ? 0.5 * (l11 + l22) : 0.5 * (l11 + l12);
+    q[2] = male ? l22 : l12;
+    q[3] = male ? l11 : l12;
+    q[4] = male ? 0.5 * (l11 + l22) : 0.5 * (l12 + l22);
+  } else if (cls == PM_CHR_Y) {
+    q[0] = female ? 1.0 : l11; q[5] = female ? 1.0 : l22;
+    q[1] = male ? l11 : 1.0; q[2] = male ? l11 : 1.0;
+    q[3] = male ? l22 : 1.0; q[4] = male ? l22 : 1.0;
+  } else {
+    q[0] = l11; q[5] = l22;
+    q[1] = 0.5 * (l11 + l22); q[2] = l22; q[3] = l11; q[4] = 0.5 * (l11 + l22);
+  }
+}
+// parentConditional on a non-autosome: CalcParentMarginal's parentGLF edits (NucFam:1049-1051) and the kid
+// products above; C[3..5] (father heterozygous) are zero.
+template <typename RecPtr>
+__device__ __forceinline__ void unit_conditionals_nonauto(RecPtr recs, int first, int nkids, int g11, int g12, int g22, int cls, int ks,
+                                                          const double *__restrict__ lut, double C[9]) {
+  uint4 rf = recs[first], rm = recs[first + 1];
+  double f11 = lut[rec_lk(rf, g11)], f22 = lut[rec_lk(rf, g22)];
+  double m11 = lut[rec_lk(rm, g11)], m12 = lut[rec_lk(rm, g12)], m22 = lut[rec_lk(rm, g22)];
+  if (cls == PM_CHR_Y) m11 = m12 = m22 = 1.0;
+  if (cls == PM_CHR_MT) m12 = 0.0;
+  double p[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+  for (int k = 0; k < nkids; k++) {
+    uint4 rk = recs[first + 2 + k];
+    double q[6];
+    onekid_nonauto(cls, ks, lut[rec_lk(rk, g11)], lut[rec_lk(rk, g12)], lut[rec_lk(rk, g22)], q);
+#pragma unroll
+    for (int j = 0; j < 6; j++) p[j] *= q[j];
+  }
+  C[0] = p[0] * (f11 * m11); C[1] = p[1] * (f11 * m12); C[2] = p[2] * (f11 * m22);
+  C[3] = 0.0; C[4] = 0.0; C[5] = 0.0;
+  C[6] = p[3] * (f22 * m11); C[7] = p[4] * (f22 * m12); C[8] = p[5] * (f22 * m22);
+}
+// SetParentPrior on a non-autosome (NucFam:333-366)
+__device__ __forceinline__ void parent_priors_nonauto(int cls, double freq, double pp[9]) {
+  const double q = 1.0 - freq;
+  pp[3] = pp[4] = pp[5] = 0.0;
+  if (cls == PM_CHR_X) {
+    pp[0] = freq * freq * freq; pp[1] = freq * freq * q * 2; pp[2] = freq * q * q;
+    pp[6] = q * freq * freq; pp[7] = q * freq * q * 2; pp[8] = q * q * q;
+  } else if (cls == PM_CHR_Y) {
+    pp[0] = pp[1] = pp[2] = freq; pp[6] = pp[7] = pp[8] = q;
+  } else {
+    pp[0] = freq * freq; pp[1] = 0.0; pp[2] = freq * q; pp[6] = q * freq; pp[7] = 0.0; pp[8] = q * q;
+  }
+}
+// L(p) = sum_j C_j prior_j(p) has degree 3 (X), 1 (Y) or 2 (MT) there; multiplied by the right power of
+// (p + q) = 1 it takes the same quartic form as on the autosomes, with non-negative terms only.
+__device__ __forceinline__ void quartic_from_conditionals_nonauto(int cls, const double C[9], double B[5]) {
+  if (cls == PM_CHR_X) {
+    const double c3 = C[0], c2 = 2.0 * C[1] + C[6], c1 = C[2] + 2.0 * C[7], c0 = C[8];
+    B[4] = c3; B[3] = c3 + c2; B[2] = c2 + c1; B[1] = c1 + c0; B[0] = c0;
+  } else if (cls == PM_CHR_Y) {
+    const double d1 = (C[0] + C[1]) + C[2], d0 = (C[6] + C[7]) + C[8];
+    B[4] = d1; B[3] = 3.0 * d1 + d0; B[2] = 3.0 * (d1 + d0); B[1] = d1 + 3.0 * d0; B[0] = d0;
+  } else {
+    const double e2 = C[0], e1 = C[2] + C[6], e0 = C[8];
+    B[4] = e2; B[3] = 2.0 * e2 + e1; B[2] = e2 + 2.0 * e1 + e0; B[1] = e1 + 2.0 * e0; B[0] = e0;
+  }
+}
+// lkSinglePerson (NucFam:987-1004) as a quartic: haploid l11 p + l22 q times (p+q)^3, a female on Y is the constant 1
+__device__ __forceinline__ bool single_person_nonauto(int cls, int sex, double l11, double l22, double B[5]) {
+  const bool male = sex == 1;
+  if (cls == PM_CHR_X && !male) return false;  // diploid, as on the autosomes
+  if (cls == PM_CHR_Y && !male) { B[4] = 1.0; B[3] = 4.0; B[2] = 6.0; B[1] = 4.0; B[0] = 1.0; return true; }
+  B[4] = l11; B[3] = 3.0 * l11 + l22; B[2] = 3.0 * (l11 + l22); B[1] = l11 + 3.0 * l22; B[0] = l22;
+  return true;
+}
+// One unit on chromosome class cls != PM_CHR_AUTO.  Under --denovo only the single founders differ from the
+// autosomal code (lkSingleFam_denovo -> lkSinglePerson); nuclear families keep CalcParentMarginal_denovo.
+template <typename RecPtr>
+__device__ __forceinline__ void unit_quartic_nonauto(RecPtr recs, const DevUnit u, int g11, int g12, int g22, bool denovo, int cls, int ks,
+                                                     const double *__restrict__ lut, const double *__restrict__ mut, double B[5]);
+
 template <typename RecPtr>
 __device__ __forceinline__ void unit_quartic(RecPtr recs, const DevUnit u, int g11, int g12, int g22, bool denovo,
                                              const double *__restrict__ lut, const double *__restrict__ mut,
@@ -158,6 +246,21 @@ __device__ __forceinline__ void unit_quartic(RecPtr recs, const DevUnit u, int g
     double C[9];
     unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, lut, mut, C);
     quartic_from_conditionals(C, B);
+  }
+}
+
+template <typename RecPtr>
+__device__ __forceinline__ void unit_quartic_nonauto(RecPtr recs, const DevUnit u, int g11, int g12, int g22, bool denovo, int cls, int ks,
+                                                     const double *__restrict__ lut, const double *__restrict__ mut, double B[5]) {
+  if (u.nkids < 0) {
+    uint4 r = recs[u.first];
+    if (!single_person_nonauto(cls, u.sex, lut[rec_lk(r, g11)], lut[rec_lk(r, g22)], B)) unit_quartic(recs, u, g11, g12, g22, denovo, lut, mut, B);
+  } else if (denovo) {
+    unit_quartic(recs, u, g11, g12, g22, true, lut, mut, B);
+  } else {
+    double C[9];
+    unit_conditionals_nonauto(recs, u.first, u.nkids, g11, g12, g22, cls, ks, lut, C);
+    quartic_from_conditionals_nonauto(cls, C, B);
   }
 }
 

@@ -32,24 +32,47 @@ __device__ __forceinline__ double tba(int i, int j, int k) {  // transmission_BA
   double ti = 0.5 * i, tj = 0.5 * j;
   return k == 0 ? (1 - ti) * (1 - tj) : (k == 2 ? ti * tj : ti * (1 - tj) + (1 - ti) * tj);
 }
+// GetTransmissionProb_BA (ES:1059-1075) with the chrX-to-female / chrX-to-male / chrY / mitochondrial tables
+// (ES:834-924) in closed form; `sex` is the offspring's.
+__device__ __forceinline__ double tba_cls(int cls, int sex, int i, int j, int k) {
+  if (cls == PM_CHR_AUTO) return tba(i, j, k);
+  const bool male = sex == 1;
+  if (cls == PM_CHR_Y && !male) return 1.0;
+  if (i == 1) return 0.0;  // a heterozygous father does not exist on these chromosomes
+  if (cls == PM_CHR_X) {
+    if (!male) return tba(i, j, k);
+    const double tj = 0.5 * j;  // a son gets his only copy from the mother
+    return k == 0 ? 1 - tj : (k == 2 ? tj : 0.0);
+  }
+  if (cls == PM_CHR_Y) return (k == i) ? 1.0 : 0.0;      // the father's copy
+  if (j == 1) return 0.0;                                // MT: the mother's copy
+  return (k == j) ? 1.0 : 0.0;
+}
 
 template <int A, typename RecPtr>
 __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
                                 bool denovo, double freq, const double *__restrict__ lut,
                                 const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
-                                int pin_geno) {
+                                int pin_geno, int cls = PM_CHR_AUTO) {
   double part[kMaxEsPersons * A];
   double mp[kMaxMp * A * A];
   const int gi[3] = {g11, g12, g22};
   const double q = 1.0 - freq;
-  const double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+  const uint8_t *sexes = run->sex + f.first;
   for (int i = 0; i < f.size; i++) {
     uint4 r = recs[f.first + i];
+    double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+    if (cls != PM_CHR_AUTO) {
+      const bool male = sexes[i] == 1;
+      if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
+      else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
+    }
     if (A == 3) {
+      const bool yfemale = cls == PM_CHR_Y && sexes[i] == 2;
       for (int j = 0; j < 3; j++) {
         double pen = lut[rec_lk(r, gi[j])];
         if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
-        part[i * 3 + j] = (i < f.founders) ? pr[j] * pen : pen;  // InitializePartials_BA, ES:1449-1465
+        part[i * 3 + j] = yfemale ? 1.0 : ((i < f.founders) ? pr[j] * pen : pen);  // InitializePartials_BA, ES:1449-1465
       }
     } else {
       for (int g = 0; g < 10; g++) {
@@ -74,7 +97,7 @@ __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, 
         for (int j = 0; j < A; j++) {
           double sum = 0;
           if (A == 3) {
-            for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k];
+            for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k];
           } else {
             const double *t = (denovo ? tden : t10) + (i * 10 + j) * 10;
             for (int k = 0; k < 10; k++) sum += t[k] * pc[k];
@@ -106,7 +129,7 @@ __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, 
         for (int i = 0; i < A; i++)
           for (int j = 0; j < A; j++) {
             double t;
-            if (A == 3) t = tba(i, j, k);
+            if (A == 3) t = tba_cls(cls, sexes[st.to0], i, j, k);
             else t = (m || !denovo) ? t10[(i * 10 + j) * 10 + k] : tden[(i * 10 + j) * 10 + k];  // ES:1383 vs 1391
             if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
             else sum += pf[i] * pm_[j] * t;
@@ -169,9 +192,10 @@ __device__ inline void site_finish_refit(const DevRun *run, pm_site_result &r, d
   r.denovo_lr = r.varllk_noprior[r.maxidx] - lk_poly;
   if (run->use_brent) r.freq = refit_freq;  // famlk[0].min is overwritten by the refit's Brent (main:570)
 }
-__device__ inline void site_store_hyp(const DevRun *run, pm_site_result &r, int h, double maxlogl, double freq) {
-  const double lp = h == 1 ? run->log_prior_ts : (h <= 3 ? run->log_prior_tv : run->log_prior_other);
-  const double ln = h == 1 ? run->log_prior_23 : (h <= 3 ? run->log_prior_16 : run->log_prior_other);  // main:472,482,492
+__device__ inline void site_store_hyp(const DevRun *run, pm_site_result &r, int h, double maxlogl, double freq, int cls) {
+  const double *cl = run->cls_log[cls];
+  const double lp = h == 1 ? cl[1] : (h <= 3 ? cl[2] : cl[3]);
+  const double ln = h == 1 ? cl[4] : (h <= 3 ? cl[5] : cl[3]);  // main:472,482,492
   double v = lp + maxlogl;
   r.varllk[h] = v;
   r.varllk_noprior[h] = v - ln;
@@ -201,6 +225,7 @@ struct NarrowEval {
   double C0[9];  // single-nuclear-family mode keeps the nine conditionals
   int g11, g12, g22;
   bool denovo;
+  int cls = PM_CHR_AUTO;  // chromosome class of the site; the hypothesis objects' stale `sex` member is 0 (see pm_device.cuh)
   int n_hyp = 0, n_eval = 0;
 
   __device__ void setup(int a1, int a2, bool dn) {
@@ -208,12 +233,18 @@ struct NarrowEval {
     denovo = dn;
     if (!run->use_brent) {
       const DevUnit u = run->units[0];
-      unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
+      if (cls == PM_CHR_AUTO || denovo) unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
+      else unit_conditionals_nonauto(recs, u.first, u.nkids, g11, g12, g22, cls, 0, sm->t.lut, C0);
       return;
     }
+    if (cls == PM_CHR_AUTO) {
 #pragma unroll
-    for (int u = 0; u < UMAX; u++)
-      if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, sm->t.lut, sm->t.mut, B[u]);
+      for (int u = 0; u < UMAX; u++)
+        if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, sm->t.lut, sm->t.mut, B[u]);
+    } else {
+      for (int u = 0; u < UMAX; u++)
+        if (u < run->n_units) unit_quartic_nonauto(recs, run->units[u], g11, g12, g22, denovo, cls, 0, sm->t.lut, sm->t.mut, B[u]);
+    }
   }
   // sum_f log10 L_f(p), FLSeq:222-240
   __device__ double loglik(double p) const {
@@ -224,8 +255,8 @@ struct NarrowEval {
       if (u < run->n_units) sum += log10(quartic_eval(B[u], m));
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
-      double lk = denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1)
-                         : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1);
+      double lk = denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls)
+                         : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls);
       sum += log10(lk);
     }
     return sum;
@@ -286,7 +317,11 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   r.maxidx = -1;
   const int ref = h.ref_base;
   if (ref < 1 || ref > 4) { r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
-  if (h.chr_class != PM_CHR_AUTO) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+  const int cls = h.chr_class;
+  if (cls > PM_CHR_MT || (run->vcf_mode && cls != PM_CHR_AUTO)) {  // chrX/Y/MT records of a VCF are not supported
+    atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return;
+  }
+  const double log_1m_prior = run->cls_log[cls][0];
   if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
     const int a2 = h.reserved & 0xff;
     NarrowEval<UMAX> ev;
@@ -318,26 +353,26 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   if (r.status != 0) { res[s] = r; status[s] = status_word(r); return; }
 
   NarrowEval<UMAX> ev;
-  ev.run = run; ev.recs = recs; ev.sm = sm;
+  ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
   r.reserved = (uint16_t)ref;
   // H0 (main:447-462)
   if (!run->denovo) {
-    r.varllk[0] = run->log_1m_prior + lk_mono;
+    r.varllk[0] = log_1m_prior + lk_mono;
   } else {
     int a1, a2;
     hyp_alleles(0, ref, a1, a2);
     ev.setup(a1, a2, true);
     double l0 = run->use_brent ? ev.loglik(1.0) : ev.loglik_fixed(true);
-    r.varllk[0] = run->log_1m_prior + l0;
+    r.varllk[0] = log_1m_prior + l0;
   }
-  r.varllk_noprior[0] = r.varllk[0] - run->log_1m_prior;
+  r.varllk_noprior[0] = r.varllk[0] - log_1m_prior;
   r.varfreq[0] = 1.0;
   for (int hix = 1; hix <= 3; hix++) {
     int a1, a2;
     hyp_alleles(hix, ref, a1, a2);
     double freq = 0.0;
     double ml = ev.optimize(a1, a2, run->denovo != 0, &freq);
-    site_store_hyp(run, r, hix, ml, freq);
+    site_store_hyp(run, r, hix, ml, freq, cls);
   }
   var_posterior(r, ref, 4);
   if (r.var_post_prob < 0.99) {  // main:499-537
@@ -346,7 +381,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
       hyp_alleles(hix, ref, a1, a2);
       double freq = 0.0;
       double ml = ev.optimize(a1, a2, run->denovo != 0, &freq);
-      site_store_hyp(run, r, hix, ml, freq);
+      site_store_hyp(run, r, hix, ml, freq, cls);
     }
     var_posterior(r, ref, 7);
   }
@@ -404,6 +439,7 @@ struct WideShared {
   int red_i[4 * 32];                  // per-warp integer partials (depth, samples, mapq, lk sum)
   double bcast[4];
   int ibcast[4];
+  int cls;                            // chromosome class of the current site (PM_CHR_*)
   unsigned long long mbar[2];         // one mbarrier per site buffer (TMA bulk copies)
   unsigned int n_hyp, n_eval;         // work counters of the current site
   unsigned int n_eval_g[kMaxChains];  // evaluations per chain driver (summed into n_eval by thread 0)
@@ -478,12 +514,17 @@ __device__ __forceinline__ void renorm_nonzero(ProdAcc &a) {
 // Out-of-line helpers: their register pressure (unrolled 10-genotype dot products, the Brent update with
 // its division, exp10/log10 in the posterior) stays out of the kernel's hot loop allocation.
 struct Quartic { double b0, b1, b2, b3, b4; };
-__device__ __noinline__ Quartic unit_quartic_ol(const uint4 *recs, int first, int nkids, int g11, int g12, int g22, int denovo,
+// mode = denovo | chr_class << 1 | (single founder's sex) << 3.  NA = the kernel instance for chrX / chrY / MT sites: a
+// separate instantiation, so that the autosomal kernel's register allocation does not pay for the rare case (the
+// callee's registers count against what the caller can keep live across the call).
+template <bool NA>
+__device__ __noinline__ Quartic unit_quartic_ol(const uint4 *recs, int first, int nkids, int g11, int g12, int g22, int mode,
                                                 const double *lut, const double *mut) {
   double B[5];
   DevUnit u;
-  u.first = first; u.nkids = nkids;
-  unit_quartic(recs, u, g11, g12, g22, denovo != 0, lut, mut, B);
+  u.first = first; u.nkids = nkids; u.sex = mode >> 3;
+  if (!NA) unit_quartic(recs, u, g11, g12, g22, (mode & 1) != 0, lut, mut, B);
+  else unit_quartic_nonauto(recs, u, g11, g12, g22, (mode & 1) != 0, (mode >> 1) & 3, 0, lut, mut, B);
   Quartic q;
   q.b0 = B[0]; q.b1 = B[1]; q.b2 = B[2]; q.b3 = B[3]; q.b4 = B[4];
   return q;
@@ -547,7 +588,7 @@ __device__ __noinline__ double log10_ol(const WideShared *ws, double m, int e) {
   return fma(l1p, 0.43429448190325182765, ws->log_tab[i]) + (double)e * kLog10_2;
 }
 
-template <int U>
+template <int U, bool NA>
 struct WideEval {
   const DevRun *run;
   const uint4 *recs;  // site records in shared memory
@@ -568,6 +609,7 @@ struct WideEval {
     if (mine) {
       const int x = a1[grp], y = a2[grp];
       const int g11 = geno_index(x, x), g12 = geno_index(x, y), g22 = geno_index(y, y);
+      const int mode = (denovo ? 1 : 0) | (NA ? (ws->cls << 1) : 0);
 #pragma unroll
       for (int k = 0; k < U; k++) {
         const int u = t + k * Tg;
@@ -575,7 +617,7 @@ struct WideEval {
           const DevUnit du = run->units[u];
           const Quartic q = (denovo && kidD && du.nkids > 0)
                                 ? unit_quartic_tab_ol(recs, du.first, du.nkids, kidD + (size_t)du.kid0 * 10, g11, g12, g22, ws->t.lut)
-                                : unit_quartic_ol(recs, du.first, du.nkids, g11, g12, g22, denovo ? 1 : 0, ws->t.lut, ws->t.mut);
+                                : unit_quartic_ol<NA>(recs, du.first, du.nkids, g11, g12, g22, NA ? (mode | (du.sex << 3)) : mode, ws->t.lut, ws->t.mut);
           // With the largest coefficient in [1,2) and p in [1e-4, 0.9999], L'(p) >= min(p,q)^4 >= 2^-54, so the
           // product over this thread's U <= 8 units cannot underflow: no exponent handling inside a round.
           double mx = fmax(fmax(fmax(q.b0, q.b1), fmax(q.b2, q.b3)), q.b4);
@@ -669,7 +711,9 @@ struct WideEval {
   }
 };
 
-template <int U, int MAXT>
+// NA = false: the autosomal instance; sites on chrX / chrY / MT are left untouched and flagged in err[1].
+// NA = true: launched right behind it, returns at once unless err[1] is set, then does only those sites.
+template <int U, int MAXT, bool NA>
 __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                                         const uint4 *__restrict__ recs_all, const double *__restrict__ mono_all,
                                                         size_t n_sites, int groups, int nbuf, int kid_table,
@@ -677,6 +721,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
                                                         int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *ws = reinterpret_cast<WideShared *>(smem_raw);
+  if (NA && err[1] == 0) return;
   const int np = run->n_person;
   const size_t site_bytes = (((size_t)np * 16 + 127) / 128) * 128;
   unsigned char *site_base = smem_raw + ((sizeof(WideShared) + 127) / 128) * 128;
@@ -696,7 +741,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
   int cur = 0;
   if (threadIdx.x == 0 && blockIdx.x < n_sites)
     tma_issue_site(site_base, recs_all + (size_t)blockIdx.x * np, (uint32_t)np * 16u, &ws->mbar[0]);
-  WideEval<U> ev;
+  WideEval<U, NA> ev;
   ev.run = run; ev.ws = ws; ev.kidD = kid_tab;
   ev.G = groups; ev.Tg = blockDim.x / groups; ev.grp = threadIdx.x / ev.Tg; ev.t = threadIdx.x % ev.Tg;
   const int G = groups;
@@ -719,7 +764,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
     const pm_site_hdr h = hdr[s];
     const int ref = h.ref_base;
     bool skip = false;
-    if (ref < 1 || ref > 4 || h.chr_class != PM_CHR_AUTO) {
+    const int cls = h.chr_class;
+    const bool bad_cls = cls > PM_CHR_MT || (run->vcf_mode && cls != PM_CHR_AUTO);  // chrX/Y/MT records of a VCF are not supported
+    if (NA && threadIdx.x == 0) ws->cls = cls;  // read by the set-up loops after the next barrier
+    const bool bad = ref < 1 || ref > 4 || bad_cls;
+    if (NA ? (bad || cls == PM_CHR_AUTO) : (!bad && cls != PM_CHR_AUTO)) {  // the other instance's site
+      if (!NA && threadIdx.x == 0) atomicExch(err + 1, 1);
+      skip = true;
+    } else if (bad) {
       if (threadIdx.x == 0) {
         pm_site_result &r = ws->r;
         memset(&r, 0, sizeof r);
@@ -802,14 +854,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
           const bool with_h0 = dn && base == 1 && c0 == 0;
           ev.optimize(nc, a1 + c0, a2 + c0, dn, with_h0);
           if (threadIdx.x == 0) {
-            for (int c = 0; c < nc; c++) site_store_hyp(run, ws->r, base + c0 + c, -ws->brent[c].fmin, ws->brent[c].min);
-            if (with_h0) { ws->r.varllk[0] = run->log_1m_prior + ws->bcast[1]; ws->n_hyp += 1; ws->n_eval += 1; }
+            for (int c = 0; c < nc; c++) site_store_hyp(run, ws->r, base + c0 + c, -ws->brent[c].fmin, ws->brent[c].min, cls);
+            if (with_h0) { ws->r.varllk[0] = run->cls_log[cls][0] + ws->bcast[1]; ws->n_hyp += 1; ws->n_eval += 1; }
           }
         }
         if (threadIdx.x == 0) {
           if (base == 1) {
-            if (!dn) ws->r.varllk[0] = run->log_1m_prior + lk_mono;
-            ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->log_1m_prior;
+            if (!dn) ws->r.varllk[0] = run->cls_log[cls][0] + lk_mono;
+            ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->cls_log[cls][0];
             ws->r.varfreq[0] = 1.0;
             var_posterior_ol(&ws->r, ref, 4);
             ws->ibcast[1] = ws->r.var_post_prob < 0.99;  // main:499
@@ -914,6 +966,31 @@ __device__ inline void store_person3(pm_person_result &o, double p0, double p1, 
   o.reserved[0] = o.reserved[1] = 0;
 }
 
+// likelihoodKidGenotype on chrX / chrY / MT (NucFam:1334-1443) for configurations 1, 2, 6, 7 (0 and 8 have no
+// special case there, 3..5 are zero); `sex` is the kid's own.
+__device__ inline void kid_cfg_nonauto(int cls, int sex, int cfg, double l11, double l12, double l22, double &lk, double &x11,
+                                       double &x12, double &x22) {
+  const bool male = sex == 1;
+  x11 = x12 = x22 = 0.0;
+  if (cls == PM_CHR_X) {
+    switch (cfg) {
+      case 1: if (male) { lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; } else { lk = 0.5 * (l11 + l12); x11 = 0.5 * l11; x12 = 0.5 * l12; } break;
+      case 2: if (male) { lk = l22; x22 = l22; } else { lk = l12; x12 = l12; } break;
+      case 6: if (male) { lk = l11; x11 = l11; } else { lk = l12; x12 = l12; } break;
+      default: if (male) { lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; } else { lk = 0.5 * (l12 + l22); x12 = 0.5 * l12; x22 = 0.5 * l22; } break;
+    }
+  } else if (cls == PM_CHR_Y) {
+    if (!male) { lk = 1.0; return; }
+    if (cfg == 1 || cfg == 2) { lk = l11; x11 = l11; } else { lk = l22; x22 = l22; }
+  } else {
+    switch (cfg) {
+      case 1: case 7: lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; break;
+      case 2: lk = l22; x22 = l22; break;
+      default: lk = l11; x11 = l11; break;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                               const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
                                               const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
@@ -958,24 +1035,40 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     // frequency the posteriors are taken at (main:576-587)
     const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
     const double q = 1.0 - freq;
+    const int cls = run->vcf_mode ? PM_CHR_AUTO : hdr[s].chr_class;
+    const bool nonauto = cls != PM_CHR_AUTO;
 
     if (f.kind == 0) {  // CalcPostProb_SinglePerson, NucFam:754-795
       for (int j = 0; j < f.size; j++) {
         uint4 rec = recs[f.first + j];
-        double m11 = lut[rec_lk(rec, g11)] * (freq * freq);
-        double m12 = lut[rec_lk(rec, g12)] * (freq * q * 2);
-        double m22 = lut[rec_lk(rec, g22)] * (q * q);
+        double pr0 = freq * freq, pr1 = freq * q * 2, pr2 = q * q;
+        const int sex = nonauto ? run->sex[f.first + j] : 0;
+        if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && sex == 1)) { pr0 = freq; pr1 = 0.0; pr2 = q; }
+        else if (cls == PM_CHR_Y) { pr0 = pr1 = pr2 = 1.0; }
+        double m11 = lut[rec_lk(rec, g11)] * pr0;
+        double m12 = lut[rec_lk(rec, g12)] * pr1;
+        double m22 = lut[rec_lk(rec, g22)] * pr2;
         double sum = m11 + m12 + m22;
-        if (sum == 0) store_person3(out[f.first + j], 0, 0, 0, best3(m11, m12, m22));
+        if (sum == 0 || (cls == PM_CHR_Y && sex == 2)) store_person3(out[f.first + j], 0, 0, 0, best3(m11, m12, m22));  // NucFam:781, 788
         else store_person3(out[f.first + j], m11 / sum, m12 / sum, m22 / sum, best3(m11, m12, m22));
       }
     } else if (f.kind == 1) {  // nuclear: NucFam:590-752
       const int nk = f.size - 2;
       double C[9], pp[9], pm9[9];
-      unit_conditionals(recs, f.first, nk, g11, g12, g22, dn, lut, mut, C);
+      const bool na = nonauto && !dn;  // the --denovo nuclear code has no chrX / chrY / MT rules
       // parent-pair prior: HW when nFam>1 (or isMono / freq==1 under --denovo), else the fixed table
       bool hw = run->n_fam > 1 || (dn ? freq == 1.0 : mono);
-      if (hw) parent_priors(freq, pp); else single_trio_priors(pp);
+      if (!na) {
+        unit_conditionals(recs, f.first, nk, g11, g12, g22, dn, lut, mut, C);
+        if (hw) parent_priors(freq, pp); else single_trio_priors(pp);
+      } else {
+        // CalcParentMarginal runs before this family's loop assigns `sex` (NucFam:606 vs 610): every kid is given the
+        // sex of the LAST member of the previous family, family 0 that of the last person of the previous emitted
+        // site's last family -- or the initial 0 in the first CalcPostProb of the process (PM_HDR_FIRST_POSTPROB).
+        const int ks = fi > 0 ? run->sex[f.first - 1] : ((hdr[s].reserved & PM_HDR_FIRST_POSTPROB) ? 0 : run->sex[np - 1]);
+        unit_conditionals_nonauto(recs, f.first, nk, g11, g12, g22, cls, ks, lut, C);
+        if (hw) parent_priors_nonauto(cls, freq, pp); else single_trio_priors(pp);
+      }
       for (int j = 0; j < 9; j++) pm9[j] = C[j] * pp[j];
       {
         double p11 = pm9[0] + pm9[1] + pm9[2], p12 = pm9[3] + pm9[4] + pm9[5], p22 = pm9[6] + pm9[7] + pm9[8];
@@ -993,6 +1086,11 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
         uint4 rf = recs[f.first], rm = recs[f.first + 1];
         double fl[3] = {lut[rec_lk(rf, g11)], lut[rec_lk(rf, g12)], lut[rec_lk(rf, g22)]};
         double ml[3] = {lut[rec_lk(rm, g11)], lut[rec_lk(rm, g12)], lut[rec_lk(rm, g22)]};
+        if (na) {  // NucFam:1049-1051
+          fl[1] = 0.0;
+          if (cls == PM_CHR_Y) ml[0] = ml[1] = ml[2] = 1.0;
+          if (cls == PM_CHR_MT) ml[1] = 0.0;
+        }
         for (int j = 0; j < 9; j++) w9[j] = (fl[j / 3] * ml[j % 3]) * pp[j];
       }
       for (int kid = 0; kid < nk; kid++) {
@@ -1006,6 +1104,10 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
               uint4 rk = recs[f.first + 2 + kk];
               double l11 = lut[rec_lk(rk, g11)], l12 = lut[rec_lk(rk, g12)], l22 = lut[rec_lk(rk, g22)];
               double lk, x11, x12, x22;
+              if (na && cfg != 0 && cfg != 8) {
+                if (cfg >= 3 && cfg <= 5) { lk = 0.0; x11 = x12 = x22 = 0.0; }
+                else kid_cfg_nonauto(cls, run->sex[f.first + 2 + kk], cfg, l11, l12, l22, lk, x11, x12, x22);
+              } else
               switch (cfg) {
                 case 0: lk = l11; x11 = l11; x12 = 0; x22 = 0; break;
                 case 1: case 3: lk = 0.5 * (l11 + l12); x11 = l11 * 0.5; x12 = l12 * 0.5; x22 = 0; break;
@@ -1083,16 +1185,17 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
       for (int j = 0; j < f.size; j++) {
         pm_person_result &o = out[f.first + j];
         if (!dn) {
-          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g11);
-          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g12);
-          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g22);
+          if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { store_person3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
+          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g11, cls);
+          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g12, cls);
+          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g22, cls);
           double sum = l11 + l12 + l22;
           if (sum == 0) store_person3(o, 0, 0, 0, best3(l11, l12, l22));
           else store_person3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
         } else {
           double lk[10], sum = 0.0;
           for (int g = 0; g < 10; g++) {
-            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, sm->tden, sm->t10, j, g);
+            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, sm->tden, sm->t10, j, g, cls);
             sum += lk[g];
           }
           double mx = 0.0;
@@ -1108,7 +1211,9 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     }
     if (fi == 0) {
       // CalculateAB (NucFam:1006-1039), only printed by the non-de-novo writer on autosomes
-      if (!dn && !run->vcf_mode) {
+      if (nonauto) {
+        r.ab = 0.0;  // not computed and not printed there (NucFam:1791-1800)
+      } else if (!dn && !run->vcf_mode) {
         double A = 0.0, Bsum = 0.0;
         const double f0 = r.freq;
         const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
@@ -1184,7 +1289,13 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   } else {
     const size_t smem = wide_smem_bytes(plan.n_person, plan.site_buffers, plan.kid_table);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
-#define PM_WIDE(U_, MT_) k_sites_wide<U_, MT_><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers, plan.kid_table, d_res, d_status, d_err)
+    cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+#define PM_WIDE(U_, MT_)                                                                                                                        \
+  k_sites_wide<U_, MT_, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers,     \
+                                                                     plan.kid_table, d_res, d_status, d_err);                                    \
+  k_sites_wide<U_, MT_, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers,      \
+                                                                    plan.kid_table, d_res, d_status, d_err)
     PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
   }
@@ -1245,8 +1356,9 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   int per_sm = 1;
   const int T = plan->threads;
 #define PM_ATTR(U_, MT_)                                                                                              \
-  e = cudaFuncSetAttribute(k_sites_wide<U_, MT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_>, T, smem)
+  e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_, false>, T, smem)
   PM_WIDE_DISPATCH(*plan, PM_ATTR);
 #undef PM_ATTR
   if (e != cudaSuccess) return e;

@@ -36,11 +36,11 @@ def families(sizes) -> PedigreeArrays:
         fam_size.append(s)
         if s == 1:
             fam_founders.append(1); fam_gen.append(1)
-            sex.append(1); father.append(-1); mother.append(-1)
+            sex.append(1 + len(fam_size) % 2); father.append(-1); mother.append(-1)
         else:
             assert s >= 3
             fam_founders.append(2); fam_gen.append(2)
-            sex += [1, 2] + [1 + (k % 2) for k in range(s - 2)]
+            sex += [1, 2] + [1 + ((k + len(fam_size)) % 2) for k in range(s - 2)]
             father += [-1, -1] + [0] * (s - 2)
             mother += [-1, -1] + [1] * (s - 2)
     return PedigreeArrays(np.array(fam_size), np.array(fam_founders), np.array(fam_gen), np.array(sex, dtype=np.uint8),

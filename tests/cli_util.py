@@ -72,6 +72,14 @@ CASES = [
     ("ext_denovo", "ext.ped", ["--denovo"], "ref_ext_denovo.vcf.gz"),
     ("ceph_denovo", "ceph.ped", ["--denovo"], "ref_ceph_denovo.sha"),
 ]
+# chrX / chrY / MT (the example's section "1" declared to be that chromosome): nuclear families, singletons, a lone
+# nuclear family (fixed parent table) and an extended pedigree, bi-allelic and --denovo.
+NONAUTO_CASES = []
+for _c, _flag in (("x", "--chrX"), ("y", "--chrY"), ("mt", "--MT")):
+    for _p, _ped in (("quartets", "test.ped"), ("mix", "test.mix.ped"), ("single", "single.ped"), ("ext", "ext.ped")):
+        _full = (_c, _p) in (("x", "quartets"), ("y", "mix"), ("mt", "ext"))
+        NONAUTO_CASES.append((f"{_c}_{_p}_ba", _ped, [_flag, "1"], f"ref_{_c}_{_p}_ba" + (".vcf.gz" if _full else ".sha")))
+        NONAUTO_CASES.append((f"{_c}_{_p}_dn", _ped, [_flag, "1", "--denovo", "--rate_denovo", "1.5e-07"], f"ref_{_c}_{_p}_dn.sha"))
 # VCF-input mode (--in_vcf): (case, pedigree, input VCF fixture, golden) — the shipped golden of run.sh command 2
 # and outputs of the unmodified reference on edge-case inputs (tests/golden/make_golden.py: make_vcf_inputs)
 VCF_CASES = [
@@ -103,7 +111,7 @@ def check_vcf_case(exe, tmpdir, case, gz_input=False, extra=()):
     return log
 
 
-SLOW_FOR_ORACLE = {"ext_denovo", "ceph_denovo"}  # minutes of CPU in the oracle; covered on the GPU and by make_golden runs
+SLOW_FOR_ORACLE = {"ext_denovo", "ceph_denovo", "x_ext_dn", "y_ext_dn", "mt_ext_dn"}  # minutes of CPU in the oracle; covered on the GPU and by make_golden runs
 
 
 def check_case(exe, glfdir, tmpdir, case):

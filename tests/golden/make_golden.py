@@ -51,6 +51,13 @@ CASES = {  # name: (ped file, extra args, keep full text?)
     "mix_denovo_loose": ("test.mix.ped", ["--denovo", "--rate_denovo", "1e-4", "--minLLR_denovo", "1e-3", "--tstv_denovo", "1.0"], True),
     "mix_strict": ("test.mix.ped", ["-c", "0.99", "--minMapQuality", "50", "--minPercSampleWithData", "90", "--theta", "0.01", "--poly_tstv", "3.0"], True),
 }
+# chrX / chrY / MT rules: the example's only section is labelled "1", so `--chrX 1` (--chrY 1, --MT 1) makes the
+# reference treat the same data as that chromosome.  Three cases keep their text, the rest sha256 + line count.
+DN = ["--denovo", "--rate_denovo", "1.5e-07"]
+for _c, _flag in (("x", "--chrX"), ("y", "--chrY"), ("mt", "--MT")):
+    for _p, _ped in (("quartets", "test.ped"), ("mix", "test.mix.ped"), ("single", "single.ped"), ("ext", "ext.ped")):
+        CASES[f"{_c}_{_p}_ba"] = (_ped, [_flag, "1"], (_c, _p) in (("x", "quartets"), ("y", "mix"), ("mt", "ext")))
+        CASES[f"{_c}_{_p}_dn"] = (_ped, [_flag, "1"] + DN, False)
 
 
 VCF_CASES = {  # name: (ped file, input vcf)

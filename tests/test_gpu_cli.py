@@ -28,6 +28,12 @@ def test_product_cli_matches_reference_golden(case, glfdir, tmp_path):
     assert "Summary of reference -- 1" in log
 
 
+@pytest.mark.parametrize("case", U.NONAUTO_CASES, ids=lambda c: c[0])
+def test_product_cli_matches_reference_on_sex_chromosomes_and_mt(case, glfdir, tmp_path):
+    """--chrX / --chrY / --MT: all 24 reference outputs (4 pedigree shapes x 3 chromosome classes x bi-allelic / --denovo)."""
+    U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+
+
 @pytest.mark.parametrize("case", U.VCF_CASES, ids=lambda c: c[0])
 def test_product_cli_vcf_input_matches_reference(case, glfdir, tmp_path):
     log = U.check_vcf_case(U.PRODUCT_CLI, str(tmp_path), case, gz_input=(case[0] == "vcf_cmd2"))

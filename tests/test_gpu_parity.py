@@ -132,14 +132,49 @@ def test_emitted_mode_is_the_ordered_subset_of_all_mode(example12, tools_built, 
     eng.close()
 
 
-def test_nonautosome_sites_fail_loudly(example12, tools_built, tmp_path):
+def test_unknown_chromosome_class_fails_loudly(example12, tools_built, tmp_path):
     ped, glf_index = F.pedigree_from_file(PED("test.ped"), str(tmp_path))
     hdr, recs = F.sites_for(example12, glf_index, 100)
-    hdr["chr_class"][50] = 1
+    hdr["chr_class"][50] = 7
     eng = Engine(ped, Params())
-    with pytest.raises(RuntimeError, match="chrX"):
+    with pytest.raises(RuntimeError, match="chr_class"):
         eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
     eng.close()
+
+
+# ---- chrX / chrY / MT (SetPolyPrior_chrX.., SetParentPrior, likelihoodONEKid, GetTransmissionProb_BA) ----
+# chr_class: 1, 2, 3 = the whole batch on that chromosome; -1 = every site draws its own class (0..3) and one site
+# in eight carries PM_HDR_FIRST_POSTPROB, so one call exercises all rule sets side by side
+NONAUTO_CASES = [(f"{pedfile}_{'dn' if kw.get('denovo') else 'ba'}_cls{cls}", pedfile, kw, n, cls)
+                 for pedfile, n in (("test.ped", 30000), ("test.mix.ped", 30000), ("single.ped", 30000), ("ext.ped", 10000), ("ceph.ped", 3000))
+                 for kw in (dict(), dict(denovo=True, denovo_mut_rate=1.5e-7))
+                 for cls in (1, 2, 3, -1)
+                 if not (kw.get("denovo") and pedfile in ("ext.ped", "ceph.ped") and cls in (2, 3))]
+
+
+def _set_classes(hdr, cls, seed=11):
+    if cls >= 0:
+        hdr["chr_class"][:] = cls
+        return
+    rng = np.random.default_rng(seed)
+    hdr["chr_class"][:] = rng.integers(0, 4, size=len(hdr))
+    hdr["reserved"][:] = (rng.integers(0, 8, size=len(hdr)) == 0).astype(np.uint16)  # PM_HDR_FIRST_POSTPROB
+
+
+@pytest.mark.parametrize("case", NONAUTO_CASES, ids=lambda c: c[0])
+def test_sex_chromosome_and_mt_parity(case, example12, oracle_built, tools_built, tmp_path):
+    name, pedfile, kw, n_sites, cls = case
+    ped, glf_index = F.pedigree_from_file(PED(pedfile), str(tmp_path))
+    if pedfile == "ceph.ped" and kw.get("denovo"):
+        n_sites = 1200   # minutes of oracle time otherwise
+    hdr, recs = F.sites_for(example12, glf_index, n_sites, 0)
+    _set_classes(hdr, cls)
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=name)
+    print(rep)
+    assert rep["emitted"] > 0
+    parity.assert_parity(rep, len(hdr))
 
 
 # ---- wide kernel (one block per site) on synthetic pedigrees -------------------------------------
@@ -151,6 +186,32 @@ WIDE_CASES = [
     ("trios1000_denovo", lambda: synth.trios(1000), dict(denovo=True), 200, 4.0),
     ("trios1000_ba", lambda: synth.trios(1000), dict(), 200, 4.0),
 ]
+# the same through the chrX / chrY / MT instance of the wide kernel (last field: chr_class, -1 = mixed per site)
+WIDE_NONAUTO_CASES = [
+    ("mixed70_x", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(), 2500, 40.0, 1),
+    ("mixed70_y", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(), 2500, 40.0, 2),
+    ("mixed70_mt", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(), 2500, 40.0, 3),
+    ("mixed70_denovo_any", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(denovo=True), 1500, 40.0, -1),
+    ("quartets_and_sibships_any", lambda: synth.families([4] * 100 + [5] * 40 + [6] * 10), dict(), 600, 10.0, -1),
+    ("trios1000_any", lambda: synth.trios(1000), dict(), 240, 4.0, -1),
+    ("trios1000_denovo_x", lambda: synth.trios(1000), dict(denovo=True), 160, 4.0, 1),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_NONAUTO_CASES, ids=lambda c: c[0])
+def test_wide_kernel_sex_chromosome_and_mt_parity(case, oracle_built):
+    name, mk, kw, n_sites, boost, cls = case
+    ped = mk()
+    h, r = synth.generate_sites(ped, n_sites, seed=20261019, cfg=synth.SynthConfig(poly_boost=boost, injected_denovo=0.02))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1).copy()
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n_sites, ped.n_person)
+    _set_classes(hdr, cls)
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=name)
+    print(rep)
+    assert rep["emitted"] > 0
+    parity.assert_parity(rep, n_sites)
 
 
 @pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: c[0])

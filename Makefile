@@ -29,9 +29,12 @@ TOOLS := polymutt_b200/bin/pm-tools
 all: lib cli tools oracle
 
 lib: $(LIB)
+# pm_post.cu (genotype posteriors: exact ties must break as in the reference) is compiled without FMA contraction
+CU_MAIN := $(filter-out polymutt_b200/csrc/pm_post.cu,$(CU_SRC))
 $(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC) polymutt_b200/csrc/host/host_error.h
 	@mkdir -p polymutt_b200/lib
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_SRC) $(HOST_LIB_SRC) -Ipolymutt_b200/csrc/host -lcudart 2> polymutt_b200/lib/ptxas.log || (cat polymutt_b200/lib/ptxas.log; exit 1)
+	$(NVCC) $(NVFLAGS) -fmad=false -Xptxas -v -c -o polymutt_b200/lib/pm_post.o polymutt_b200/csrc/pm_post.cu 2> polymutt_b200/lib/ptxas_post.log || (cat polymutt_b200/lib/ptxas_post.log; exit 1)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_MAIN) polymutt_b200/lib/pm_post.o $(HOST_LIB_SRC) -Ipolymutt_b200/csrc/host -lcudart 2> polymutt_b200/lib/ptxas.log || (cat polymutt_b200/lib/ptxas.log; exit 1)
 
 tools: $(TOOLS)
 $(TOOLS): polymutt_b200/csrc/tools/pm_tools.cpp $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h)

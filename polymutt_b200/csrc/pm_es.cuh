@@ -1,0 +1,140 @@
+// pm_es.cuh — thread-serial Elston-Stewart peel and the shared-memory tables, used by the narrow site kernel
+// (pm_kernels.cu) and by the posterior kernel (pm_post.cu).
+#pragma once
+#include "pm_device.cuh"
+
+namespace pm {
+
+// ================================================================================================
+// Elston–Stewart peel, thread-serial (ES:990-1057, 1078-1395).  A = 3 (bi-allelic) or 10 (--denovo).
+// pin_person >= 0 zeroes that person's penetrance except genotype pin_geno (FillZeroPenetrance,
+// FLSeq:327-356), which is how the reference gets per-person posteriors in extended pedigrees.
+// ================================================================================================
+__device__ __forceinline__ double tba(int i, int j, int k) {  // transmission_BA, ES:824-832
+  double ti = 0.5 * i, tj = 0.5 * j;
+  return k == 0 ? (1 - ti) * (1 - tj) : (k == 2 ? ti * tj : ti * (1 - tj) + (1 - ti) * tj);
+}
+// GetTransmissionProb_BA (ES:1059-1075) with the chrX-to-female / chrX-to-male / chrY / mitochondrial tables
+// (ES:834-924) in closed form; `sex` is the offspring's.
+__device__ __forceinline__ double tba_cls(int cls, int sex, int i, int j, int k) {
+  if (cls == PM_CHR_AUTO) return tba(i, j, k);
+  const bool male = sex == 1;
+  if (cls == PM_CHR_Y && !male) return 1.0;
+  if (i == 1) return 0.0;  // a heterozygous father does not exist on these chromosomes
+  if (cls == PM_CHR_X) {
+    if (!male) return tba(i, j, k);
+    const double tj = 0.5 * j;  // a son gets his only copy from the mother
+    return k == 0 ? 1 - tj : (k == 2 ? tj : 0.0);
+  }
+  if (cls == PM_CHR_Y) return (k == i) ? 1.0 : 0.0;      // the father's copy
+  if (j == 1) return 0.0;                                // MT: the mother's copy
+  return (k == j) ? 1.0 : 0.0;
+}
+
+template <int A, typename RecPtr>
+__device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                bool denovo, double freq, const double *__restrict__ lut,
+                                const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
+                                int pin_geno, int cls = PM_CHR_AUTO) {
+  double part[kMaxEsPersons * A];
+  double mp[kMaxMp * A * A];
+  const int gi[3] = {g11, g12, g22};
+  const double q = 1.0 - freq;
+  const uint8_t *sexes = run->sex + f.first;
+  for (int i = 0; i < f.size; i++) {
+    uint4 r = recs[f.first + i];
+    double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+    if (cls != PM_CHR_AUTO) {
+      const bool male = sexes[i] == 1;
+      if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
+      else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
+    }
+    if (A == 3) {
+      const bool yfemale = cls == PM_CHR_Y && sexes[i] == 2;
+      for (int j = 0; j < 3; j++) {
+        double pen = lut[rec_lk(r, gi[j])];
+        if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
+        part[i * 3 + j] = yfemale ? 1.0 : ((i < f.founders) ? pr[j] * pen : pen);  // InitializePartials_BA, ES:1449-1465
+      }
+    } else {
+      for (int g = 0; g < 10; g++) {
+        double pen = lut[rec_lk(r, g)];
+        if (i == pin_person && g != pin_geno) pen = 0.0;
+        if (i < f.founders) {  // InitializePartials, ES:1434-1446
+          double prior = g == g11 ? pr[0] : (g == g12 ? pr[1] : (g == g22 ? pr[2] : 0.0));
+          part[i * 10 + g] = prior * pen;
+        } else {
+          part[i * 10 + g] = pen;
+        }
+      }
+    }
+  }
+  const DevStep *steps = run->steps + f.step_first;
+  for (int s = 0; s < f.n_steps; s++) {
+    const DevStep st = steps[s];
+    if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
+      double *m = mp + st.mp * A * A;
+      const double *pc = part + st.from0 * A;
+      for (int i = 0; i < A; i++)
+        for (int j = 0; j < A; j++) {
+          double sum = 0;
+          if (A == 3) {
+            for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k];
+          } else {
+            const double *t = (denovo ? tden : t10) + (i * 10 + j) * 10;
+            for (int k = 0; k < 10; k++) sum += t[k] * pc[k];
+          }
+          m[i * A + j] = st.flag ? sum : m[i * A + j] * sum;  // a fresh marriage partial starts at 1
+        }
+    } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
+      const double *pf = part + st.from0 * A;
+      double *pt = part + st.to0 * A;
+      if (st.mp < 0) {
+        double sum = 0.0;
+        for (int j = 0; j < A; j++) sum += pf[j];
+        for (int i = 0; i < A; i++) pt[i] *= sum;
+      } else {
+        const double *m = mp + st.mp * A * A;
+        for (int i = 0; i < A; i++) {
+          double sum = 0.0;
+          if (st.flag) for (int j = 0; j < A; j++) sum += pf[j] * m[j * A + i];
+          else for (int j = 0; j < A; j++) sum += pf[j] * m[i * A + j];
+          pt[i] *= sum;
+        }
+      }
+    } else {
+      const double *pf = part + st.from0 * A, *pm_ = part + st.from1 * A;
+      double *pc = part + st.to0 * A;
+      const double *m = st.mp >= 0 ? mp + st.mp * A * A : nullptr;
+      for (int k = 0; k < A; k++) {
+        double sum = 0.0;
+        for (int i = 0; i < A; i++)
+          for (int j = 0; j < A; j++) {
+            double t;
+            if (A == 3) t = tba_cls(cls, sexes[st.to0], i, j, k);
+            else t = (m || !denovo) ? t10[(i * 10 + j) * 10 + k] : tden[(i * 10 + j) * 10 + k];  // ES:1383 vs 1391
+            if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
+            else sum += pf[i] * pm_[j] * t;
+          }
+        pc[k] *= sum;
+      }
+    }
+  }
+  const double *pfin = part + steps[f.n_steps - 1].to0 * A;
+  double lk = 0.0;
+  for (int i = 0; i < A; i++) lk += pfin[i];
+  return lk;
+}
+
+// shared tables at the start of dynamic shared memory
+struct SmemTables {
+  double lut[256];
+  double mut[100];
+};
+
+__device__ __forceinline__ void load_tables(const DevRun *run, SmemTables *t) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t->lut[i] = run->lut[i];
+  for (int i = threadIdx.x; i < 100; i += blockDim.x) t->mut[i] = run->mut[i];
+}
+
+}  // namespace pm

@@ -1,0 +1,331 @@
+// pm_post.cu — genotype posteriors / GQ / dosage / AB for the emitted sites (sm_100a).
+//
+// Built with -fmad=false: a genotype call is an argmax over posteriors that can tie EXACTLY (a haploid male on chrX
+// with PL 112,0,112, two untouched transversion alleles ...).  The reference resolves such ties by the rounding of its
+// own unfused multiply-then-add sequence (x86-64 without FMA contraction), so this kernel keeps the same operation
+// order and lets no multiply-add pair be contracted.  <= 1 % of the sites reach it; it is not on the roofline.
+#include <cstdio>
+#include <cstdlib>
+
+#include "pm_device.cuh"
+#include "pm_es.cuh"
+#include "pm_kernels.h"
+
+namespace pm {
+
+// ================================================================================================
+// posteriors for emitted sites: one thread per (row, family)
+// ================================================================================================
+struct PostSmem {
+  SmemTables t;
+  double tden[1000];
+  double t10[1000];
+};
+
+__device__ inline void store_person3(pm_person_result &o, double p0, double p1, double p2, int best) {
+  o.post[0] = p0; o.post[1] = p1; o.post[2] = p2;
+  for (int g = 3; g < 10; g++) o.post[g] = 0.0;
+  o.dosage = p1 + p2 * 2;
+  o.best = best;
+  o.gq = gq_of(best == 0 ? p0 : (best == 1 ? p1 : p2));
+  o.ten_state = 0;
+  o.reserved[0] = o.reserved[1] = 0;
+}
+
+// likelihoodKidGenotype on chrX / chrY / MT (NucFam:1334-1443) for configurations 1, 2, 6, 7 (0 and 8 have no
+// special case there, 3..5 are zero); `sex` is the kid's own.
+__device__ inline void kid_cfg_nonauto(int cls, int sex, int cfg, double l11, double l12, double l22, double &lk, double &x11,
+                                       double &x12, double &x22) {
+  const bool male = sex == 1;
+  x11 = x12 = x22 = 0.0;
+  if (cls == PM_CHR_X) {
+    switch (cfg) {
+      case 1: if (male) { lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; } else { lk = 0.5 * (l11 + l12); x11 = 0.5 * l11; x12 = 0.5 * l12; } break;
+      case 2: if (male) { lk = l22; x22 = l22; } else { lk = l12; x12 = l12; } break;
+      case 6: if (male) { lk = l11; x11 = l11; } else { lk = l12; x12 = l12; } break;
+      default: if (male) { lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; } else { lk = 0.5 * (l12 + l22); x12 = 0.5 * l12; x22 = 0.5 * l22; } break;
+    }
+  } else if (cls == PM_CHR_Y) {
+    if (!male) { lk = 1.0; return; }
+    if (cfg == 1 || cfg == 2) { lk = l11; x11 = l11; } else { lk = l22; x22 = l22; }
+  } else {
+    switch (cfg) {
+      case 1: case 7: lk = 0.5 * (l11 + l22); x11 = 0.5 * l11; x22 = 0.5 * l22; break;
+      case 2: lk = l22; x22 = l22; break;
+      default: lk = l11; x11 = l11; break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                              const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
+                                              const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
+                                              size_t res_cap, pm_site_result *__restrict__ res_out,
+                                              pm_person_result *__restrict__ person_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
+  load_tables(run, &sm->t);
+  for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
+    sm->tden[i] = run->tden[i];
+    int gi = i / 100, gj = (i / 10) % 10, gk = i % 10;
+    const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
+    double v = 0.0;
+    for (int x = 0; x < 2; x++)
+      for (int y = 0; y < 2; y++)
+        if (geno_index(al[gi][x], al[gj][y]) == gk) v += 0.25;
+    sm->t10[i] = v;
+  }
+  __syncthreads();
+  const uint32_t n_emit = *n_emit_ptr;
+  const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
+  const size_t total = n_rows * (size_t)run->n_fam;
+  const int np = run->n_person;
+  const double *lut = sm->t.lut, *mut = sm->t.mut;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = w / run->n_fam;
+    const int fi = (int)(w % run->n_fam);
+    const uint32_t s = emit_sites[row];
+    pm_site_result r = res_all[s];
+    const uint4 *recs = recs_all + (size_t)s * np;
+    pm_person_result *out = person_out + row * (size_t)np;
+    const DevFam f = run->fams[fi];
+    if (r.status != PM_SITE_EMITTED) {  // PM_OUT_ALL rows of sites that print nothing
+      if (fi == 0) res_out[row] = r;
+      for (int j = 0; j < f.size; j++) memset(&out[f.first + j], 0, sizeof(pm_person_result));
+      continue;
+    }
+    const int a1 = r.allele1, a2 = r.allele2;
+    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+    const bool mono = (r.flags & PM_FLAG_MONO) != 0;
+    const bool dn = run->denovo != 0 && !run->vcf_mode;
+    // frequency the posteriors are taken at (main:576-587)
+    const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
+    const double q = 1.0 - freq;
+    const int cls = run->vcf_mode ? PM_CHR_AUTO : hdr[s].chr_class;
+    const bool nonauto = cls != PM_CHR_AUTO;
+
+    if (f.kind == 0) {  // CalcPostProb_SinglePerson, NucFam:754-795
+      for (int j = 0; j < f.size; j++) {
+        uint4 rec = recs[f.first + j];
+        double pr0 = freq * freq, pr1 = freq * q * 2, pr2 = q * q;
+        const int sex = nonauto ? run->sex[f.first + j] : 0;
+        if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && sex == 1)) { pr0 = freq; pr1 = 0.0; pr2 = q; }
+        else if (cls == PM_CHR_Y) { pr0 = pr1 = pr2 = 1.0; }
+        double m11 = lut[rec_lk(rec, g11)] * pr0;
+        double m12 = lut[rec_lk(rec, g12)] * pr1;
+        double m22 = lut[rec_lk(rec, g22)] * pr2;
+        double sum = m11 + m12 + m22;
+        if (sum == 0 || (cls == PM_CHR_Y && sex == 2)) store_person3(out[f.first + j], 0, 0, 0, best3(m11, m12, m22));  // NucFam:781, 788
+        else store_person3(out[f.first + j], m11 / sum, m12 / sum, m22 / sum, best3(m11, m12, m22));
+      }
+    } else if (f.kind == 1) {  // nuclear: NucFam:590-752
+      const int nk = f.size - 2;
+      double C[9], pp[9], pm9[9];
+      const bool na = nonauto && !dn;  // the --denovo nuclear code has no chrX / chrY / MT rules
+      // parent-pair prior: HW when nFam>1 (or isMono / freq==1 under --denovo), else the fixed table
+      bool hw = run->n_fam > 1 || (dn ? freq == 1.0 : mono);
+      if (!na) {
+        unit_conditionals(recs, f.first, nk, g11, g12, g22, dn, lut, mut, C);
+        if (hw) parent_priors(freq, pp); else single_trio_priors(pp);
+      } else {
+        // CalcParentMarginal runs before this family's loop assigns `sex` (NucFam:606 vs 610): every kid is given the
+        // sex of the LAST member of the previous family, family 0 that of the last person of the previous emitted
+        // site's last family -- or the initial 0 in the first CalcPostProb of the process (PM_HDR_FIRST_POSTPROB).
+        const int ks = fi > 0 ? run->sex[f.first - 1] : ((hdr[s].reserved & PM_HDR_FIRST_POSTPROB) ? 0 : run->sex[np - 1]);
+        unit_conditionals_nonauto(recs, f.first, nk, g11, g12, g22, cls, ks, lut, C);
+        if (hw) parent_priors_nonauto(cls, freq, pp); else single_trio_priors(pp);
+      }
+      for (int j = 0; j < 9; j++) pm9[j] = C[j] * pp[j];
+      {
+        double p11 = pm9[0] + pm9[1] + pm9[2], p12 = pm9[3] + pm9[4] + pm9[5], p22 = pm9[6] + pm9[7] + pm9[8];
+        double sum = p11 + p12 + p22;
+        if (sum == 0) store_person3(out[f.first], 0, 0, 0, best3(p11, p12, p22));
+        else store_person3(out[f.first], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+        p11 = pm9[0] + pm9[3] + pm9[6]; p12 = pm9[1] + pm9[4] + pm9[7]; p22 = pm9[2] + pm9[5] + pm9[8];
+        sum = p11 + p12 + p22;
+        if (sum == 0) store_person3(out[f.first + 1], 0, 0, 0, best3(p11, p12, p22));
+        else store_person3(out[f.first + 1], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+      }
+      // parentGLF * parentPrior per configuration (NucFam:815-823)
+      double w9[9];
+      {
+        uint4 rf = recs[f.first], rm = recs[f.first + 1];
+        double fl[3] = {lut[rec_lk(rf, g11)], lut[rec_lk(rf, g12)], lut[rec_lk(rf, g22)]};
+        double ml[3] = {lut[rec_lk(rm, g11)], lut[rec_lk(rm, g12)], lut[rec_lk(rm, g22)]};
+        if (na) {  // NucFam:1049-1051
+          fl[1] = 0.0;
+          if (cls == PM_CHR_Y) ml[0] = ml[1] = ml[2] = 1.0;
+          if (cls == PM_CHR_MT) ml[1] = 0.0;
+        }
+        for (int j = 0; j < 9; j++) w9[j] = (fl[j / 3] * ml[j % 3]) * pp[j];
+      }
+      for (int kid = 0; kid < nk; kid++) {
+        pm_person_result &o = out[f.first + 2 + kid];
+        if (!dn) {
+          // KidJointGenoLikelihood + likelihoodKidGenotype, NucFam:798-835, 1334-1443
+          double J[3] = {0, 0, 0};
+          for (int cfg = 0; cfg < 9; cfg++) {
+            double G[3] = {1.0, 1.0, 1.0};
+            for (int kk = 0; kk < nk; kk++) {
+              uint4 rk = recs[f.first + 2 + kk];
+              double l11 = lut[rec_lk(rk, g11)], l12 = lut[rec_lk(rk, g12)], l22 = lut[rec_lk(rk, g22)];
+              double lk, x11, x12, x22;
+              if (na && cfg != 0 && cfg != 8) {
+                if (cfg >= 3 && cfg <= 5) { lk = 0.0; x11 = x12 = x22 = 0.0; }
+                else kid_cfg_nonauto(cls, run->sex[f.first + 2 + kk], cfg, l11, l12, l22, lk, x11, x12, x22);
+              } else
+              switch (cfg) {
+                case 0: lk = l11; x11 = l11; x12 = 0; x22 = 0; break;
+                case 1: case 3: lk = 0.5 * (l11 + l12); x11 = l11 * 0.5; x12 = l12 * 0.5; x22 = 0; break;
+                case 2: case 6: lk = l12; x11 = 0; x12 = l12; x22 = 0; break;
+                case 4: lk = 0.25 * l11 + 0.5 * l12 + 0.25 * l22; x11 = l11 * 0.25; x12 = l12 * 0.5; x22 = l22 * 0.25; break;
+                case 5: case 7: lk = 0.5 * (l12 + l22); x11 = 0; x12 = l12 * 0.5; x22 = l22 * 0.5; break;
+                default: lk = l22; x11 = 0; x12 = 0; x22 = l22; break;
+              }
+              if (kk != kid) { G[0] *= lk; G[1] *= lk; G[2] *= lk; }
+              else { G[0] *= x11; G[1] *= x12; G[2] *= x22; }
+            }
+            for (int t = 0; t < 3; t++) J[t] = cfg == 0 ? G[t] * w9[cfg] : J[t] + G[t] * w9[cfg];
+          }
+          double sum = J[0] + J[1] + J[2];
+          double p0 = 0, p1 = 0, p2 = 0;
+          if (sum != 0.0) { p0 = J[0] / sum; p1 = J[1] / sum; p2 = J[2] / sum; }
+          store_person3(o, p0, p1, p2, best3(p0, p1, p2));
+        } else {
+          // KidJointGenoLikelihood_denovo, NucFam:838-868, 1446-1551
+          double geno[10];
+          for (int g = 0; g < 10; g++) geno[g] = 0.0;
+          const double *M1 = mut + g11 * 10, *M2 = mut + g12 * 10, *M3 = mut + g22 * 10;
+          for (int cfg = 0; cfg < 9; cfg++) {
+            double lkg[10];
+            for (int g = 0; g < 10; g++) lkg[g] = 1.0;
+            for (int kk = 0; kk < nk; kk++) {
+              uint4 rk = recs[f.first + 2 + kk];
+              if (kk != kid) {
+                double d11 = 0, d12 = 0, d22 = 0;
+                for (int g = 0; g < 10; g++) {
+                  double l = lut[rec_lk(rk, g)];
+                  d11 += M1[g] * l; d12 += M2[g] * l; d22 += M3[g] * l;
+                }
+                double lk;
+                switch (cfg) {
+                  case 0: lk = d11; break;
+                  case 1: case 3: lk = 0.5 * (d11 + d12); break;
+                  case 2: case 6: lk = d12; break;
+                  case 4: lk = 0.25 * d11 + 0.5 * d12 + 0.25 * d22; break;
+                  case 5: case 7: lk = 0.5 * (d12 + d22); break;
+                  default: lk = d22; break;
+                }
+                for (int g = 0; g < 10; g++) lkg[g] *= lk;
+              } else {
+                for (int g = 0; g < 10; g++) {
+                  double l = lut[rec_lk(rk, g)], wgt;
+                  switch (cfg) {
+                    case 0: wgt = M1[g]; break;
+                    case 1: case 3: wgt = 0.5 * M1[g] + 0.5 * M2[g]; break;
+                    case 2: case 6: wgt = M2[g]; break;
+                    case 4: wgt = 0.25 * M1[g] + 0.5 * M2[g] + 0.25 * M3[g]; break;
+                    case 5: case 7: wgt = 0.5 * M2[g] + 0.5 * M3[g]; break;
+                    default: wgt = M3[g]; break;
+                  }
+                  lkg[g] *= wgt * l;
+                }
+              }
+            }
+            for (int g = 0; g < 10; g++) geno[g] += lkg[g] * w9[cfg];
+          }
+          double sum = 0.0;
+          for (int g = 0; g < 10; g++) sum += geno[g];
+          double mx = 0.0;
+          int best = 0;
+          for (int g = 0; g < 10; g++) {
+            double pg = sum == 0.0 ? 0.0 : geno[g] / sum;
+            o.post[g] = pg;
+            if (mx < pg) { mx = pg; best = g; }
+          }
+          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
+          o.reserved[0] = o.reserved[1] = 0;
+        }
+      }
+    } else {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216)
+      for (int j = 0; j < f.size; j++) {
+        pm_person_result &o = out[f.first + j];
+        if (!dn) {
+          if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { store_person3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
+          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g11, cls);
+          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g12, cls);
+          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g22, cls);
+          double sum = l11 + l12 + l22;
+          if (sum == 0) store_person3(o, 0, 0, 0, best3(l11, l12, l22));
+          else store_person3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
+        } else {
+          double lk[10], sum = 0.0;
+          for (int g = 0; g < 10; g++) {
+            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, sm->tden, sm->t10, j, g, cls);
+            sum += lk[g];
+          }
+          double mx = 0.0;
+          int best = 0;
+          for (int g = 0; g < 10; g++) {
+            o.post[g] = sum == 0 ? 0.0 : lk[g] / sum;
+            if (mx < lk[g]) { mx = lk[g]; best = g; }
+          }
+          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
+          o.reserved[0] = o.reserved[1] = 0;
+        }
+      }
+    }
+    if (fi == 0) {
+      // CalculateAB (NucFam:1006-1039), only printed by the non-de-novo writer on autosomes
+      if (nonauto) {
+        r.ab = 0.0;  // not computed and not printed there (NucFam:1791-1800)
+      } else if (!dn && !run->vcf_mode) {
+        double A = 0.0, Bsum = 0.0;
+        const double f0 = r.freq;
+        const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
+        for (int i = 0; i < np; i++) {
+          uint4 rec = recs[i];
+          int depth = rec_depth(rec);
+          int u11 = rec_lk(rec, g11), u12 = rec_lk(rec, g12), u22 = rec_lk(rec, g22);
+          double l11 = lut[u11], l12 = lut[u12], l22 = lut[u22];
+          double phet = (p12 * l12) / (p11 * l11 + p12 * l12 + p22 * l22);
+          if (phet > 1e-05 && depth > 0) {
+            int scale = u22 + u11 - 2 * u12 + 6 * depth;
+            int minimum = abs(u22 - u11);
+            if (scale < 4) scale = 4;
+            if (scale < minimum) scale = minimum;
+            int nref = (int)(0.5 * depth * (1 + (u22 - u11) / (scale + 1e-30)));
+            A += phet * nref;
+            Bsum += phet * depth;
+          }
+        }
+        r.ab = (0.05 + A) / (0.1 + Bsum);
+      } else {
+        r.ab = 0.5;
+      }
+      res_out[row] = r;
+    }
+  }
+}
+
+
+cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
+                        const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
+                        size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
+                        int sm_count, cudaStream_t stream) {
+  if (max_rows == 0) return cudaSuccess;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostSmem));
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  size_t want = (max_rows * (size_t)n_fam + 127) / 128;
+  size_t cap = (size_t)sm_count * 16;
+  unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (grid == 0) grid = 1;
+  k_post<<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out);
+  return cudaGetLastError();
+}
+
+}  // namespace pm

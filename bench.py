@@ -309,9 +309,20 @@ def main():
         achieved_tflops = flops_per_launch / (main_ms * 1e-3) / 1e12
         bytes_per_launch = algorithmic_bytes_per_site(npers) * S
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        # DRAM traffic of the kernel: not measurable from inside this process; taken per site from the committed
+        # `ncu --set full` capture of the same kernel on the same workload and scaled to this launch's sites
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tj = json.load(f)
+            per_site = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["sites_in_capture"]
+            traffic = per_site * S
+            traffic_src = "%s: %.0f DRAM bytes/site (algorithmic %d)" % (tj["source"], per_site, algorithmic_bytes_per_site(npers))
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {
             "bound": "fp64", "kernel": "k_sites_wide", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-            "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": None,
+            "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
             "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
             "flops_per_site": flops_per_site, "log10_per_site": log10_per_site,
             "hypotheses_per_site": hyp_per_site, "evaluations_per_site": ev_per_site, "kernel_ms_per_launch": main_ms,

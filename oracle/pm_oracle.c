@@ -284,6 +284,7 @@ struct pmo_ctx {
   double prior; /* polyPrior, autosome */
   double prior_class[4]; /* GetPolyPrior per PM_CHR_* class (NucFam:231-304) */
   int chrX, chrY, chrMT;  /* SetNonAutosomeFlags of the current site's chromosome (main:312-315) */
+  int unrelated;          /* --quick_call pre-pass: MakeUnrelated() is in force (FLSeq:55-60), founders == count everywhere */
   /* current site */
   pm_site_hdr hdr;
   const pm_person_site *ps;
@@ -467,9 +468,10 @@ static double lkSinglePerson(const pmo_ctx *c, const famlk_t *k, int person, dou
 }
 /* NucFam:941-975 */
 static double lkSingleFam(const pmo_ctx *c, famlk_t *k, int i, double freq, int denovo) {
-  if (c->famSize[i] == c->famFounders[i]) {
+  if (c->unrelated || c->famSize[i] == c->famFounders[i]) {
+    const int founders = c->unrelated ? c->famSize[i] : c->famFounders[i];
     double lk = 1.0;
-    for (int j = 0; j < c->famFounders[i]; j++) lk *= lkSinglePerson(c, k, c->famFirst[i] + j, freq);
+    for (int j = 0; j < founders; j++) lk *= lkSinglePerson(c, k, c->famFirst[i] + j, freq);
     return lk;
   }
   double sum = 0.0;
@@ -651,7 +653,7 @@ static double CalcAllFamLogLikelihood(pmo_ctx *c, famlk_t *k, double freq) {
   double loglk = 0.0;
   k->n_eval++;
   for (int i = 0; i < c->nFam; i++) {
-    if (fam_isNuclear(c, i) || c->famSize[i] == c->famFounders[i])
+    if (c->unrelated || fam_isNuclear(c, i) || c->famSize[i] == c->famFounders[i])
       loglk += log10(lkSingleFam(c, k, i, freq, c->par.denovo));
     else
       loglk += c->par.denovo ? log10(CalcSingleFamLikelihood_denovo(c, k, i, freq)) : log10(CalcSingleFamLikelihood_BA(c, k, i, freq));
@@ -728,7 +730,8 @@ static double OptimizeFrequency(pmo_ctx *c, famlk_t *k) {
 /* FLSeq:91-104 */
 static double PolymorphismLogLikelihood(pmo_ctx *c, famlk_t *k, int a1, int a2) {
   SetAlleles(k, a1, a2);
-  if (c->nFam > 1 || (c->nFam == 1 && !fam_isNuclear(c, 0))) {
+  /* with founders == count no family isNuclear() (generations == 2 needs a third member): always Brent */
+  if (c->unrelated || c->nFam > 1 || (c->nFam == 1 && !fam_isNuclear(c, 0))) {
     OptimizeFrequency(c, k);
     return -k->fmin;
   }
@@ -1262,7 +1265,25 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
   if (fl[0].avgMapQual < par->min_map_quality) { r->status = PM_SITE_MIN_MAPQ; return 0; }
 
   int ts = poly_ts(refBase), tvs1 = poly_tvs1(refBase), tvs2 = poly_tvs2(refBase);
-  if (par->quick_call) { set_err("oracle: --quick_call is not restated yet"); return PM_EUNSUPPORTED; }
+  if (par->quick_call) { /* main:354-437: the same four (seven) hypotheses with everybody unrelated */
+    c->unrelated = 1;
+    const double polyPrior_unr = polyPrior; /* GetPolyPrior_unr() == GetPolyPrior(): both read nFounders (NucFam:295-311) */
+    fl[0].varllk[0] = log10(1 - polyPrior_unr) + MonomorphismLogLikelihood(c, refBase);
+    fl[0].varllk[1] = log10(polyPrior_unr * prior_ts) + PolymorphismLogLikelihood(c, &fl[1], refBase, ts);
+    fl[0].varllk[2] = log10(polyPrior_unr * prior_tv) + PolymorphismLogLikelihood(c, &fl[2], refBase, tvs1);
+    fl[0].varllk[3] = log10(polyPrior_unr * prior_tv) + PolymorphismLogLikelihood(c, &fl[3], refBase, tvs2);
+    int qidx = CalcVarPosterior(&fl[0], refBase, 4);
+    if (fl[0].varPostProb < 0.99) {
+      fl[0].varllk[4] = log10(polyPrior_unr * 0.001) + PolymorphismLogLikelihood(c, &fl[4], ts, tvs1);
+      fl[0].varllk[5] = log10(polyPrior_unr * 0.001) + PolymorphismLogLikelihood(c, &fl[5], ts, tvs2);
+      fl[0].varllk[6] = log10(polyPrior_unr * 0.001) + PolymorphismLogLikelihood(c, &fl[6], tvs1, tvs2);
+      qidx = CalcVarPosterior(&fl[0], refBase, 7);
+    }
+    /* the two `continue`s below skip RestoreFounderCount() in the reference; the next site's pre-pass calls
+       MakeUnrelated() again and nothing in between reads the founder counts, so the leak is not observable */
+    c->unrelated = 0;
+    if (fl[0].varPostProb < par->posterior_cutoff || qidx == 0) { r->status = PM_SITE_QUICK_SKIP; return 0; }
+  }
 
   /* main:439-495 */
   if (!par->denovo) {

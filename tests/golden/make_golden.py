@@ -57,7 +57,7 @@ DN = ["--denovo", "--rate_denovo", "1.5e-07"]
 for _c, _flag in (("x", "--chrX"), ("y", "--chrY"), ("mt", "--MT")):
     for _p, _ped in (("quartets", "test.ped"), ("mix", "test.mix.ped"), ("single", "single.ped"), ("ext", "ext.ped")):
         CASES[f"{_c}_{_p}_ba"] = (_ped, [_flag, "1"], (_c, _p) in (("x", "quartets"), ("y", "mix"), ("mt", "ext")))
-        CASES[f"{_c}_{_p}_dn"] = (_ped, [_flag, "1"] + DN, False)
+        CASES[f"{_c}_{_p}_dn"] = (_ped, [_flag, "1"] + DN, (_c, _p) == ("y", "ext"))  # y_ext_dn: see FLAT_OBJECTIVE_ROWS in cli_util.py
 
 
 VCF_CASES = {  # name: (ped file, input vcf)

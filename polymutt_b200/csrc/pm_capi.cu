@@ -36,6 +36,13 @@ struct pm_ctx {
   pm::DevFam *d_fams = nullptr;
   pm::DevUnit *d_units = nullptr;
   uint8_t *d_sex = nullptr;
+  // --quick_call pre-pass (main.cpp:354-437): the same kernels on a second description of the run in which everybody
+  // is an unrelated founder; its per-site verdicts overrule the real pass (k_quick_merge)
+  pm::LaunchPlan plan_q;
+  pm::DevRun *d_run_q = nullptr;
+  pm::DevUnit *d_units_q = nullptr;
+  pm_site_result *d_res_q = nullptr;
+  uint16_t *d_status_q = nullptr;
   int32_t *d_es = nullptr;
   pm::DevStep *d_steps = nullptr;
   int *d_err = nullptr;
@@ -79,6 +86,10 @@ int ensure_scratch(pm_ctx *c, size_t n_sites) {
   int rc;
   if ((rc = dev_alloc(&c->d_res_all, n_sites))) return rc;
   if ((rc = dev_alloc(&c->d_emit_sites, n_sites))) return rc;
+  if (c->par.quick_call) {
+    if ((rc = dev_alloc(&c->d_res_q, n_sites))) return rc;
+    if ((rc = dev_alloc(&c->d_status_q, n_sites))) return rc;
+  }
   c->cap_sites = n_sites;
   return PM_OK;
 }
@@ -104,7 +115,7 @@ void build_tden(const double *mut, double *tden) {
 extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const double *lut256, int device) {
   pmh::clear_error();
   if (!ped || !par || ped->n_fam <= 0 || ped->n_person <= 0) { fail(PM_EINVAL, "pm_create: empty pedigree or missing parameters"); return nullptr; }
-  if (par->quick_call) { fail(PM_EUNSUPPORTED, "pm_create: --quick_call is not implemented on the device path yet"); return nullptr; }
+  if (par->quick_call && par->vcf_input) { fail(PM_EINVAL, "pm_create: --quick_call does not exist for VCF input"); return nullptr; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) { fail(PM_ECUDA, "pm_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e)); return nullptr; }
@@ -267,6 +278,29 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
          cudaMemcpy(c->d_run, &run, sizeof run, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemset(c->d_err, 0, 2 * sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
   }
+  if (ok && par->quick_call) {
+    // MakeUnrelated() (FLSeq.cpp:55-60): founders = count in every family, so every person is a single founder, no
+    // family isNuclear() and PolymorphismLogLikelihood always runs Brent (FLSeq.cpp:94).  The pre-pass never uses the
+    // --denovo model for H0 (main.cpp:370) and stops at the `continue`s of main.cpp:432-433.
+    std::vector<pm::DevUnit> units_q;
+    for (int i = 0; i < ped->n_person; i++) units_q.push_back({i, -1, 0, (int32_t)ped->sex[i]});
+    pm::DevRun run_q = run;
+    run_q.n_units = ped->n_person; run_q.n_es = 0; run_q.n_kids = 0; run_q.use_brent = 1;
+    run_q.denovo = 0; run_q.force_call = 0; run_q.out_all_sites = 0;
+    run_q.counters = c->d_counters + 8;  // its work is counted apart
+    e = pm::plan_launch(&c->plan_q, c->n_person, ped->n_person, 0, 0, c->sm_count);
+    if (e != cudaSuccess) {
+      fail(e == cudaErrorNotSupported ? PM_EUNSUPPORTED : PM_ECUDA, "--quick_call: the unrelated pre-pass needs %d single-founder units (%s)", ped->n_person, cudaGetErrorString(e));
+      pm_destroy(c);
+      return nullptr;
+    }
+    ok = dev_alloc(&c->d_run_q, 1) == PM_OK && dev_alloc(&c->d_units_q, units_q.size()) == PM_OK;
+    if (ok) {
+      run_q.units = c->d_units_q;
+      ok = cudaMemcpy(c->d_units_q, units_q.data(), units_q.size() * sizeof(pm::DevUnit), cudaMemcpyHostToDevice) == cudaSuccess &&
+           cudaMemcpy(c->d_run_q, &run_q, sizeof run_q, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+  }
   if (!ok) {
     if (!*pmh::last_error()) fail(PM_ECUDA, "pm_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
     pm_destroy(c);
@@ -279,7 +313,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_sex);
+  cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
   cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
@@ -320,7 +354,10 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
   if (rc) return rc;
   uint32_t *d_cnt = d_n_res ? d_n_res : c->d_n_emit;
   CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  if (c->par.quick_call)
+    CUDA_TRY(pm::launch_sites(c->plan_q, c->d_run_q, d_hdr, (const uint4 *)d_person_site, nullptr, n_sites, c->d_res_q, c->d_status_q, c->d_err, c->stream));
   CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
+  if (c->par.quick_call) CUDA_TRY(pm::launch_quick_merge(c->d_status_q, n_sites, c->d_res_all, d_status_out, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
@@ -328,6 +365,7 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                            d_person_out, c->sm_count, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
   c->launches = c->plan.kind == pm::LaunchPlan::WIDE ? 4 : 3;  // wide: the autosomal instance + the (normally empty) chrX/Y/MT one
+  if (c->par.quick_call) c->launches += (c->plan_q.kind == pm::LaunchPlan::WIDE ? 2 : 1) + 1;
   c->timing_cached = false;
   return PM_OK;
 }

@@ -776,6 +776,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
 }
 
 // ================================================================================================
+// --quick_call (main.cpp:354-437): the verdict of the everybody-unrelated pre-pass overrules the real pass
+// ================================================================================================
+__global__ void k_quick_merge(const uint16_t *__restrict__ status_q, size_t n_sites, pm_site_result *__restrict__ res,
+                              uint16_t *__restrict__ status) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sites) return;
+  const int code_q = status_q[s] & 0xf;
+  if (code_q != PM_SITE_NOCALL && code_q != PM_SITE_MONO) return;  // called a variant, or filtered out in both passes alike
+  const pm_site_result old = res[s];
+  pm_site_result r;
+  memset(&r, 0, sizeof r);
+  r.site = old.site; r.maxidx = -1; r.status = PM_SITE_QUICK_SKIP;
+  r.total_depth = old.total_depth; r.num_samp = old.num_samp; r.perc_samp = old.perc_samp; r.avg_map_qual = old.avg_map_qual;
+  res[s] = r;
+  status[s] = PM_SITE_QUICK_SKIP;
+}
+
+// ================================================================================================
 // ordered compaction of emitted sites (deterministic, single block)
 // ================================================================================================
 __global__ void __launch_bounds__(1024) k_compact(const uint16_t *__restrict__ status, size_t n_sites,
@@ -940,6 +958,12 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   plan->grid = sm_count * per_sm;  // persistent: a multiple of the SM count
   plan->blocks_per_sm = per_sm;
   return cudaSuccess;
+}
+
+cudaError_t launch_quick_merge(const uint16_t *d_status_q, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, cudaStream_t stream) {
+  if (n_sites == 0) return cudaSuccess;
+  k_quick_merge<<<(unsigned)((n_sites + 255) / 256), 256, 0, stream>>>(d_status_q, n_sites, d_res, d_status);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,

@@ -32,6 +32,9 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
                          const double *d_mono, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err,
                          cudaStream_t stream);
 
+// --quick_call: sites the unrelated pre-pass did not call (no-call or hom-ref there) become PM_SITE_QUICK_SKIP
+cudaError_t launch_quick_merge(const uint16_t *d_status_q, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, cudaStream_t stream);
+
 cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,
                            cudaStream_t stream);
 

@@ -81,6 +81,16 @@ for _c, _flag in (("x", "--chrX"), ("y", "--chrY"), ("mt", "--MT")):
         NONAUTO_CASES.append((f"{_c}_{_p}_ba", _ped, [_flag, "1"], f"ref_{_c}_{_p}_ba" + (".vcf.gz" if _full else ".sha")))
         NONAUTO_CASES.append((f"{_c}_{_p}_dn", _ped, [_flag, "1", "--denovo", "--rate_denovo", "1.5e-07"],
                               f"ref_{_c}_{_p}_dn" + (".vcf.gz" if (_c, _p) == ("y", "ext") else ".sha")))
+# --quick_call: outputs of the unmodified reference with the everybody-unrelated pre-pass switched on
+QUICK_CASES = [
+    ("q_quartets", "test.ped", ["--quick_call"], "ref_q_quartets.sha"),
+    ("q_mix", "test.mix.ped", ["--quick_call"], "ref_q_mix.sha"),
+    ("q_single", "single.ped", ["--quick_call"], "ref_q_single.sha"),
+    ("q_ext", "ext.ped", ["--quick_call"], "ref_q_ext.sha"),
+    ("q_quartets_dn", "test.ped", ["--quick_call", "--denovo", "--rate_denovo", "1.5e-07"], "ref_q_quartets_dn.vcf.gz"),
+    ("q_mix_c099", "test.mix.ped", ["--quick_call", "-c", "0.99"], "ref_q_mix_c099.sha"),
+    ("q_x_quartets", "test.ped", ["--quick_call", "--chrX", "1"], "ref_q_x_quartets.sha"),
+]
 # Rows whose allele frequency is rounding noise in the reference itself: the objective Brent minimises there does not
 # depend on p at all (every likelihood that multiplies p equals the one that multiplies q, so L(p) = l (p + q)), its
 # value wobbles in the last bit and the reference's optimiser ends wherever that noise sends it.  No other

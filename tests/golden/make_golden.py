@@ -51,6 +51,16 @@ CASES = {  # name: (ped file, extra args, keep full text?)
     "mix_denovo_loose": ("test.mix.ped", ["--denovo", "--rate_denovo", "1e-4", "--minLLR_denovo", "1e-3", "--tstv_denovo", "1.0"], True),
     "mix_strict": ("test.mix.ped", ["-c", "0.99", "--minMapQuality", "50", "--minPercSampleWithData", "90", "--theta", "0.01", "--poly_tstv", "3.0"], True),
 }
+# --quick_call (the everybody-unrelated pre-pass of main.cpp:354-437)
+CASES.update({
+    "q_quartets": ("test.ped", ["--quick_call"], False),
+    "q_mix": ("test.mix.ped", ["--quick_call"], False),
+    "q_single": ("single.ped", ["--quick_call"], False),
+    "q_ext": ("ext.ped", ["--quick_call"], False),
+    "q_quartets_dn": ("test.ped", ["--quick_call", "--denovo", "--rate_denovo", "1.5e-07"], True),
+    "q_mix_c099": ("test.mix.ped", ["--quick_call", "-c", "0.99"], False),
+    "q_x_quartets": ("test.ped", ["--quick_call", "--chrX", "1"], False),
+})
 # chrX / chrY / MT rules: the example's only section is labelled "1", so `--chrX 1` (--chrY 1, --MT 1) makes the
 # reference treat the same data as that chromosome.  Three cases keep their text, the rest sha256 + line count.
 DN = ["--denovo", "--rate_denovo", "1.5e-07"]

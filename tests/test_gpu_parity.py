@@ -33,6 +33,11 @@ EXAMPLE_CASES = [
     ("ceph_ba", "ceph.ped", dict(), 40000, 0),
     ("ceph_denovo", "ceph.ped", dict(denovo=True), 2500, 0),
     ("ceph_all_sites", "ceph.ped", dict(out_all_sites=True), 3000, 5000),
+    # --quick_call: the everybody-unrelated pre-pass (main.cpp:354-437) decides which sites the real model sees
+    ("quartets_quick", "test.ped", dict(quick_call=True), None, 0),
+    ("mix_quick_denovo", "test.mix.ped", dict(quick_call=True, denovo=True, denovo_mut_rate=1.5e-7), None, 0),
+    ("single_quick", "single.ped", dict(quick_call=True), 40000, 0),
+    ("ext_quick", "ext.ped", dict(quick_call=True, posterior_cutoff=0.9), 30000, 0),
 ]
 
 
@@ -185,6 +190,8 @@ WIDE_CASES = [
     ("quartets_and_sibships", lambda: synth.families([4] * 100 + [5] * 40 + [6] * 10), dict(), 500, 10.0),
     ("trios1000_denovo", lambda: synth.trios(1000), dict(denovo=True), 200, 4.0),
     ("trios1000_ba", lambda: synth.trios(1000), dict(), 200, 4.0),
+    ("mixed70_quick", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(quick_call=True), 2500, 40.0),
+    ("trios300_quick_denovo", lambda: synth.trios(300), dict(quick_call=True, denovo=True), 400, 10.0),
 ]
 # the same through the chrX / chrY / MT instance of the wide kernel (last field: chr_class, -1 = mixed per site)
 WIDE_NONAUTO_CASES = [

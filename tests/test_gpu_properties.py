@@ -125,4 +125,4 @@ def test_unsupported_shapes_fail_loudly():
     with pytest.raises(RuntimeError, match="not supported"):
         Engine(ped, Params())
     with pytest.raises(RuntimeError, match="quick_call"):
-        Engine(synth.trios(3), Params(quick_call=True))
+        Engine(synth.trios(3), Params(quick_call=True, vcf_input=True))

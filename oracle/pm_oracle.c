@@ -1283,6 +1283,10 @@ static int call_site(pmo_ctx *c, uint32_t site, pm_site_result *r, pm_person_res
        MakeUnrelated() again and nothing in between reads the founder counts, so the leak is not observable */
     c->unrelated = 0;
     if (fl[0].varPostProb < par->posterior_cutoff || qidx == 0) { r->status = PM_SITE_QUICK_SKIP; return 0; }
+    /* A lone nuclear family does not run Brent in the real pass (FLSeq:94-103), so in the reference famlk[1..6].min
+       keep the pre-pass optima (or older sites' ones) and leak into famlk[0].min.  Nothing prints it there (no AF, no
+       AB for a single nuclear family, NucFam:1795-1802); the restatement reports the same 0 as without --quick_call. */
+    if (c->nFam == 1 && fam_isNuclear(c, 0)) for (int h = 1; h < 7; h++) fl[h].min = 0.0;
   }
 
   /* main:439-495 */

@@ -205,6 +205,13 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   if (lut256) memcpy(run.lut, lut256, sizeof run.lut); else pm_fill_lut(run.lut);
   pm_genotype_mutation_matrix(par->denovo_mut_rate, par->denovo_tstv, run.mut);
   build_tden(run.mut, run.tden);
+  {  // transmission[i][j][k], ES:752-785
+    static const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
+    for (int i = 0; i < 10; i++)
+      for (int j = 0; j < 10; j++)
+        for (int x = 0; x < 2; x++)
+          for (int y = 0; y < 2; y++) run.t10[(i * 10 + j) * 10 + pm::geno_index(al[i][x], al[j][y])] += 0.25;
+  }
   // SetPolyPrior (NucFam:231-242) and the per-hypothesis prior terms of main:447-533
   double prior = 0;
   for (int i = 1; i <= 2 * founders_total; i++) prior += 1.0 / i;

@@ -457,13 +457,23 @@ __device__ __noinline__ double log10_ol(const WideShared *ws, double m, int e) {
   return fma(l1p, 0.43429448190325182765, ws->log_tab[i]) + (double)e * kLog10_2;
 }
 
-template <int U, bool NA>
+template <int U, bool NA, bool ES>
 struct WideEval {
   const DevRun *run;
   const uint4 *recs;  // site records in shared memory
   WideShared *ws;
   const double *kidD;  // per-site kid table in shared memory (nullptr = build D on the fly)
   int G, Tg, grp, t;  // groups, threads per group, my group, my index inside the group
+  int eg11, eg12, eg22;  // ES: genotype indices of the current hypothesis (the peel has no per-hypothesis set-up)
+
+  // ES: extended families take part in every evaluation through a thread-serial Elston-Stewart peel, family e on
+  // thread e of the group (FLSeq.cpp:222-240 sums log10 over all families; here: one more factor of the product).
+  __device__ __noinline__ double es_factor(int e, bool denovo, double p) const {
+    const DevFam f = run->fams[run->es_fams[e]];
+    const int cls = NA ? ws->cls : PM_CHR_AUTO;
+    return denovo ? es_likelihood<10>(run, f, recs, eg11, eg12, eg22, true, p, ws->t.lut, run->tden, run->t10, -1, -1, cls)
+                  : es_likelihood<3>(run, f, recs, eg11, eg12, eg22, false, p, ws->t.lut, run->tden, run->t10, -1, -1, cls);
+  }
   double B[U][5];     // per unit, scaled by an exact power of two so that the largest coefficient is in [1,2)
   int K;              // sum over my units of the exponents taken out: prod_u L_u = 2^K * prod_u L'_u
 
@@ -478,6 +488,7 @@ struct WideEval {
     if (mine) {
       const int x = a1[grp], y = a2[grp];
       const int g11 = geno_index(x, x), g12 = geno_index(x, y), g22 = geno_index(y, y);
+      if (ES) { eg11 = g11; eg12 = g12; eg22 = g22; }
       const int mode = (denovo ? 1 : 0) | (NA ? (ws->cls << 1) : 0);
 #pragma unroll
       for (int k = 0; k < U; k++) {
@@ -540,6 +551,8 @@ struct WideEval {
           }
           fa.m = (v0 * v1) * (v2 * v3);
         }
+        if (ES)
+          for (int e = t; e < run->n_es; e += Tg) fprod_mul(fa, es_factor(e, denovo, p));
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[grp][wg] = acc.m; ws->warp_e[grp][wg] = acc.e; }
@@ -549,6 +562,8 @@ struct WideEval {
         fa.m = 1.0; fa.e = K;   // B[k][4] carries the same power-of-two scaling as the unit
 #pragma unroll
         for (int k = 0; k < U; k++) fprod_mul(fa, B[k][4]);
+        if (ES)  // a founder's prior at p = 1 is (1, 0, 0) whatever the second allele: H1's alleles give H0's value
+          for (int e = t; e < run->n_es; e += Tg) fprod_mul(fa, es_factor(e, true, 1.0));
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[kMaxChains][wg] = acc.m; ws->warp_e[kMaxChains][wg] = acc.e; }
@@ -582,7 +597,8 @@ struct WideEval {
 
 // NA = false: the autosomal instance; sites on chrX / chrY / MT are left untouched and flagged in err[1].
 // NA = true: launched right behind it, returns at once unless err[1] is set, then does only those sites.
-template <int U, int MAXT, bool NA>
+// ES = the pedigree also has extended families (evaluated by WideEval::es_factor); again separate instances.
+template <int U, int MAXT, bool NA, bool ES>
 __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                                         const uint4 *__restrict__ recs_all, const double *__restrict__ mono_all,
                                                         size_t n_sites, int groups, int nbuf, int kid_table,
@@ -610,7 +626,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
   int cur = 0;
   if (threadIdx.x == 0 && blockIdx.x < n_sites)
     tma_issue_site(site_base, recs_all + (size_t)blockIdx.x * np, (uint32_t)np * 16u, &ws->mbar[0]);
-  WideEval<U, NA> ev;
+  WideEval<U, NA, ES> ev;
   ev.run = run; ev.ws = ws; ev.kidD = kid_tab;
   ev.G = groups; ev.Tg = blockDim.x / groups; ev.grp = threadIdx.x / ev.Tg; ev.t = threadIdx.x % ev.Tg;
   const int G = groups;
@@ -883,13 +899,18 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
     cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
-#define PM_WIDE(U_, MT_)                                                                                                                        \
-  k_sites_wide<U_, MT_, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers,     \
-                                                                     plan.kid_table, d_res, d_status, d_err);                                    \
-  k_sites_wide<U_, MT_, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers,      \
-                                                                    plan.kid_table, d_res, d_status, d_err)
+#define PM_WIDE_ARGS d_run, d_hdr, d_recs, d_mono, n_sites, plan.chains, plan.site_buffers, plan.kid_table, d_res, d_status, d_err
+#define PM_WIDE(U_, MT_)                                                                       \
+  if (plan.es) {                                                                               \
+    k_sites_wide<U_, MT_, false, true><<<grid, plan.threads, smem, stream>>>(PM_WIDE_ARGS);    \
+    k_sites_wide<U_, MT_, true, true><<<grid, plan.threads, smem, stream>>>(PM_WIDE_ARGS);     \
+  } else {                                                                                     \
+    k_sites_wide<U_, MT_, false, false><<<grid, plan.threads, smem, stream>>>(PM_WIDE_ARGS);   \
+    k_sites_wide<U_, MT_, true, false><<<grid, plan.threads, smem, stream>>>(PM_WIDE_ARGS);    \
+  }
     PM_WIDE_DISPATCH(plan, PM_WIDE);
 #undef PM_WIDE
+#undef PM_WIDE_ARGS
   }
   return cudaGetLastError();
 }
@@ -900,6 +921,7 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   plan->kid_table = 0;
   plan->site_buffers = 1;
   plan->low_regs = 0;
+  plan->es = 0;
   if (n_units <= kNarrowMaxUnits) {
     plan->kind = LaunchPlan::NARROW;
     plan->threads = kNarrowThreads;
@@ -908,8 +930,8 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
     plan->blocks_per_sm = 0;
     return cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
   }
-  if (n_es > 0) return cudaErrorNotSupported;
   plan->kind = LaunchPlan::WIDE;
+  plan->es = n_es > 0 ? 1 : 0;  // extended families ride along as thread-serial peels (WideEval::es_factor)
   // G groups (one Brent chain each) x Tg threads x U units per thread, Tg * U >= n_units.
   // Measured on B200 (1,000 trios, --denovo): one chain per block with three independent blocks per SM
   // (6.7 M sites/s) beats three chains in one 384-thread block (5.6 M): independent blocks overlap each
@@ -948,9 +970,15 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   int per_sm = 1;
   const int T = plan->threads;
 #define PM_ATTR(U_, MT_)                                                                                              \
-  e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_, false>, T, smem)
+  if (plan->es) {                                                                                                        \
+    e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_, false, true>, T, smem); \
+  } else {                                                                                                               \
+    e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U_, MT_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sites_wide<U_, MT_, false, false>, T, smem); \
+  }
   PM_WIDE_DISPATCH(*plan, PM_ATTR);
 #undef PM_ATTR
   if (e != cudaSuccess) return e;

@@ -23,6 +23,7 @@ struct LaunchPlan {
   int site_buffers;       // wide: 2 = the next site is prefetched by TMA while this one is computed
   int low_regs;           // wide: use the 128-register instantiation (more resident blocks per SM)
   int kid_table;          // wide, --denovo: kids' ten mutation-mixed likelihoods are built once per site in shared memory
+  int es;                 // wide: the pedigree has extended families too (the ES instances of the kernel)
   int n_person;
 };
 

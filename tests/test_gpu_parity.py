@@ -35,7 +35,7 @@ EXAMPLE_CASES = [
     ("ceph_all_sites", "ceph.ped", dict(out_all_sites=True), 3000, 5000),
     # --quick_call: the everybody-unrelated pre-pass (main.cpp:354-437) decides which sites the real model sees
     ("quartets_quick", "test.ped", dict(quick_call=True), None, 0),
-    ("mix_quick_denovo", "test.mix.ped", dict(quick_call=True, denovo=True, denovo_mut_rate=1.5e-7), None, 0),
+    ("mix_quick_denovo", "test.mix.ped", dict(quick_call=True, denovo=True, denovo_mut_rate=1e-4, denovo_min_llr=1e-3, denovo_tstv=1.0), None, 0),
     ("single_quick", "single.ped", dict(quick_call=True), 40000, 0),
     ("ext_quick", "ext.ped", dict(quick_call=True, posterior_cutoff=0.9), 30000, 0),
 ]

@@ -81,6 +81,13 @@ for _c, _flag in (("x", "--chrX"), ("y", "--chrY"), ("mt", "--MT")):
         NONAUTO_CASES.append((f"{_c}_{_p}_ba", _ped, [_flag, "1"], f"ref_{_c}_{_p}_ba" + (".vcf.gz" if _full else ".sha")))
         NONAUTO_CASES.append((f"{_c}_{_p}_dn", _ped, [_flag, "1", "--denovo", "--rate_denovo", "1.5e-07"],
                               f"ref_{_c}_{_p}_dn" + (".vcf.gz" if (_c, _p) == ("y", "ext") else ".sha")))
+# an extended family next to more than eight nuclear / single units: one block per site AND a peel (the ES instances of
+# the wide kernel)
+MIXEXT_CASES = [
+    ("mixext_ba", "mixext.ped", [], "ref_mixext_ba.sha"),
+    ("mixext_dn", "mixext.ped", ["--denovo", "--rate_denovo", "1.5e-07"], "ref_mixext_dn.vcf.gz"),
+    ("mixext_x", "mixext.ped", ["--chrX", "1"], "ref_mixext_x.sha"),
+]
 # --quick_call: outputs of the unmodified reference with the everybody-unrelated pre-pass switched on
 QUICK_CASES = [
     ("q_quartets", "test.ped", ["--quick_call"], "ref_q_quartets.sha"),

@@ -51,6 +51,13 @@ CASES = {  # name: (ped file, extra args, keep full text?)
     "mix_denovo_loose": ("test.mix.ped", ["--denovo", "--rate_denovo", "1e-4", "--minLLR_denovo", "1e-3", "--tstv_denovo", "1.0"], True),
     "mix_strict": ("test.mix.ped", ["-c", "0.99", "--minMapQuality", "50", "--minPercSampleWithData", "90", "--theta", "0.01", "--poly_tstv", "3.0"], True),
 }
+# an extended family next to more than eight nuclear / single units (the wide kernel's ES instances); GLFs re-used
+MIXEXT_PED = EXT_PED + "".join(f"s{i}\ts{i}\t0\t0\t{1 + i % 2}\t{1 + (i * 5) % 12}\n" for i in range(1, 11))
+CASES.update({
+    "mixext_ba": ("mixext.ped", [], False),
+    "mixext_dn": ("mixext.ped", ["--denovo", "--rate_denovo", "1.5e-07"], True),
+    "mixext_x": ("mixext.ped", ["--chrX", "1"], False),
+})
 # --quick_call (the everybody-unrelated pre-pass of main.cpp:354-437)
 CASES.update({
     "q_quartets": ("test.ped", ["--quick_call"], False),
@@ -145,6 +152,7 @@ def main():
         shutil.copy(os.path.join(REF, name), os.path.join(HERE, "peds", name))
     open(os.path.join(HERE, "peds", "ext.ped"), "w").write(EXT_PED)
     open(os.path.join(HERE, "peds", "ceph.ped"), "w").write(CEPH_PED)
+    open(os.path.join(HERE, "peds", "mixext.ped"), "w").write(MIXEXT_PED)
     with tempfile.TemporaryDirectory() as tmp:
         for f in os.listdir(REF):
             if f.endswith(".glf") or f in ("test.gif", "test.dat"):

@@ -34,6 +34,11 @@ def test_product_cli_matches_reference_on_sex_chromosomes_and_mt(case, glfdir, t
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
 
 
+@pytest.mark.parametrize("case", U.MIXEXT_CASES, ids=lambda c: c[0])
+def test_product_cli_extended_family_among_many_units(case, glfdir, tmp_path):
+    U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+
+
 @pytest.mark.parametrize("case", U.QUICK_CASES, ids=lambda c: c[0])
 def test_product_cli_quick_call_matches_reference(case, glfdir, tmp_path):
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)

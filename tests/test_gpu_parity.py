@@ -190,6 +190,9 @@ WIDE_CASES = [
     ("quartets_and_sibships", lambda: synth.families([4] * 100 + [5] * 40 + [6] * 10), dict(), 500, 10.0),
     ("trios1000_denovo", lambda: synth.trios(1000), dict(denovo=True), 200, 4.0),
     ("trios1000_ba", lambda: synth.trios(1000), dict(), 200, 4.0),
+    # extended families among many units: the ES instances of the wide kernel
+    ("trios20_ceph", lambda: synth.concat(synth.trios(20), synth.ceph()), dict(), 1500, 20.0),
+    ("ceph_trios12_ceph_denovo", lambda: synth.concat(synth.ceph(5), synth.trios(12), synth.ceph(3)), dict(denovo=True), 250, 20.0),
     ("mixed70_quick", lambda: synth.concat(synth.trios(40), synth.families([4] * 10 + [1] * 20)), dict(quick_call=True), 2500, 40.0),
     ("trios300_quick_denovo", lambda: synth.trios(300), dict(quick_call=True, denovo=True), 400, 10.0),
 ]
@@ -202,6 +205,7 @@ WIDE_NONAUTO_CASES = [
     ("quartets_and_sibships_any", lambda: synth.families([4] * 100 + [5] * 40 + [6] * 10), dict(), 600, 10.0, -1),
     ("trios1000_any", lambda: synth.trios(1000), dict(), 240, 4.0, -1),
     ("trios1000_denovo_x", lambda: synth.trios(1000), dict(denovo=True), 160, 4.0, 1),
+    ("trios20_ceph_any", lambda: synth.concat(synth.trios(20), synth.ceph()), dict(), 1200, 20.0, -1),
 ]
 
 

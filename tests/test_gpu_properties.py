@@ -120,9 +120,5 @@ def test_unsupported_shapes_fail_loudly():
     # more quartic units than the largest plan holds
     with pytest.raises(RuntimeError, match="not supported"):
         Engine(synth.trios(5000), Params())
-    # many nuclear families plus an extended one: not covered yet
-    ped = synth.concat(synth.trios(20), synth.ceph())
-    with pytest.raises(RuntimeError, match="not supported"):
-        Engine(ped, Params())
     with pytest.raises(RuntimeError, match="quick_call"):
         Engine(synth.trios(3), Params(quick_call=True, vcf_input=True))

@@ -638,7 +638,7 @@ static double CalcAllFamLogLikelihood_VCF(pmo_ctx *c, famlk_t *k, double freq) {
       double llk = 0.0;
       for (int j = 0; j < c->famSize[i]; j++) llk += log10(lkSinglePerson(c, k, c->famFirst[i] + j, freq));
       loglk += llk;
-    } else if (fam_isNuclear(c, i) && c->nFam > 1) {
+    } else if (fam_isNuclear(c, i) && c->nFam > 1 && !c->chrX && !c->chrY && !c->chrMT) { /* FLSeq_VCF:101 */
       loglk += log10(lkSingleFam(c, k, i, freq, 0));
     } else {
       loglk += log10(CalcSingleFamLikelihood_BA(c, k, i, freq));
@@ -1439,7 +1439,7 @@ int pmo_call_vcf_records(pmo_ctx *c, const pm_site_hdr *hdr, const pm_person_sit
     for (int i = 0; i < c->nFam; i++) {
       if (c->famSize[i] == c->famFounders[i]) {
         for (int j = 0; j < c->famFounders[i]; j++) CalcPostProb_SinglePerson(c, k, c->famFirst[i] + j, freq);
-      } else if (fam_isNuclear(c, i) && c->nFam > 1) {
+      } else if (fam_isNuclear(c, i) && c->nFam > 1 && !c->chrX && !c->chrY && !c->chrMT) { /* FLSeq_VCF:148 */
         CalcPostProb_SingleNucFam(c, k, i, freq);
       } else {
         CalcPostProb_SingleExtendedPed_BA(c, k, i, freq);

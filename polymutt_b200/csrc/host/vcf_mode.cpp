@@ -282,6 +282,12 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   double last_qual = 0.0, last_min = 0.0;
   std::vector<int> last_best((size_t)np, 0), last_gq((size_t)np, 0);
   bool last_labeled = false;  // bestGenoLabel is still "" until the first computed record
+  int last_cls = PM_CHR_AUTO; // chromosome class of the record those labels were made on (haploid / "." labels)
+  std::vector<int> col_sex((size_t)np, 0);
+  {
+    int c = 0;
+    for (int idx : ped.columns()) col_sex[(size_t)c++] = ped.persons[idx].sex;
+  }
   int DP_index = -1, GL_idx = -1, PL_idx = -1;
   bool announced = false;
 
@@ -361,6 +367,10 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     const double fmin = from_row ? res[(size_t)L.src].freq : last_min;
     const pm_person_result *pr = from_row ? &pres[(size_t)L.src * (size_t)np] : nullptr;
     const bool labeled = from_row || last_labeled;
+    // GetBestGenoLabel_vcfv4 (NucFam.cpp:1587-1608) on the record the labels were made on: haploid labels on Y / MT and
+    // for males on X, "." for females on Y (FLSeq_VCF.cpp:204, 221-227)
+    const int lcls = from_row ? (int)hdr[(size_t)L.src].chr_class : last_cls;
+    static const char *lab_hap[3] = {"0", "ERROR", "1"};
     auto best_of = [&](int c) { return pr ? (int)pr[c].best : last_best[(size_t)c]; };
     auto gq_of = [&](int c) { return pr ? (int)pr[c].gq : last_gq[(size_t)c]; };
     const int dpi = L.dp_index;
@@ -397,7 +407,10 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       const Tok &s = toks[L.samp0 + i];
       const int gq = gq_of(c);
       o.push_back('\t');
-      o += gq > 0 ? (labeled ? lab[best_of(c)] : "") : "./.";
+      const int sex = col_sex[(size_t)c];
+      const char *label = !labeled ? "" : (lcls == PM_CHR_Y && sex == 2) ? "."
+                          : (lcls == PM_CHR_Y || lcls == PM_CHR_MT || (lcls == PM_CHR_X && sex == 1)) ? lab_hap[best_of(c)] : lab[best_of(c)];
+      o += (gq > 0 || !strcmp(label, ".")) ? label : "./.";   // FLSeq_VCF.cpp:507
       o.push_back(':'); append_int(o, gq); o.push_back(':');
       Tok dps; dps.p = "."; dps.n = 1;
       if (dpi > 0) {
@@ -512,7 +525,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     fflush(out);
     if (n_rows) {  // what the next chunk's leading no-data records print
       const size_t r = n_rows - 1;
-      last_qual = res[r].poly_qual; last_min = res[r].freq; last_labeled = true;
+      last_qual = res[r].poly_qual; last_min = res[r].freq; last_labeled = true; last_cls = hdr[r].chr_class;
       for (int c = 0; c < np; c++) { last_best[(size_t)c] = pres[r * (size_t)np + c].best; last_gq[(size_t)c] = pres[r * (size_t)np + c].gq; }
     }
   }

@@ -43,6 +43,16 @@ struct pm_ctx {
   pm::DevUnit *d_units_q = nullptr;
   pm_site_result *d_res_q = nullptr;
   uint16_t *d_status_q = nullptr;
+  // VCF input: a second description in which every family with non-founders is peeled, for chrX / chrY / MT records
+  // (FamilyLikelihoodSeq_VCF.cpp:101, 148); each description only does the records of its chromosome class
+  bool have_x = false;
+  bool batch_has_nonauto = false;
+  pm::LaunchPlan plan_x;
+  pm::DevRun *d_run_x = nullptr;
+  pm::DevFam *d_fams_x = nullptr;
+  pm::DevUnit *d_units_x = nullptr;
+  int32_t *d_es_x = nullptr;
+  pm::DevStep *d_steps_x = nullptr;
   int32_t *d_es = nullptr;
   pm::DevStep *d_steps = nullptr;
   int *d_err = nullptr;
@@ -133,11 +143,22 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   c->n_fam = ped->n_fam;
 
   // ---- host-side descriptors ----
-  std::vector<pm::DevFam> fams((size_t)ped->n_fam);
-  std::vector<pm::DevUnit> units;
-  std::vector<int32_t> es;
-  std::vector<pm::DevStep> steps;
-  int first = 0, founders_total = 0, kids_total = 0;
+  // all_peeled: every family with non-founders is an extended family (VCF input on chrX / chrY / MT, FLSeq_VCF.cpp:101)
+  struct Desc {
+    std::vector<pm::DevFam> fams;
+    std::vector<pm::DevUnit> units;
+    std::vector<int32_t> es;
+    std::vector<pm::DevStep> steps;
+    int founders_total = 0, kids_total = 0;
+  };
+  auto build_desc = [&](Desc &D, bool all_peeled) -> bool {
+  std::vector<pm::DevFam> &fams = D.fams;
+  std::vector<pm::DevUnit> &units = D.units;
+  std::vector<int32_t> &es = D.es;
+  std::vector<pm::DevStep> &steps = D.steps;
+  int &founders_total = D.founders_total, &kids_total = D.kids_total;
+  fams.assign((size_t)ped->n_fam, pm::DevFam());
+  int first = 0;
   for (int f = 0; f < ped->n_fam; f++) {
     pm::DevFam &d = fams[(size_t)f];
     memset(&d, 0, sizeof d);
@@ -146,7 +167,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     founders_total += nf;
     // VCF mode uses the nuclear-family formula only when there are several families (FamilyLikelihoodSeq_VCF.cpp:98-103);
     // a lone nuclear family goes through the bi-allelic Elston-Stewart peel there.
-    const bool nuclear = ped->fam_generations[f] == 2 && nf == 2 && !(par->vcf_input && ped->n_fam == 1);
+    const bool nuclear = ped->fam_generations[f] == 2 && nf == 2 && !(par->vcf_input && ped->n_fam == 1) && !all_peeled;
     if (size == nf) {
       d.kind = 0;
       for (int j = 0; j < size; j++) units.push_back({first + j, -1, kids_total, (int32_t)ped->sex[first + j]});
@@ -156,10 +177,10 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
       kids_total += size - 2;
     } else {
       d.kind = 2;
-      if (size > pm::kMaxEsPersons) { fail(PM_EUNSUPPORTED, "extended family %d has %d members; the device peel workspace holds %d", f, size, pm::kMaxEsPersons); delete c; return nullptr; }
-      if (!ped->peel || !ped->peel_first) { fail(PM_EINVAL, "pm_create: extended family %d but no peeling order was supplied", f); delete c; return nullptr; }
+      if (size > pm::kMaxEsPersons) { fail(PM_EUNSUPPORTED, "extended family %d has %d members; the device peel workspace holds %d", f, size, pm::kMaxEsPersons); return false; }
+      if (!ped->peel || !ped->peel_first) { fail(PM_EINVAL, "pm_create: extended family %d but no peeling order was supplied", f); return false; }
       const int p0 = ped->peel_first[f], p1 = ped->peel_first[f + 1];
-      if (p1 <= p0) { fail(PM_EINVAL, "pm_create: extended family %d has an empty peeling order", f); delete c; return nullptr; }
+      if (p1 <= p0) { fail(PM_EINVAL, "pm_create: extended family %d has an empty peeling order", f); return false; }
       d.step_first = (int16_t)steps.size(); d.n_steps = (int16_t)(p1 - p0);
       // resolve the std::map<pair,...> marriage_partials lookups of the reference (ES:1084-1087,
       // 1147, 1236) once: exact (first, second) key match.
@@ -185,18 +206,27 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
           auto it = slots.find(std::make_pair(ps.from0, ps.from1));
           if (it != slots.end()) ds.mp = (int8_t)it->second;
         } else {
-          fail(PM_EINVAL, "pm_create: bad peeling step type %d", ps.type); delete c; return nullptr;
+          fail(PM_EINVAL, "pm_create: bad peeling step type %d", ps.type); return false;
         }
         steps.push_back(ds);
       }
-      if ((int)slots.size() > pm::kMaxMp) { fail(PM_EUNSUPPORTED, "extended family %d needs %zu marriage partials; the device workspace holds %d", f, slots.size(), pm::kMaxMp); delete c; return nullptr; }
+      if ((int)slots.size() > pm::kMaxMp) { fail(PM_EUNSUPPORTED, "extended family %d needs %zu marriage partials; the device workspace holds %d", f, slots.size(), pm::kMaxMp); return false; }
       d.n_mp = (int8_t)slots.size();
       es.push_back(f);
     }
     first += size;
   }
-  if (first != ped->n_person) { fail(PM_EINVAL, "pm_create: n_person != sum(fam_size)"); delete c; return nullptr; }
-  if (founders_total == 0) { fail(PM_EINVAL, "Family size is zero"); delete c; return nullptr; }
+  if (first != ped->n_person) { fail(PM_EINVAL, "pm_create: n_person != sum(fam_size)"); return false; }
+  if (founders_total == 0) { fail(PM_EINVAL, "Family size is zero"); return false; }
+  return true;
+  };
+  Desc D0;
+  if (!build_desc(D0, false)) { delete c; return nullptr; }
+  std::vector<pm::DevFam> &fams = D0.fams;
+  std::vector<pm::DevUnit> &units = D0.units;
+  std::vector<int32_t> &es = D0.es;
+  std::vector<pm::DevStep> &steps = D0.steps;
+  const int founders_total = D0.founders_total, kids_total = D0.kids_total;
   c->n_units = (int)units.size();
   c->n_es = (int)es.size();
 
@@ -252,6 +282,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   }
   run.use_brent = (ped->n_fam > 1 || fams[0].kind != 1 || par->vcf_input) ? 1 : 0;  // FLSeq:94; always in VCF mode
   run.vcf_mode = par->vcf_input ? 1 : 0;
+  run.site_filter = par->vcf_input ? 1 : 0;
   // PedVCF::tstv_ratio is hard-wired to 2.0 (PedVCF.cpp:7); GetPolyPrior_indel returns the SNP prior (NucFam:313)
   run.vcf_log_ts = log10(2.0 / (2.0 + 1));
   run.vcf_log_tv = log10(0.5 / (2.0 + 1));
@@ -284,6 +315,26 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
          (steps.empty() || cudaMemcpy(c->d_steps, steps.data(), steps.size() * sizeof(pm::DevStep), cudaMemcpyHostToDevice) == cudaSuccess) &&
          cudaMemcpy(c->d_run, &run, sizeof run, cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemset(c->d_err, 0, 2 * sizeof(int)) == cudaSuccess && cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long)) == cudaSuccess;
+  }
+  if (ok && par->vcf_input) {
+    Desc D1;
+    if (!build_desc(D1, true)) { pm_destroy(c); return nullptr; }
+    pm::DevRun run_x = run;
+    run_x.n_units = (int)D1.units.size(); run_x.n_es = (int)D1.es.size(); run_x.n_kids = 0; run_x.site_filter = 2;
+    cudaError_t ex = pm::plan_launch(&c->plan_x, c->n_person, run_x.n_units, run_x.n_es, 0, c->sm_count);
+    if (ex == cudaSuccess) {
+      ok = dev_alloc(&c->d_run_x, 1) == PM_OK && dev_alloc(&c->d_fams_x, D1.fams.size()) == PM_OK && dev_alloc(&c->d_units_x, D1.units.size()) == PM_OK &&
+           dev_alloc(&c->d_es_x, D1.es.size()) == PM_OK && dev_alloc(&c->d_steps_x, D1.steps.size()) == PM_OK;
+      if (ok) {
+        run_x.fams = c->d_fams_x; run_x.units = c->d_units_x; run_x.es_fams = c->d_es_x; run_x.steps = c->d_steps_x;
+        ok = cudaMemcpy(c->d_fams_x, D1.fams.data(), D1.fams.size() * sizeof(pm::DevFam), cudaMemcpyHostToDevice) == cudaSuccess &&
+             (D1.units.empty() || cudaMemcpy(c->d_units_x, D1.units.data(), D1.units.size() * sizeof(pm::DevUnit), cudaMemcpyHostToDevice) == cudaSuccess) &&
+             (D1.es.empty() || cudaMemcpy(c->d_es_x, D1.es.data(), D1.es.size() * sizeof(int32_t), cudaMemcpyHostToDevice) == cudaSuccess) &&
+             (D1.steps.empty() || cudaMemcpy(c->d_steps_x, D1.steps.data(), D1.steps.size() * sizeof(pm::DevStep), cudaMemcpyHostToDevice) == cudaSuccess) &&
+             cudaMemcpy(c->d_run_x, &run_x, sizeof run_x, cudaMemcpyHostToDevice) == cudaSuccess;
+        c->have_x = ok;
+      }
+    }  // else: chrX / chrY / MT records are refused when they come (pm_call_vcf_records)
   }
   if (ok && par->quick_call) {
     // MakeUnrelated() (FLSeq.cpp:55-60): founders = count in every family, so every person is a single founder, no
@@ -320,6 +371,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_run_x); cudaFree(c->d_fams_x); cudaFree(c->d_units_x); cudaFree(c->d_es_x); cudaFree(c->d_steps_x);
   cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
   cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
@@ -365,11 +417,18 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
     CUDA_TRY(pm::launch_sites(c->plan_q, c->d_run_q, d_hdr, (const uint4 *)d_person_site, nullptr, n_sites, c->d_res_q, c->d_status_q, c->d_err, c->stream));
   CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
   if (c->par.quick_call) CUDA_TRY(pm::launch_quick_merge(c->d_status_q, n_sites, c->d_res_all, d_status_out, c->stream));
+  const bool second = c->par.vcf_input && c->have_x && c->batch_has_nonauto;
+  if (second)
+    CUDA_TRY(pm::launch_sites(c->plan_x, c->d_run_x, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                            out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
                            d_person_out, c->sm_count, c->stream));
+  if (second)
+    CUDA_TRY(pm::launch_post(c->d_run_x, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
+                             out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
+                             d_person_out, c->sm_count, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
   c->launches = c->plan.kind == pm::LaunchPlan::WIDE ? 4 : 3;  // wide: the autosomal instance + the (normally empty) chrX/Y/MT one
   if (c->par.quick_call) c->launches += (c->plan_q.kind == pm::LaunchPlan::WIDE ? 2 : 1) + 1;
@@ -385,7 +444,7 @@ extern "C" int pm_sync(pm_ctx *c) {
   CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (err) {
     cudaMemset(c->d_err, 0, sizeof(int));
-    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "a site's chr_class is not one of PM_CHR_* (chrX/chrY/MT records of a VCF are not implemented)");
+    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "a site's chr_class is not one of PM_CHR_*");
     return fail(err, "device-side error %d", err);
   }
   return PM_OK;
@@ -502,7 +561,9 @@ extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_p
     const int a2 = hdr[s].reserved & 0xff;
     if (hdr[s].ref_base < 1 || hdr[s].ref_base > 4 || a2 < 1 || a2 > 4 || a2 == hdr[s].ref_base)
       return fail(PM_EINVAL, "record %zu: alleles must be two different bases in 1..4 (got %d, %d)", s, hdr[s].ref_base, a2);
-    if (hdr[s].chr_class != PM_CHR_AUTO) return fail(PM_EUNSUPPORTED, "record %zu: chrX/chrY/MT records are not implemented on the device path yet", s);
+    if (hdr[s].chr_class > PM_CHR_MT) return fail(PM_EINVAL, "record %zu: chr_class %d is not one of PM_CHR_*", s, (int)hdr[s].chr_class);
+    if (hdr[s].chr_class != PM_CHR_AUTO && !c->have_x)
+      return fail(PM_EUNSUPPORTED, "record %zu: chrX/chrY/MT records need every family peeled, which the device kernels cannot do for this pedigree", s);
   }
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t np = (size_t)c->n_person;
@@ -530,6 +591,8 @@ extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_p
     CUDA_TRY(cudaMemcpyAsync(c->d_hdr[0], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_recs[0], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->d_mono, mono + base, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->batch_has_nonauto = false;
+    for (size_t r = 0; r < m; r++) c->batch_has_nonauto |= hdr[base + r].chr_class != PM_CHR_AUTO;
     rc = run_device(c, c->d_hdr[0], (const pm_person_site *)c->d_recs[0], c->d_mono, m, PM_OUT_ALL, c->d_status, c->d_res_out,
                     c->d_person_out, c->cap_out_rows, c->d_n_emit);
     if (rc) return rc;

@@ -67,6 +67,8 @@ struct DevRun {
   double theta, posterior_cutoff, precision, denovo_min_llr, min_ps;
   int32_t min_map_quality, min_total_depth, max_total_depth;
   int32_t denovo, force_call, out_all_sites;
+  int32_t site_filter;        // 0 = every site; 1 = autosomal sites only, 2 = chrX / chrY / MT only: VCF input keeps two
+                              // descriptions of the pedigree and each one leaves the other's records untouched
   int32_t vcf_mode;           // 1 = records come from a VCF (src/PedVCF.cpp:116-163): one hypothesis (REF, ALT), QUAL formula
   int32_t n_person, n_fam, n_units, n_es, n_kids;
   int32_t use_brent;          // nFam>1 || !nuclear  (FLSeq:94)

@@ -187,14 +187,13 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   const int ref = h.ref_base;
   if (ref < 1 || ref > 4) { r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
   const int cls = h.chr_class;
-  if (cls > PM_CHR_MT || (run->vcf_mode && cls != PM_CHR_AUTO)) {  // chrX/Y/MT records of a VCF are not supported
-    atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return;
-  }
+  if (cls > PM_CHR_MT) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+  if ((run->site_filter == 1 && cls != PM_CHR_AUTO) || (run->site_filter == 2 && cls == PM_CHR_AUTO)) return;  // the other description's record
   const double log_1m_prior = run->cls_log[cls][0];
   if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
     const int a2 = h.reserved & 0xff;
     NarrowEval<UMAX> ev;
-    ev.run = run; ev.recs = recs; ev.sm = sm;
+    ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
     double freq = 0.0;
     const double poly = ev.optimize(ref, a2, false, &freq);
     vcf_record_result(run, r, ref, a2, (h.reserved & 0x100) != 0, mono_all[s], poly, freq);
@@ -606,7 +605,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
                                                         int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *ws = reinterpret_cast<WideShared *>(smem_raw);
-  if (NA && err[1] == 0) return;
+  if (NA ? ((err[1] == 0 && run->site_filter != 2) || run->site_filter == 1) : run->site_filter == 2) return;
   const int np = run->n_person;
   const size_t site_bytes = (((size_t)np * 16 + 127) / 128) * 128;
   unsigned char *site_base = smem_raw + ((sizeof(WideShared) + 127) / 128) * 128;
@@ -650,7 +649,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_sites_wide(const DevRun *__restrict
     const int ref = h.ref_base;
     bool skip = false;
     const int cls = h.chr_class;
-    const bool bad_cls = cls > PM_CHR_MT || (run->vcf_mode && cls != PM_CHR_AUTO);  // chrX/Y/MT records of a VCF are not supported
+    const bool bad_cls = cls > PM_CHR_MT;
     if (NA && threadIdx.x == 0) ws->cls = cls;  // read by the set-up loops after the next barrier
     const bool bad = ref < 1 || ref > 4 || bad_cls;
     if (NA ? (bad || cls == PM_CHR_AUTO) : (!bad && cls != PM_CHR_AUTO)) {  // the other instance's site

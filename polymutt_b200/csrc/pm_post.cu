@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     const size_t row = w / run->n_fam;
     const int fi = (int)(w % run->n_fam);
     const uint32_t s = emit_sites[row];
+    if ((run->site_filter == 1 && hdr[s].chr_class != PM_CHR_AUTO) || (run->site_filter == 2 && hdr[s].chr_class == PM_CHR_AUTO)) continue;
     pm_site_result r = res_all[s];
     const uint4 *recs = recs_all + (size_t)s * np;
     pm_person_result *out = person_out + row * (size_t)np;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     // frequency the posteriors are taken at (main:576-587)
     const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
     const double q = 1.0 - freq;
-    const int cls = run->vcf_mode ? PM_CHR_AUTO : hdr[s].chr_class;
+    const int cls = hdr[s].chr_class;
     const bool nonauto = cls != PM_CHR_AUTO;
 
     if (f.kind == 0) {  // CalcPostProb_SinglePerson, NucFam:754-795

@@ -56,7 +56,7 @@ MIXEXT_PED = EXT_PED + "".join(f"s{i}\ts{i}\t0\t0\t{1 + i % 2}\t{1 + (i * 5) % 1
 CASES.update({
     "mixext_ba": ("mixext.ped", [], False),
     "mixext_dn": ("mixext.ped", ["--denovo", "--rate_denovo", "1.5e-07"], True),
-    "mixext_x": ("mixext.ped", ["--chrX", "1"], False),
+    "mixext_x": ("mixext.ped", ["--chrX", "1"], True),   # full text: see TIED_GENOTYPE_ROWS in cli_util.py
 })
 # --quick_call (the everybody-unrelated pre-pass of main.cpp:354-437)
 CASES.update({
@@ -83,6 +83,16 @@ VCF_CASES = {  # name: (ped file, input vcf)
     "vcf_single_family_edge": ("single.ped", "vcf_in_edge.vcf.gz"),
     "vcf_ext_edge": ("ext.ped", "vcf_in_edge.vcf.gz"),
     "vcf_quartets_gl": ("test.ped", "vcf_in_gl.vcf.gz"),
+}
+# chrX / chrY / MT under --in_vcf: name -> (ped file, input vcf, extra args)
+VCF_NONAUTO_CASES = {
+    "vcf_x_quartets": ("test.ped", "vcf_in_full.vcf.gz", ["--chrX", "1"]),
+    "vcf_y_mix": ("test.mix.ped", "vcf_in_full.vcf.gz", ["--chrY", "1"]),
+    "vcf_mt_quartets": ("test.ped", "vcf_in_full.vcf.gz", ["--MT", "1"]),
+    "vcf_x_ext_edge": ("ext.ped", "vcf_in_edge.vcf.gz", ["--chrX", "1"]),
+    "vcf_y_single_edge": ("single.ped", "vcf_in_edge.vcf.gz", ["--chrY", "1"]),
+    "vcf_mt_mix_edge": ("test.mix.ped", "vcf_in_edge.vcf.gz", ["--MT", "1"]),
+    "vcf_y_ext_edge": ("ext.ped", "vcf_in_edge.vcf.gz", ["--chrY", "1"]),
 }
 SINGLE_PED = "fam1\t1\t0\t0\t1\t1\nfam1\t2\t0\t0\t2\t2\nfam1\t3\t1\t2\t2\t3\nfam1\t4\t1\t2\t1\t4\n"
 
@@ -172,14 +182,16 @@ def main():
             open(os.path.join(HERE, "peds", "single.ped"), "w").write(SINGLE_PED)
             shutil.copy(os.path.join(HERE, "peds", "single.ped"), tmp)
             make_vcf_inputs()
-            for name, (ped, vin) in VCF_CASES.items():
+            for name, spec in list(VCF_CASES.items()) + list(VCF_NONAUTO_CASES.items()):
+                ped, vin = spec[0], spec[1]
+                more = spec[2] if len(spec) > 2 else []
                 if only and name not in only and "vcf" not in only:
                     continue
                 raw = os.path.join(tmp, vin[:-3])
                 with gzip.open(os.path.join(HERE, vin), "rb") as src, open(raw, "wb") as dst:
                     dst.write(src.read())
                 out = os.path.join(tmp, name + ".vcf")
-                subprocess.run([REFBIN, "-p", ped, "-d", "test.dat", "--in_vcf", raw, "--out_vcf", out], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
+                subprocess.run([REFBIN, "-p", ped, "-d", "test.dat", "--in_vcf", raw, "--out_vcf", out] + more, cwd=tmp, check=True, stdout=subprocess.DEVNULL)
                 text = body(out)
                 with gzip.GzipFile(os.path.join(HERE, f"ref_{name}.vcf.gz"), "wb", 9, mtime=0) as dst:
                     dst.write(text)

@@ -50,6 +50,11 @@ def test_product_cli_vcf_input_matches_reference(case, glfdir, tmp_path):
     assert "Total samples in both VCF and PED files" in log
 
 
+@pytest.mark.parametrize("case", U.VCF_NONAUTO_CASES, ids=lambda c: c[0])
+def test_product_cli_vcf_input_on_sex_chromosomes_and_mt(case, glfdir, tmp_path):
+    U.check_vcf_case(U.PRODUCT_CLI, str(tmp_path), case)
+
+
 def test_product_cli_small_batches_and_multi_gpu(glfdir, tmp_path):
     """Many small batches through the double-buffered host entry point; with more than one GPU on the box the batches
     are also sharded over all of them (--gpus N) and concatenated in order."""

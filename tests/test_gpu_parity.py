@@ -263,11 +263,18 @@ def _vcf_records_from_sites(hdr, recs, rng):
     return h, out, mono
 
 
-@pytest.mark.parametrize("pedfile,n", [("test.ped", 20000), ("test.mix.ped", 20000), ("single.ped", 20000), ("ext.ped", 8000), ("ceph.ped", 4000)])
-def test_vcf_records_parity(pedfile, n, example12, oracle_built, tools_built, tmp_path):
+@pytest.mark.parametrize("pedfile,n,mixed_classes", [("test.ped", 20000, False), ("test.mix.ped", 20000, False), ("single.ped", 20000, False),
+                                                    ("ext.ped", 8000, False), ("ceph.ped", 4000, False),
+                                                    # every record draws its chromosome class: chrX / chrY / MT records go through the
+                                                    # all-families-peeled description (FLSeq_VCF.cpp:101, 148), autosomal ones do not
+                                                    ("test.ped", 12000, True), ("test.mix.ped", 12000, True), ("single.ped", 12000, True),
+                                                    ("ext.ped", 6000, True), ("mixext.ped", 6000, True)])
+def test_vcf_records_parity(pedfile, n, mixed_classes, example12, oracle_built, tools_built, tmp_path):
     ped, glf_index = F.pedigree_from_file(PED(pedfile), str(tmp_path))
     hdr, recs = F.sites_for(example12, glf_index, n)
     h, r, mono = _vcf_records_from_sites(hdr, recs, np.random.default_rng(3))
+    if mixed_classes:
+        h["chr_class"][:] = np.random.default_rng(5).integers(0, 4, size=len(h))
     lut = np.array([pow(10, -float(i) / 10.0) for i in range(256)])
     params = Params(vcf_input=True)
     eng = Engine(ped, params, lut=lut)

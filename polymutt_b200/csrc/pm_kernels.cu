@@ -382,6 +382,7 @@ __device__ __forceinline__ void renorm_nonzero(ProdAcc &a) {
 // Out-of-line helpers: their register pressure (unrolled 10-genotype dot products, the Brent update with
 // its division, exp10/log10 in the posterior) stays out of the kernel's hot loop allocation.
 struct Quartic { double b0, b1, b2, b3, b4; };
+
 // mode = denovo | chr_class << 1 | (single founder's sex) << 3.  NA = the kernel instance for chrX / chrY / MT sites: a
 // separate instantiation, so that the autosomal kernel's register allocation does not pay for the rare case (the
 // callee's registers count against what the caller can keep live across the call).
@@ -456,6 +457,18 @@ __device__ __noinline__ double log10_ol(const WideShared *ws, double m, int e) {
   return fma(l1p, 0.43429448190325182765, ws->log_tab[i]) + (double)e * kLog10_2;
 }
 
+// ES instances: extended families take part in every evaluation through a thread-serial Elston-Stewart peel, family e
+// on thread e of the group (FLSeq.cpp:222-240 sums log10 over all families; here: one more factor of the product).
+// A free function on purpose, and only ever named under `if constexpr (ES)`: a member function would let `this`
+// escape, the evaluator's pointers would lose their address space and the hot loop's LDS turn into generic LD
+// (measured: -15 % on the autosomal instance even though it never calls this).
+__device__ __noinline__ double es_factor(const DevRun *run, const uint4 *recs, const double *lut, int cls, int e, int g11, int g12, int g22,
+                                         bool denovo, double p) {
+  const DevFam f = run->fams[run->es_fams[e]];
+  return denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, lut, run->tden, run->t10, -1, -1, cls)
+                : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, lut, run->tden, run->t10, -1, -1, cls);
+}
+
 template <int U, bool NA, bool ES>
 struct WideEval {
   const DevRun *run;
@@ -464,15 +477,6 @@ struct WideEval {
   const double *kidD;  // per-site kid table in shared memory (nullptr = build D on the fly)
   int G, Tg, grp, t;  // groups, threads per group, my group, my index inside the group
   int eg11, eg12, eg22;  // ES: genotype indices of the current hypothesis (the peel has no per-hypothesis set-up)
-
-  // ES: extended families take part in every evaluation through a thread-serial Elston-Stewart peel, family e on
-  // thread e of the group (FLSeq.cpp:222-240 sums log10 over all families; here: one more factor of the product).
-  __device__ __noinline__ double es_factor(int e, bool denovo, double p) const {
-    const DevFam f = run->fams[run->es_fams[e]];
-    const int cls = NA ? ws->cls : PM_CHR_AUTO;
-    return denovo ? es_likelihood<10>(run, f, recs, eg11, eg12, eg22, true, p, ws->t.lut, run->tden, run->t10, -1, -1, cls)
-                  : es_likelihood<3>(run, f, recs, eg11, eg12, eg22, false, p, ws->t.lut, run->tden, run->t10, -1, -1, cls);
-  }
   double B[U][5];     // per unit, scaled by an exact power of two so that the largest coefficient is in [1,2)
   int K;              // sum over my units of the exponents taken out: prod_u L_u = 2^K * prod_u L'_u
 
@@ -487,7 +491,7 @@ struct WideEval {
     if (mine) {
       const int x = a1[grp], y = a2[grp];
       const int g11 = geno_index(x, x), g12 = geno_index(x, y), g22 = geno_index(y, y);
-      if (ES) { eg11 = g11; eg12 = g12; eg22 = g22; }
+      if constexpr (ES) { eg11 = g11; eg12 = g12; eg22 = g22; }
       const int mode = (denovo ? 1 : 0) | (NA ? (ws->cls << 1) : 0);
 #pragma unroll
       for (int k = 0; k < U; k++) {
@@ -550,8 +554,9 @@ struct WideEval {
           }
           fa.m = (v0 * v1) * (v2 * v3);
         }
-        if (ES)
-          for (int e = t; e < run->n_es; e += Tg) fprod_mul(fa, es_factor(e, denovo, p));
+        if constexpr (ES)
+          for (int e = t; e < run->n_es; e += Tg)
+            fprod_mul(fa, es_factor(run, recs, ws->t.lut, NA ? ws->cls : PM_CHR_AUTO, e, eg11, eg12, eg22, denovo, p));
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[grp][wg] = acc.m; ws->warp_e[grp][wg] = acc.e; }
@@ -561,8 +566,9 @@ struct WideEval {
         fa.m = 1.0; fa.e = K;   // B[k][4] carries the same power-of-two scaling as the unit
 #pragma unroll
         for (int k = 0; k < U; k++) fprod_mul(fa, B[k][4]);
-        if (ES)  // a founder's prior at p = 1 is (1, 0, 0) whatever the second allele: H1's alleles give H0's value
-          for (int e = t; e < run->n_es; e += Tg) fprod_mul(fa, es_factor(e, true, 1.0));
+        if constexpr (ES)  // a founder's prior at p = 1 is (1, 0, 0) whatever the second allele: H1's alleles give H0's value
+          for (int e = t; e < run->n_es; e += Tg)
+            fprod_mul(fa, es_factor(run, recs, ws->t.lut, NA ? ws->cls : PM_CHR_AUTO, e, eg11, eg12, eg22, true, 1.0));
         ProdAcc acc = fprod_finish(fa);
         warp_product(acc);
         if (lane == 0) { renorm_nonzero(acc); ws->warp_m[kMaxChains][wg] = acc.m; ws->warp_e[kMaxChains][wg] = acc.e; }

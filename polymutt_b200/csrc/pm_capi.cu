@@ -431,8 +431,9 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                              out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
                              d_person_out, c->sm_count, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-  c->launches = c->plan.kind == pm::LaunchPlan::WIDE ? 4 : 3;  // wide: the autosomal instance + the (normally empty) chrX/Y/MT one
-  if (c->par.quick_call) c->launches += (c->plan_q.kind == pm::LaunchPlan::WIDE ? 2 : 1) + 1;
+  c->launches = 4;  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact, k_post
+  if (c->par.quick_call) c->launches += 3;
+  if (second) c->launches += 3;
   c->timing_cached = false;
   return PM_OK;
 }

@@ -31,26 +31,30 @@ __device__ __forceinline__ double tba_cls(int cls, int sex, int i, int j, int k)
   return (k == j) ? 1.0 : 0.0;
 }
 
-template <int A, typename RecPtr>
-__device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
-                                bool denovo, double freq, const double *__restrict__ lut,
-                                const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
-                                int pin_geno, int cls = PM_CHR_AUTO) {
+// NA = false is the autosomal code with none of the chrX / chrY / MT rules compiled in (cls_ ignored): the rules sit in
+// the innermost loops of the peel and cost the narrow kernel 40 % when they were runtime branches.
+template <int A, bool NA, typename RecPtr>
+__device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                     bool denovo, double freq, const double *__restrict__ lut,
+                                     const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
+                                     int pin_geno, int cls_) {
   double part[kMaxEsPersons * A];
   double mp[kMaxMp * A * A];
   const int gi[3] = {g11, g12, g22};
   const double q = 1.0 - freq;
-  const uint8_t *sexes = run->sex + f.first;
+  const int cls = NA ? cls_ : PM_CHR_AUTO;
+  const uint8_t *sexes = NA ? run->sex + f.first : nullptr;
   for (int i = 0; i < f.size; i++) {
     uint4 r = recs[f.first + i];
     double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
-    if (cls != PM_CHR_AUTO) {
+    if constexpr (NA) {
       const bool male = sexes[i] == 1;
       if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
       else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
     }
     if (A == 3) {
-      const bool yfemale = cls == PM_CHR_Y && sexes[i] == 2;
+      bool yfemale = false;
+      if constexpr (NA) yfemale = cls == PM_CHR_Y && sexes[i] == 2;
       for (int j = 0; j < 3; j++) {
         double pen = lut[rec_lk(r, gi[j])];
         if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
@@ -79,7 +83,8 @@ __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, 
         for (int j = 0; j < A; j++) {
           double sum = 0;
           if (A == 3) {
-            for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k];
+            if constexpr (NA) { for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k]; }
+            else { for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k]; }
           } else {
             const double *t = (denovo ? tden : t10) + (i * 10 + j) * 10;
             for (int k = 0; k < 10; k++) sum += t[k] * pc[k];
@@ -111,7 +116,7 @@ __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, 
         for (int i = 0; i < A; i++)
           for (int j = 0; j < A; j++) {
             double t;
-            if (A == 3) t = tba_cls(cls, sexes[st.to0], i, j, k);
+            if (A == 3) { if constexpr (NA) t = tba_cls(cls, sexes[st.to0], i, j, k); else t = tba(i, j, k); }
             else t = (m || !denovo) ? t10[(i * 10 + j) * 10 + k] : tden[(i * 10 + j) * 10 + k];  // ES:1383 vs 1391
             if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
             else sum += pf[i] * pm_[j] * t;
@@ -124,6 +129,15 @@ __device__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, 
   double lk = 0.0;
   for (int i = 0; i < A; i++) lk += pfin[i];
   return lk;
+}
+
+template <int A, typename RecPtr>
+__device__ __forceinline__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                                bool denovo, double freq, const double *__restrict__ lut,
+                                                const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
+                                                int pin_geno, int cls = PM_CHR_AUTO) {
+  if (cls == PM_CHR_AUTO) return es_likelihood_impl<A, false>(run, f, recs, g11, g12, g22, denovo, freq, lut, tden, t10, pin_person, pin_geno, cls);
+  return es_likelihood_impl<A, true>(run, f, recs, g11, g12, g22, denovo, freq, lut, tden, t10, pin_person, pin_geno, cls);
 }
 
 // shared tables at the start of dynamic shared memory

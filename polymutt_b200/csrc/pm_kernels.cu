@@ -85,7 +85,8 @@ struct NarrowSmem {
   double t10[1000];
 };
 
-template <int UMAX>
+// NA = the instance for chrX / chrY / MT sites (see k_sites_wide): the autosomal one has none of those rules compiled in.
+template <int UMAX, bool NA>
 struct NarrowEval {
   const DevRun *run;
   const uint4 *recs;  // this site's records
@@ -102,11 +103,11 @@ struct NarrowEval {
     denovo = dn;
     if (!run->use_brent) {
       const DevUnit u = run->units[0];
-      if (cls == PM_CHR_AUTO || denovo) unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
+      if (!NA || denovo) unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
       else unit_conditionals_nonauto(recs, u.first, u.nkids, g11, g12, g22, cls, 0, sm->t.lut, C0);
       return;
     }
-    if (cls == PM_CHR_AUTO) {
+    if constexpr (!NA) {
 #pragma unroll
       for (int u = 0; u < UMAX; u++)
         if (u < run->n_units) unit_quartic(recs, run->units[u], g11, g12, g22, denovo, sm->t.lut, sm->t.mut, B[u]);
@@ -124,8 +125,8 @@ struct NarrowEval {
       if (u < run->n_units) sum += log10(quartic_eval(B[u], m));
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
-      double lk = denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls)
-                         : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls);
+      double lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls)
+                         : es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls);
       sum += log10(lk);
     }
     return sum;
@@ -152,7 +153,7 @@ struct NarrowEval {
   }
 };
 
-template <int UMAX>
+template <int UMAX, bool NA>
 __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
                                                                   const pm_site_hdr *__restrict__ hdr,
                                                                   const uint4 *__restrict__ recs_all,
@@ -161,6 +162,8 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
                                                                   uint16_t *__restrict__ status, int *__restrict__ err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NarrowSmem *sm = reinterpret_cast<NarrowSmem *>(smem_raw);
+  // which instance does what: see k_sites_wide (err[1] = the autosomal instance met a chrX / chrY / MT site)
+  if (NA ? ((err[1] == 0 && run->site_filter != 2) || run->site_filter == 1) : run->site_filter == 2) return;
   load_tables(run, &sm->t);
   for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
     sm->tden[i] = run->tden[i];
@@ -186,13 +189,16 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   r.maxidx = -1;
   const int ref = h.ref_base;
   if (ref < 1 || ref > 4) { r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
-  const int cls = h.chr_class;
-  if (cls > PM_CHR_MT) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
-  if ((run->site_filter == 1 && cls != PM_CHR_AUTO) || (run->site_filter == 2 && cls == PM_CHR_AUTO)) return;  // the other description's record
+  if (h.chr_class > PM_CHR_MT) { atomicExch(err, PM_EUNSUPPORTED); r.status = PM_SITE_BAD_REF; res[s] = r; status[s] = status_word(r); return; }
+  if (NA ? h.chr_class == PM_CHR_AUTO : h.chr_class != PM_CHR_AUTO) {  // the other instance's site
+    if (!NA) atomicExch(err + 1, 1);
+    return;
+  }
+  const int cls = NA ? h.chr_class : PM_CHR_AUTO;
   const double log_1m_prior = run->cls_log[cls][0];
   if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
     const int a2 = h.reserved & 0xff;
-    NarrowEval<UMAX> ev;
+    NarrowEval<UMAX, NA> ev;
     ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
     double freq = 0.0;
     const double poly = ev.optimize(ref, a2, false, &freq);
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   else if (r.avg_map_qual < run->min_map_quality) r.status = PM_SITE_MIN_MAPQ;
   if (r.status != 0) { res[s] = r; status[s] = status_word(r); return; }
 
-  NarrowEval<UMAX> ev;
+  NarrowEval<UMAX, NA> ev;
   ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
   r.reserved = (uint16_t)ref;
   // H0 (main:447-462)
@@ -898,7 +904,10 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   if (n_sites == 0) return cudaSuccess;
   if (plan.kind == LaunchPlan::NARROW) {
     const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
-    k_sites_narrow<kNarrowMaxUnits><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
+    cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    k_sites_narrow<kNarrowMaxUnits, false><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
+    k_sites_narrow<kNarrowMaxUnits, true><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
   } else {
     const size_t smem = wide_smem_bytes(plan.n_person, plan.site_buffers, plan.kid_table);
     const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
@@ -933,7 +942,9 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
     plan->units_per_thread = kNarrowMaxUnits;
     plan->grid = 0;
     plan->blocks_per_sm = 0;
-    return cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
   }
   plan->kind = LaunchPlan::WIDE;
   plan->es = n_es > 0 ? 1 : 0;  // extended families ride along as thread-serial peels (WideEval::es_factor)

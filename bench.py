@@ -32,6 +32,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_JSON_OUT = None   # the original stdout when library chatter has been redirected (multi-rank runs)
 sys.path.insert(0, ROOT)
 
 METRIC = "sites/sec for family variant+de novo calling"
@@ -234,8 +235,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # rank 0's stdout carries exactly one JSON line: NCCL's version banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # rank 0's stdout carries exactly one JSON line: whatever the libraries print on file descriptor 1 (NCCL's
+        # version banner comes with the first collective) is sent to stderr; the JSON line goes to the saved descriptor
+        global _JSON_OUT
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     ped = synth.trios(N_TRIOS)
@@ -380,7 +385,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_sites_per_core)
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)[:200]}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

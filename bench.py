@@ -302,6 +302,43 @@ def main():
     ms_max = float(t.item())
     value = world * K * S / (ms_max * 1e-3)
 
+    # ---- e2e through the host-buffer C-ABI call, pinned host memory: every rank at the same time (they share the
+    # host's memory and PCIe root complexes), whole-job value = all ranks' sites / the slowest rank's time ----
+    Se = min(args.e2e_sites, S)
+    h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
+    h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
+    h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
+    cap_e = max(1024, Se // 8)   # emitted rows are ~0.1 % of the sites of this workload
+    h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
+    h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+    h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    nres = C.c_size_t(0)
+
+    def e2e_step():
+        rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
+                                       h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
+        if rc != 0:
+            raise RuntimeError(eng.lib.pm_last_error().decode())
+
+    e2e_step()  # warm-up (allocates the staging buffers)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e2e_dt = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_dt = float(te.item())
+    rows = nres.value
+    e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8),
+           "d2h_bytes_per_step": world * (Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
+           "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world,
+           "note": "pm_call_glf_sites from pinned host buffers; H2D of the packed sites and D2H of status + emitted rows inside the timed "
+                   "region; all ranks run it at the same time, time = max over ranks"}
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (k_sites_wide) ----
@@ -338,37 +375,6 @@ def main():
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "copy_kernel_gbs_live": copy_bw / 1e9},
         }
-
-        # ---- e2e through the host-buffer C-ABI call, pinned host memory ----
-        Se = min(args.e2e_sites, S)
-        h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
-        h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
-        h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
-        cap_e = max(1024, Se // 8)   # emitted rows are ~0.1 % of the sites of this workload
-        h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
-        h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-        h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-        torch.cuda.synchronize()
-        nres = C.c_size_t(0)
-
-        def e2e_step():
-            rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
-                                           h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
-            if rc != 0:
-                raise RuntimeError(eng.lib.pm_last_error().decode())
-
-        e2e_step()  # warm-up (allocates the staging buffers)
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        e2e_dt = (time.perf_counter() - t0) / args.e2e_steps
-        rows = nres.value
-        e2e = {"value": Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": Se * (npers * 16 + 8),
-               "d2h_bytes_per_step": Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4,
-               "sites_per_step": Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": 1,
-               "note": "pm_call_glf_sites from pinned host buffers; H2D of the packed sites and D2H of status + emitted rows inside the timed region"}
-        if world > 1:
-            e2e["note"] += "; measured on rank 0 only (ranks are independent)"
 
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,

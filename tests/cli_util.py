@@ -88,6 +88,23 @@ MIXEXT_CASES = [
     ("mixext_dn", "mixext.ped", ["--denovo", "--rate_denovo", "1.5e-07"], "ref_mixext_dn.vcf.gz"),
     ("mixext_x", "mixext.ped", ["--chrX", "1"], "ref_mixext_x.vcf.gz"),
 ]
+# --pos FILE (force-call the listed positions, stop after the last one; duplicate and foreign-chromosome lines in the
+# list count towards the stop rule, src/main.cpp:332-337, 593)
+POS_CASES = [
+    ("pos_mix", "test.mix.ped", ["--pos", os.path.join(GOLDEN, "pos_300.txt")], "ref_pos_mix.sha"),
+    ("pos_quartets_dn", "test.ped", ["--pos", os.path.join(GOLDEN, "pos_300.txt"), "--denovo", "--rate_denovo", "1.5e-07"], "ref_pos_quartets_dn.sha"),
+    ("pos_ext_dup", "ext.ped", ["--pos", os.path.join(GOLDEN, "pos_dup.txt")], "ref_pos_ext_dup.sha"),
+    ("pos_single_c099", "single.ped", ["--pos", os.path.join(GOLDEN, "pos_300.txt"), "-c", "0.99"], "ref_pos_single_c099.sha"),
+]
+# GLF files with three sections ("1", "2", "X": the example cut in three, tests/fixtures_util.py): --chr2process, the
+# per-chromosome class switch, --gl_off, one summary block per processed chromosome
+MS_CASES = [
+    ("ms_all", "test.mix.ped", ["--chrX", "X"], "ref_ms_all.sha"),
+    ("ms_chr2", "test.mix.ped", ["--chr2process", "2,X", "--chrX", "X"], "ref_ms_chr2.sha"),
+    ("ms_gl_off", "test.ped", ["--chr2process", "1", "--gl_off"], "ref_ms_gl_off.sha"),
+    ("ms_denovo", "test.ped", ["--denovo", "--rate_denovo", "1.5e-07", "--chrX", "X"], "ref_ms_denovo.sha"),
+    ("ms_y_mt", "ext.ped", ["--chrY", "2", "--MT", "X"], "ref_ms_y_mt.sha"),
+]
 # --quick_call: outputs of the unmodified reference with the everybody-unrelated pre-pass switched on
 QUICK_CASES = [
     ("q_quartets", "test.ped", ["--quick_call"], "ref_q_quartets.sha"),

@@ -27,3 +27,33 @@ def sites_for(example12, glf_index, n_sites=None, start=0):
         if gi > 0:
             recs[:, c] = src[:, gi - 1]
     return hdr, recs
+
+
+# three "chromosomes" cut out of the example's single section (site index ranges), the last one named X
+MULTI_SECTIONS = [("1", 0, 30000), ("2", 30000, 55000), ("X", 55000, None)]
+
+
+def write_multisection_glfs(example12, outdir):
+    """One GLF per example stream (GLF_Index 1..12) holding MULTI_SECTIONS back to back, plus the gif file.
+    Returns the gif path.  Positions are kept, every section's maxPosition is its last position + 1."""
+    from polymutt_b200 import glfio
+    os.makedirs(outdir, exist_ok=True)
+    hdr, recs = example12.hdr, example12.recs
+    gif = []
+    for g in range(recs.shape[1]):
+        blob = b""
+        for k, (label, a, b) in enumerate(MULTI_SECTIONS):
+            b = len(hdr) if b is None else b
+            tmp = os.path.join(outdir, "sec.tmp")
+            pos = hdr["pos"][a:b].astype(np.int64)
+            glfio.write_glf(tmp, label, int(pos.max()) + 1, pos, hdr["ref_base"][a:b], recs[a:b, g])
+            raw = open(tmp, "rb").read()
+            blob += raw if k == 0 else raw[8:]   # later sections go without the 8-byte file header
+        path = os.path.join(outdir, f"ms{g + 1}.glf")
+        open(path, "wb").write(blob)
+        gif.append(f"{g + 1} {path}\n")
+    os.remove(os.path.join(outdir, "sec.tmp"))
+    gif_path = os.path.join(outdir, "gif")   # names that cli_util.run_cli expects in a GLF directory
+    open(gif_path, "w").write("".join(gif))
+    open(os.path.join(outdir, "dat"), "w").write(open(os.path.join(U.GOLDEN, "peds", "test.dat")).read())
+    return gif_path

@@ -58,6 +58,13 @@ CASES.update({
     "mixext_dn": ("mixext.ped", ["--denovo", "--rate_denovo", "1.5e-07"], True),
     "mixext_x": ("mixext.ped", ["--chrX", "1"], True),   # full text: see TIED_GENOTYPE_ROWS in cli_util.py
 })
+# --pos (pos_300.txt: 300 random positions of section "1"; pos_dup.txt: 50 of them, one twice, one on another chromosome)
+CASES.update({
+    "pos_mix": ("test.mix.ped", ["--pos", os.path.join(HERE, "pos_300.txt")], False),
+    "pos_quartets_dn": ("test.ped", ["--pos", os.path.join(HERE, "pos_300.txt"), "--denovo", "--rate_denovo", "1.5e-07"], False),
+    "pos_ext_dup": ("ext.ped", ["--pos", os.path.join(HERE, "pos_dup.txt")], False),
+    "pos_single_c099": ("single.ped", ["--pos", os.path.join(HERE, "pos_300.txt"), "-c", "0.99"], False),
+})
 # --quick_call (the everybody-unrelated pre-pass of main.cpp:354-437)
 CASES.update({
     "q_quartets": ("test.ped", ["--quick_call"], False),

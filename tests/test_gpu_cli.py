@@ -34,6 +34,24 @@ def test_product_cli_matches_reference_on_sex_chromosomes_and_mt(case, glfdir, t
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
 
 
+@pytest.fixture(scope="module")
+def msdir(example12, tools_built, tmp_path_factory):
+    import fixtures_util as F
+    d = str(tmp_path_factory.mktemp("multisection"))
+    F.write_multisection_glfs(example12, d)
+    return d
+
+
+@pytest.mark.parametrize("case", U.MS_CASES, ids=lambda c: c[0])
+def test_product_cli_multi_section_glfs(case, msdir, glfdir, tmp_path):
+    U.check_case(U.PRODUCT_CLI, msdir, str(tmp_path), case)
+
+
+@pytest.mark.parametrize("case", U.POS_CASES, ids=lambda c: c[0])
+def test_product_cli_pos_list_matches_reference(case, glfdir, tmp_path):
+    U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
+
+
 @pytest.mark.parametrize("case", U.MIXEXT_CASES, ids=lambda c: c[0])
 def test_product_cli_extended_family_among_many_units(case, glfdir, tmp_path):
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)

@@ -453,14 +453,13 @@ __device__ __noinline__ double log10_ol(const WideShared *ws, double m, int e) {
   if (!(m > 0.0)) return -CUDART_INF;
   const int i = (__double2hiint(m) >> 13) & 127;
   const double r = fma(m, ws->log_inv[i], -1.0);
-  double q = 1.0 / 7.0;
-  q = fma(q, r, -1.0 / 6.0);
-  q = fma(q, r, 1.0 / 5.0);
-  q = fma(q, r, -0.25);
-  q = fma(q, r, 1.0 / 3.0);
-  q = fma(q, r, -0.5);
-  const double l1p = fma(q * r, r, r);
-  return fma(l1p, 0.43429448190325182765, ws->log_tab[i]) + (double)e * kLog10_2;
+  // log1p(r) = r + r^2 (c0 + c1 r + ... + c5 r^5), Estrin's scheme: this is on the serial tail of every Brent round
+  const double r2 = r * r;
+  const double a = fma(1.0 / 3.0, r, -0.5), b = fma(1.0 / 5.0, r, -0.25), c = fma(1.0 / 7.0, r, -1.0 / 6.0);
+  const double r4 = r2 * r2;
+  const double q = fma(c, r4, fma(b, r2, a));
+  const double l1p = fma(r2, q, r);
+  return fma((double)e, kLog10_2, fma(l1p, 0.43429448190325182765, ws->log_tab[i]));
 }
 
 // ES instances: extended families take part in every evaluation through a thread-serial Elston-Stewart peel, family e
@@ -584,8 +583,15 @@ struct WideEval {
       // serial tails: the first thread of every live group, in parallel
       if (t == 0 && live) {
         ProdAcc a;
-        a.m = 1.0; a.e = 0;
-        for (int w = 0; w < nwg; w++) prod_merge(a, ws->warp_m[grp][w], ws->warp_e[grp][w]);
+        {  // the warps' mantissas are in [1,2): two running products halve the dependent chain
+          double m0 = 1.0, m1 = 1.0;
+          int e = 0;
+          for (int w = 0; w < nwg; w += 2) {
+            m0 *= ws->warp_m[grp][w]; e += ws->warp_e[grp][w];
+            if (w + 1 < nwg) { m1 *= ws->warp_m[grp][w + 1]; e += ws->warp_e[grp][w + 1]; }
+          }
+          a.m = m0 * m1; a.e = e;
+        }
         renorm_nonzero(a);  // log10_ol wants the mantissa back in [1,2)
         const double ll = log10_ol(ws, a.m, a.e);
         const bool more = brent_feed_ol(&ws->brent[grp], -ll, run->precision) != 0;

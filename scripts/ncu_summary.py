@@ -23,6 +23,7 @@ KEYS = [
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_local_st.sum",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.avg",
+    "derived__smsp__sass_thread_inst_executed_op_dfma_pred_on_x2",  # 2 x DFMA thread instructions = executed DFMA flops (millions)
 ]
 for r in rows[2:]:
     print("== raw metrics ==")

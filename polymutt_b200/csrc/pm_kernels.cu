@@ -442,7 +442,14 @@ __device__ __noinline__ void kid_table_row_ol(const uint4 rk, const double *lut,
     out[x] = d;
   }
 }
-__device__ __noinline__ int brent_feed_ol(BrentState *s, double fu, double tol) { return brent_feed(*s, fu, tol) ? 1 : 0; }
+// works on a register copy of the state: one batch of loads, the branchy update without memory traffic, one batch of stores
+// Returns the next evaluation point, or -1 when the minimisation is over.
+__device__ __noinline__ double brent_feed_ol(BrentState *s, double fu, double tol) {
+  BrentState t = *s;
+  const bool more = brent_feed(t, fu, tol);
+  *s = t;
+  return more ? t.u : -1.0;
+}
 __device__ __noinline__ void var_posterior_ol(pm_site_result *r, int ref, int n) { var_posterior(*r, ref, n); }
 __device__ __noinline__ int site_decide_ol(const DevRun *run, pm_site_result *r, double lk_mono) { return site_decide(run, *r, lk_mono) ? 1 : 0; }
 // log10(m * 2^e) for a mantissa m in [1,2) (or 0 -> -inf).  m = c (1 + r) with c from a 128-entry table,
@@ -538,6 +545,7 @@ struct WideEval {
     __syncthreads();
     PM_TICK(2);
     bool first = true;
+    unsigned n_eval_mine = 0;  // rounds driven by this thread (the first of its group)
     for (;;) {
       const double p0 = ws->p[0], p1 = ws->p[1], p2 = ws->p[2];
       if (p0 < 0.0 && p1 < 0.0 && p2 < 0.0) break;
@@ -594,9 +602,8 @@ struct WideEval {
         }
         renorm_nonzero(a);  // log10_ol wants the mantissa back in [1,2)
         const double ll = log10_ol(ws, a.m, a.e);
-        const bool more = brent_feed_ol(&ws->brent[grp], -ll, run->precision) != 0;
-        ws->p[grp] = more ? ws->brent[grp].u : -1.0;
-        ws->n_eval_g[grp]++;
+        ws->p[grp] = brent_feed_ol(&ws->brent[grp], -ll, run->precision);
+        n_eval_mine++;
       }
       if (h0 && t == (Tg > 32 ? 32 : 0)) {
         ProdAcc a;
@@ -609,6 +616,7 @@ struct WideEval {
       __syncthreads();
       PM_TICK(4);
     }
+    if (t == 0 && mine) ws->n_eval_g[grp] += n_eval_mine;  // read by thread 0 after the site's last barrier
   }
 };
 

@@ -201,28 +201,6 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def bind_to_gpu_numa_node(index):
-    """Pins this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned host buffers of the
-    e2e leg are allocated next to it; returns the node, or None when the platform does not say."""
-    try:
-        p = torch.cuda.get_device_properties(index)
-        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
-        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return node
-    except (OSError, ValueError, AttributeError):
-        pass
-    return None
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,8 +233,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    all_cpus = os.sched_getaffinity(0)
-    numa = bind_to_gpu_numa_node(local_rank)   # pinned staging buffers then come from the GPU's own socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # rank 0's stdout carries exactly one JSON line: whatever the libraries print on file descriptor 1 (NCCL's
@@ -359,11 +335,9 @@ def main():
     rows = nres.value
     e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8),
            "d2h_bytes_per_step": world * (Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
-           "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world, "rank0_numa_node": numa,
+           "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world,
            "note": "pm_call_glf_sites from pinned host buffers; H2D of the packed sites and D2H of status + emitted rows inside the timed "
                    "region; all ranks run it at the same time, time = max over ranks"}
-
-    os.sched_setaffinity(0, all_cpus)   # the CPU baseline below gets every host core again
 
     line = None
     if rank == 0:

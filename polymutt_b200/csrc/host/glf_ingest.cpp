@@ -63,6 +63,41 @@ void GlfBatchReader::Stream::compact() {
 void GlfBatchReader::Stream::decode(size_t want_records) {
   compact();
   while (!ended && pending() < want_records) {
+    // fast path: a run of base records that are completely inside the buffer goes into pre-sized arrays without the
+    // per-record refill / capacity checks of the general path below
+    {
+      const size_t avail = (raw_end - raw_beg) / 20, room = want_records - pending();
+      size_t n = avail < room ? avail : room;
+      if (n > 0) {
+        const size_t old = pos.size();
+        pos.resize(old + n); ref.resize(old + n); rec.resize(old + n);
+        const unsigned char *r = raw.data() + raw_beg;
+        size_t k = 0;
+        int p = position, lp = last_pos;
+        for (; k < n && (r[0] >> 4) == 1; k++, r += 20) {
+          uint32_t offset, dm;
+          memcpy(&offset, r + 1, 4);
+          memcpy(&dm, r + 5, 4);
+          p += (int)offset;
+          if (lp == p && lp >= 0 && offset == 0) {
+            pos.resize(old + k); ref.resize(old + k); rec.resize(old + k);
+            throw std::runtime_error("GLF stream repeats a position (offset 0): not supported by the batched reader");
+          }
+          pm_person_site &o = rec[old + k];
+          memcpy(o.lk, r + 10, 10);
+          o.depth[0] = (uint8_t)(dm & 0xff); o.depth[1] = (uint8_t)((dm >> 8) & 0xff); o.depth[2] = (uint8_t)((dm >> 16) & 0xff);
+          o.map_quality = r[9];
+          o.pad[0] = o.pad[1] = 0;
+          pos[old + k] = p;
+          ref[old + k] = kTranslateBase[r[0] & 0xf];
+          lp = p;
+        }
+        position = p; last_pos = lp;
+        raw_beg += 20 * k;
+        if (k < n) { pos.resize(old + k); ref.resize(old + k); rec.resize(old + k); }
+        if (k > 0) continue;
+      }
+    }
     if (!fill(1)) { ended = true; break; }  // premature end of file = end of section
     const unsigned char b0 = raw[raw_beg];
     const int type = b0 >> 4;

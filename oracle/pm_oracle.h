@@ -7,9 +7,9 @@
  *
  * Parity status: PINNED.  The restatement (plus the host front end and VCF writers) reproduces the
  * four golden VCFs shipped in the reference's example/ directory byte for byte (non-## lines), and
- * is checked field by field (doubles) against the unmodified reference built by oracle/build_ref.sh
- * on extended-pedigree / --denovo / --all_sites cases (tests/test_oracle_vs_reference.py,
- * fixtures under tests/golden/).
+ * reproduces byte for byte the outputs of the unmodified reference built by oracle/build_ref.sh on
+ * extended pedigrees, --denovo, --all_sites, --pos, --quick_call, chrX / chrY / MT, multi-section GLFs and
+ * VCF input (tests/test_oracle_golden.py, fixtures + generating script under tests/golden/).
  *
  * It shares the data contract (structs) of include/polymutt_b200.h so that results can be
  * compared field by field with the CUDA path.

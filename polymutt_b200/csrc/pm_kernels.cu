@@ -284,14 +284,14 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
 // wide kernel: one block per site, one thread GROUP per Brent chain
 //
 // One objective evaluation is cheap (5 FMAs per unit) but every Brent step ends in a serial tail —
-// product reduction, one log10, the Brent update with its division, two block barriers.  To keep the
-// FP64 pipes busy during that tail the three hypotheses H1..H3 (and H4..H6 when needed) are optimised
-// CONCURRENTLY: the block is G = 3 groups of Tg threads, group g owns chain g; every thread keeps the
-// quartic coefficients of its U units of ITS chain in registers, one round evaluates all live chains,
-// and the first thread of each group finishes the reduction, takes the log10 and advances its own
-// Brent state.  Under --denovo the hom-ref hypothesis H0 is the product of chain 0's p^4 coefficients
-// (the (ref,ref) conditional is the same in H0 and H1..H3), so it rides along in the first round.
-// Very large pedigrees fall back to G = 1 (one chain at a time).
+// product reduction, one log10, the Brent update with its division, two block barriers.  The kernel can
+// optimise up to three hypotheses concurrently (G = 3 groups of Tg threads, group g owns chain g, the first
+// thread of each group drives its own Brent state); measured on B200, G = 1 with three INDEPENDENT blocks
+// per SM is faster (the blocks overlap each other's tails without sharing a barrier), so that is what
+// plan_launch picks and G = 3 is only reachable through the PM_WIDE_PLAN tuning hook.  Every thread keeps
+// the quartic coefficients of its U units in registers for the whole Brent run.  Under --denovo the hom-ref
+// hypothesis H0 is the product of chain 0's p^4 coefficients (the (ref,ref) conditional is the same in H0 and
+// H1..H3), so it rides along in the first round.
 // ================================================================================================
 constexpr int kMaxChains = 3;
 

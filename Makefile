@@ -19,22 +19,36 @@ FRONT_SRC := polymutt_b200/csrc/host/driver.cpp polymutt_b200/csrc/host/params.c
 CU_SRC    := $(wildcard polymutt_b200/csrc/*.cu)
 CU_HDR    := $(wildcard polymutt_b200/csrc/*.cuh) $(wildcard polymutt_b200/csrc/*.h) include/polymutt_b200.h
 
-LIB := polymutt_b200/lib/libpolymutt_b200.so
+LIB ?= polymutt_b200/lib/libpolymutt_b200.so
 CLI := polymutt_b200/bin/polymutt-b200
 ORACLE_LIB := oracle/_build/libpm_oracle.so
 ORACLE_CLI := oracle/_build/polymutt_oracle_cli
 TOOLS := polymutt_b200/bin/pm-tools
 
-.PHONY: all lib cli tools oracle ref clean
+.PHONY: all lib cli tools oracle ref clean timing
 all: lib cli tools oracle
 
 lib: $(LIB)
-# pm_post.cu (genotype posteriors: exact ties must break as in the reference) is compiled without FMA contraction
-CU_MAIN := $(filter-out polymutt_b200/csrc/pm_post.cu,$(CU_SRC))
-$(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC) polymutt_b200/csrc/host/host_error.h
-	@mkdir -p polymutt_b200/lib
-	$(NVCC) $(NVFLAGS) -fmad=false -Xptxas -v -c -o polymutt_b200/lib/pm_post.o polymutt_b200/csrc/pm_post.cu 2> polymutt_b200/lib/ptxas_post.log || (cat polymutt_b200/lib/ptxas_post.log; exit 1)
-	$(NVCC) $(NVFLAGS) -Xptxas -v -shared -o $@ $(CU_MAIN) polymutt_b200/lib/pm_post.o $(HOST_LIB_SRC) -Ipolymutt_b200/csrc/host -lcudart 2> polymutt_b200/lib/ptxas.log || (cat polymutt_b200/lib/ptxas.log; exit 1)
+# One object per translation unit (so that `make -j` compiles them side by side); pm_post.cu (genotype posteriors:
+# exact ties must break as in the reference) is compiled without FMA contraction.  The ptxas summaries
+# (registers, spills) of every kernel land next to the objects.
+OBJDIR ?= polymutt_b200/lib/obj
+CU_OBJ := $(patsubst polymutt_b200/csrc/%.cu,$(OBJDIR)/%.o,$(CU_SRC))
+HOSTLIB_OBJ := $(patsubst polymutt_b200/csrc/host/%.cpp,$(OBJDIR)/host_%.o,$(HOST_LIB_SRC))
+$(OBJDIR)/pm_post.o: NVEXTRA := -fmad=false
+$(OBJDIR)/%.o: polymutt_b200/csrc/%.cu $(CU_HDR) polymutt_b200/csrc/host/host_error.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(NVEXTRA) -Ipolymutt_b200/csrc/host -Xptxas -v -c -o $@ $< 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+$(OBJDIR)/host_%.o: polymutt_b200/csrc/host/%.cpp $(wildcard polymutt_b200/csrc/host/*.h) include/polymutt_b200.h
+	@mkdir -p $(OBJDIR)
+	$(HOSTCXX) $(CXXFLAGS) -c -o $@ $<
+$(LIB): $(CU_OBJ) $(HOSTLIB_OBJ)
+	$(NVCC) $(CUDA_ARCH) -shared -o $@ $(CU_OBJ) $(HOSTLIB_OBJ) -lcudart
+	@cat $(OBJDIR)/*.ptxas.log > $(OBJDIR)/ptxas_all.log
+
+# the same library with per-phase cycle counters in the wide kernel (scripts/gpu_phase_timing.py; never the product)
+timing:
+	$(MAKE) lib PM_DEFS=-DPM_PHASE_TIMING OBJDIR=polymutt_b200/lib/obj_timing LIB=polymutt_b200/lib/libpolymutt_b200_timing.so
 
 tools: $(TOOLS)
 $(TOOLS): polymutt_b200/csrc/tools/pm_tools.cpp $(FRONT_SRC) $(HOST_LIB_SRC) $(wildcard polymutt_b200/csrc/host/*.h)

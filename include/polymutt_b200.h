@@ -242,6 +242,11 @@ int pm_last_timing(pm_ctx *ctx, float *ms_main_kernel, float *ms_total, int *n_l
 /* Human-readable description of the kernel plan chosen for this pedigree (bench.py prints it). */
 int pm_describe_plan(pm_ctx *ctx, char *buf, size_t len);
 
+/* Test / tuning hook, not needed in production: re-plans the main pass on instantiation `variant` of the block-per-site
+ * kernel (pm_wide.cu, PM_WIDE_VARIANTS) with `threads` threads per block, also for pedigrees small enough for the
+ * thread-per-site kernel.  The parity tests use it to put every edge case through every kernel. */
+int pm_force_wide_plan(pm_ctx *ctx, int variant, int threads);
+
 /* Device-side stopwatch on the ctx stream (CUDA events): pm_timer_start records an event, pm_timer_stop
  * records a second one, waits for it and returns the elapsed milliseconds.  bench.py brackets its K
  * timed steps with these so that the number is taken on the stream the kernels are launched on. */

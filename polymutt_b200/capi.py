@@ -21,7 +21,8 @@ class LibraryNotBuilt(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "libpolymutt_b200.so")
+    # PM_LIB: an alternative build of the same library (scripts/gpu_phase_timing.py uses a -DPM_PHASE_TIMING one)
+    return os.environ.get("PM_LIB") or os.path.join(_HERE, "lib", "libpolymutt_b200.so")
 
 
 # ---- bulk record dtypes -------------------------------------------------------------------------
@@ -212,6 +213,8 @@ def _declare(lib):
     lib.pm_measure_copy_bw.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.pm_describe_plan.restype = C.c_int
     lib.pm_describe_plan.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.pm_force_wide_plan.restype = C.c_int
+    lib.pm_force_wide_plan.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.pm_timer_start.restype = C.c_int
     lib.pm_timer_start.argtypes = [C.c_void_p]
     lib.pm_timer_stop.restype = C.c_int
@@ -320,6 +323,10 @@ class Engine:
         buf = C.create_string_buffer(512)
         self._check(self.lib.pm_describe_plan(self.ctx, buf, 512))
         return buf.value.decode()
+
+    def force_wide_plan(self, variant: int, threads: int):
+        """Test / tuning hook: run the main pass on instantiation `variant` of the block-per-site kernel."""
+        self._check(self.lib.pm_force_wide_plan(self.ctx, variant, threads))
 
     def timer_start(self):
         self._check(self.lib.pm_timer_start(self.ctx))

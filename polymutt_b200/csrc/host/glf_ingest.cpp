@@ -41,9 +41,16 @@ bool GlfBatchReader::Stream::fill(size_t need) {
     raw_end -= raw_beg;
     raw_beg = 0;
   }
+  if (need > raw.size()) raw.resize(need + (1 << 16));  // an indel record can carry up to 2 x 32 KiB of allele text
   while (raw_end < need && !file_eof) {
     int got = gzread(f, raw.data() + raw_end, (unsigned)(raw.size() - raw_end));
-    if (got <= 0) { file_eof = true; break; }
+    if (got < 0) {  // a damaged .gz is an error, not the end of the chromosome (the run would exit 0 with a partial VCF)
+      int errnum = 0;
+      const char *msg = gzerror(f, &errnum);
+      if (errnum == Z_BUF_ERROR) { file_eof = true; break; }  // truncated last block: premature end of file, as the reference
+      throw std::runtime_error(std::string("GLF stream: read error (") + (msg ? msg : "?") + ")");
+    }
+    if (got == 0) { file_eof = true; break; }
     raw_end += (size_t)got;
   }
   return raw_end - raw_beg >= need;

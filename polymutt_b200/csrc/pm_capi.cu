@@ -6,6 +6,7 @@
 // PM_ECUDA otherwise.
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -39,7 +40,7 @@ struct pm_ctx {
   uint8_t *d_sex = nullptr;
   // --quick_call pre-pass (main.cpp:354-437): the same kernels on a second description of the run in which everybody
   // is an unrelated founder; its per-site verdicts overrule the real pass (k_quick_merge)
-  pm::LaunchPlan plan_q;
+  pm::LaunchPlan plan_q{};
   pm::DevRun *d_run_q = nullptr;
   pm::DevUnit *d_units_q = nullptr;
   pm_site_result *d_res_q = nullptr;
@@ -48,7 +49,7 @@ struct pm_ctx {
   // (FamilyLikelihoodSeq_VCF.cpp:101, 148); each description only does the records of its chromosome class
   bool have_x = false;
   bool batch_has_nonauto = false;
-  pm::LaunchPlan plan_x;
+  pm::LaunchPlan plan_x{};
   pm::DevRun *d_run_x = nullptr;
   pm::DevFam *d_fams_x = nullptr;
   pm::DevUnit *d_units_x = nullptr;
@@ -57,6 +58,8 @@ struct pm_ctx {
   int32_t *d_es = nullptr;
   pm::DevStep *d_steps = nullptr;
   int *d_err = nullptr;
+  double *d_spill = nullptr;  // wide kernel: coefficients of the units beyond threads * units_per_thread (shared by the passes of a batch: stream-ordered)
+  size_t cap_spill = 0;
   unsigned long long *d_counters = nullptr;
   cudaEvent_t tm0 = nullptr, tm1 = nullptr;
   // scratch (grown on demand)
@@ -92,9 +95,22 @@ int dev_alloc(T **p, size_t n) {
   return PM_OK;
 }
 
+int ensure_spill(pm_ctx *c) {
+  size_t need = 0;
+  for (const pm::LaunchPlan *p : {&c->plan, &c->plan_q, &c->plan_x})
+    if (p->kind == pm::LaunchPlan::WIDE) need = std::max(need, (size_t)p->grid * (size_t)p->n_spill * 5);
+  if (need <= c->cap_spill) return PM_OK;
+  c->cap_spill = 0;
+  int rc = dev_alloc(&c->d_spill, need);
+  if (rc) return rc;
+  c->cap_spill = need;
+  return PM_OK;
+}
+
 int ensure_scratch(pm_ctx *c, size_t n_sites) {
   if (n_sites <= c->cap_sites) return PM_OK;
   int rc;
+  c->cap_sites = 0;
   if ((rc = dev_alloc(&c->d_res_all, n_sites))) return rc;
   if ((rc = dev_alloc(&c->d_emit_sites, n_sites))) return rc;
   if (c->par.quick_call) {
@@ -182,7 +198,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
       if (!ped->peel || !ped->peel_first) { fail(PM_EINVAL, "pm_create: extended family %d but no peeling order was supplied", f); return false; }
       const int p0 = ped->peel_first[f], p1 = ped->peel_first[f + 1];
       if (p1 <= p0) { fail(PM_EINVAL, "pm_create: extended family %d has an empty peeling order", f); return false; }
-      d.step_first = (int16_t)steps.size(); d.n_steps = (int16_t)(p1 - p0);
+      d.step_first = (int32_t)steps.size(); d.n_steps = (int16_t)(p1 - p0);
       // resolve the std::map<pair,...> marriage_partials lookups of the reference (ES:1084-1087,
       // 1147, 1236) once: exact (first, second) key match.
       std::map<std::pair<int, int>, int> slots;
@@ -289,7 +305,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   run.vcf_log_tv = log10(0.5 / (2.0 + 1));
   run.vcf_log_indel = log10(prior);
 
-  e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, par->denovo ? kids_total : 0, c->sm_count);
+  e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, c->sm_count, nullptr);
   if (e == cudaErrorNotSupported) {
     fail(PM_EUNSUPPORTED, "pedigree shape not supported by the device kernels yet (%d quartic units, %d extended families, %d persons)", c->n_units, c->n_es, c->n_person);
     delete c; return nullptr;
@@ -322,7 +338,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     if (!build_desc(D1, true)) { pm_destroy(c); return nullptr; }
     pm::DevRun run_x = run;
     run_x.n_units = (int)D1.units.size(); run_x.n_es = (int)D1.es.size(); run_x.n_kids = 0; run_x.site_filter = 2;
-    cudaError_t ex = pm::plan_launch(&c->plan_x, c->n_person, run_x.n_units, run_x.n_es, 0, c->sm_count);
+    cudaError_t ex = pm::plan_launch(&c->plan_x, c->n_person, run_x.n_units, run_x.n_es, c->sm_count, nullptr);
     if (ex == cudaSuccess) {
       ok = dev_alloc(&c->d_run_x, 1) == PM_OK && dev_alloc(&c->d_fams_x, D1.fams.size()) == PM_OK && dev_alloc(&c->d_units_x, D1.units.size()) == PM_OK &&
            dev_alloc(&c->d_es_x, D1.es.size()) == PM_OK && dev_alloc(&c->d_steps_x, D1.steps.size()) == PM_OK;
@@ -347,7 +363,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     run_q.n_units = ped->n_person; run_q.n_es = 0; run_q.n_kids = 0; run_q.use_brent = 1;
     run_q.denovo = 0; run_q.force_call = 0; run_q.out_all_sites = 0;
     run_q.counters = c->d_counters + 8;  // its work is counted apart
-    e = pm::plan_launch(&c->plan_q, c->n_person, ped->n_person, 0, 0, c->sm_count);
+    e = pm::plan_launch(&c->plan_q, c->n_person, ped->n_person, 0, c->sm_count, nullptr);
     if (e != cudaSuccess) {
       fail(e == cudaErrorNotSupported ? PM_EUNSUPPORTED : PM_ECUDA, "--quick_call: the unrelated pre-pass needs %d single-founder units (%s)", ped->n_person, cudaGetErrorString(e));
       pm_destroy(c);
@@ -360,6 +376,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
            cudaMemcpy(c->d_run_q, &run_q, sizeof run_q, cudaMemcpyHostToDevice) == cudaSuccess;
     }
   }
+  if (ok && ensure_spill(c) != PM_OK) ok = false;
   if (!ok) {
     if (!*pmh::last_error()) fail(PM_ECUDA, "pm_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
     pm_destroy(c);
@@ -372,10 +389,11 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream_h2d) cudaStreamSynchronize(c->stream_h2d);  // a copy issued before an error return may still be reading the caller's buffer
   cudaFree(c->d_run_x); cudaFree(c->d_fams_x); cudaFree(c->d_units_x); cudaFree(c->d_es_x); cudaFree(c->d_steps_x);
   cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
-  cudaFree(c->d_err); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
+  cudaFree(c->d_err); cudaFree(c->d_spill); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->h_rows) cudaFreeHost(c->h_rows);
@@ -415,12 +433,12 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
   uint32_t *d_cnt = d_n_res ? d_n_res : c->d_n_emit;
   CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
   if (c->par.quick_call)
-    CUDA_TRY(pm::launch_sites(c->plan_q, c->d_run_q, d_hdr, (const uint4 *)d_person_site, nullptr, n_sites, c->d_res_q, c->d_status_q, c->d_err, c->stream));
-  CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
+    CUDA_TRY(pm::launch_sites(c->plan_q, c->d_run_q, d_hdr, (const uint4 *)d_person_site, nullptr, n_sites, c->d_spill, c->d_res_q, c->d_status_q, c->d_err, c->stream));
+  CUDA_TRY(pm::launch_sites(c->plan, c->d_run, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_spill, c->d_res_all, d_status_out, c->d_err, c->stream));
   if (c->par.quick_call) CUDA_TRY(pm::launch_quick_merge(c->d_status_q, n_sites, c->d_res_all, d_status_out, c->stream));
   const bool second = c->par.vcf_input && c->have_x && c->batch_has_nonauto;
   if (second)
-    CUDA_TRY(pm::launch_sites(c->plan_x, c->d_run_x, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_res_all, d_status_out, c->d_err, c->stream));
+    CUDA_TRY(pm::launch_sites(c->plan_x, c->d_run_x, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_spill, c->d_res_all, d_status_out, c->d_err, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
@@ -614,13 +632,31 @@ extern "C" void *pm_host_alloc(size_t bytes) {
 }
 extern "C" void pm_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-// "narrow" or "wide T=<threads> U=<units/thread> NC=<chains> grid=<blocks> (<blocks/SM>/SM)"
+// Human-readable description of the kernel plan
 extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
   if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
   if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", pm::kNarrowMaxUnits, c->plan.threads);
-  else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site = %d group(s) (one Brent chain each) x %d threads x %d units/thread, persistent grid %d (%d blocks/SM), one TMA bulk copy per site",
-                c->plan.units_per_thread, c->plan.threads, c->plan.chains, c->plan.threads / c->plan.chains, c->plan.units_per_thread, c->plan.grid, c->plan.blocks_per_sm);
+  else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site, %d units/thread in registers (%d units, %d in the L2 scratch), persistent grid %d (%d blocks/SM), "
+                "one TMA bulk copy per site, one block barrier per Brent round",
+                c->plan.units_per_thread, c->plan.threads, c->plan.units_per_thread, c->n_units, c->plan.n_spill, c->plan.grid, c->plan.blocks_per_sm);
   return PM_OK;
+}
+
+// Test / tuning hook: re-plans the main pass on a given instantiation of the wide kernel (pm_wide.cu: PM_WIDE_VARIANTS) with
+// `threads` threads per block, also for pedigrees the narrow kernel would normally take.  Extended families need the ES instances,
+// which every variant has.
+extern "C" int pm_force_wide_plan(pm_ctx *c, int variant, int threads) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int force[2] = {variant, threads};
+  pm::LaunchPlan p{};
+  cudaError_t e = pm::plan_launch(&p, c->n_person, c->n_units, c->n_es, c->sm_count, force);
+  if (e == cudaErrorInvalidValue) return fail(PM_EINVAL, "pm_force_wide_plan: no variant %d with %d threads", variant, threads);
+  if (e == cudaErrorNotSupported) return fail(PM_EUNSUPPORTED, "pm_force_wide_plan: variant %d with %d threads cannot hold this pedigree", variant, threads);
+  if (e != cudaSuccess) return fail(PM_ECUDA, "pm_force_wide_plan: %s", cudaGetErrorString(e));
+  c->plan = p;
+  return ensure_spill(c);
 }
 
 extern "C" int pm_timer_start(pm_ctx *c) {

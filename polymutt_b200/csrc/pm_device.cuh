@@ -39,9 +39,10 @@ struct DevFam {       // one pedigree family, VCF column order
   int16_t size, founders;
   int8_t kind;        // 0 = founders only, 1 = nuclear, 2 = extended (Elston-Stewart)
   int8_t n_mp;
-  int16_t step_first, n_steps;
-  int16_t pad;
+  int16_t n_steps;
+  int32_t step_first; // index into the run-wide concatenation of all families' peel steps (can pass 32,767)
 };
+static_assert(sizeof(DevFam) == 16, "DevFam is copied to the device as 16-byte records");
 
 struct DevUnit {      // one factor of the objective that has the quartic form
   int32_t first;      // column of the first member

@@ -16,22 +16,26 @@ constexpr int kNarrowMaxUnits = 8;  // quartic units a single thread keeps in re
 struct LaunchPlan {
   enum Kind { NARROW = 0, WIDE = 1 } kind;
   int threads;            // block size
-  int units_per_thread;   // wide: template parameter U
-  int chains;             // wide: Brent chains optimised concurrently (template parameter NC)
+  int units_per_thread;   // wide: units whose coefficients a thread keeps in registers (template parameter U)
+  int variant;            // wide: which (U, MAXT, MINB) instantiation (pm_wide.cu)
+  int n_spill;            // wide: units beyond threads * units_per_thread, coefficients in a global-memory scratch
   int grid;               // wide: persistent grid (multiple of the SM count); narrow: derived from n_sites
   int blocks_per_sm;
-  int site_buffers;       // wide: 2 = the next site is prefetched by TMA while this one is computed
-  int low_regs;           // wide: use the 128-register instantiation (more resident blocks per SM)
-  int kid_table;          // wide, --denovo: kids' ten mutation-mixed likelihoods are built once per site in shared memory
   int es;                 // wide: the pedigree has extended families too (the ES instances of the kernel)
   int n_person;
 };
 
-cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int n_kids_denovo, int sm_count);
+// force_wide (tests, tuning scripts): {variant, threads} overrides the choice and sends even small pedigrees to the wide kernel
+cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count, const int *force_wide);
+cudaError_t plan_wide(LaunchPlan *plan, int n_person, int n_units, int n_es, int sm_count, const int *force);
 
+// d_spill: plan.grid * plan.n_spill * 5 doubles when plan.n_spill > 0, else unused
 cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
-                         const double *d_mono, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, int *d_err,
+                         const double *d_mono, size_t n_sites, double *d_spill, pm_site_result *d_res, uint16_t *d_status, int *d_err,
                          cudaStream_t stream);
+cudaError_t launch_sites_wide(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs,
+                              const double *d_mono, size_t n_sites, double *d_spill, pm_site_result *d_res, uint16_t *d_status,
+                              int *d_err, cudaStream_t stream);
 
 // --quick_call: sites the unrelated pre-pass did not call (no-call or hom-ref there) become PM_SITE_QUICK_SKIP
 cudaError_t launch_quick_merge(const uint16_t *d_status_q, size_t n_sites, pm_site_result *d_res, uint16_t *d_status, cudaStream_t stream);

@@ -8,6 +8,7 @@ from polymutt_b200 import Engine, Params, capi, synth
 ped = synth.trios(1000); n = 32768
 dev = torch.device("cuda", 0)
 eng = Engine(ped, Params(denovo=True))
+if len(sys.argv) > 2: eng.force_wide_plan(int(sys.argv[1]), int(sys.argv[2]))
 hdr = torch.empty((n, 8), dtype=torch.uint8, device=dev); recs = torch.empty((n, ped.n_person, 16), dtype=torch.uint8, device=dev)
 synth.generate_sites(ped, n, seed=5, device=dev, out_hdr=hdr, out_recs=recs, chunk=4096)
 status = torch.empty(n, dtype=torch.uint16, device=dev); res = torch.empty((n, 256), dtype=torch.uint8, device=dev)
@@ -18,9 +19,9 @@ step(); eng.sync(); eng.reset_counters(); step(); eng.sync()
 c = eng.counters(); out = np.zeros(8, dtype=np.uint64)
 eng.lib.pm_debug_phase_cycles.argtypes = [C.c_void_p, C.c_void_p]
 eng.lib.pm_debug_phase_cycles(eng.ctx, out.ctypes.data)
-names = ["tma_wait", "stats", "setup", "eval_to_barrier", "serial_tail", "decide_write"]
-sites = c["sites_evaluated"]; tot = float(out[:6].sum())
+names = ["tma_wait", "stats", "setup", "spec_resolve", "generic_brent_step", "decide_write", "spec_eval_reduce", "generic_eval_reduce"]
+sites = c["sites_evaluated"]; tot = float(out[:8].sum())
 print(eng.describe_plan()); print("main kernel ms", eng.last_timing()[0], "evals/site", c["evaluations"] / sites)
 for k, nm in enumerate(names):
     print(f"{nm:16s} {out[k] / sites:10.0f} cycles/site  {100 * out[k] / tot:5.1f}%")
-print("total cycles/site (thread 0 of a block)", tot / sites, " per evaluation: eval", out[3] / c["evaluations"], "tail", out[4] / c["evaluations"])
+print("total cycles/site (thread 0 of a block)", tot / sites, " per evaluation:", {names[k]: round(out[k] / c["evaluations"]) for k in (6, 3, 7, 4)})

@@ -6,9 +6,11 @@ sys.path.insert(0, ROOT)
 import torch
 from polymutt_b200 import Engine, Params, capi, synth
 
-def run(name, ped, params, n_sites, reps=3):
+def run(name, ped, params, n_sites, reps=3, plan=None):
     dev = torch.device("cuda", 0)
     eng = Engine(ped, params)
+    if plan:
+        eng.force_wide_plan(*plan)
     hdr = torch.empty((n_sites, 8), dtype=torch.uint8, device=dev)
     recs = torch.empty((n_sites, ped.n_person, 16), dtype=torch.uint8, device=dev)
     synth.generate_sites(ped, n_sites, seed=5, device=dev, out_hdr=hdr, out_recs=recs, chunk=max(256, (1 << 22) // ped.n_person))
@@ -46,9 +48,11 @@ if __name__ == "__main__":
         "ceph20_dn": (S.ceph(), Params(denovo=True), 1 << 16),
         "single_trio_ba": (S.trios(1), Params(), 1 << 21),
     }
-    for k, (ped, par, n) in shapes.items():
-        if which == ["all"] or k in which:
-            try:
-                run(k, ped, par, n)
-            except Exception as e:
-                print(json.dumps(dict(name=k, error=repr(e)[:300])), flush=True)
+    # "name" or "name@variant,threads" (pm_force_wide_plan: a given instantiation of the block-per-site kernel)
+    todo = [(k, None) for k in shapes] if which == ["all"] else [(w.split("@")[0], tuple(int(x) for x in w.split("@")[1].split(",")) if "@" in w else None) for w in which]
+    for k, plan in todo:
+        ped, par, n = shapes[k]
+        try:
+            run(k if not plan else f"{k}@{plan[0]},{plan[1]}", ped, par, n, plan=plan)
+        except Exception as e:
+            print(json.dumps(dict(name=k, plan=plan, error=repr(e)[:300])), flush=True)

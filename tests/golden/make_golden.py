@@ -163,7 +163,35 @@ def body(path):
         return b"".join(l for l in f if not l.startswith(b"##"))
 
 
+def make_baseline_shapes(only):
+    """BASELINE.json configs 2, 4, 5 in miniature (tests/baseline_shapes.py): the unmodified reference on seeded synthetic
+    inputs of those shapes.  ref_<name>.sha = sha256 and line count of the non-## output + sha256 of the generated input;
+    the first 40 data rows, cut to their first 14 columns, are kept as text for post-mortems."""
+    import resource
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import baseline_shapes as B
+    soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+    resource.setrlimit(resource.RLIMIT_NOFILE, (min(max(4096, soft), hard), hard))
+    for name in B.SHAPES:
+        if only and name not in only and "cfg" not in only:
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            argv, digest = B.materialise(name, tmp)
+            out = os.path.join(tmp, name + ".vcf")
+            subprocess.run([REFBIN] + argv + ["--nthreads", "1", "--out_vcf", out], check=True, stdout=subprocess.DEVNULL)
+            text = body(out)
+        with open(os.path.join(HERE, f"ref_{name}.sha"), "w") as f:
+            f.write("%s %d %s\n" % (hashlib.sha256(text).hexdigest(), text.count(b"\n"), digest))
+        head = b"".join(b"\t".join(l.split(b"\t")[:14]) + b"\n" for l in text.splitlines()[:41])
+        with gzip.GzipFile(os.path.join(HERE, f"ref_{name}.head.vcf.gz"), "wb", 9, mtime=0) as dst:
+            dst.write(head)
+        print(name, len(text), "bytes", text.count(b"\n"), "lines")
+
+
 def main():
+    if sys.argv[1:] and all(a.startswith("cfg") for a in sys.argv[1:]):
+        return make_baseline_shapes(set(sys.argv[1:]))
     os.makedirs(os.path.join(HERE, "peds"), exist_ok=True)
     for name in ("test.ped", "test.mix.ped", "test.dat"):
         shutil.copy(os.path.join(REF, name), os.path.join(HERE, "peds", name))
@@ -215,6 +243,8 @@ def main():
             with open(os.path.join(HERE, f"ref_{name}.sha"), "w") as f:
                 f.write("%s %d\n" % (hashlib.sha256(text).hexdigest(), text.count(b"\n")))
             print(name, len(text), "bytes", text.count(b"\n"), "lines")
+        if not only:
+            make_baseline_shapes(set())
 
 
 if __name__ == "__main__":

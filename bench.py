@@ -1,21 +1,29 @@
 #!/usr/bin/env python3
 """bench.py — sites/sec of the per-site family-likelihood hot path on B200, with roofline and CPU baseline.
 
-Workload (BASELINE.json configs[1]): 1,000 independent trios (3,000 people), --denovo, synthetic GLF
-sites (polymutt_b200/synth.py).  A step = one pass of the hot path (k_sites_* -> k_compact -> k_post)
-over one batch of `--sites-per-step` packed sites that already sits in HBM; consecutive steps cycle
-through `--resident-batches` distinct batches, each far larger than the 126 MB L2, so no L2 flush is
-needed.  The 10M-site job of the config is 10M / sites-per-step such steps; sites are independent, so
-N GPUs each take their own contiguous site range (weak scaling: per-GPU batch fixed) with no
-collective on the data path.
+Default workload (BASELINE.json configs[1]): 1,000 independent trios (3,000 people), --denovo, synthetic GLF sites
+(polymutt_b200/synth.py).  `--workload` selects the other BASELINE configs (same JSON contract, their own
+algorithmic flop / byte formulas from SURVEY.md 8d):
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one JSON line on rank 0)
-  python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's own CPU path
-                                                                      (oracle/_ref/polymutt) on a bounded sample
+  trios1000_dn   configs[1]  1,000 trios, --denovo                       block-per-site kernel  (default)
+  ceph20_ba      configs[2]  20-member 3-generation pedigree             thread-per-site kernel, bi-allelic peel
+  ceph20_dn      configs[2]  the same under --denovo                     thread-per-site kernel, ten-state peel
+  vcf200x5       configs[3]  --in_vcf, 200 nuclear families x 5, PL      block-per-site kernel through pm_call_vcf_records
+  mixed100       configs[4]  50 trios + 50 quartets                      block-per-site kernel (one warp per site)
 
-`value` is device-resident throughput timed with CUDA events on the library's own stream
-(pm_timer_start/stop), max over ranks.  `e2e` is the same metric through the host-buffer C-ABI call
-(pm_call_glf_sites) from pinned host memory, H2D and D2H copies inside the timed region.
+A step = one pass of the hot path (k_sites_* -> k_compact -> k_post) over one batch of `--sites-per-step` packed sites
+that already sits in HBM; consecutive steps cycle through `--resident-batches` distinct batches, each far larger than
+the 126 MB L2, so no L2 flush is needed.  Sites are independent, so N GPUs each take their own contiguous site range
+(weak scaling: per-GPU batch fixed) with no collective on the data path.
+
+  python bench.py [--workload W] [--gpus N] [--steps K] [--warmup W]     our arm (one JSON line on rank 0)
+  python bench.py --impl reference [--workload W] --steps K --warmup W   the reference's own CPU path
+                                                                          (oracle/_ref/polymutt) on a bounded sample
+
+`value` is device-resident throughput timed with CUDA events on the library's own stream (pm_timer_start/stop), max
+over ranks.  `e2e` is the same metric through the host-buffer C-ABI call (pm_call_glf_sites / pm_call_vcf_records) from
+pinned host memory, H2D and D2H copies inside the timed region.  The `cpu_baseline` leg also runs the drop-in
+executable on the very shards the reference just processed and compares the two VCFs (`parity_checked_sites`).
 """
 from __future__ import annotations
 
@@ -37,20 +45,51 @@ sys.path.insert(0, ROOT)
 
 METRIC = "sites/sec for family variant+de novo calling"
 UNIT = "sites/s"
-WORKLOAD = "configs[1]: 1,000 independent trios (3,000 people), --denovo, synthetic GLF sites"
-N_TRIOS = 1000
 SEED = 20261018
 
-# Algorithmic work per site (DESIGN.md "Roofline"): per (family, hypothesis) coefficient
-# set-up S = 87k+18 flops under --denovo (36k+9 otherwise), k = kids; per objective evaluation 18 flops
-# per family + 20 for the shared priors (+ one log10 per family, counted separately, costed at 0 flops).
-def algorithmic_flops(n_fam, kids_per_fam, denovo, hypotheses, evaluations):
-    setup = (87 * kids_per_fam + 18) if denovo else (36 * kids_per_fam + 9)
-    return hypotheses * n_fam * setup + evaluations * (18 * n_fam + 20)
+
+# ------------------------------------------------------------------------------------------------
+# workloads: pedigree, parameters, step size, algorithmic work per site
+# ------------------------------------------------------------------------------------------------
+def _workloads():
+    from polymutt_b200 import Params, synth
+    S = synth
+    return {
+        "trios1000_dn": dict(title="configs[1]: 1,000 independent trios (3,000 people), --denovo, synthetic GLF sites",
+                             ped=lambda: S.trios(1000), params=Params(denovo=True), ref_args=["--denovo"], sites=1 << 17, vcf=False,
+                             kernel="k_sites_wide", nuclear=(1000, 1.0), peel=None),
+        "ceph20_ba": dict(title="configs[2]: 3-generation 20-member CEPH-like pedigree (4 grandparents, 2 parents, 14 kids), synthetic GLF sites",
+                          ped=lambda: S.ceph(), params=Params(), ref_args=[], sites=1 << 21, vcf=False,
+                          kernel="k_sites_narrow", nuclear=None, peel=(3, 14, 2, 1, 20)),
+        "ceph20_dn": dict(title="configs[2]: 3-generation 20-member CEPH-like pedigree, --denovo (ten-state peel), synthetic GLF sites",
+                          ped=lambda: S.ceph(), params=Params(denovo=True), ref_args=["--denovo"], sites=1 << 18, vcf=False,
+                          kernel="k_sites_narrow", nuclear=None, peel=(10, 14, 2, 1, 20)),
+        "vcf200x5": dict(title="configs[3]: --in_vcf, 200 nuclear families x 5 members (1,000 samples), PL records",
+                         ped=lambda: S.families([5] * 200), params=Params(vcf_input=True), ref_args=[], sites=1 << 18, vcf=True,
+                         kernel="k_sites_wide", nuclear=(200, 3.0), peel=None),
+        "mixed100": dict(title="configs[4]: 50 trios + 50 quartets (350 people), synthetic GLF sites",
+                         ped=lambda: S.concat(S.trios(50), S.families([4] * 50)), params=Params(), ref_args=[], sites=1 << 19, vcf=False,
+                         kernel="k_sites_wide", nuclear=(100, 1.5), peel=None),
+    }
 
 
-def algorithmic_bytes_per_site(n_person):
-    return 14 * n_person + 5  # 10 likelihood bytes + 3 depth + 1 mapQ per person; 4 pos + 1 ref per site
+def algorithmic_flops(w, denovo, hypotheses, evaluations):
+    """FP64 flops per site of the REFERENCE's formulation (FMA = 2), SURVEY.md 8d.
+    Nuclear families: coefficient set-up S = 87k+18 (--denovo) or 36k+9 per (family, hypothesis), k kids; one objective
+    evaluation = 18 flops per family + 20 for the shared priors (one log10 per family counted apart, costed at 0).
+    Elston-Stewart: per peel  leaf 2A^3, roof ~4A^3, spouse 2A^2, init 2A*famSize  with A states."""
+    if w["nuclear"]:
+        n_fam, kids = w["nuclear"]
+        setup = (87 * kids + 18) if denovo else (36 * kids + 9)
+        return hypotheses * n_fam * setup + evaluations * (18 * n_fam + 20)
+    A, leaves, roofs, spouses, fam_size = w["peel"]
+    per_peel = leaves * 2 * A ** 3 + roofs * 4 * A ** 3 + spouses * 2 * A ** 2 + 2 * A * fam_size
+    return evaluations * per_peel
+
+
+def algorithmic_bytes_per_site(n_person, vcf):
+    # GLF: 10 likelihood bytes + 3 depth + 1 mapQ per person, 4 pos + 1 ref per site; VCF: 3 PL bytes per person + 8
+    return 3 * n_person + 8 if vcf else 14 * n_person + 5
 
 
 class ClockSampler:
@@ -109,31 +148,37 @@ def reference_binary():
     return p, "port"
 
 
-def prepare_reference_shards(n_sites, n_shards, tmp):
-    """Writes the sample as n_shards disjoint site shards (each: 3,000 GLF files + ped/dat/gif)."""
-    import numpy as np
+def prepare_reference_shards(w, n_sites, n_shards, tmp):
+    """Writes the sample as n_shards disjoint site shards (each: one GLF file per person + ped/dat/gif, or ped/dat/VCF).
+    Returns the argument lists (without --out_vcf) for a polymutt-compatible executable."""
     from polymutt_b200 import capi, glfio, synth
-    ped = synth.trios(N_TRIOS)
-    h, r = synth.generate_sites(ped, n_sites, seed=SEED + 7919, device="cpu")
+    ped = w["ped"]()
+    h, r = synth.generate_sites(ped, n_sites, seed=SEED + 7919, device="cpu", cfg=synth.SynthConfig(poly_boost=50.0) if w["vcf"] else None)
     hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1)
     recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n_sites, ped.n_person)
     shards = []
     for k in range(n_shards):
         lo, hi = k * n_sites // n_shards, (k + 1) * n_sites // n_shards
-        shards.append(glfio.write_run_dir(os.path.join(tmp, f"shard{k}"), ped, hdr[lo:hi], recs[lo:hi]))
-    return shards
+        d = os.path.join(tmp, f"shard{k}")
+        if w["vcf"]:
+            p = glfio.write_vcf_run_dir(d, ped, hdr[lo:hi], recs[lo:hi])
+            shards.append(["-p", p[0], "-d", p[1], "--in_vcf", p[2]] + w["ref_args"])
+        else:
+            p = glfio.write_run_dir(d, ped, hdr[lo:hi], recs[lo:hi])
+            shards.append(["-p", p[0], "-d", p[1], "-g", p[2]] + w["ref_args"])
+    return shards, ped.n_person
 
 
-def run_reference_once(exe, shards, tmp):
+def run_reference_once(exe, shards, tmp, n_person, tag="o"):
     """The reference has no site-level parallelism (its OpenMP sections scale 1.6x on 8 threads), so
     "all the host cores" = one single-threaded process per disjoint site shard, run concurrently; wall time of all."""
     soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
-    want = 3 * N_TRIOS + 256
+    want = n_person + 256
     if soft < want:
         resource.setrlimit(resource.RLIMIT_NOFILE, (min(max(want, soft), hard), hard))
     t0 = time.perf_counter()
-    procs = [subprocess.Popen([exe, "-p", p[0], "-d", p[1], "-g", p[2], "--denovo", "--nthreads", "1", "--out_vcf", os.path.join(tmp, f"o{k}.vcf")],
-                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for k, p in enumerate(shards)]
+    procs = [subprocess.Popen([exe] + a + ["--nthreads", "1", "--out_vcf", os.path.join(tmp, f"{tag}{k}.vcf")],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for k, a in enumerate(shards)]
     rcs = [p.wait() for p in procs]
     dt = time.perf_counter() - t0
     if any(rcs):
@@ -148,24 +193,54 @@ def host_cores():
         return max(1, min(os.cpu_count() or 1, 32))
 
 
-def cpu_baseline(sites_per_core=300):
+def _vcf_body(path):
+    with open(path, "rb") as f:
+        return [l for l in f if not l.startswith(b"##")]
+
+
+def parity_check(shards, tmp, n_shards, sites_per_shard):
+    """Runs the drop-in executable (CUDA engine) on the first shards the reference has just processed and compares the
+    VCF bodies line by line.  Returns (sites checked, rows compared, differing rows)."""
+    cli = os.path.join(ROOT, "polymutt_b200", "bin", "polymutt-b200")
+    if not os.path.exists(cli):
+        return 0, 0, None
+    rows = bad = 0
+    for k in range(n_shards):
+        out = os.path.join(tmp, f"gpu{k}.vcf")
+        p = subprocess.run([cli] + shards[k] + ["--out_vcf", out], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        if p.returncode != 0:
+            raise RuntimeError("polymutt-b200 failed on a reference shard: " + p.stderr.decode(errors="replace")[-300:])
+        a, b = _vcf_body(out), _vcf_body(os.path.join(tmp, f"o{k}.vcf"))
+        rows += max(len(a), len(b))
+        bad += sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
+    return n_shards * sites_per_shard, rows, bad
+
+
+def cpu_baseline(w, sites_per_core):
     """~10-30 s of the reference on this box's host cores; returns the cpu_baseline object."""
     exe, kind = reference_binary()
     cores = host_cores()
     n_sites = sites_per_core * cores
     tmp = tempfile.mkdtemp(prefix="pm_cpu_base_")
     try:
-        shards = prepare_reference_shards(n_sites, cores, tmp)
-        dt = run_reference_once(exe, shards, tmp)
+        shards, n_person = prepare_reference_shards(w, n_sites, cores, tmp)
+        dt = run_reference_once(exe, shards, tmp, n_person)
+        checked, rows, bad = parity_check(shards, tmp, min(2, cores), sites_per_core)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
-    return {"value": n_sites / dt, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{n_sites} synthetic sites of the same workload as {cores} disjoint shards of {sites_per_core} sites (3,000 GLF files "
-                      f"each), one single-threaded reference process per shard run concurrently; wall time {dt:.1f} s incl. opening "
-                      f"the files and VCF writing"}
+    out = {"value": n_sites / dt, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{n_sites} synthetic sites of the same workload as {cores} disjoint shards of {sites_per_core} sites (one input file per "
+                     f"person each), one single-threaded reference process per shard run concurrently; wall time {dt:.1f} s incl. opening "
+                     f"the files and VCF writing",
+           "parity_checked_sites": checked, "parity_rows_compared": rows, "parity_rows_differing": bad,
+           "parity_note": "the drop-in executable (CUDA engine) re-ran the first shards of this sample; its VCF is compared line by line "
+                          "(non-## lines) with the reference's"}
+    if bad:
+        raise RuntimeError(f"parity check failed: {bad} of {rows} VCF rows differ from the reference's on the bench workload")
+    return out
 
 
-def reference_arm(args):
+def reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -174,22 +249,22 @@ def reference_arm(args):
     n_sites = args.ref_sites_per_core * cores
     tmp = tempfile.mkdtemp(prefix="pm_ref_arm_")
     try:
-        shards = prepare_reference_shards(n_sites, cores, tmp)
+        shards, n_person = prepare_reference_shards(w, n_sites, cores, tmp)
         for _ in range(args.warmup):
-            run_reference_once(exe, shards, tmp)
-        t = [run_reference_once(exe, shards, tmp) for _ in range(args.steps)]
+            run_reference_once(exe, shards, tmp, n_person)
+        t = [run_reference_once(exe, shards, tmp, n_person) for _ in range(args.steps)]
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     total = sum(t)
     value = n_sites * args.steps / total
-    sample = (f"{n_sites} synthetic sites per step as {cores} disjoint shards, one single-threaded reference process per shard run "
-              f"concurrently (the reference cannot shard sites itself)")
+    sample = (f"{n_sites} synthetic sites per step as {cores} disjoint shards of {args.ref_sites_per_core} sites, one single-threaded reference "
+              f"process per shard run concurrently (the reference cannot shard sites itself)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sites_per_step": n_sites, "persons": 3 * N_TRIOS, "families": N_TRIOS,
-                   "note": "each step = the unmodified reference binary end to end on a bounded sample (GLF files in, VCF out) on all host cores"},
+        "config": {"workload": w["title"], "sites_per_step": n_sites, "persons": n_person,
+                   "note": "each step = the unmodified reference binary end to end on a bounded sample (input files in, VCF out) on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,16 +282,19 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sites-per-step", type=int, default=1 << 17)
+    ap.add_argument("--workload", default="trios1000_dn", choices=["trios1000_dn", "ceph20_ba", "ceph20_dn", "vcf200x5", "mixed100"])
+    ap.add_argument("--sites-per-step", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--resident-batches", type=int, default=2)
-    ap.add_argument("--e2e-sites", type=int, default=1 << 13)
+    ap.add_argument("--e2e-sites", type=int, default=0, help="0 = about 400 MB of packed input")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-sites-per-core", type=int, default=100)
+    ap.add_argument("--ref-sites-per-core", type=int, default=300)
     ap.add_argument("--cpu-baseline-sites-per-core", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    W = _workloads()
+    w = W[args.workload]
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, w)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -224,7 +302,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from polymutt_b200 import Engine, Params, capi, synth
+    from polymutt_b200 import Engine, capi, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -243,21 +321,39 @@ def main():
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
-    ped = synth.trios(N_TRIOS)
+    ped = w["ped"]()
     npers = ped.n_person
-    S, R, K, W = args.sites_per_step, args.resident_batches, args.steps, args.warmup
-    params = Params(denovo=True)
-    eng = Engine(ped, params, device=local_rank)
+    params = w["params"]
+    vcf = w["vcf"]
+    S = args.sites_per_step or w["sites"]
+    R, K, Wm = args.resident_batches, args.steps, args.warmup
+    lut = np.array([pow(10, -float(i) / 10.0) for i in range(256)]) if vcf else None   # FamilyLikelihoodSeq_VCF.cpp:21-22
+    eng = Engine(ped, params, device=local_rank, lut=lut)
 
     # ---- synthetic batches, generated on the device; rank r owns sites [r*R*S, (r+1)*R*S) of the job ----
+    gi = lambda a, b: torch.where(a < b, (a - 1) * (10 - a) // 2 + (b - a), (b - 1) * (10 - b) // 2 + (a - b))
     batches = []
     for b in range(R):
         hdr = torch.empty((S, 8), dtype=torch.uint8, device=dev)
         recs = torch.empty((S, npers, 16), dtype=torch.uint8, device=dev)
-        synth.generate_sites(ped, S, seed=SEED + 1000 * rank + b, device=dev, out_hdr=hdr, out_recs=recs, chunk=1 << 12,
-                             pos0=(rank * R + b) * S)
-        batches.append((hdr, recs))
-    cap = max(4096, S // 16)
+        synth.generate_sites(ped, S, seed=SEED + 1000 * rank + b, device=dev, out_hdr=hdr, out_recs=recs, chunk=max(256, (1 << 24) // npers),
+                             pos0=(rank * R + b) * S, cfg=synth.SynthConfig(poly_boost=50.0) if vcf else None)
+        mono = None
+        if vcf:
+            # a VCF record of the site: (REF, ALT) = (ref, its transition), the three PLs of that pair kept, the rest cleared;
+            # mono = sum over samples of -PL[ref/ref]/10 (what the host front end computes while tokenising)
+            ref = hdr[:, 4].long()
+            alt = ((ref - 1) ^ 2) + 1
+            g = torch.stack([gi(ref, ref), gi(ref, alt), gi(alt, alt)], dim=1)                     # [S, 3]
+            keep = torch.zeros((S, 16), dtype=torch.bool, device=dev)
+            keep.scatter_(1, g, True)
+            keep[:, 10:14] = True
+            recs *= keep[:, None, :].to(torch.uint8)
+            hdr[:, 6] = alt.to(torch.uint8)
+            hdr[:, 7] = 0
+            mono = -(recs.gather(2, g[:, None, :1].expand(S, npers, 1))[:, :, 0].to(torch.float64)).sum(dim=1) / 10.0
+        batches.append((hdr, recs, mono))
+    cap = S if vcf else max(4096, S // 16)
     status = torch.empty(S, dtype=torch.uint16, device=dev)
     res_out = torch.empty((cap, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     per_out = torch.empty((cap, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
@@ -265,15 +361,17 @@ def main():
     torch.cuda.synchronize()
 
     def step(i):
-        hdr, recs = batches[i % R]
-        eng.call_glf_sites_device(hdr.data_ptr(), recs.data_ptr(), S, capi.PM_OUT_EMITTED, status.data_ptr(), res_out.data_ptr(),
-                                  per_out.data_ptr(), cap, n_res.data_ptr())
+        hdr, recs, mono = batches[i % R]
+        if vcf:
+            eng.call_vcf_records_device(hdr.data_ptr(), recs.data_ptr(), mono.data_ptr(), S, False, status.data_ptr(), res_out.data_ptr(), per_out.data_ptr())
+        else:
+            eng.call_glf_sites_device(hdr.data_ptr(), recs.data_ptr(), S, capi.PM_OUT_EMITTED, status.data_ptr(), res_out.data_ptr(),
+                                      per_out.data_ptr(), cap, n_res.data_ptr())
 
-    for i in range(W):
+    for i in range(Wm):
         step(i)
     eng.sync()
     eng.reset_counters()
-    main_ms = 0.0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -290,8 +388,8 @@ def main():
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     counters = eng.counters()
-    emitted_last = int(n_res.item())
-    # main-kernel time per launch (CUDA events around k_sites_wide inside the library), from one more step
+    emitted_last = S if vcf else int(n_res.item())
+    # main-kernel time per launch (CUDA events around the site kernel inside the library), from one more step
     step(0)
     eng.sync()
     main_ms, total_ms, launches_per_step = eng.last_timing()
@@ -304,20 +402,28 @@ def main():
 
     # ---- e2e through the host-buffer C-ABI call, pinned host memory: every rank at the same time (they share the
     # host's memory and PCIe root complexes), whole-job value = all ranks' sites / the slowest rank's time ----
-    Se = min(args.e2e_sites, S)
+    Se = min(args.e2e_sites or max(2048, (400 << 20) // (npers * 16)), S)
     h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
     h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
     h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
-    cap_e = max(1024, Se // 8)   # emitted rows are ~0.1 % of the sites of this workload
+    cap_e = Se if vcf else max(1024, Se // 8)
     h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
     h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
     h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+    h_mono = None
+    if vcf:
+        h_mono = torch.empty(Se, dtype=torch.float64, pin_memory=True)
+        h_mono.copy_(batches[0][2][:Se])
     torch.cuda.synchronize()
     nres = C.c_size_t(0)
 
     def e2e_step():
-        rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
-                                       h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
+        if vcf:
+            rc = eng.lib.pm_call_vcf_records(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), h_mono.data_ptr(), Se, h_res.data_ptr(), h_per.data_ptr())
+            nres.value = Se
+        else:
+            rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
+                                           h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
         if rc != 0:
             raise RuntimeError(eng.lib.pm_last_error().decode())
 
@@ -333,53 +439,55 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_dt = float(te.item())
     rows = nres.value
-    e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8),
+    e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8 + (8 if vcf else 0)),
            "d2h_bytes_per_step": world * (Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
            "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world,
-           "note": "pm_call_glf_sites from pinned host buffers; H2D of the packed sites and D2H of status + emitted rows inside the timed "
-                   "region; all ranks run it at the same time, time = max over ranks"}
+           "note": ("pm_call_vcf_records" if vcf else "pm_call_glf_sites") + " from pinned host buffers; H2D of the packed sites and D2H of status + "
+                   "result rows inside the timed region; all ranks run it at the same time, time = max over ranks"}
 
-    line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_sites_wide) ----
+        # ---- roofline of the dominant kernel ----
         fp64_peak = eng.measure_fp64_peak()
         copy_bw = eng.measure_copy_bw()
         peaks = measured_peaks()
-        hyp_per_site = counters["hypotheses"] / max(1, counters["sites_evaluated"])
-        ev_per_site = counters["evaluations"] / max(1, counters["sites_evaluated"])
-        flops_per_site = algorithmic_flops(N_TRIOS, 1, True, hyp_per_site, ev_per_site)
-        log10_per_site = ev_per_site * N_TRIOS
+        sites_ev = max(1, counters["sites_evaluated"])
+        hyp_per_site = counters["hypotheses"] / sites_ev
+        ev_per_site = counters["evaluations"] / sites_ev
+        flops_per_site = algorithmic_flops(w, bool(params.denovo), hyp_per_site, ev_per_site)
         flops_per_launch = flops_per_site * S
         achieved_tflops = flops_per_launch / (main_ms * 1e-3) / 1e12
-        bytes_per_launch = algorithmic_bytes_per_site(npers) * S
+        bytes_per_launch = algorithmic_bytes_per_site(npers, vcf) * S
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         # DRAM traffic of the kernel: not measurable from inside this process; taken per site from the committed
         # `ncu --set full` capture of the same kernel on the same workload and scaled to this launch's sites
         traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tj = json.load(f)
+                tj = json.load(f).get(args.workload)
             per_site = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["sites_in_capture"]
             traffic = per_site * S
-            traffic_src = "%s: %.0f DRAM bytes/site (algorithmic %d)" % (tj["source"], per_site, algorithmic_bytes_per_site(npers))
-        except (OSError, KeyError, ValueError):
+            traffic_src = "%s: %.0f DRAM bytes/site (algorithmic %d)" % (tj["source"], per_site, algorithmic_bytes_per_site(npers, vcf))
+        except (OSError, KeyError, ValueError, TypeError):
             pass
+        hbm_frac = bytes_per_launch / (main_ms * 1e-3) / 1e9 / hbm_peak
+        fp_frac = achieved_tflops / (fp64_peak / 1e12)
+        bound = "fp64" if fp_frac >= hbm_frac else "hbm"
         roofline = {
-            "bound": "fp64", "kernel": "k_sites_wide", "achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-            "frac": achieved_tflops / (fp64_peak / 1e12), "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
-            "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-            "flops_per_site": flops_per_site, "log10_per_site": log10_per_site,
-            "hypotheses_per_site": hyp_per_site, "evaluations_per_site": ev_per_site, "kernel_ms_per_launch": main_ms,
-            "hbm": {"achieved": bytes_per_launch / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_per_launch / (main_ms * 1e-3) / 1e9 / hbm_peak,
+            "bound": bound, "kernel": w["kernel"], "achieved": achieved_tflops if bound == "fp64" else bytes_per_launch / (main_ms * 1e-3) / 1e9,
+            "peak": fp64_peak / 1e12 if bound == "fp64" else hbm_peak, "unit": "TFLOP/s" if bound == "fp64" else "GB/s",
+            "frac": max(fp_frac, hbm_frac), "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+            "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak; method and history: profiles/fp64_peak.json); "
+                           "MEASURED_PEAKS.json has no FP64 figure",
+            "flops_per_site": flops_per_site, "hypotheses_per_site": hyp_per_site, "evaluations_per_site": ev_per_site, "kernel_ms_per_launch": main_ms,
+            "fp64": {"achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": fp_frac},
+            "hbm": {"achieved": bytes_per_launch / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                     "copy_kernel_gbs_live": copy_bw / 1e9},
         }
-
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sites_per_step_per_gpu": S, "persons": npers, "families": N_TRIOS,
+            "config": {"workload": w["title"], "workload_key": args.workload, "sites_per_step_per_gpu": S, "persons": npers,
                        "resident_batches": R, "input_bytes_per_step": S * (npers * 16 + 8),
                        "l2": "each step reads a different resident batch of %.1f GB, far larger than the 126 MB L2 (no flush needed)" % (S * npers * 16 / 1e9),
                        "kernel_plan": eng.describe_plan(),
@@ -388,9 +496,9 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args.cpu_baseline_sites_per_core)
+                line["cpu_baseline"] = cpu_baseline(w, args.cpu_baseline_sites_per_core)
             except Exception as ex:  # the baseline is reported, never required for the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)[:200]}
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(ex)[:300]}
         print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
     eng.close()
     if world > 1:

@@ -230,6 +230,13 @@ int pm_sync(pm_ctx *ctx);
 int pm_call_vcf_records(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
                         size_t n_records, pm_site_result *res_out, pm_person_result *person_out);
 
+/* The same on buffers in this ctx's device memory (asynchronous on the ctx stream, pm_sync before reading).  Every
+ * record gets a row: d_res_out[n_records], d_person_out[n_records * n_person], d_status_out[n_records].
+ * has_nonauto: the batch holds chrX / chrY / MT records (they take a second pass over the batch). */
+int pm_call_vcf_records_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                               size_t n_records, int has_nonauto, uint16_t *d_status_out, pm_site_result *d_res_out,
+                               pm_person_result *d_person_out);
+
 /* Page-locked host memory for the buffers handed to pm_call_glf_sites (lets its H2D/D2H copies overlap
  * the kernels).  Optional: pageable buffers are accepted too. */
 void *pm_host_alloc(size_t bytes);

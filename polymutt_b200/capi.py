@@ -199,6 +199,8 @@ def _declare(lib):
     lib.pm_call_glf_sites_device.restype = C.c_int
     lib.pm_call_glf_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pm_call_vcf_records_device.restype = C.c_int
+    lib.pm_call_vcf_records_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_host_alloc.restype = C.c_void_p
     lib.pm_host_alloc.argtypes = [C.c_size_t]
     lib.pm_host_free.restype = None
@@ -310,6 +312,10 @@ class Engine:
         """Device-buffer entry point (raw device pointers, e.g. torch tensors' data_ptr()); asynchronous."""
         self._check(self.lib.pm_call_glf_sites_device(self.ctx, d_hdr, d_recs, n_sites, out_mode, d_status, d_res, d_person,
                                                       res_cap, d_n_res))
+
+    def call_vcf_records_device(self, d_hdr: int, d_recs: int, d_mono: int, n: int, has_nonauto: bool, d_status: int, d_res: int, d_person: int):
+        """Device-buffer VCF entry point (raw device pointers); asynchronous."""
+        self._check(self.lib.pm_call_vcf_records_device(self.ctx, d_hdr, d_recs, d_mono, n, 1 if has_nonauto else 0, d_status, d_res, d_person))
 
     def sync(self):
         self._check(self.lib.pm_sync(self.ctx))

@@ -121,22 +121,6 @@ int ensure_scratch(pm_ctx *c, size_t n_sites) {
   return PM_OK;
 }
 
-// transmission_denovo = transmission x genoMut, summed in the reference's order (ES:787-810)
-void build_tden(const double *mut, double *tden) {
-  static const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
-  for (int i = 0; i < 10; i++)
-    for (int j = 0; j < 10; j++) {
-      double t[10] = {0};
-      for (int x = 0; x < 2; x++)
-        for (int y = 0; y < 2; y++) t[pm::geno_index(al[i][x], al[j][y])] += 0.25;
-      for (int k = 0; k < 10; k++) {
-        double sum = .0;
-        for (int m = 0; m < 10; m++) sum += t[m] * mut[m * 10 + k];
-        tden[(i * 10 + j) * 10 + k] = sum;
-      }
-    }
-}
-
 }  // namespace
 
 extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const double *lut256, int device) {
@@ -251,14 +235,6 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   memset(&run, 0, sizeof run);
   if (lut256) memcpy(run.lut, lut256, sizeof run.lut); else pm_fill_lut(run.lut);
   pm_genotype_mutation_matrix(par->denovo_mut_rate, par->denovo_tstv, run.mut);
-  build_tden(run.mut, run.tden);
-  {  // transmission[i][j][k], ES:752-785
-    static const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
-    for (int i = 0; i < 10; i++)
-      for (int j = 0; j < 10; j++)
-        for (int x = 0; x < 2; x++)
-          for (int y = 0; y < 2; y++) run.t10[(i * 10 + j) * 10 + pm::geno_index(al[i][x], al[j][y])] += 0.25;
-  }
   // SetPolyPrior (NucFam:231-242) and the per-hypothesis prior terms of main:447-533
   double prior = 0;
   for (int i = 1; i <= 2 * founders_total; i++) prior += 1.0 / i;
@@ -622,6 +598,18 @@ extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_p
     for (size_t r = 0; r < m; r++) res_out[base + r].site += (uint32_t)base;
   }
   return PM_OK;
+}
+
+// Device-buffer variant of pm_call_vcf_records (bench.py's device-resident leg): every record gets a row.
+extern "C" int pm_call_vcf_records_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                                          size_t n, int has_nonauto, uint16_t *d_status_out, pm_site_result *d_res_out,
+                                          pm_person_result *d_person_out) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  if (!c->par.vcf_input) return fail(PM_EINVAL, "pm_call_vcf_records_device: the ctx was not created with pm_params.vcf_input = 1");
+  if (has_nonauto && !c->have_x) return fail(PM_EUNSUPPORTED, "chrX/chrY/MT records need every family peeled, which the device kernels cannot do for this pedigree");
+  if (n && !d_mono) return fail(PM_EINVAL, "pm_call_vcf_records_device: null buffer");
+  c->batch_has_nonauto = has_nonauto != 0;
+  return run_device(c, d_hdr, d_person_site, d_mono, n, PM_OUT_ALL, d_status_out, d_res_out, d_person_out, n, c->d_n_emit);
 }
 
 extern "C" void *pm_host_alloc(size_t bytes) {

@@ -55,8 +55,6 @@ struct DevUnit {      // one factor of the objective that has the quartic form
 struct DevRun {
   double lut[256];            // 10^(-i/10)   (core/BaseQualityHelper.cpp:12-13), host-computed
   double mut[100];            // genotype mutation matrix (src/MutationModel.cpp:46-90), host-computed
-  double tden[1000];          // transmission_denovo[i][j][k] (ES:787-810), host-computed
-  double t10[1000];           // transmission[i][j][k] (ES:752-785): a quarter per gamete pair
   double log_inv[128];        // 1/c_i, c_i = 1 + (i+0.5)/128: table-driven log10 of a mantissa in [1,2)
   double log_tab[128];        // -log10(log_inv[i]) (computed in long double on the host)
   // host-computed log10 constants (same libm as the reference)

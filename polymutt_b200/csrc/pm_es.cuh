@@ -31,13 +31,165 @@ __device__ __forceinline__ double tba_cls(int cls, int sex, int i, int j, int k)
   return (k == j) ? 1.0 : 0.0;
 }
 
+// ================================================================================================
+// Ten-state peel (--denovo), factorised.  The reference contracts dense 10 x 10 x 10 tensors
+// (transmission / transmission_denovo, ES:752-810) in every step: ~36 kflop per likelihood of the 20-member CEPH
+// pedigree.  The tensors have structure the contraction can use:
+//   * transmission[i][j][k] = 1/4 for each of the four (allele of i, allele of j) pairs that make genotype k, and
+//     transmission_denovo = transmission x M (M = the 10 x 10 genotype mutation matrix).  So
+//       sum_k tden[i][j][k] pc[k] = 1/4 sum_{x in i, y in j} (M pc)[g(x,y)]
+//     = 1/4 (R[a_i][j] + R[b_i][j]),  R[x][j] = A[x][c_j] + A[x][d_j],  A[x][y] = (M pc)[g(x,y)]:
+//     100 FMAs for M pc, 40 + 55 additions, instead of 1,000 FMAs per child;
+//   * the result is symmetric in (i, j), so a marriage partial is kept as 55 numbers (i <= j);
+//   * a couple without marriage partial sends to its child  sum_ij pf[i] pm[j] T[i][j][k] = the gamete product
+//     gf[x] gm[y] (+ gf[y] gm[x]), gf[x] = sum_i pf[i] * (copies of x in i) / 2: ~60 flops instead of 3,000.
+// Same sums in a different order: results agree with the dense contraction to ~1e-15 relative; a likelihood that
+// is exactly zero (no compatible genotype configuration) is exactly zero here too (all terms are non-negative).
+// Quirk kept: a couple WITH a marriage partial sends through `transmission` without mutation (ES:1391).
+// ================================================================================================
+__device__ __forceinline__ constexpr int g10(int a, int b) { return a <= b ? a * 4 - a * (a - 1) / 2 + (b - a) : b * 4 - b * (b - 1) / 2 + (a - b); }
+__device__ __forceinline__ constexpr int sym55(int i, int j) { return i <= j ? i * 10 - i * (i - 1) / 2 + (j - i) : j * 10 - j * (j - 1) / 2 + (i - j); }
+__device__ __forceinline__ constexpr int al10(int g, int w) {
+  // alleles of genotype g in the order AA AC AG AT CC CG CT GG GT TT
+  return w == 0 ? (g < 4 ? 0 : (g < 7 ? 1 : (g < 9 ? 2 : 3))) : (g < 4 ? g : (g < 7 ? g - 3 : (g < 9 ? g - 5 : 3)));
+}
+constexpr int kMaxMp10 = 8;
+
+template <bool NA, typename RecPtr>
+__device__ double es_likelihood10(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22, bool denovo, double freq,
+                                  const double *__restrict__ lut, const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
+  double part[kMaxEsPersons * 10];
+  double mp[kMaxMp10 * 55];
+  const double q = 1.0 - freq;
+  const int cls = NA ? cls_ : PM_CHR_AUTO;
+  const uint8_t *sexes = NA ? run->sex + f.first : nullptr;
+  for (int i = 0; i < f.size; i++) {  // SetFounderPriors / InitializePartials, ES:643-664, 1434-1446
+    const uint4 r = recs[f.first + i];
+    double pr[3] = {freq * freq, 2 * freq * q, q * q};
+    if constexpr (NA) {
+      const bool male = sexes[i] == 1;
+      if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
+      else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
+    }
+#pragma unroll
+    for (int g = 0; g < 10; g++) {
+      double pen = lut[rec_lk(r, g)];
+      if (i == pin_person && g != pin_geno) pen = 0.0;
+      if (i < f.founders) pen *= g == g11 ? pr[0] : (g == g12 ? pr[1] : (g == g22 ? pr[2] : 0.0));
+      part[i * 10 + g] = pen;
+    }
+  }
+  const DevStep *steps = run->steps + f.step_first;
+  for (int s = 0; s < f.n_steps; s++) {
+    const DevStep st = steps[s];
+    if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
+      double pc[10], pcm[10];
+#pragma unroll
+      for (int k = 0; k < 10; k++) pc[k] = part[st.from0 * 10 + k];
+      if (denovo) {
+#pragma unroll
+        for (int m = 0; m < 10; m++) {
+          double a = 0.0, b = 0.0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) { a = fma(mut[m * 10 + k], pc[k], a); b = fma(mut[m * 10 + 5 + k], pc[5 + k], b); }
+          pcm[m] = 0.25 * (a + b);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 10; m++) pcm[m] = 0.25 * pc[m];
+      }
+      double R[4][10];  // R[x][j] = A[x][c_j] + A[x][d_j]
+#pragma unroll
+      for (int x = 0; x < 4; x++)
+#pragma unroll
+        for (int j = 0; j < 10; j++) R[x][j] = pcm[g10(x, al10(j, 0))] + pcm[g10(x, al10(j, 1))];
+      double *m = mp + st.mp * 55;
+#pragma unroll
+      for (int i = 0; i < 10; i++)
+#pragma unroll
+        for (int j = i; j < 10; j++) {
+          const double v = R[al10(i, 0)][j] + R[al10(i, 1)][j];
+          m[sym55(i, j)] = st.flag ? v : m[sym55(i, j)] * v;  // a fresh marriage partial starts at 1
+        }
+    } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
+      const double *pf = part + st.from0 * 10;
+      double *pt = part + st.to0 * 10;
+      if (st.mp < 0) {
+        double sum = 0.0;
+        for (int j = 0; j < 10; j++) sum += pf[j];
+        for (int i = 0; i < 10; i++) pt[i] *= sum;
+      } else {
+        const double *m = mp + st.mp * 55;  // symmetric: the same whichever spouse is folded in
+        double ps[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) ps[j] = pf[j];
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = 0; j < 10; j++) sum = fma(ps[j], m[sym55(i, j)], sum);
+          pt[i] *= sum;
+        }
+      }
+    } else {
+      const double *pf = part + st.from0 * 10, *pm_ = part + st.from1 * 10;
+      double *pc = part + st.to0 * 10;
+      double w[10];
+      if (st.mp < 0) {  // gamete vectors
+        double gf[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+          const double hf = 0.5 * pf[i], hm = 0.5 * pm_[i];
+          gf[al10(i, 0)] += hf; gf[al10(i, 1)] += hf;
+          gm[al10(i, 0)] += hm; gm[al10(i, 1)] += hm;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+          const int x = al10(k, 0), y = al10(k, 1);
+          w[k] = x == y ? gf[x] * gm[x] : fma(gf[x], gm[y], gf[y] * gm[x]);
+        }
+        if (denovo) {  // ES:1383: transmission_denovo = transmission x M
+          double o[10];
+#pragma unroll
+          for (int k = 0; k < 10; k++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int m = 0; m < 10; m++) sum = fma(w[m], mut[m * 10 + k], sum);
+            o[k] = sum;
+          }
+#pragma unroll
+          for (int k = 0; k < 10; k++) w[k] = o[k];
+        }
+      } else {  // ES:1391: with a marriage partial the plain transmission tensor, also under --denovo
+        const double *m = mp + st.mp * 55;
+#pragma unroll
+        for (int k = 0; k < 10; k++) w[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < 10; i++)
+#pragma unroll
+          for (int j = 0; j < 10; j++) {
+            const double v = 0.25 * (pf[i] * m[sym55(i, j)] * pm_[j]);
+            w[g10(al10(i, 0), al10(j, 0))] += v; w[g10(al10(i, 0), al10(j, 1))] += v;
+            w[g10(al10(i, 1), al10(j, 0))] += v; w[g10(al10(i, 1), al10(j, 1))] += v;
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < 10; k++) pc[k] *= w[k];
+    }
+  }
+  const double *pfin = part + steps[f.n_steps - 1].to0 * 10;
+  double lk = 0.0;
+  for (int i = 0; i < 10; i++) lk += pfin[i];
+  return lk;
+}
+
 // NA = false is the autosomal code with none of the chrX / chrY / MT rules compiled in (cls_ ignored): the rules sit in
 // the innermost loops of the peel and cost the narrow kernel 40 % when they were runtime branches.
 template <int A, bool NA, typename RecPtr>
 __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
                                      bool denovo, double freq, const double *__restrict__ lut,
-                                     const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
-                                     int pin_geno, int cls_) {
+                                     const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
+  if constexpr (A == 10) return es_likelihood10<NA>(run, f, recs, g11, g12, g22, denovo, freq, lut, mut, pin_person, pin_geno, cls_);
   double part[kMaxEsPersons * A];
   double mp[kMaxMp * A * A];
   const int gi[3] = {g11, g12, g22};
@@ -85,9 +237,6 @@ __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFa
           if (A == 3) {
             if constexpr (NA) { for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k]; }
             else { for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k]; }
-          } else {
-            const double *t = (denovo ? tden : t10) + (i * 10 + j) * 10;
-            for (int k = 0; k < 10; k++) sum += t[k] * pc[k];
           }
           m[i * A + j] = st.flag ? sum : m[i * A + j] * sum;  // a fresh marriage partial starts at 1
         }
@@ -116,8 +265,7 @@ __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFa
         for (int i = 0; i < A; i++)
           for (int j = 0; j < A; j++) {
             double t;
-            if (A == 3) { if constexpr (NA) t = tba_cls(cls, sexes[st.to0], i, j, k); else t = tba(i, j, k); }
-            else t = (m || !denovo) ? t10[(i * 10 + j) * 10 + k] : tden[(i * 10 + j) * 10 + k];  // ES:1383 vs 1391
+            if constexpr (NA) t = tba_cls(cls, sexes[st.to0], i, j, k); else t = tba(i, j, k);
             if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
             else sum += pf[i] * pm_[j] * t;
           }
@@ -134,10 +282,10 @@ __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFa
 template <int A, typename RecPtr>
 __device__ __forceinline__ double es_likelihood(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
                                                 bool denovo, double freq, const double *__restrict__ lut,
-                                                const double *__restrict__ tden, const double *__restrict__ t10, int pin_person,
+                                                const double *__restrict__ mut, int pin_person,
                                                 int pin_geno, int cls = PM_CHR_AUTO) {
-  if (cls == PM_CHR_AUTO) return es_likelihood_impl<A, false>(run, f, recs, g11, g12, g22, denovo, freq, lut, tden, t10, pin_person, pin_geno, cls);
-  return es_likelihood_impl<A, true>(run, f, recs, g11, g12, g22, denovo, freq, lut, tden, t10, pin_person, pin_geno, cls);
+  if (cls == PM_CHR_AUTO) return es_likelihood_impl<A, false>(run, f, recs, g11, g12, g22, denovo, freq, lut, mut, pin_person, pin_geno, cls);
+  return es_likelihood_impl<A, true>(run, f, recs, g11, g12, g22, denovo, freq, lut, mut, pin_person, pin_geno, cls);
 }
 
 // shared tables at the start of dynamic shared memory

@@ -27,8 +27,6 @@ constexpr int kNarrowThreads = 128;
 
 struct NarrowSmem {
   SmemTables t;
-  double tden[1000];
-  double t10[1000];
 };
 
 // NA = the instance for chrX / chrY / MT sites (see k_sites_wide): the autosomal one has none of those rules compiled in.
@@ -71,8 +69,8 @@ struct NarrowEval {
       if (u < run->n_units) sum += log10(quartic_eval(B[u], m));
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
-      double lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls)
-                         : es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->tden, sm->t10, -1, -1, cls);
+      double lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
+                         : es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
       sum += log10(lk);
     }
     return sum;
@@ -111,17 +109,6 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   // which instance does what: see k_sites_wide (err[1] = the autosomal instance met a chrX / chrY / MT site)
   if (NA ? ((err[1] == 0 && run->site_filter != 2) || run->site_filter == 1) : run->site_filter == 2) return;
   load_tables(run, &sm->t);
-  for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
-    sm->tden[i] = run->tden[i];
-    // transmission[i][j][k] (ES:752-785): a quarter per gamete pair
-    int gi = i / 100, gj = (i / 10) % 10, gk = i % 10;
-    const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
-    double v = 0.0;
-    for (int x = 0; x < 2; x++)
-      for (int y = 0; y < 2; y++)
-        if (geno_index(al[gi][x], al[gj][y]) == gk) v += 0.25;
-    sm->t10[i] = v;
-  }
   __syncthreads();
   const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sites) return;

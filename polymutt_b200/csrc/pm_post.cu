@@ -18,8 +18,6 @@ namespace pm {
 // ================================================================================================
 struct PostSmem {
   SmemTables t;
-  double tden[1000];
-  double t10[1000];
 };
 
 __device__ inline void store_person3(pm_person_result &o, double p0, double p1, double p2, int best) {
@@ -65,16 +63,6 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
   load_tables(run, &sm->t);
-  for (int i = threadIdx.x; i < 1000; i += blockDim.x) {
-    sm->tden[i] = run->tden[i];
-    int gi = i / 100, gj = (i / 10) % 10, gk = i % 10;
-    const int al[10][2] = {{1, 1}, {1, 2}, {1, 3}, {1, 4}, {2, 2}, {2, 3}, {2, 4}, {3, 3}, {3, 4}, {4, 4}};
-    double v = 0.0;
-    for (int x = 0; x < 2; x++)
-      for (int y = 0; y < 2; y++)
-        if (geno_index(al[gi][x], al[gj][y]) == gk) v += 0.25;
-    sm->t10[i] = v;
-  }
   __syncthreads();
   const uint32_t n_emit = *n_emit_ptr;
   const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
@@ -253,16 +241,16 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
         pm_person_result &o = out[f.first + j];
         if (!dn) {
           if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { store_person3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
-          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g11, cls);
-          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g12, cls);
-          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, sm->tden, sm->t10, j, g22, cls);
+          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g11, cls);
+          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g12, cls);
+          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g22, cls);
           double sum = l11 + l12 + l22;
           if (sum == 0) store_person3(o, 0, 0, 0, best3(l11, l12, l22));
           else store_person3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
         } else {
           double lk[10], sum = 0.0;
           for (int g = 0; g < 10; g++) {
-            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, sm->tden, sm->t10, j, g, cls);
+            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, mut, j, g, cls);
             sum += lk[g];
           }
           double mx = 0.0;

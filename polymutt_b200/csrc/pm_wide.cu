@@ -392,8 +392,8 @@ __device__ __noinline__ double unit_ref_likelihood_ol(const uint4 *recs, int fir
 // evaluator's shared-memory pointers lose their address space).
 __device__ __noinline__ double es_factor(const DevRun *run, const uint4 *recs, int cls, int e, int g11, int g12, int g22, bool denovo, double p) {
   const DevFam f = run->fams[run->es_fams[e]];
-  return denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, s_lut, run->tden, run->t10, -1, -1, cls)
-                : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, s_lut, run->tden, run->t10, -1, -1, cls);
+  return denovo ? es_likelihood<10>(run, f, recs, g11, g12, g22, true, p, s_lut, s_mut, -1, -1, cls)
+                : es_likelihood<3>(run, f, recs, g11, g12, g22, false, p, s_lut, s_mut, -1, -1, cls);
 }
 
 // packed unit descriptor kept in a register for the whole kernel: first | (nkids + 1) << 20 | sex << 28; -1 = no unit

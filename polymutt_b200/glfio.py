@@ -66,3 +66,43 @@ def write_run_dir(outdir: str, ped, hdr: np.ndarray, recs: np.ndarray, label: st
     open(paths[1], "w").write("T\tGLF_Index\n")
     open(paths[2], "w").write("".join(gif))
     return paths
+
+
+def _gi(a, b):
+    a, b = min(a, b), max(a, b)
+    return (a - 1) * (10 - a) // 2 + (b - a)
+
+
+def write_vcf_run_dir(outdir, ped, hdr, recs):
+    """--in_vcf inputs for a packed batch: ped/dat + a VCF whose records carry REF / ALT (the transition of REF, every
+    third record a transversion), DP and the three PLs of that allele pair per sample; returns (ped, dat, vcf) paths."""
+    os.makedirs(outdir, exist_ok=True)
+    names, lines = [], []
+    col = 0
+    for f in range(ped.n_fam):
+        ids = [f"F{f + 1:04d}_{j + 1}" for j in range(int(ped.fam_size[f]))]
+        for j, pid in enumerate(ids):
+            fa, mo = int(ped.father[col]), int(ped.mother[col])
+            lines.append(f"fam{f + 1:04d}\t{pid}\t{ids[fa] if fa >= 0 else 0}\t{ids[mo] if mo >= 0 else 0}\t{int(ped.sex[col])}\t0\n")
+            col += 1
+        names += ids
+    paths = [os.path.join(outdir, n) for n in ("v.ped", "v.dat", "v.vcf")]
+    open(paths[0], "w").writelines(lines)
+    open(paths[1], "w").write("T\tGLF_Index\n")
+    bases = "ACGT"
+    ts = {1: 3, 2: 4, 3: 1, 4: 2}
+    depth = recs["depth"][:, :, 0].astype(np.int64) | (recs["depth"][:, :, 1].astype(np.int64) << 8)
+    with open(paths[2], "w") as fh:
+        fh.write("##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(names) + "\n")
+        for s in range(len(hdr)):
+            r = int(hdr["ref_base"][s])
+            a = ts[r] if s % 3 else (r % 4) + 1     # mostly transitions, every third record a transversion
+            g = (_gi(r, r), _gi(r, a), _gi(a, a))
+            lk = recs["lk"][s]
+            cols = []
+            for c in range(len(names)):
+                pl = [int(lk[c, g[0]]), int(lk[c, g[1]]), int(lk[c, g[2]])]
+                m = min(pl)
+                cols.append(f"0/0:{int(depth[s, c])}:{pl[0] - m},{pl[1] - m},{pl[2] - m}")
+            fh.write(f"1\t{int(hdr['pos'][s]) + 1}\t.\t{bases[r - 1]}\t{bases[a - 1]}\t50\tPASS\tNS={len(names)}\tGT:DP:PL\t" + "\t".join(cols) + "\n")
+    return paths

@@ -203,3 +203,28 @@ def check_case(exe, glfdir, tmpdir, case):
         want = golden_text(golden)
         assert got == want, f"{name}: " + first_diff(got, want)
     return log
+
+
+# BASELINE.json configs 2, 4, 5 in miniature (tests/baseline_shapes.py): seeded synthetic inputs, outputs of the unmodified
+# reference committed as sha256 + line count (+ the sha256 of the generated input)
+BASELINE_SHAPES = ["cfg2_trios1000_dn", "cfg5_mixed100_ba", "cfg5_mixed100_dn", "cfg4_vcf200x5"]
+
+
+def check_baseline_shape(exe, tmpdir, name, extra=()):
+    import resource
+    import baseline_shapes as B
+    soft, hard = resource.getrlimit(resource.RLIMIT_NOFILE)
+    if soft < 4096:
+        resource.setrlimit(resource.RLIMIT_NOFILE, (min(4096, hard), hard))
+    sha, lines, input_sha = open(os.path.join(GOLDEN, f"ref_{name}.sha")).read().split()
+    argv, digest = B.materialise(name, tmpdir)
+    assert digest == input_sha, f"{name}: the synthetic generator no longer produces the input the reference output was made from"
+    out = os.path.join(tmpdir, name + ".out.vcf")
+    p = subprocess.run([exe] + argv + ["--out_vcf", out] + list(extra), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1800)
+    assert p.returncode == 0, p.stdout.decode(errors="replace")[-2000:]
+    got = body(open(out, "rb").read())
+    if sha_of(got) != (sha, int(lines)):
+        head = golden_text(f"ref_{name}.head.vcf.gz").splitlines()
+        mine = [b"\t".join(l.split(b"\t")[:14]) for l in got.splitlines()[:41]]
+        diff = next((f"row {i}: got {a[:200]!r} expected {b[:200]!r}" for i, (a, b) in enumerate(zip(mine, head)) if a != b), "first 40 rows agree")
+        raise AssertionError(f"{name}: sha/line count {sha_of(got)} vs reference {(sha, int(lines))}; {diff}")

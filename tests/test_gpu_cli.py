@@ -88,3 +88,10 @@ def test_cli_reports_missing_inputs(tmp_path):
     p = subprocess.run([U.PRODUCT_CLI, "-p", "nope.ped", "-d", "nope.dat", "-g", "nope.gif", "--out_vcf", str(tmp_path / "o.vcf")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert p.returncode == 1 and b"FATAL ERROR" in p.stdout
+
+
+@pytest.mark.parametrize("name", U.BASELINE_SHAPES)
+def test_product_cli_matches_reference_on_baseline_shapes(name, glfdir, tmp_path):
+    """The drop-in executable (block-per-site kernel, GLF ingest / VCF tokeniser, writers) against outputs of the
+    unmodified reference on BASELINE.json's configs 2, 4 and 5 in miniature."""
+    U.check_baseline_shape(U.PRODUCT_CLI, str(tmp_path), name)

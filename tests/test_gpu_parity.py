@@ -240,6 +240,94 @@ def test_wide_kernel_parity_on_synthetic_pedigrees(case, oracle_built):
     parity.assert_parity(rep, n_sites)
 
 
+# ---- the block-per-site kernel on the edge cases, every instantiation ------------------------------
+# (variant, threads) of pm_wide.cu's PM_WIDE_VARIANTS; test.mix.ped has 10 units, so every plan holds it
+WIDE_PLANS = [(0, 32), (1, 32), (2, 32), (3, 32), (4, 64), (4, 128), (5, 256)]
+
+
+def _run_wide(ped, params, hdr, recs, plan):
+    eng = Engine(ped, params)
+    eng.force_wide_plan(*plan)
+    assert "k_sites_wide" in eng.describe_plan()
+    g = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    eng.close()
+    return g
+
+
+@pytest.mark.parametrize("plan", WIDE_PLANS, ids=lambda p: f"v{p[0]}_t{p[1]}")
+def test_wide_kernel_edge_cases_every_plan(plan, example12, oracle_built, tools_built, tmp_path):
+    """The edge block of test_edge_cases_missing_data_bad_ref_and_filters (N reference, people and whole sites without
+    data, saturated likelihoods, 24-bit depths, filters) through k_sites_wide: pm_force_wide_plan sends the 10-unit
+    mixture pedigree to every instantiation instead of the thread-per-site kernel."""
+    ped, glf_index = F.pedigree_from_file(PED("test.mix.ped"), str(tmp_path))
+    hdr, recs = F.sites_for(example12, glf_index, 5000, 1000)
+    rng = np.random.default_rng(5)
+    hdr["ref_base"][rng.integers(0, len(hdr), 250)] = 0
+    drop = rng.random(recs.shape) < 0.15
+    recs[drop] = np.zeros((), dtype=recs.dtype)
+    recs[100:140] = np.zeros((), dtype=recs.dtype)
+    recs["lk"][200:260, :, :] = 255
+    recs["depth"][300:330, :, 2] = 1
+    for kw in (dict(), dict(min_total_depth=100, max_total_depth=170, min_ps=80.0, min_map_quality=90),
+               dict(denovo=True, denovo_mut_rate=1e-6), dict(out_all_sites=True)):
+        params = Params(**kw)
+        g = _run_wide(ped, params, hdr, recs, plan)
+        ora = OracleEngine(ped, params)
+        o = ora.call_glf_sites(hdr, recs)
+        ora.close()
+        rep = parity.compare(*g, *o, denovo=params.denovo, label=f"wide-edge{plan}{kw}")
+        print(rep)
+        parity.assert_parity(rep, len(hdr))
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(denovo=True), dict(out_all_sites=True)], ids=["ba", "denovo", "all_sites"])
+def test_wide_kernel_family_likelihood_underflow_gives_minus_infinity(kw, oracle_built):
+    """Sibships of 14 and 16 with saturated likelihoods: 16+ factors of 10^-25.5 underflow, the family likelihood is
+    exactly 0 in the reference and log10(0) = -inf runs through its objective (FamilyLikelihoodSeq.cpp:222-240,
+    NucFamGenotypeLikelihood.cpp:941-985).  The kernel evaluates such families the reference's way ("fragile units")."""
+    ped = synth.families([3] * 30 + [16, 18] + [1] * 6)
+    n = 400
+    h, r = synth.generate_sites(ped, n, seed=31, cfg=synth.SynthConfig(poly_boost=100.0, injected_denovo=0.05))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1).copy()
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n, ped.n_person).copy()
+    first = int(ped.family_first()[30])
+    rng = np.random.default_rng(3)
+    sat = rng.random(n) < 0.5
+    recs["lk"][sat, first:first + 34, :] = 255            # both big sibships saturated: every conditional underflows
+    half = rng.random(n) < 0.3
+    recs["lk"][half, first + 16:first + 34, :] = 254      # ... or only the second one, one phred off
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    assert np.isneginf(o[1]["varllk"][:, 1]).sum() > 50, "the fixture is meant to make the reference's objective -inf"
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=f"underflow{kw}")
+    print(rep)
+    parity.assert_parity(rep, n)
+    both_inf = np.isneginf(g[1]["varllk"][:, 1]) == np.isneginf(o[1]["varllk"][:, 1])
+    assert both_inf.all()
+
+
+@pytest.mark.parametrize("n_fam,kw", [(4400, dict(denovo=True)), (4500, dict())], ids=["4400_trios_denovo", "4500_trios_ba"])
+def test_wide_kernel_more_units_than_registers_hold(n_fam, kw, oracle_built):
+    """More than 4,096 units: 512 threads x 8 units in registers, the rest in the L2 scratch.  (What bounds the pedigree
+    now is the site buffer: one site's 16 bytes x persons must fit in shared memory, about 14,000 people.)"""
+    ped = synth.trios(n_fam)
+    n = 24
+    h, r = synth.generate_sites(ped, n, seed=78, cfg=synth.SynthConfig(poly_boost=5.0, injected_denovo=0.1))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1)
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n, ped.n_person)
+    params = Params(**kw)
+    eng = Engine(ped, params)
+    assert "in the L2 scratch" in eng.describe_plan() and f"{n_fam - 4096} in the L2" in eng.describe_plan()
+    g = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    eng.close()
+    ora = OracleEngine(ped, params)
+    o = ora.call_glf_sites(hdr, recs)
+    ora.close()
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=f"{n_fam} trios")
+    print(rep)
+    parity.assert_parity(rep, n)
+
+
 # ---- VCF-input records through the C ABI ---------------------------------------------------------
 def _vcf_records_from_sites(hdr, recs, rng):
     """Turns packed GLF sites into VCF-mode records: (REF, ALT) = (ref, a random other base), the three PLs of that
@@ -261,6 +349,44 @@ def _vcf_records_from_sites(hdr, recs, rng):
     for c in range(npers):                            # sequential sum in column order, as the host front end does
         mono += -out["lk"][np.arange(n), c, g0].astype(np.float64) / 10.0
     return h, out, mono
+
+
+@pytest.mark.parametrize("shape,n", [("fam200x5", 1500), ("trios334", 800), ("mixed_350", 2500)])
+def test_vcf_records_parity_wide_plans(shape, n, oracle_built):
+    """BASELINE config 4's own shape (200 nuclear families x 5 = 1,000 samples: one warp x 8 units per record) and two
+    more many-unit pedigrees through pm_call_vcf_records, against the oracle."""
+    ped = {"fam200x5": lambda: synth.families([5] * 200), "trios334": lambda: synth.trios(334),
+           "mixed_350": lambda: synth.concat(synth.trios(50), synth.families([4] * 50))}[shape]()
+    hh, rr = synth.generate_sites(ped, n, seed=41, cfg=synth.SynthConfig(poly_boost=150.0, injected_denovo=0.02))
+    hdr = hh.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1).copy()
+    recs = rr.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n, ped.n_person).copy()
+    h, r, mono = _vcf_records_from_sites(hdr, recs, np.random.default_rng(4))
+    lut = np.array([pow(10, -float(i) / 10.0) for i in range(256)])
+    params = Params(vcf_input=True)
+    eng = Engine(ped, params, lut=lut)
+    assert "k_sites_wide" in eng.describe_plan()
+    res_g, per_g = eng.call_vcf_records(h, r, mono)
+    eng.close()
+    ora = OracleEngine(eng.ped, params, lut=lut)
+    res_o, per_o = ora.call_vcf_records(h, r, mono)
+    ora.close()
+    close = lambda a, b, rt=1e-6, at=0.0: parity._close(a, b, rt, at)
+    freq_bad = ~close(res_g["freq"], res_o["freq"], 1e-6, 1e-9)
+    same_optimum = close(res_g["varllk_noprior"][:, 1], res_o["varllk_noprior"][:, 1], 1e-12, 1e-11)
+    knife = freq_bad & same_optimum
+    ok = ~knife
+    bad = {
+        "llk_ref": int(np.sum(~close(res_g["varllk"][:, 0], res_o["varllk"][:, 0]))),
+        "llk_alt": int(np.sum(~close(res_g["varllk"][:, 1], res_o["varllk"][:, 1]))),
+        "qual": int(np.sum(~close(res_g["poly_qual"], res_o["poly_qual"], 1e-6, 1e-5))),
+        "freq_not_knife_edge": int(np.sum(freq_bad & ~same_optimum)),
+        "best": int(np.sum(per_g["best"][ok] != per_o["best"][ok])),
+        "post": int(np.sum(~close(per_g["post"][ok], per_o["post"][ok], 1e-6, 1e-15))),
+        "gq": int(np.sum(np.abs(per_g["gq"][ok].astype(int) - per_o["gq"][ok].astype(int)) > 1)),
+    }
+    print(shape, bad, "knife-edge records:", int(knife.sum()), "of", n)
+    assert not any(bad.values()), bad
+    assert knife.sum() <= max(2, n // 1000), int(knife.sum())
 
 
 @pytest.mark.parametrize("pedfile,n,mixed_classes", [("test.ped", 20000, False), ("test.mix.ped", 20000, False), ("single.ped", 20000, False),

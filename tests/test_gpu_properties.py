@@ -117,7 +117,7 @@ def test_large_pedigrees(n_fam, kw, oracle_built):
 
 
 def test_unsupported_shapes_fail_loudly():
-    # more quartic units than the largest plan holds
+    # one site of 15,000 people (240 KB) does not fit in an SM's shared memory
     with pytest.raises(RuntimeError, match="not supported"):
         Engine(synth.trios(5000), Params())
     with pytest.raises(RuntimeError, match="quick_call"):

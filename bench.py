@@ -409,17 +409,18 @@ def main():
     cap_e = Se if vcf else max(1024, Se // 8)
     h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
     h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-    h_per = torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-    h_mono = None
+    h_per = None if vcf else torch.empty((cap_e, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+    h_mono = h_calls = None
     if vcf:
         h_mono = torch.empty(Se, dtype=torch.float64, pin_memory=True)
         h_mono.copy_(batches[0][2][:Se])
+        h_calls = torch.empty((Se, npers), dtype=torch.uint16, pin_memory=True)   # best | gq << 8: what the --in_vcf writer prints from
     torch.cuda.synchronize()
     nres = C.c_size_t(0)
 
     def e2e_step():
         if vcf:
-            rc = eng.lib.pm_call_vcf_records(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), h_mono.data_ptr(), Se, h_res.data_ptr(), h_per.data_ptr())
+            rc = eng.lib.pm_call_vcf_records_calls(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), h_mono.data_ptr(), Se, h_res.data_ptr(), h_calls.data_ptr())
             nres.value = Se
         else:
             rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
@@ -440,9 +441,10 @@ def main():
         e2e_dt = float(te.item())
     rows = nres.value
     e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8 + (8 if vcf else 0)),
-           "d2h_bytes_per_step": world * (Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
+           "d2h_bytes_per_step": world * (Se * (capi.SITE_RESULT_DTYPE.itemsize + npers * 2) if vcf else
+                                          Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
            "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world,
-           "note": ("pm_call_vcf_records" if vcf else "pm_call_glf_sites") + " from pinned host buffers; H2D of the packed sites and D2H of status + "
+           "note": ("pm_call_vcf_records_calls" if vcf else "pm_call_glf_sites") + " from pinned host buffers; H2D of the packed sites and D2H of status + "
                    "result rows inside the timed region; all ranks run it at the same time, time = max over ranks"}
 
     if rank == 0:

@@ -230,6 +230,12 @@ int pm_sync(pm_ctx *ctx);
 int pm_call_vcf_records(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
                         size_t n_records, pm_site_result *res_out, pm_person_result *person_out);
 
+/* The same with the per-sample results reduced to what the --in_vcf writer prints from (src/FamilyLikelihoodSeq_VCF.cpp:
+ * 499-517: GT from bestGenoIdx, GQ): calls_out[n_records * n_person] = best | gq << 8.  2 bytes per sample come back
+ * over PCIe instead of 96. */
+int pm_call_vcf_records_calls(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                              size_t n_records, pm_site_result *res_out, uint16_t *calls_out);
+
 /* The same on buffers in this ctx's device memory (asynchronous on the ctx stream, pm_sync before reading).  Every
  * record gets a row: d_res_out[n_records], d_person_out[n_records * n_person], d_status_out[n_records].
  * has_nonauto: the batch holds chrX / chrY / MT records (they take a second pass over the batch). */

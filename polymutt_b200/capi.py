@@ -199,6 +199,8 @@ def _declare(lib):
     lib.pm_call_glf_sites_device.restype = C.c_int
     lib.pm_call_glf_sites_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pm_call_vcf_records_calls.restype = C.c_int
+    lib.pm_call_vcf_records_calls.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.pm_call_vcf_records_device.restype = C.c_int
     lib.pm_call_vcf_records_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_host_alloc.restype = C.c_void_p
@@ -312,6 +314,17 @@ class Engine:
         """Device-buffer entry point (raw device pointers, e.g. torch tensors' data_ptr()); asynchronous."""
         self._check(self.lib.pm_call_glf_sites_device(self.ctx, d_hdr, d_recs, n_sites, out_mode, d_status, d_res, d_person,
                                                       res_cap, d_n_res))
+
+    def call_vcf_records_calls(self, hdr: np.ndarray, recs: np.ndarray, mono: np.ndarray):
+        """VCF-input entry point with compact per-sample output.  Returns (results[n], calls[n, n_person] = best | gq << 8)."""
+        hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+        recs = np.ascontiguousarray(recs, dtype=PERSON_SITE_DTYPE)
+        mono = np.ascontiguousarray(mono, dtype=np.float64)
+        n, npers = len(hdr), self.ped.n_person
+        res = np.zeros(max(n, 1), dtype=SITE_RESULT_DTYPE)
+        calls = np.zeros((max(n, 1), npers), dtype=np.uint16)
+        self._check(self.lib.pm_call_vcf_records_calls(self.ctx, hdr.ctypes.data, recs.ctypes.data, mono.ctypes.data, n, res.ctypes.data, calls.ctypes.data))
+        return res[:n], calls[:n]
 
     def call_vcf_records_device(self, d_hdr: int, d_recs: int, d_mono: int, n: int, has_nonauto: bool, d_status: int, d_res: int, d_person: int):
         """Device-buffer VCF entry point (raw device pointers); asynchronous."""

@@ -23,6 +23,10 @@ struct Engine {
   // Same contract as pm_call_vcf_records (--in_vcf); nullptr if the engine has no VCF-input path.
   int (*call_vcf)(void *ctx, const pm_site_hdr *, const pm_person_site *, const double *mono, size_t n, pm_site_result *res,
                   pm_person_result *person) = nullptr;
+  // optional: same with the per-sample results reduced to calls[n * n_person] = best | gq << 8 (pm_call_vcf_records_calls):
+  // all the --in_vcf writer prints from; used when present
+  int (*call_vcf_calls)(void *ctx, const pm_site_hdr *, const pm_person_site *, const double *mono, size_t n, pm_site_result *res,
+                        uint16_t *calls) = nullptr;
   // optional: page-locked allocation for the batch buffers (nullptr = plain malloc)
   void *(*host_alloc)(size_t bytes) = nullptr;
   void (*host_free)(void *p) = nullptr;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -297,7 +298,9 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   std::vector<pm_person_site> recs;
   std::vector<double> mono;
   std::vector<pm_site_result> res;
-  std::vector<pm_person_result> pres;
+  std::vector<pm_person_result> pres;   // per-sample results, or (engines with call_vcf_calls) ...
+  std::vector<uint16_t> calls;           // ... best | gq << 8 per sample
+  const bool compact = engine.call_vcf_calls != nullptr;
   std::vector<std::string> text;
   std::vector<std::vector<double>> scratch((size_t)threads, std::vector<double>((size_t)np));
   static const char *lab[3] = {"0/0", "0/1", "1/1"};
@@ -365,14 +368,15 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     const bool from_row = L.src >= 0;
     const double qual = from_row ? res[(size_t)L.src].poly_qual : last_qual;
     const double fmin = from_row ? res[(size_t)L.src].freq : last_min;
-    const pm_person_result *pr = from_row ? &pres[(size_t)L.src * (size_t)np] : nullptr;
+    const pm_person_result *pr = from_row && !compact ? &pres[(size_t)L.src * (size_t)np] : nullptr;
+    const uint16_t *cl = from_row && compact ? &calls[(size_t)L.src * (size_t)np] : nullptr;
     const bool labeled = from_row || last_labeled;
     // GetBestGenoLabel_vcfv4 (NucFam.cpp:1587-1608) on the record the labels were made on: haploid labels on Y / MT and
     // for males on X, "." for females on Y (FLSeq_VCF.cpp:204, 221-227)
     const int lcls = from_row ? (int)hdr[(size_t)L.src].chr_class : last_cls;
     static const char *lab_hap[3] = {"0", "ERROR", "1"};
-    auto best_of = [&](int c) { return pr ? (int)pr[c].best : last_best[(size_t)c]; };
-    auto gq_of = [&](int c) { return pr ? (int)pr[c].gq : last_gq[(size_t)c]; };
+    auto best_of = [&](int c) { return pr ? (int)pr[c].best : (cl ? (int)(cl[c] & 0xff) : last_best[(size_t)c]); };
+    auto gq_of = [&](int c) { return pr ? (int)pr[c].gq : (cl ? (int)(cl[c] >> 8) : last_gq[(size_t)c]); };
     const int dpi = L.dp_index;
     int AC = 0, totalDepth = 0;
     bool missing = false;
@@ -433,7 +437,10 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   int rc = PM_OK;
   std::string fail;
   bool more = true;
+  double tm[5] = {0, 0, 0, 0, 0};  // PM_TIMING: read, tokenise + parse, engine, format, write
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
   while (more && rc == PM_OK && fail.empty()) {
+    const auto t_begin = std::chrono::steady_clock::now();
     // ---- one chunk of whole lines, tokenised by tabs ----
     if (!rd.eof && rd.have - rd.start < ((size_t)4 << 20)) rd.refill();
     lines.clear();
@@ -450,6 +457,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       continue;
     }
     const size_t nl = lines.size();
+    const auto t_read = std::chrono::steady_clock::now();
     toks.assign(nl * n_names, Tok());
     parallel_for(nl, threads, [&](size_t li, int) {
       LineRec &L = lines[li];
@@ -488,6 +496,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     if (!announced) { printf("Total samples in both VCF and PED files: %d\n\n", n_in_both); announced = true; }
     if (recs.size() < nl * (size_t)np) recs.resize(nl * (size_t)np);
     parallel_for(nl, threads, parse_line);
+    const auto t_parse = std::chrono::steady_clock::now();
     // ---- in line order: warnings, the first error, engine rows, which row each line prints ----
     size_t n_rows = 0, n_use = nl;
     long src = -1;
@@ -515,20 +524,30 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       L.src = src;
     }
     if (n_rows) {
-      if (res.size() < n_rows) { res.resize(n_rows); pres.resize(n_rows * (size_t)np); }
-      rc = engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
+      if (res.size() < n_rows) { res.resize(n_rows); if (compact) calls.resize(n_rows * (size_t)np); else pres.resize(n_rows * (size_t)np); }
+      rc = compact ? engine.call_vcf_calls(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), calls.data())
+                   : engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
       if (rc != PM_OK) break;
     }
+    const auto t_engine = std::chrono::steady_clock::now();
     if (text.size() < nl) text.resize(nl);
     parallel_for(n_use, threads, format_line);
+    const auto t_format = std::chrono::steady_clock::now();
     for (size_t li = 0; li < n_use; li++) if (!text[li].empty()) fwrite(text[li].data(), 1, text[li].size(), out);
     fflush(out);
+    const auto t_write = std::chrono::steady_clock::now();
+    tm[0] += secs(t_begin, t_read); tm[1] += secs(t_read, t_parse); tm[2] += secs(t_parse, t_engine); tm[3] += secs(t_engine, t_format); tm[4] += secs(t_format, t_write);
     if (n_rows) {  // what the next chunk's leading no-data records print
       const size_t r = n_rows - 1;
       last_qual = res[r].poly_qual; last_min = res[r].freq; last_labeled = true; last_cls = hdr[r].chr_class;
-      for (int c = 0; c < np; c++) { last_best[(size_t)c] = pres[r * (size_t)np + c].best; last_gq[(size_t)c] = pres[r * (size_t)np + c].gq; }
+      for (int c = 0; c < np; c++) {
+        last_best[(size_t)c] = compact ? (int)(calls[r * (size_t)np + c] & 0xff) : pres[r * (size_t)np + c].best;
+        last_gq[(size_t)c] = compact ? (int)(calls[r * (size_t)np + c] >> 8) : pres[r * (size_t)np + c].gq;
+      }
     }
   }
+  if (getenv("PM_TIMING"))
+    printf("[pm timing] vcf mode: read %.3f s, tokenise+parse %.3f s, engine %.3f s, format %.3f s, write %.3f s; %d threads\n", tm[0], tm[1], tm[2], tm[3], tm[4], threads);
   std::string err = rc == PM_OK ? std::string() : std::string("engine '") + engine.name + "': " + engine.last_error();
   engine.destroy(ctx);
   fclose(out);

@@ -69,7 +69,8 @@ struct pm_ctx {
   uint32_t *d_n_emit = nullptr;
   // staging for the host-buffer entry point
   size_t cap_in_sites = 0, cap_out_rows = 0;
-  double *d_mono = nullptr; size_t cap_mono = 0;
+  double *d_mono[2] = {nullptr, nullptr}; size_t cap_mono = 0;
+  uint16_t *d_calls = nullptr; size_t cap_calls = 0;
   pm_site_hdr *d_hdr[2] = {nullptr, nullptr};   // two input slots: H2D of chunk k+1 overlaps compute of chunk k
   uint4 *d_recs[2] = {nullptr, nullptr};
   cudaStream_t stream_h2d = nullptr;
@@ -373,7 +374,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->h_rows) cudaFreeHost(c->h_rows);
-  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono);
+  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono[0]); cudaFree(c->d_mono[1]); cudaFree(c->d_calls);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -386,6 +387,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
 static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
                       size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
                       pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res);
+static int check_device_error(pm_ctx *c);
 
 extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
                                         size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
@@ -436,14 +438,7 @@ extern "C" int pm_sync(pm_ctx *c) {
   if (!c) return fail(PM_EINVAL, "null context");
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  int err = 0;
-  CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (err) {
-    cudaMemset(c->d_err, 0, sizeof(int));
-    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "a site's chr_class is not one of PM_CHR_*");
-    return fail(err, "device-side error %d", err);
-  }
-  return PM_OK;
+  return check_device_error(c);
 }
 
 extern "C" int pm_last_timing(pm_ctx *c, float *ms_main_kernel, float *ms_total, int *n_launches) {
@@ -486,6 +481,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   if (chunk > n_sites) chunk = n_sites;
   int rc;
   if (chunk > c->cap_in_sites) {
+    c->cap_in_sites = 0;  // a failed allocation below must not leave a stale capacity behind
     for (int k = 0; k < 2; k++) {
       if ((rc = dev_alloc(&c->d_hdr[k], chunk))) return rc;
       if ((rc = dev_alloc(&c->d_recs[k], chunk * np))) return rc;
@@ -494,6 +490,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     c->cap_in_sites = chunk;
   }
   if (chunk > c->cap_out_rows) {  // a chunk can emit at most `chunk` rows
+    c->cap_out_rows = 0;
     if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
     if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
     c->cap_out_rows = chunk;
@@ -509,33 +506,38 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_h2d[slot], c->stream_h2d);
     return e;
   };
+  // an error return must not leave a copy in flight that still reads (or writes) the caller's buffers
+  auto bail = [&](int code) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); return code; };
   size_t total_rows = 0;
   bool overflow = false;
   float ms_main = 0.f, ms_total = 0.f;
   int launches = 0;
-  CUDA_TRY(issue_h2d(0));
+  cudaError_t e = issue_h2d(0);
+  if (e != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
   for (size_t k = 0; k < n_chunks; k++) {
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, n = chunk_len(k);
     // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
-    if (k + 1 < n_chunks) CUDA_TRY(issue_h2d(k + 1));
-    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+    if (k + 1 < n_chunks && (e = issue_h2d(k + 1)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
+    if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
     rc = pm_call_glf_sites_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], n, out_mode, c->d_status, c->d_res_out,
                                   c->d_person_out, c->cap_out_rows, c->d_n_emit);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(c->h_rows, c->d_n_emit, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (status_out) CUDA_TRY(cudaMemcpyAsync(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = pm_sync(c))) return rc;
+    if (rc) return bail(rc);
+    e = cudaMemcpyAsync(c->h_rows, c->d_n_emit, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites chunk %zu: %s", k, cudaGetErrorString(e)));
     float a = 0.f, b = 0.f;
     pm_last_timing(c, &a, &b, nullptr);
     ms_main += a; ms_total += b; launches += c->launches;
     const uint32_t rows = *c->h_rows;
     if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
     if (rows) {
-      CUDA_TRY(cudaMemcpyAsync(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream));
-      if (person_out)
-        CUDA_TRY(cudaMemcpyAsync(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream));
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      e = cudaMemcpyAsync(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess && person_out)
+        e = cudaMemcpyAsync(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites chunk %zu results: %s", k, cudaGetErrorString(e)));
       for (size_t r = 0; r < rows; r++) res_out[total_rows + r].site += (uint32_t)base;
     }
     total_rows += rows;
@@ -543,16 +545,32 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   c->ms_main = ms_main; c->ms_total = ms_total; c->launches = launches;
   c->timing_cached = true;
   if (n_res) *n_res = total_rows;
+  if ((rc = check_device_error(c))) return rc;  // the error word a kernel sets: polled once per call
   if (overflow) return fail(PM_EINVAL, "pm_call_glf_sites: res_cap %zu too small, %zu rows needed", res_cap, total_rows);
   return PM_OK;
 }
 
-extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
-                                   size_t n, pm_site_result *res_out, pm_person_result *person_out) {
+// Checks the device-side error word (set by a kernel that met a site it cannot handle); one small blocking copy, so once per call.
+static int check_device_error(pm_ctx *c) {
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) {
+    cudaMemset(c->d_err, 0, sizeof(int));
+    if (err == PM_EUNSUPPORTED) return fail(PM_EUNSUPPORTED, "a site's chr_class is not one of PM_CHR_*");
+    return fail(err, "device-side error %d", err);
+  }
+  return PM_OK;
+}
+
+// VCF-input records from host buffers, in chunks of ~48 MB of packed input through two input slots: the H2D copy of
+// chunk k+1 runs on its own stream while chunk k is computed and its results are copied back.  person_out (96 bytes per
+// sample) and calls_out (2 bytes per sample: best | gq << 8, all the --in_vcf writer prints from) are both optional.
+static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono, size_t n,
+                               pm_site_result *res_out, pm_person_result *person_out, uint16_t *calls_out) {
   if (!c) return fail(PM_EINVAL, "null context");
   if (!c->par.vcf_input) return fail(PM_EINVAL, "pm_call_vcf_records: the ctx was not created with pm_params.vcf_input = 1");
   if (n == 0) return PM_OK;
-  if (!hdr || !person_site || !mono || !res_out || !person_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
+  if (!hdr || !person_site || !mono || !res_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
   for (size_t s = 0; s < n; s++) {
     const int a2 = hdr[s].reserved & 0xff;
     if (hdr[s].ref_base < 1 || hdr[s].ref_base > 4 || a2 < 1 || a2 > 4 || a2 == hdr[s].ref_base)
@@ -569,6 +587,7 @@ extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_p
   if (chunk > n) chunk = n;
   int rc;
   if (chunk > c->cap_in_sites) {
+    c->cap_in_sites = 0;
     for (int k = 0; k < 2; k++) {
       if ((rc = dev_alloc(&c->d_hdr[k], chunk))) return rc;
       if ((rc = dev_alloc(&c->d_recs[k], chunk * np))) return rc;
@@ -577,27 +596,77 @@ extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_p
     c->cap_in_sites = chunk;
   }
   if (chunk > c->cap_out_rows) {
+    c->cap_out_rows = 0;
     if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
     if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
     c->cap_out_rows = chunk;
   }
-  if (chunk > c->cap_mono) { if ((rc = dev_alloc(&c->d_mono, chunk))) return rc; c->cap_mono = chunk; }
-  for (size_t base = 0; base < n; base += chunk) {
-    const size_t m = n - base < chunk ? n - base : chunk;
-    CUDA_TRY(cudaMemcpyAsync(c->d_hdr[0], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_recs[0], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(c->d_mono, mono + base, m * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (chunk > c->cap_mono) {
+    c->cap_mono = 0;
+    for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_mono[k], chunk))) return rc;
+    c->cap_mono = chunk;
+  }
+  if (calls_out && chunk * np > c->cap_calls) {
+    c->cap_calls = 0;
+    if ((rc = dev_alloc(&c->d_calls, chunk * np))) return rc;
+    c->cap_calls = chunk * np;
+  }
+  const size_t n_chunks = (n + chunk - 1) / chunk;
+  auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n - k * chunk; };
+  auto issue_h2d = [&](size_t k) -> cudaError_t {
+    const int slot = (int)(k & 1);
+    const size_t base = k * chunk, m = chunk_len(k);
+    cudaError_t e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_recs[slot], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_mono[slot], mono + base, m * sizeof(double), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_h2d[slot], c->stream_h2d);
+    return e;
+  };
+  auto bail = [&](int code) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); return code; };  // nothing may still read the caller's buffers
+  cudaError_t e = issue_h2d(0);
+  if (e != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
+  float ms_main = 0.f, ms_total = 0.f;
+  int launches = 0;
+  for (size_t k = 0; k < n_chunks; k++) {
+    const int slot = (int)(k & 1);
+    const size_t base = k * chunk, m = chunk_len(k);
+    // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
+    if (k + 1 < n_chunks && (e = issue_h2d(k + 1)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
+    if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
     c->batch_has_nonauto = false;
     for (size_t r = 0; r < m; r++) c->batch_has_nonauto |= hdr[base + r].chr_class != PM_CHR_AUTO;
-    rc = run_device(c, c->d_hdr[0], (const pm_person_site *)c->d_recs[0], c->d_mono, m, PM_OUT_ALL, c->d_status, c->d_res_out,
+    rc = run_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], c->d_mono[slot], m, PM_OUT_ALL, c->d_status, c->d_res_out,
                     c->d_person_out, c->cap_out_rows, c->d_n_emit);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(res_out + base, c->d_res_out, m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaMemcpyAsync(person_out + base * np, c->d_person_out, m * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = pm_sync(c))) return rc;
+    if (rc) return bail(rc);
+    e = cudaMemcpyAsync(res_out + base, c->d_res_out, m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && person_out)
+      e = cudaMemcpyAsync(person_out + base * np, c->d_person_out, m * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && calls_out) {
+      e = pm::launch_pack_calls(c->d_person_out, m * np, c->d_calls, c->sm_count, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(calls_out + base * np, c->d_calls, m * np * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return bail(fail(PM_ECUDA, "VCF records chunk %zu: %s", k, cudaGetErrorString(e)));
+    float a = 0.f, b = 0.f;
+    pm_last_timing(c, &a, &b, nullptr);
+    ms_main += a; ms_total += b; launches += c->launches;
     for (size_t r = 0; r < m; r++) res_out[base + r].site += (uint32_t)base;
   }
-  return PM_OK;
+  c->ms_main = ms_main; c->ms_total = ms_total; c->launches = launches;
+  c->timing_cached = true;
+  return check_device_error(c);
+}
+
+extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                                   size_t n, pm_site_result *res_out, pm_person_result *person_out) {
+  if (n && !person_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
+  return vcf_records_chunked(c, hdr, person_site, mono, n, res_out, person_out, nullptr);
+}
+
+extern "C" int pm_call_vcf_records_calls(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
+                                         size_t n, pm_site_result *res_out, uint16_t *calls_out) {
+  if (n && !calls_out) return fail(PM_EINVAL, "pm_call_vcf_records_calls: null buffer");
+  return vcf_records_chunked(c, hdr, person_site, mono, n, res_out, nullptr, calls_out);
 }
 
 // Device-buffer variant of pm_call_vcf_records (bench.py's device-resident leg): every record gets a row.

@@ -20,8 +20,8 @@
 
 namespace pm {
 
-constexpr int kMaxEsPersons = 32;  // largest extended family the per-thread peel workspace holds
-constexpr int kMaxMp = 8;          // marriage-partial slots per extended family
+constexpr int kMaxEsPersons = 64;  // largest extended family the per-thread peel workspace holds (local memory; only the used part is touched)
+constexpr int kMaxMp = 16;         // marriage-partial slots per extended family
 constexpr double kLog10_2 = 0.30102999566398119521;
 
 // One resolved peel step (ES:990-1057): which marriage-partial slot it touches is static, so the

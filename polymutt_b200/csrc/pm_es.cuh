@@ -53,13 +53,12 @@ __device__ __forceinline__ constexpr int al10(int g, int w) {
   // alleles of genotype g in the order AA AC AG AT CC CG CT GG GT TT
   return w == 0 ? (g < 4 ? 0 : (g < 7 ? 1 : (g < 9 ? 2 : 3))) : (g < 4 ? g : (g < 7 ? g - 3 : (g < 9 ? g - 5 : 3)));
 }
-constexpr int kMaxMp10 = 8;
 
 template <bool NA, typename RecPtr>
 __device__ double es_likelihood10(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22, bool denovo, double freq,
                                   const double *__restrict__ lut, const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
   double part[kMaxEsPersons * 10];
-  double mp[kMaxMp10 * 55];
+  double mp[kMaxMp * 55];
   const double q = 1.0 - freq;
   const int cls = NA ? cls_ : PM_CHR_AUTO;
   const uint8_t *sexes = NA ? run->sex + f.first : nullptr;

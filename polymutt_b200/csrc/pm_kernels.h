@@ -48,6 +48,8 @@ cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
                         int sm_count, cudaStream_t stream);
 
+cudaError_t launch_pack_calls(const pm_person_result *d_person, size_t n, uint16_t *d_calls, int sm_count, cudaStream_t stream);
+
 cudaError_t launch_dfma_peak(double *d_out, int blocks, int threads, int iters, cudaStream_t stream);
 cudaError_t launch_copy(const void *src, void *dst, size_t bytes, int sm_count, cudaStream_t stream);
 

@@ -303,17 +303,24 @@ cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
                         int sm_count, cudaStream_t stream) {
   if (max_rows == 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PostSmem));
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
+  static_assert(sizeof(PostSmem) <= 48 * 1024, "k_post's tables fit in the default dynamic shared memory limit");
   size_t want = (max_rows * (size_t)n_fam + 127) / 128;
   size_t cap = (size_t)sm_count * 16;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if (grid == 0) grid = 1;
   k_post<<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out);
+  return cudaGetLastError();
+}
+
+// The two bytes per sample the VCF-input writer prints from (GT from bestGenoIdx, GQ): best | gq << 8.
+__global__ void k_pack_calls(const pm_person_result *__restrict__ person, size_t n, uint16_t *__restrict__ calls) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    calls[i] = (uint16_t)((person[i].best & 0xff) | ((unsigned)person[i].gq << 8));
+}
+cudaError_t launch_pack_calls(const pm_person_result *d_person, size_t n, uint16_t *d_calls, int sm_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+  k_pack_calls<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(d_person, n, d_calls);
   return cudaGetLastError();
 }
 

@@ -357,6 +357,102 @@ __device__ __noinline__ int slot_single_ol(const uint4 *recs, int d, int g11, in
   return one_slot(recs, d, g11, g12, g22, mode, out);
 }
 
+// One slot, the three hypotheses H1..H3 = (ref, ts), (ref, tv1), (ref, tv2) of a site at once (autosome).  They share the
+// reference-homozygous genotype and, above all, every byte extraction and table look-up of the slot's records: the
+// ten likelihoods of a kid are fetched once, seven rows of the mutation matrix (ref/ref, three ref/alt, three alt/alt)
+// give the mutation-mixed likelihoods of all three hypotheses — 70 multiply-adds and 11 look-ups per kid instead of
+// 90 and 30 — and the seventeen independent dependency chains keep the FP64 pipe busy where one hypothesis alone
+// waits on latency.  out0..out2: 5 scaled coefficients each; returns the three slot codes (scale_slot).
+struct Codes3 { int c0, c1, c2; };
+__device__ __noinline__ Codes3 slot_h123_ol(const uint4 *recs, int d, int ref, int denovo, double *out0, double *out1, double *out2) {
+  Codes3 ret;
+  double *const out[3] = {out0, out1, out2};
+  if (d < 0) {
+#pragma unroll
+    for (int h = 0; h < 3; h++) { out[h][0] = 0.25; out[h][1] = 1.0; out[h][2] = 1.5; out[h][3] = 1.0; out[h][4] = 0.25; }
+    ret.c0 = ret.c1 = ret.c2 = kSlotNeutral;
+    return ret;
+  }
+  const int first = d & 0xfffff, nkids = ((d >> 20) & 0xff) - 1;
+  const int alt[3] = {poly_ts(ref), poly_tvs1(ref), poly_tvs2(ref)};
+  const int grr = geno_index(ref, ref);
+  int gra[3], gaa[3];
+#pragma unroll
+  for (int h = 0; h < 3; h++) { gra[h] = geno_index(ref, alt[h]); gaa[h] = geno_index(alt[h], alt[h]); }
+  const uint8_t *rb = reinterpret_cast<const uint8_t *>(recs + first);
+  double b[3][5];
+  if (nkids < 0) {  // lkSinglePerson, NucFam:987-1004, times (p+q)^2
+    const double l11 = s_lut[rb[grr]];
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      const double l12 = s_lut[rb[gra[h]]], l22 = s_lut[rb[gaa[h]]];
+      b[h][4] = l11; b[h][3] = 2.0 * (l11 + l12); b[h][2] = l11 + 4.0 * l12 + l22; b[h][1] = 2.0 * (l12 + l22); b[h][0] = l22;
+    }
+  } else {
+    const double frr = s_lut[rb[grr]], mrr = s_lut[rb[16 + grr]];
+    double fra[3], faa[3], mra[3], maa[3];
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      fra[h] = s_lut[rb[gra[h]]]; faa[h] = s_lut[rb[gaa[h]]];
+      mra[h] = s_lut[rb[16 + gra[h]]]; maa[h] = s_lut[rb[16 + gaa[h]]];
+    }
+    double p0 = 1.0, p1[3], p2[3], p4[3], p5[3], p8[3];  // kid products (p1 carries 2^nkids, p4 4^nkids, p5 2^nkids)
+#pragma unroll
+    for (int h = 0; h < 3; h++) p1[h] = p2[h] = p4[h] = p5[h] = p8[h] = 1.0;
+    for (int k = 0; k < nkids; k++) {
+      double drr, dra[3], daa[3];
+      if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
+        const uint4 rk = recs[first + 2 + k];
+        double l[10];
+        l[0] = s_lut[__byte_perm(rk.x, 0, 0x4440)]; l[1] = s_lut[__byte_perm(rk.x, 0, 0x4441)];
+        l[2] = s_lut[__byte_perm(rk.x, 0, 0x4442)]; l[3] = s_lut[__byte_perm(rk.x, 0, 0x4443)];
+        l[4] = s_lut[__byte_perm(rk.y, 0, 0x4440)]; l[5] = s_lut[__byte_perm(rk.y, 0, 0x4441)];
+        l[6] = s_lut[__byte_perm(rk.y, 0, 0x4442)]; l[7] = s_lut[__byte_perm(rk.y, 0, 0x4443)];
+        l[8] = s_lut[__byte_perm(rk.z, 0, 0x4440)]; l[9] = s_lut[__byte_perm(rk.z, 0, 0x4441)];
+        auto row = [&](int g) {
+          const double2 *r = reinterpret_cast<const double2 *>(s_mut + g * 10);
+          double a = 0.0, c = 0.0;
+#pragma unroll
+          for (int i = 0; i < 5; i++) { const double2 x = r[i]; a = fma(x.x, l[2 * i], a); c = fma(x.y, l[2 * i + 1], c); }
+          return a + c;
+        };
+        drr = row(grr);
+#pragma unroll
+        for (int h = 0; h < 3; h++) { dra[h] = row(gra[h]); daa[h] = row(gaa[h]); }
+      } else {
+        const uint8_t *kb = reinterpret_cast<const uint8_t *>(recs + first + 2 + k);
+        drr = s_lut[kb[grr]];
+#pragma unroll
+        for (int h = 0; h < 3; h++) { dra[h] = s_lut[kb[gra[h]]]; daa[h] = s_lut[kb[gaa[h]]]; }
+      }
+      // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome), the halves and quarters taken out
+      p0 *= drr;
+#pragma unroll
+      for (int h = 0; h < 3; h++) {
+        p1[h] *= drr + dra[h];
+        p2[h] *= dra[h];
+        p4[h] *= fma(2.0, dra[h], drr) + daa[h];
+        p5[h] *= dra[h] + daa[h];
+        p8[h] *= daa[h];
+      }
+    }
+    const double h1 = __hiloint2double((1023 + 1 - nkids) << 20, 0), h4 = __hiloint2double((1023 + 2 - 2 * nkids) << 20, 0);
+    const double b4 = p0 * (frr * mrr);
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      b[h][4] = b4;
+      b[h][3] = (p1[h] * h1) * fma(frr, mra[h], fra[h] * mrr);
+      b[h][2] = fma(p4[h] * h4, fra[h] * mra[h], p2[h] * fma(frr, maa[h], faa[h] * mrr));
+      b[h][1] = (p5[h] * h1) * fma(fra[h], maa[h], faa[h] * mra[h]);
+      b[h][0] = p8[h] * (faa[h] * maa[h]);
+    }
+  }
+  ret.c0 = scale_slot(b[0], nkids >= 0, out0);
+  ret.c1 = scale_slot(b[1], nkids >= 0, out1);
+  ret.c2 = scale_slot(b[2], nkids >= 0, out2);
+  return ret;
+}
+
 // chrX / chrY / MT slot; mode = denovo | chr_class << 1
 __device__ __noinline__ int slot_na_ol(const uint4 *recs, int d, int g11, int g12, int g22, int mode, double *out) {
   if (d < 0) { out[0] = 0.25; out[1] = 1.0; out[2] = 1.5; out[3] = 1.0; out[4] = 0.25; return kSlotNeutral; }
@@ -547,7 +643,17 @@ struct WideEval {
   // PolymorphismLogLikelihood (FLSeq:91-104) for alleles (a1, a2).  On return (after a block barrier) s_ws.brent holds
   // min / fmin, s_ws.n_eval the rounds, s_ws.h0 the H0 term.
   // with_h0: also the product of the p^4 coefficients (the hom-ref hypothesis under --denovo, main:455-462).
-  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo, bool with_h0) {
+  // Coefficients of H1..H3 for all my slots in one pass over the site (slot_h123_ol): pre[h][k][0..4], codes[h][k].
+  __device__ __forceinline__ void setup3(int ref, bool denovo, double (&pre)[3][U][5], int (&codes)[3][U]) {
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const Codes3 c = slot_h123_ol(recs, desc[k], ref, denovo ? 1 : 0, pre[0][k], pre[1][k], pre[2][k]);
+      codes[0][k] = c.c0; codes[1][k] = c.c1; codes[2][k] = c.c2;
+    }
+  }
+
+  // pre / pre_codes: this hypothesis' coefficients from setup3, or nullptr to build them here.
+  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo, bool with_h0, const double (*pre)[5] = nullptr, const int *pre_codes = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (T + 31) >> 5;
     const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
     const int mode = (denovo ? 1 : 0) | (NA ? (cls << 1) : 0);
@@ -566,7 +672,14 @@ struct WideEval {
     // The out-of-line slot builders write into a staging array in local memory (their results would be spilled around
     // the calls anyway); the coefficients move to registers once, after the last call.
     double stage[U][5];
-    if constexpr (NA) {
+    if (pre) {
+#pragma unroll
+      for (int k = 0; k < U; k++) {
+        account(pre_codes[k], k);
+#pragma unroll
+        for (int a = 0; a < 5; a++) stage[k][a] = pre[k][a];
+      }
+    } else if constexpr (NA) {
 #pragma unroll
       for (int k = 0; k < U; k++) account(slot_na_ol(recs, desc[k], g11, g12, g22, mode, stage[k]), k);
     } else if constexpr (U == 1) {
@@ -879,6 +992,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
       // polymorphic de novo call (main:567-573).
       const bool dn = run->denovo != 0;
       int step = vcf ? 0 : 1;
+      // H1..H3 are built together, in one pass over the site's records (autosomal instance, no units in the L2 scratch)
+#ifdef PM_NO_FUSE  // A/B builds only
+      const bool fuse = false;
+#else
+      const bool fuse = !NA && !vcf && ev.spill == nullptr;
+#endif
+      double pre[3][U][5];
+      int pre_codes[3][U];
+      if (fuse) ev.setup3(ref, dn, pre, pre_codes);
       if (vcf && threadIdx.x == 0) { memset(&ws->r, 0, sizeof ws->r); ws->r.site = (uint32_t)s; }
       for (;;) {
         int a1, a2;
@@ -886,7 +1008,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
         if (step == 0) { a1 = ref; a2 = h.reserved & 0xff; }
         else if (step <= 6) { hyp_alleles(step, ref, a1, a2); dnc = dn; with_h0 = dn && step == 1; }
         else { a1 = ws->r.allele1; a2 = ws->r.allele2; }
-        ev.optimize(a1, a2, dnc, with_h0);  // ends with a block barrier: thread 0's state is final
+        if (fuse && step >= 1 && step <= 3) ev.optimize(a1, a2, dnc, with_h0, pre[step - 1], pre_codes[step - 1]);
+        else ev.optimize(a1, a2, dnc, with_h0);
+        // (optimize ends with a block barrier: thread 0's state is final)
         if (threadIdx.x == 0) { n_hyp += with_h0 ? 2 : 1; n_eval += ws->n_eval + (with_h0 ? 1 : 0); }
         if (step == 0) {
           if (threadIdx.x == 0) vcf_record_result(run, ws->r, a1, a2, (h.reserved & 0x100) != 0, mono_all[s], -ws->brent.fmin, ws->brent.min);

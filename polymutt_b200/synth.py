@@ -57,6 +57,25 @@ def ceph(n_kids: int = 14) -> PedigreeArrays:
     return PedigreeArrays(np.array([n]), np.array([4]), np.array([3]), np.array(sex, dtype=np.uint8), np.array(father), np.array(mother))
 
 
+def clan(n_children: int = 10, kids_per_couple: int = 2) -> PedigreeArrays:
+    """Three generations, many marriage nodes: a founder couple with n_children children, every child married to a founder
+    and every such couple with kids_per_couple kids.  One family of 2 + 2 n_children + n_children kids_per_couple members and
+    1 + n_children couples.  Column order: founders first (the couple, then the n_children spouses), then the children,
+    then the grandchildren."""
+    nf = 2 + n_children
+    sex = [1, 2] + [2 - (c % 2) for c in range(n_children)]                  # spouse of child c has the opposite sex of the child
+    father, mother = [-1] * nf, [-1] * nf
+    for c in range(n_children):                                              # child c: sex alternates
+        sex.append(1 + (c % 2)); father.append(0); mother.append(1)
+    for c in range(n_children):
+        child, spouse = nf + c, 2 + c
+        fa, mo = (child, spouse) if sex[child] == 1 else (spouse, child)
+        for k in range(kids_per_couple):
+            sex.append(1 + ((c + k) % 2)); father.append(fa); mother.append(mo)
+    n = len(sex)
+    return PedigreeArrays(np.array([n]), np.array([nf]), np.array([3]), np.array(sex, dtype=np.uint8), np.array(father), np.array(mother))
+
+
 def concat(*peds: PedigreeArrays) -> PedigreeArrays:
     return PedigreeArrays(*(np.concatenate([getattr(p, k) for p in peds]) for k in
                             ("fam_size", "fam_founders", "fam_generations", "sex", "father", "mother")))

@@ -240,6 +240,31 @@ def test_wide_kernel_parity_on_synthetic_pedigrees(case, oracle_built):
     parity.assert_parity(rep, n_sites)
 
 
+# ---- extended families beyond round 1's workspace (32 members / 8 marriage nodes) -------------------
+BIG_ES_CASES = [
+    ("ceph40_ba", lambda: synth.ceph(34), dict(), 4000, 30.0),                 # 40 members, 3 couples
+    ("ceph40_denovo", lambda: synth.ceph(34), dict(denovo=True), 700, 30.0),
+    ("clan42_ba", lambda: synth.clan(10, 2), dict(), 3000, 30.0),              # 42 members, 11 couples
+    ("clan42_denovo", lambda: synth.clan(10, 2), dict(denovo=True), 400, 30.0),
+    ("clan58_quartets_ba", lambda: synth.concat(synth.clan(14, 2), synth.families([4] * 12)), dict(), 1500, 30.0),  # 58 members, 15 couples, + 12 units: wide kernel
+]
+
+
+@pytest.mark.parametrize("case", BIG_ES_CASES, ids=lambda c: c[0])
+def test_large_extended_families(case, oracle_built):
+    name, mk, kw, n_sites, boost = case
+    ped = mk()
+    h, r = synth.generate_sites(ped, n_sites, seed=20261020, cfg=synth.SynthConfig(poly_boost=boost, injected_denovo=0.02))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1)
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n_sites, ped.n_person)
+    params = Params(**kw)
+    g, o = _run_both(ped, params, hdr, recs)
+    rep = parity.compare(*g, *o, denovo=params.denovo, label=name)
+    print(rep)
+    assert rep["emitted"] > 0
+    parity.assert_parity(rep, n_sites)
+
+
 # ---- the block-per-site kernel on the edge cases, every instantiation ------------------------------
 # (variant, threads) of pm_wide.cu's PM_WIDE_VARIANTS; test.mix.ped has 10 units, so every plan holds it
 WIDE_PLANS = [(0, 32), (1, 32), (2, 32), (3, 32), (4, 64), (4, 128), (5, 256)]
@@ -366,7 +391,10 @@ def test_vcf_records_parity_wide_plans(shape, n, oracle_built):
     eng = Engine(ped, params, lut=lut)
     assert "k_sites_wide" in eng.describe_plan()
     res_g, per_g = eng.call_vcf_records(h, r, mono)
+    res_c, calls = eng.call_vcf_records_calls(h, r, mono)   # the compact form the executable uses: best | gq << 8
     eng.close()
+    assert np.array_equal(calls, (per_g["best"].astype(np.uint16) & 0xff) | (per_g["gq"].astype(np.uint16) << 8))
+    assert np.array_equal(res_c["poly_qual"], res_g["poly_qual"]) and np.array_equal(res_c["freq"], res_g["freq"])
     ora = OracleEngine(eng.ped, params, lut=lut)
     res_o, per_o = ora.call_vcf_records(h, r, mono)
     ora.close()

@@ -103,6 +103,8 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     return fatal(e.what());
   }
   if (!opt.vcf_in.empty()) return run_vcf_mode(opt, ped, engine);  // main.cpp:238-246
+  auto wall = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_ped_done = wall();
 
   std::map<std::string, std::string> glf_map;
   if (!read_glf_index(opt.glf_index_file, &glf_map, &err)) return fatal(err);
@@ -122,8 +124,36 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     }
     paths.push_back(it->second);
   }
+  // The engine contexts (CUDA initialisation, module load: the longest single step of the set-up) are created on a
+  // background thread while the GLF files are opened and their headers read.
+  pm_params par;
+  opt.to_params(&par);
+  double lut[256];
+  pm_fill_lut(lut);
+  // One engine context per GPU (--gpus N, ours): batches of consecutive sites go to the GPUs round-robin, each on
+  // its own host thread, and are consumed strictly in site order, so the VCF is the ordered concatenation of the
+  // per-GPU shards (SURVEY.md 8e).  No communication between GPUs.
+  const int n_gpu = opt.gpus > 0 ? opt.gpus : 1;
+  std::vector<void *> ctxs;
+  auto destroy_all = [&]() { for (void *c : ctxs) engine.destroy(c); ctxs.clear(); };
+  std::string ctx_error;
+  double t_ctx = 0.0;
+  std::future<bool> ctx_ready = std::async(std::launch::async, [&]() -> bool {
+    const double t0 = wall();
+    for (int g = 0; g < n_gpu; g++) {
+      void *c = engine.create(ped.view(), &par, lut, opt.device + g);
+      if (!c) { ctx_error = engine.last_error(); return false; }
+      ctxs.push_back(c);
+    }
+    t_ctx = wall() - t0;
+    return true;
+  });
   GlfBatchReader glf;  // multi-threaded block decode + merge (glf_ingest.h); GlfSet in glf.h is the one-site-at-a-time form
-  if (!glf.open(paths, opt.ingest_threads, &err)) return fatal(err);
+  const bool glf_ok = glf.open(paths, opt.ingest_threads, &err);
+  const double t_open_done = wall();
+  const bool ctx_ok = ctx_ready.get();
+  if (!glf_ok) { destroy_all(); return fatal(err); }
+  if (!ctx_ok) { destroy_all(); return fatal(std::string("engine '") + engine.name + "': " + ctx_error); }
 
   std::set<std::string> positions;  // --pos: "chr:pos" (src/main.cpp:39-55)
   if (!opt.pos_file.empty()) {
@@ -142,23 +172,9 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     while (std::getline(ss, c, ',')) if (!c.empty()) chrs[c]++;
   }
 
-  pm_params par;
-  opt.to_params(&par);
-  double lut[256];
-  pm_fill_lut(lut);
-  // One engine context per GPU (--gpus N, ours): batches of consecutive sites go to the GPUs round-robin, each on
-  // its own host thread, and are consumed strictly in site order, so the VCF is the ordered concatenation of the
-  // per-GPU shards (SURVEY.md 8e).  No communication between GPUs.
-  const int n_gpu = opt.gpus > 0 ? opt.gpus : 1;
-  std::vector<void *> ctxs;
-  auto destroy_all = [&]() { for (void *c : ctxs) engine.destroy(c); ctxs.clear(); };
-  for (int g = 0; g < n_gpu; g++) {
-    void *c = engine.create(ped.view(), &par, lut, opt.device + g);
-    if (!c) { std::string m = engine.last_error(); destroy_all(); return fatal(std::string("engine '") + engine.name + "': " + m); }
-    ctxs.push_back(c);
-  }
   std::vector<std::mutex> ctx_lock((size_t)n_gpu);
 
+  const double t_buf0 = wall();
   const int np = ped.n_person();
   size_t batch = opt.batch_sites > 0 ? (size_t)opt.batch_sites : (size_t)1 << 16;
   // keep a batch of packed input below ~256 MB
@@ -398,9 +414,10 @@ int run_cli(int argc, char **argv, const Engine &engine) {
     return fatal(e.what());
   }
   if (timing)
-    fprintf(stderr, "[pm timing] setup %.3f s (pedigree, GLF open, %d engine context(s), %zu x %zu-site batch buffers); loop %.3f s = ingest %.3f + "
-                    "waiting for the engine/formatting %.3f + writing %.3f\n",
-            t_setup_done - t_start, n_gpu, n_slots, batch, now() - t_setup_done, t_ingest, t_wait, t_write);
+    fprintf(stderr, "[pm timing] setup %.3f s (flags + pedigree %.3f, GLF open %.3f alongside %d engine context(s) %.3f, %zu x %zu-site batch buffers %.3f); "
+                    "loop %.3f s = ingest %.3f + waiting for the engine/formatting %.3f + writing %.3f\n",
+            t_setup_done - t_start, t_ped_done - t_start, t_open_done - t_ped_done, n_gpu, t_ctx, n_slots, batch, t_setup_done - t_buf0,
+            now() - t_setup_done, t_ingest, t_wait, t_write);
   destroy_all();
   fclose(vcf);
   return 0;

@@ -3,8 +3,10 @@
 #include <sys/resource.h>
 
 #include <algorithm>
-#include <atomic>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -13,8 +15,11 @@ namespace pmh {
 
 static const uint8_t kTranslateBase[16] = {0, 1, 2, 0, 3, 0, 0, 0, 4, 0, 0, 0, 0, 0, 0, 0};  // core/glfHandler.cpp:4
 
+static double g_t[4];
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 GlfBatchReader::~GlfBatchReader() {
   for (auto &s : streams_) if (s.f) gzclose(s.f);
+  if (getenv("PM_TIMING")) fprintf(stderr, "[pm timing] ingest: decode %.3f s, window+mark %.3f s, rows %.3f s, fill %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3]);
 }
 
 template <typename F>
@@ -34,16 +39,18 @@ void GlfBatchReader::parallel_streams(F fn) {
   for (auto &e : errs) if (e) std::rethrow_exception(e);
 }
 
+// Makes `need` undecoded bytes available at raw_dec.  Bytes of records that are decoded but not consumed yet
+// (from raw_keep on) stay where the record offsets point: the buffer is compacted relative to raw_keep.
 bool GlfBatchReader::Stream::fill(size_t need) {
-  if (raw_end - raw_beg >= need) return true;
-  if (raw_beg > 0) {
-    memmove(raw.data(), raw.data() + raw_beg, raw_end - raw_beg);
-    raw_end -= raw_beg;
-    raw_beg = 0;
+  if (raw_end - raw_dec >= need) return true;
+  if (raw_keep > 0 && (raw_keep >= raw.size() / 2 || raw_dec - raw_keep + need > raw.size() - raw_keep)) {
+    memmove(raw.data(), raw.data() + raw_keep, raw_end - raw_keep);
+    for (size_t k = head; k < off.size(); k++) off[k] -= (uint32_t)raw_keep;
+    raw_dec -= raw_keep; raw_end -= raw_keep; raw_keep = 0;
   }
-  if (need > raw.size()) raw.resize(need + (1 << 16));  // an indel record can carry up to 2 x 32 KiB of allele text
-  while (raw_end < need && !file_eof) {
-    int got = gzread(f, raw.data() + raw_end, (unsigned)(raw.size() - raw_end));
+  if (raw_dec + need > raw.size()) raw.resize(std::max(raw.size() * 2, raw_dec + need + (1 << 16)));  // an indel record can carry 2 x 32 KiB of allele text
+  while (raw_end - raw_dec < need && !file_eof) {
+    int got = gzread(f, raw.data() + raw_end, (unsigned)std::min<size_t>(raw.size() - raw_end, 1u << 30));
     if (got < 0) {  // a damaged .gz is an error, not the end of the chromosome (the run would exit 0 with a partial VCF)
       int errnum = 0;
       const char *msg = gzerror(f, &errnum);
@@ -53,94 +60,75 @@ bool GlfBatchReader::Stream::fill(size_t need) {
     if (got == 0) { file_eof = true; break; }
     raw_end += (size_t)got;
   }
-  return raw_end - raw_beg >= need;
+  return raw_end - raw_dec >= need;
 }
 
 void GlfBatchReader::Stream::compact() {
   if (head == 0) return;
-  if (head == pos.size()) { pos.clear(); ref.clear(); rec.clear(); head = 0; return; }
+  if (head == pos.size()) { pos.clear(); off.clear(); head = 0; raw_keep = raw_dec; return; }
+  raw_keep = off[head];
   if (head < pos.size() / 2) return;  // amortise
   pos.erase(pos.begin(), pos.begin() + (long)head);
-  ref.erase(ref.begin(), ref.begin() + (long)head);
-  rec.erase(rec.begin(), rec.begin() + (long)head);
+  off.erase(off.begin(), off.begin() + (long)head);
   head = 0;
 }
 
-// glfHandler::NextEntry (core/glfHandler.cpp:186-261) on a byte buffer
+// glfHandler::NextEntry (core/glfHandler.cpp:186-261) on a byte buffer.  Base records are NOT copied: a pending record
+// is its position and the offset of its 20 bytes in `raw`.
 void GlfBatchReader::Stream::decode(size_t want_records) {
   compact();
   while (!ended && pending() < want_records) {
-    // fast path: a run of base records that are completely inside the buffer goes into pre-sized arrays without the
-    // per-record refill / capacity checks of the general path below
-    {
-      const size_t avail = (raw_end - raw_beg) / 20, room = want_records - pending();
-      size_t n = avail < room ? avail : room;
+    // refill in big steps: the window of undecoded bytes should cover what is still wanted
+    if (raw_end - raw_dec < 20) {
+      const size_t want_bytes = std::min<size_t>((want_records - pending()) * 20 + 1, (size_t)4 << 20);
+      fill(want_bytes);
+      if (raw_end == raw_dec) { ended = true; break; }  // premature end of file = end of section
+    }
+    {  // fast path: a run of base records that are completely inside the buffer
+      const size_t avail = (raw_end - raw_dec) / 20, room = want_records - pending();
+      const size_t n = avail < room ? avail : room;
       if (n > 0) {
         const size_t old = pos.size();
-        pos.resize(old + n); ref.resize(old + n); rec.resize(old + n);
-        const unsigned char *r = raw.data() + raw_beg;
+        pos.resize(old + n); off.resize(old + n);
+        const unsigned char *r = raw.data() + raw_dec;
         size_t k = 0;
         int p = position, lp = last_pos;
         for (; k < n && (r[0] >> 4) == 1; k++, r += 20) {
-          uint32_t offset, dm;
+          uint32_t offset;
           memcpy(&offset, r + 1, 4);
-          memcpy(&dm, r + 5, 4);
           p += (int)offset;
           if (lp == p && lp >= 0 && offset == 0) {
-            pos.resize(old + k); ref.resize(old + k); rec.resize(old + k);
+            pos.resize(old + k); off.resize(old + k);
             throw std::runtime_error("GLF stream repeats a position (offset 0): not supported by the batched reader");
           }
-          pm_person_site &o = rec[old + k];
-          memcpy(o.lk, r + 10, 10);
-          o.depth[0] = (uint8_t)(dm & 0xff); o.depth[1] = (uint8_t)((dm >> 8) & 0xff); o.depth[2] = (uint8_t)((dm >> 16) & 0xff);
-          o.map_quality = r[9];
-          o.pad[0] = o.pad[1] = 0;
           pos[old + k] = p;
-          ref[old + k] = kTranslateBase[r[0] & 0xf];
+          off[old + k] = (uint32_t)(raw_dec + 20 * k);
           lp = p;
         }
         position = p; last_pos = lp;
-        raw_beg += 20 * k;
-        if (k < n) { pos.resize(old + k); ref.resize(old + k); rec.resize(old + k); }
+        raw_dec += 20 * k;
+        if (k < n) { pos.resize(old + k); off.resize(old + k); }
         if (k > 0) continue;
       }
     }
-    if (!fill(1)) { ended = true; break; }  // premature end of file = end of section
-    const unsigned char b0 = raw[raw_beg];
+    if (!fill(1)) { ended = true; break; }
+    const unsigned char b0 = raw[raw_dec];
     const int type = b0 >> 4;
-    if (type == 0) { raw_beg += 1; ended = true; break; }
-    if (type == 1) {
-      if (!fill(20)) { raw_beg = raw_end; ended = true; break; }
-      const unsigned char *r = raw.data() + raw_beg;
-      uint32_t offset, dm;
-      memcpy(&offset, r + 1, 4);
-      memcpy(&dm, r + 5, 4);
-      position += (int)offset;
-      if (last_pos == position && last_pos >= 0 && offset == 0)
-        throw std::runtime_error("GLF stream repeats a position (offset 0): not supported by the batched reader");
-      pm_person_site p;
-      memset(&p, 0, sizeof p);
-      memcpy(p.lk, r + 10, 10);
-      p.depth[0] = (uint8_t)(dm & 0xff); p.depth[1] = (uint8_t)((dm >> 8) & 0xff); p.depth[2] = (uint8_t)((dm >> 16) & 0xff);
-      p.map_quality = r[9];
-      pos.push_back(position);
-      ref.push_back(kTranslateBase[b0 & 0xf]);
-      rec.push_back(p);
-      last_pos = position;
-      raw_beg += 20;
+    if (type == 0) { raw_dec += 1; ended = true; break; }
+    if (type == 1) {  // a base record that straddles the end of what has been read
+      if (!fill(20)) { raw_dec = raw_end; ended = true; break; }
       continue;
     }
     if (type == 2) {  // indel: 17 fixed bytes + two allele strings, skipped (NextBaseEntry)
-      if (!fill(17)) { raw_beg = raw_end; ended = true; break; }
-      const unsigned char *r = raw.data() + raw_beg;
+      if (!fill(17)) { raw_dec = raw_end; ended = true; break; }
       uint32_t offset;
-      memcpy(&offset, r + 1, 4);
+      memcpy(&offset, raw.data() + raw_dec + 1, 4);
       int16_t len[2];
-      memcpy(len, r + 13, 4);
+      memcpy(len, raw.data() + raw_dec + 13, 4);
       const size_t extra = (size_t)(len[0] < 0 ? -len[0] : len[0]) + (size_t)(len[1] < 0 ? -len[1] : len[1]);
-      if (!fill(17 + extra)) { raw_beg = raw_end; ended = true; break; }
+      if (!fill(17 + extra)) { raw_dec = raw_end; ended = true; break; }
       position += (int)offset;
-      raw_beg += 17 + extra;
+      raw_dec += 17 + extra;
       continue;
     }
     ended = true;  // unknown record type: the reference's NextEntry returns false
@@ -160,25 +148,35 @@ bool GlfBatchReader::open(const std::vector<std::string> &paths, int threads, st
       setrlimit(RLIMIT_NOFILE, &rl);
     }
   }
-  for (size_t i = 0; i < paths.size(); i++) {
-    if (paths[i].empty()) continue;
-    Stream &s = streams_[i];
-    s.f = gzopen(paths[i].c_str(), "rb");
-    if (!s.f) { if (err) *err = "GLF file " + paths[i] + " can  not be opened!"; return false; }
-    gzbuffer(s.f, 1 << 16);
-    s.raw.resize(1 << 16);
-    if (!s.fill(8) || memcmp(s.raw.data(), "GLF\3", 4) != 0) { if (err) *err = "GLF file " + paths[i] + ": invalid format or unsupported version"; return false; }
-    uint32_t hl;
-    memcpy(&hl, s.raw.data() + 4, 4);
-    if (hl > 1024 * 1024) { if (err) *err = "GLF file " + paths[i] + ": header too large -- bailing"; return false; }
-    s.raw_beg = 8;
-    size_t left = hl;  // skip the header text
-    while (left) {
-      if (!s.fill(1)) { if (err) *err = "GLF file " + paths[i] + ": unexpected end of file"; return false; }
-      size_t take = std::min(left, s.raw_end - s.raw_beg);
-      s.raw_beg += take; left -= take;
+  // thousands of files: opened and their headers read by the thread pool; the first failure in column order is reported
+  std::vector<std::string> errs(paths.size());
+  parallel_streams([&](int lo, int hi, int) {
+    for (int i = lo; i < hi; i++) {
+      if (paths[(size_t)i].empty()) continue;
+      Stream &s = streams_[(size_t)i];
+      const std::string &path = paths[(size_t)i];
+      s.f = gzopen(path.c_str(), "rb");
+      if (!s.f) { errs[(size_t)i] = "GLF file " + path + " can  not be opened!"; continue; }
+      gzbuffer(s.f, 1 << 17);
+      s.raw.resize(1 << 16);
+      if (!s.fill(8) || memcmp(s.raw.data(), "GLF\3", 4) != 0) { errs[(size_t)i] = "GLF file " + path + ": invalid format or unsupported version"; continue; }
+      uint32_t hl;
+      memcpy(&hl, s.raw.data() + 4, 4);
+      if (hl > 1024 * 1024) { errs[(size_t)i] = "GLF file " + path + ": header too large -- bailing"; continue; }
+      s.raw_dec = 8;
+      size_t left = hl;  // skip the header text
+      while (left) {
+        if (!s.fill(1)) { errs[(size_t)i] = "GLF file " + path + ": unexpected end of file"; break; }
+        size_t take = std::min(left, s.raw_end - s.raw_dec);
+        s.raw_dec += take; left -= take;
+        s.raw_keep = s.raw_dec;
+      }
+      s.raw_keep = s.raw_dec;
     }
-    if (lead_ < 0) lead_ = (int)i;
+  });
+  for (size_t i = 0; i < paths.size(); i++) {
+    if (!errs[i].empty()) { if (err) *err = errs[i]; return false; }
+    if (lead_ < 0 && streams_[i].f) lead_ = (int)i;
   }
   if (lead_ < 0) { if (err) *err = "no GLF file could be opened"; return false; }
   section_done_ = true;
@@ -192,19 +190,21 @@ bool GlfBatchReader::next_section() {
     for (int i = lo; i < hi; i++) {
       Stream &s = streams_[(size_t)i];
       if (!s.f) continue;
-      while (!s.ended) { s.pos.clear(); s.ref.clear(); s.rec.clear(); s.head = 0; s.decode(4096); }  // drain the old section
-      s.pos.clear(); s.ref.clear(); s.rec.clear(); s.head = 0;
+      while (!s.ended) { s.head = s.pos.size(); s.decode(4096); }  // drain the old section
+      s.pos.clear(); s.off.clear(); s.head = 0; s.raw_keep = s.raw_dec;
       s.position = 0; s.last_pos = -1;
       int32_t label_len = 0;
       if (!s.fill(4)) { ok[(size_t)i] = 0; continue; }
-      memcpy(&label_len, s.raw.data() + s.raw_beg, 4);
-      s.raw_beg += 4;
+      memcpy(&label_len, s.raw.data() + s.raw_dec, 4);
+      s.raw_dec += 4;
+      s.raw_keep = s.raw_dec;
       const size_t ll = (size_t)(label_len > 0 ? label_len : 0);
       if (!s.fill(ll + 4)) { ok[(size_t)i] = 0; continue; }
-      s.label = std::string(std::string((const char *)s.raw.data() + s.raw_beg, ll).c_str());
-      s.raw_beg += ll;
-      memcpy(&s.max_position, s.raw.data() + s.raw_beg, 4);
-      s.raw_beg += 4;
+      s.label = std::string(std::string((const char *)s.raw.data() + s.raw_dec, ll).c_str());
+      s.raw_dec += ll;
+      memcpy(&s.max_position, s.raw.data() + s.raw_dec, 4);
+      s.raw_dec += 4;
+      s.raw_keep = s.raw_dec;
       s.ended = false;
       if (s.max_position <= 0) ok[(size_t)i] = 0;
     }
@@ -229,6 +229,7 @@ bool GlfBatchReader::next_section() {
 size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t max_sites) {
   if (section_done_ || max_sites == 0) return 0;
   const size_t np = streams_.size();
+  const double t0 = now_s();
   // 1. every live stream gets at least `want` pending records (or reaches its end)
   size_t want = std::max<size_t>(64, std::min<size_t>(max_sites, ((size_t)96 << 20) / (np * 24)));
   parallel_streams([&](int lo, int hi, int) {
@@ -237,6 +238,7 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
       if (s.f && !s.ended && s.pending() < want) s.decode(want);
     }
   });
+  const double t1 = now_s();
   // 2. window: every position <= wend is completely known
   long long base = LLONG_MAX, wend = LLONG_MAX;
   long long T = LLONG_MAX;  // min over ended streams of their last base-record position (-1: none at all)
@@ -262,50 +264,91 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
       for (size_t k = s.head; k < s.pos.size() && s.pos[k] <= wend; k++) mark_[(size_t)(s.pos[k] - base)] = 1;
     }
   });
+  const double t2 = now_s();
   // 3. rows, with the reference's termination rules
-  row_.assign(width, -1);
-  size_t n = 0;
-  long long limit = base - 1;
-  for (size_t w = 0; w < width && n < max_sites; w++) {
+  rowpos_.clear();
+  for (size_t w = 0; w < width && rowpos_.size() < max_sites; w++) {
     if (!mark_[w]) continue;
     const long long p = base + (long long)w;
     // Move2NextBaseEntry top check: some stream read its end marker in an earlier call
     if (prev1_ > 0 && T <= prev2_) { section_done_ = true; break; }
     if (p > max_position_) { section_done_ = true; break; }
-    row_[w] = (int32_t)n++;
-    limit = p;
+    rowpos_.push_back((int32_t)p);
     prev2_ = prev1_; prev1_ = p;
   }
+  const size_t n = rowpos_.size();
   if (n == 0) { section_done_ = true; return 0; }
-  // 4. scatter (parallel over streams), reference base = lead stream's if present, else the lowest column's
-  memset(out, 0, n * np * sizeof(pm_person_site));
-  owner_.assign(n, UINT32_MAX);
-  std::atomic<uint32_t> *own = reinterpret_cast<std::atomic<uint32_t> *>(owner_.data());
-  parallel_streams([&](int lo, int hi, int) {
-    for (int i = lo; i < hi; i++) {
-      Stream &s = streams_[(size_t)i];
-      if (!s.f) continue;
-      const uint32_t key = (i == lead_) ? 0u : (uint32_t)i + 1u;
-      size_t k = s.head;
-      for (; k < s.pos.size() && s.pos[k] <= limit; k++) {
-        const int32_t r = row_[(size_t)(s.pos[k] - base)];
-        if (r < 0) continue;
-        out[(size_t)r * np + (size_t)i] = s.rec[k];
-        const uint32_t v = (key << 8) | s.ref[k];
-        uint32_t cur = own[r].load(std::memory_order_relaxed);
-        while (v < cur && !own[r].compare_exchange_weak(cur, v, std::memory_order_relaxed)) {}
+  // 4. fill, row by row: a thread owns a contiguous range of columns and writes its stretch of every site's row in
+  // one go (records and the zeros of people without a record alike), walking its streams' cursors in step.  The
+  // reference base of a site comes from the lead stream if it has a record there, else from the lowest column that has
+  // one: every thread reports its best (priority, base) per row, merged below.
+  const double t3 = now_s();
+  const int Tn = std::max(1, std::min(threads_, (int)np));
+  owner_.assign(n * (size_t)Tn, UINT32_MAX);
+  parallel_streams([&](int lo, int hi, int t) {
+    // tiles of 4 columns (one 64-byte line of a site's row) x 256 rows: the four streams are read sequentially, every
+    // line of the batch is written once and completely
+    uint32_t *own = owner_.data() + (size_t)t * n;
+    constexpr int CW = 4;
+    constexpr size_t RB = 256;
+    for (int c0 = lo; c0 < hi; c0 += CW) {
+      const int cw = std::min(CW, hi - c0);
+      const int32_t *pp[CW], *pe[CW];
+      const uint32_t *op[CW];
+      const unsigned char *rawp[CW];
+      uint32_t prio[CW];
+      for (int j = 0; j < cw; j++) {
+        const Stream &s = streams_[(size_t)(c0 + j)];
+        pp[j] = s.pos.data() + s.head; pe[j] = s.pos.data() + s.pos.size();
+        op[j] = s.off.data() + s.head; rawp[j] = s.raw.data();
+        prio[j] = ((c0 + j == lead_) ? 0u : (uint32_t)(c0 + j) + 1u) << 8;
       }
-      s.head = k;
+      for (size_t r0 = 0; r0 < n; r0 += RB) {
+        const size_t r1 = std::min(n, r0 + RB);
+        for (size_t r = r0; r < r1; r++) {
+          const int32_t p = rowpos_[r];
+          pm_person_site *row = out + r * np + (size_t)c0;
+          uint32_t best = own[r];
+          for (int j = 0; j < cw; j++) {
+            pm_person_site &o = row[j];
+            if (pp[j] < pe[j] && *pp[j] == p) {
+              // 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
+              // 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) as two 8-byte words (little endian)
+              const unsigned char *rec = rawp[j] + *op[j];
+              uint64_t lo8;
+              uint32_t dm;
+              uint16_t lk89;
+              memcpy(&lo8, rec + 10, 8);
+              memcpy(&lk89, rec + 18, 2);
+              memcpy(&dm, rec + 5, 4);
+              const uint64_t hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
+              memcpy(reinterpret_cast<unsigned char *>(&o), &lo8, 8);
+              memcpy(reinterpret_cast<unsigned char *>(&o) + 8, &hi8, 8);
+              const uint32_t v = prio[j] | kTranslateBase[rec[0] & 0xf];
+              if (v < best) best = v;
+              pp[j]++; op[j]++;
+            } else {
+              memset(&o, 0, sizeof o);
+            }
+          }
+          own[r] = best;
+        }
+      }
+      for (int j = 0; j < cw; j++) {
+        Stream &s = streams_[(size_t)(c0 + j)];
+        s.head = (size_t)(pp[j] - s.pos.data());
+      }
     }
   });
-  size_t w = 0;
   for (size_t r = 0; r < n; r++) {
-    while (row_[w] != (int32_t)r) w++;
-    hdr[r].pos = (uint32_t)(base + (long long)w);
-    hdr[r].ref_base = (uint8_t)(owner_[r] & 0xff);
+    uint32_t best = UINT32_MAX;
+    for (int t = 0; t < Tn; t++) best = std::min(best, owner_[(size_t)t * n + r]);
+    hdr[r].pos = (uint32_t)rowpos_[r];
+    hdr[r].ref_base = (uint8_t)(best & 0xff);
     hdr[r].chr_class = PM_CHR_AUTO;
     hdr[r].reserved = 0;
   }
+  g_t[0] += t1 - t0; g_t[1] += t2 - t1; g_t[2] += t3 - t2; g_t[3] += now_s() - t3;
   return n;
 }
 

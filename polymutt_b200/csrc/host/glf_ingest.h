@@ -1,9 +1,10 @@
 // Batched, multi-threaded GLF ingest: the N-way merge of PedigreeGLF::Move2NextBaseEntry
 // (src/PedigreeGLF.cpp:282-324) restated for throughput.  The reference advances N cursors one site at a
 // time with two tiny reads per person-site; with thousands of people that merge, not the likelihood engine,
-// bounds the executable.  Here every stream is block-decoded (gz-transparent) into arrays of
-// (position, ref base, 16-byte packed record) by a pool of threads, the site list of a window is the union of
-// the streams' positions (a bitmap), and every stream scatters its own records into the site-major batch.
+// bounds the executable.  Here a pool of threads scans every stream's (gz-transparent) bytes for record boundaries
+// and positions only, the site list of a window is the union of the streams' positions (a bitmap), and the batch is
+// filled row by row: a thread owns a contiguous range of columns and writes its stretch of every site's row in one go,
+// straight from the 20-byte file records into the 16-byte packed ones.
 //
 // Semantics kept bit for bit (checked against GlfSet on ragged fixtures, tests/test_host.py):
 //   * a site exists wherever at least one stream has a base record; people without a record there are zeros;
@@ -40,20 +41,21 @@ class GlfBatchReader {
  private:
   struct Stream {
     gzFile f = nullptr;
-    std::vector<unsigned char> raw;   // undecoded bytes
-    size_t raw_beg = 0, raw_end = 0;
+    // Bytes of the (inflated) stream: [raw_keep, raw_dec) holds the records that are decoded but not consumed yet,
+    // [raw_dec, raw_end) what has been read but not looked at.  Base records are never copied out: a pending record is
+    // (pos[k], off[k]) = its position and the offset of its 20 bytes in `raw`.
+    std::vector<unsigned char> raw;
+    size_t raw_keep = 0, raw_dec = 0, raw_end = 0;
     bool file_eof = false;
-    // decoded, not yet consumed base records of the current section
     std::vector<int32_t> pos;
-    std::vector<uint8_t> ref;
-    std::vector<pm_person_site> rec;
-    size_t head = 0;
+    std::vector<uint32_t> off;
+    size_t head = 0;                  // first pending record
     int position = 0;                 // running position of the decoder
     bool ended = true;                // end-of-section marker (or end of file) reached by the decoder
     int last_pos = -1;                // position of the last base record of the section (valid once ended)
     std::string label;
     int max_position = 0;
-    bool fill(size_t need);           // makes `need` raw bytes available at raw_beg
+    bool fill(size_t need);           // makes `need` undecoded bytes available at raw_dec
     void decode(size_t want_records); // decodes until want_records are pending, or the section ends
     size_t pending() const { return pos.size() - head; }
     void compact();
@@ -66,8 +68,8 @@ class GlfBatchReader {
   bool section_done_ = true;
   long long prev1_ = -1, prev2_ = -1; // positions of the last two sites handed out (termination rule)
   std::vector<uint8_t> mark_;         // per position of the window: some stream has a record
-  std::vector<int32_t> row_;          // per position of the window: row in the batch, -1 = none
-  std::vector<uint32_t> owner_;       // per row: (priority << 8) | ref base of the stream that names the reference base
+  std::vector<int32_t> rowpos_;       // position of every row of the batch
+  std::vector<uint32_t> owner_;       // per (thread, row): (priority << 8) | ref base of the best stream of that thread's column range
   template <typename F>
   void parallel_streams(F fn);
 };

@@ -692,7 +692,7 @@ extern "C" void pm_host_free(void *p) { if (p) cudaFreeHost(p); }
 // Human-readable description of the kernel plan
 extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
   if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
-  if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", pm::kNarrowMaxUnits, c->plan.threads);
+  if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", c->plan.units_per_thread, c->plan.threads);
   else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site, %d units/thread in registers (%d units, %d in the L2 scratch), persistent grid %d (%d blocks/SM), "
                 "one TMA bulk copy per site, one block barrier per Brent round",
                 c->plan.units_per_thread, c->plan.threads, c->plan.units_per_thread, c->n_units, c->plan.n_spill, c->plan.grid, c->plan.blocks_per_sm);

@@ -82,34 +82,50 @@ __device__ double es_likelihood10(const DevRun *__restrict__ run, const DevFam f
   for (int s = 0; s < f.n_steps; s++) {
     const DevStep st = steps[s];
     if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
-      double pc[10], pcm[10];
+      // A run of children of the same couple (consecutive steps into one marriage partial: 14 of them in the CEPH
+      // pedigree): the 55 products are accumulated in REGISTERS over the whole run and stored once — the per-child
+      // read-modify-write of the marriage partial in local memory was what bound this kernel (ncu: the top stall was
+      // the local-memory scoreboard, 31 KB of DRAM write-back per site).
+      double acc[55];
+      bool have = false;
+      if (!st.flag) {
 #pragma unroll
-      for (int k = 0; k < 10; k++) pc[k] = part[st.from0 * 10 + k];
-      if (denovo) {
-#pragma unroll
-        for (int m = 0; m < 10; m++) {
-          double a = 0.0, b = 0.0;
-#pragma unroll
-          for (int k = 0; k < 5; k++) { a = fma(mut[m * 10 + k], pc[k], a); b = fma(mut[m * 10 + 5 + k], pc[5 + k], b); }
-          pcm[m] = 0.25 * (a + b);
-        }
-      } else {
-#pragma unroll
-        for (int m = 0; m < 10; m++) pcm[m] = 0.25 * pc[m];
+        for (int e = 0; e < 55; e++) acc[e] = mp[st.mp * 55 + e];
+        have = true;
       }
-      double R[4][10];  // R[x][j] = A[x][c_j] + A[x][d_j]
+      int s2 = s;
+      for (; s2 < f.n_steps; s2++) {
+        const DevStep sk = steps[s2];
+        if (sk.type != PM_PEEL_CHILD_TO_PARENTS || sk.mp != st.mp) break;
+        double pc[10], pcm[10];
 #pragma unroll
-      for (int x = 0; x < 4; x++)
+        for (int k = 0; k < 10; k++) pc[k] = part[sk.from0 * 10 + k];
+        if (denovo) {
 #pragma unroll
-        for (int j = 0; j < 10; j++) R[x][j] = pcm[g10(x, al10(j, 0))] + pcm[g10(x, al10(j, 1))];
-      double *m = mp + st.mp * 55;
+          for (int m = 0; m < 10; m++) {
+            double a = 0.0, b = 0.0;
 #pragma unroll
-      for (int i = 0; i < 10; i++)
+            for (int k = 0; k < 5; k++) { a = fma(mut[m * 10 + k], pc[k], a); b = fma(mut[m * 10 + 5 + k], pc[5 + k], b); }
+            pcm[m] = 0.25 * (a + b);
+          }
+        } else {
 #pragma unroll
-        for (int j = i; j < 10; j++) {
-          const double v = R[al10(i, 0)][j] + R[al10(i, 1)][j];
-          m[sym55(i, j)] = st.flag ? v : m[sym55(i, j)] * v;  // a fresh marriage partial starts at 1
+          for (int m = 0; m < 10; m++) pcm[m] = 0.25 * pc[m];
         }
+#pragma unroll
+        for (int i = 0; i < 10; i++)
+#pragma unroll
+          for (int j = i; j < 10; j++) {
+            // 1/4 sum over (allele of i, allele of j) of (M pc)[g(x, y)]
+            const double v = (pcm[g10(al10(i, 0), al10(j, 0))] + pcm[g10(al10(i, 0), al10(j, 1))]) +
+                             (pcm[g10(al10(i, 1), al10(j, 0))] + pcm[g10(al10(i, 1), al10(j, 1))]);
+            acc[sym55(i, j)] = have ? acc[sym55(i, j)] * v : v;  // a fresh marriage partial starts at 1
+          }
+        have = true;
+      }
+#pragma unroll
+      for (int e = 0; e < 55; e++) mp[st.mp * 55 + e] = acc[e];
+      s = s2 - 1;
     } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
       const double *pf = part + st.from0 * 10;
       double *pt = part + st.to0 * 10;

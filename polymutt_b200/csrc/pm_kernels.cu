@@ -30,12 +30,13 @@ struct NarrowSmem {
 };
 
 // NA = the instance for chrX / chrY / MT sites (see k_sites_wide): the autosomal one has none of those rules compiled in.
-template <int UMAX, bool NA>
+// ES = the pedigree has extended families (the peel's registers are only paid for where there is something to peel)
+template <int UMAX, bool NA, bool ES>
 struct NarrowEval {
   const DevRun *run;
   const uint4 *recs;  // this site's records
   const NarrowSmem *sm;
-  double B[UMAX][5];
+  double B[UMAX > 0 ? UMAX : 1][5];  // UMAX = 0: the instance for pedigrees made of extended families only (no quartic unit)
   double C0[9];  // single-nuclear-family mode keeps the nine conditionals
   int g11, g12, g22;
   bool denovo;
@@ -45,7 +46,7 @@ struct NarrowEval {
   __device__ void setup(int a1, int a2, bool dn) {
     g11 = geno_index(a1, a1); g12 = geno_index(a1, a2); g22 = geno_index(a2, a2);
     denovo = dn;
-    if (!run->use_brent) {
+    if (UMAX > 0 && !run->use_brent) {
       const DevUnit u = run->units[0];
       if (!NA || denovo) unit_conditionals(recs, u.first, u.nkids, g11, g12, g22, denovo, sm->t.lut, sm->t.mut, C0);
       else unit_conditionals_nonauto(recs, u.first, u.nkids, g11, g12, g22, cls, 0, sm->t.lut, C0);
@@ -67,6 +68,7 @@ struct NarrowEval {
 #pragma unroll
     for (int u = 0; u < UMAX; u++)
       if (u < run->n_units) sum += log10(quartic_eval(B[u], m));
+    if constexpr (ES)
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
       double lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
@@ -87,7 +89,7 @@ struct NarrowEval {
   __device__ double optimize(int a1, int a2, bool dn, double *freq) {
     setup(a1, a2, dn);
     n_hyp++;
-    if (!run->use_brent) { n_eval++; return loglik_fixed(false); }
+    if (UMAX > 0 && !run->use_brent) { n_eval++; return loglik_fixed(false); }
     BrentState st;
     brent_begin(st);
     double f;
@@ -97,7 +99,7 @@ struct NarrowEval {
   }
 };
 
-template <int UMAX, bool NA>
+template <int UMAX, bool NA, bool ES>
 __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
                                                                   const pm_site_hdr *__restrict__ hdr,
                                                                   const uint4 *__restrict__ recs_all,
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   const double log_1m_prior = run->cls_log[cls][0];
   if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
     const int a2 = h.reserved & 0xff;
-    NarrowEval<UMAX, NA> ev;
+    NarrowEval<UMAX, NA, ES> ev;
     ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
     double freq = 0.0;
     const double poly = ev.optimize(ref, a2, false, &freq);
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   else if (r.avg_map_qual < run->min_map_quality) r.status = PM_SITE_MIN_MAPQ;
   if (r.status != 0) { res[s] = r; status[s] = status_word(r); return; }
 
-  NarrowEval<UMAX, NA> ev;
+  NarrowEval<UMAX, NA, ES> ev;
   ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
   r.reserved = (uint16_t)ref;
   // H0 (main:447-462)
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
     int a1, a2;
     hyp_alleles(0, ref, a1, a2);
     ev.setup(a1, a2, true);
-    double l0 = run->use_brent ? ev.loglik(1.0) : ev.loglik_fixed(true);
+    double l0 = (UMAX == 0 || run->use_brent) ? ev.loglik(1.0) : ev.loglik_fixed(true);
     r.varllk[0] = log_1m_prior + l0;
   }
   r.varllk_noprior[0] = r.varllk[0] - log_1m_prior;
@@ -300,8 +302,16 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
   cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
-  k_sites_narrow<kNarrowMaxUnits, false><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
-  k_sites_narrow<kNarrowMaxUnits, true><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);
+#define PM_NARROW(U_, ES_)                                                                                                                       \
+  do {                                                                                                                                         \
+    k_sites_narrow<U_, false, ES_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err); \
+    k_sites_narrow<U_, true, ES_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);  \
+  } while (0)
+  // three instances: quartic units only (nuclear families, singletons), units + extended families, extended families only
+  if (!plan.es) PM_NARROW(kNarrowMaxUnits, false);
+  else if (plan.units_per_thread == 0) PM_NARROW(0, true);
+  else PM_NARROW(kNarrowMaxUnits, true);
+#undef PM_NARROW
   return cudaGetLastError();
 }
 
@@ -311,11 +321,9 @@ cudaError_t plan_launch(LaunchPlan *plan, int n_person, int n_units, int n_es, i
   if (n_units <= kNarrowMaxUnits && !force_wide) {
     plan->kind = LaunchPlan::NARROW;
     plan->threads = kNarrowThreads;
-    plan->units_per_thread = kNarrowMaxUnits;
-    // (the attribute is per kernel and per device: always the same value, so contexts cannot lower each other's limit)
-    cudaError_t e = cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_sites_narrow<kNarrowMaxUnits, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NarrowSmem));
+    plan->units_per_thread = n_units == 0 ? 0 : kNarrowMaxUnits;
+    plan->es = n_es > 0 ? 1 : 0;
+    return cudaSuccess;  // (NarrowSmem fits in the default dynamic shared memory limit: no attribute to set)
   }
   return plan_wide(plan, n_person, n_units, n_es, sm_count, force_wide);
 }

@@ -324,7 +324,12 @@ __device__ __forceinline__ int one_slot(const uint4 *recs, int d, int g11, int g
 // Two slots of a thread per call (slot = packed unit descriptor, -1 = none): when both are nuclear families with the
 // same number of kids they go through the lockstep code above.  out0 / out1: 5 doubles each (the caller's staging
 // array).  Returns the two slots' codes (20 bits + flags each) in an int2.
-__device__ __noinline__ int2 slot_pair_ol(const uint4 *recs, int d0, int d1, int g11, int g12, int g22, int mode, double *out0, double *out1) {
+#ifdef PM_INLINE_SLOTS
+#define PM_SLOT_INLINE __forceinline__
+#else
+#define PM_SLOT_INLINE __noinline__
+#endif
+__device__ PM_SLOT_INLINE int2 slot_pair_ol(const uint4 *recs, int d0, int d1, int g11, int g12, int g22, int mode, double *out0, double *out1) {
   int2 ret;
   const int nk0 = ((d0 >> 20) & 0xff) - 1, nk1 = ((d1 >> 20) & 0xff) - 1;
   if (d0 >= 0 && d1 >= 0 && nk0 == nk1 && nk0 >= 1) {
@@ -353,7 +358,7 @@ __device__ __forceinline__ int one_slot(const uint4 *recs, int d, int g11, int g
   }
   return scale_slot(b[0], nkids >= 0, out);
 }
-__device__ __noinline__ int slot_single_ol(const uint4 *recs, int d, int g11, int g12, int g22, int mode, double *out) {
+__device__ PM_SLOT_INLINE int slot_single_ol(const uint4 *recs, int d, int g11, int g12, int g22, int mode, double *out) {
   return one_slot(recs, d, g11, g12, g22, mode, out);
 }
 
@@ -996,7 +1001,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
 #ifdef PM_NO_FUSE  // A/B builds only
       const bool fuse = false;
 #else
-      const bool fuse = !NA && !vcf && ev.spill == nullptr;
+      // (measured on B200: +14 % on 50 trios + 50 quartets at U = 4; at U = 8 the three coefficient sets waiting in local memory
+      // cost as much DRAM write-back as the shared look-ups save: 8.6 against 8.7 M sites/s on 1,000 trios)
+      const bool fuse = !NA && !vcf && ev.spill == nullptr && U <= 4;
 #endif
       double pre[3][U][5];
       int pre_codes[3][U];

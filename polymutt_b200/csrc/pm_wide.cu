@@ -376,6 +376,77 @@ __device__ PM_SLOT_INLINE int slot_single_ol(const uint4 *recs, int d, int g11, 
 // 90 and 30 — and the seventeen independent dependency chains keep the FP64 pipe busy where one hypothesis alone
 // waits on latency.  out0..out2: 5 scaled coefficients each; returns the three slot codes (scale_slot).
 struct Codes3 { int c0, c1, c2; };
+// The unscaled coefficients b[h][0..4] of one unit (first column, nkids; -1 = a single founder) for H1..H3.
+__device__ __forceinline__ void unit_h123(const uint4 *recs, int first, int nkids, int ref, int denovo, double (&b)[3][5]) {
+  const int alt[3] = {poly_ts(ref), poly_tvs1(ref), poly_tvs2(ref)};
+  const int grr = geno_index(ref, ref);
+  int gra[3], gaa[3];
+#pragma unroll
+  for (int h = 0; h < 3; h++) { gra[h] = geno_index(ref, alt[h]); gaa[h] = geno_index(alt[h], alt[h]); }
+  const uint8_t *rb = reinterpret_cast<const uint8_t *>(recs + first);
+  if (nkids < 0) {  // lkSinglePerson, NucFam:987-1004, times (p+q)^2
+    const double l11 = s_lut[rb[grr]];
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      const double l12 = s_lut[rb[gra[h]]], l22 = s_lut[rb[gaa[h]]];
+      b[h][4] = l11; b[h][3] = 2.0 * (l11 + l12); b[h][2] = l11 + 4.0 * l12 + l22; b[h][1] = 2.0 * (l12 + l22); b[h][0] = l22;
+    }
+    return;
+  }
+  double p0 = 1.0, p1[3], p2[3], p4[3], p5[3], p8[3];  // kid products (p1 carries 2^nkids, p4 4^nkids, p5 2^nkids)
+#pragma unroll
+  for (int h = 0; h < 3; h++) p1[h] = p2[h] = p4[h] = p5[h] = p8[h] = 1.0;
+  for (int k = 0; k < nkids; k++) {
+    double drr, dra[3], daa[3];
+    if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
+      const uint4 rk = recs[first + 2 + k];
+      double l[10];
+      l[0] = s_lut[__byte_perm(rk.x, 0, 0x4440)]; l[1] = s_lut[__byte_perm(rk.x, 0, 0x4441)];
+      l[2] = s_lut[__byte_perm(rk.x, 0, 0x4442)]; l[3] = s_lut[__byte_perm(rk.x, 0, 0x4443)];
+      l[4] = s_lut[__byte_perm(rk.y, 0, 0x4440)]; l[5] = s_lut[__byte_perm(rk.y, 0, 0x4441)];
+      l[6] = s_lut[__byte_perm(rk.y, 0, 0x4442)]; l[7] = s_lut[__byte_perm(rk.y, 0, 0x4443)];
+      l[8] = s_lut[__byte_perm(rk.z, 0, 0x4440)]; l[9] = s_lut[__byte_perm(rk.z, 0, 0x4441)];
+      auto row = [&](int g) {
+        const double2 *r = reinterpret_cast<const double2 *>(s_mut + g * 10);
+        double a = 0.0, c = 0.0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) { const double2 x = r[i]; a = fma(x.x, l[2 * i], a); c = fma(x.y, l[2 * i + 1], c); }
+        return a + c;
+      };
+      drr = row(grr);
+#pragma unroll
+      for (int h = 0; h < 3; h++) { dra[h] = row(gra[h]); daa[h] = row(gaa[h]); }
+    } else {
+      const uint8_t *kb = reinterpret_cast<const uint8_t *>(recs + first + 2 + k);
+      drr = s_lut[kb[grr]];
+#pragma unroll
+      for (int h = 0; h < 3; h++) { dra[h] = s_lut[kb[gra[h]]]; daa[h] = s_lut[kb[gaa[h]]]; }
+    }
+    // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome), the halves and quarters taken out
+    p0 *= drr;
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      p1[h] *= drr + dra[h];
+      p2[h] *= dra[h];
+      p4[h] *= fma(2.0, dra[h], drr) + daa[h];
+      p5[h] *= dra[h] + daa[h];
+      p8[h] *= daa[h];
+    }
+  }
+  // the parents' look-ups come after the kid loop: fourteen values less to keep alive across it
+  const double frr = s_lut[rb[grr]], mrr = s_lut[rb[16 + grr]];
+  const double h1 = __hiloint2double((1023 + 1 - nkids) << 20, 0), h4 = __hiloint2double((1023 + 2 - 2 * nkids) << 20, 0);
+  const double b4 = p0 * (frr * mrr);
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    const double fra = s_lut[rb[gra[h]]], faa = s_lut[rb[gaa[h]]], mra = s_lut[rb[16 + gra[h]]], maa = s_lut[rb[16 + gaa[h]]];
+    b[h][4] = b4;
+    b[h][3] = (p1[h] * h1) * fma(frr, mra, fra * mrr);
+    b[h][2] = fma(p4[h] * h4, fra * mra, p2[h] * fma(frr, maa, faa * mrr));
+    b[h][1] = (p5[h] * h1) * fma(fra, maa, faa * mra);
+    b[h][0] = p8[h] * (faa * maa);
+  }
+}
 __device__ __noinline__ Codes3 slot_h123_ol(const uint4 *recs, int d, int ref, int denovo, double *out0, double *out1, double *out2) {
   Codes3 ret;
   double *const out[3] = {out0, out1, out2};
@@ -386,79 +457,8 @@ __device__ __noinline__ Codes3 slot_h123_ol(const uint4 *recs, int d, int ref, i
     return ret;
   }
   const int first = d & 0xfffff, nkids = ((d >> 20) & 0xff) - 1;
-  const int alt[3] = {poly_ts(ref), poly_tvs1(ref), poly_tvs2(ref)};
-  const int grr = geno_index(ref, ref);
-  int gra[3], gaa[3];
-#pragma unroll
-  for (int h = 0; h < 3; h++) { gra[h] = geno_index(ref, alt[h]); gaa[h] = geno_index(alt[h], alt[h]); }
-  const uint8_t *rb = reinterpret_cast<const uint8_t *>(recs + first);
   double b[3][5];
-  if (nkids < 0) {  // lkSinglePerson, NucFam:987-1004, times (p+q)^2
-    const double l11 = s_lut[rb[grr]];
-#pragma unroll
-    for (int h = 0; h < 3; h++) {
-      const double l12 = s_lut[rb[gra[h]]], l22 = s_lut[rb[gaa[h]]];
-      b[h][4] = l11; b[h][3] = 2.0 * (l11 + l12); b[h][2] = l11 + 4.0 * l12 + l22; b[h][1] = 2.0 * (l12 + l22); b[h][0] = l22;
-    }
-  } else {
-    const double frr = s_lut[rb[grr]], mrr = s_lut[rb[16 + grr]];
-    double fra[3], faa[3], mra[3], maa[3];
-#pragma unroll
-    for (int h = 0; h < 3; h++) {
-      fra[h] = s_lut[rb[gra[h]]]; faa[h] = s_lut[rb[gaa[h]]];
-      mra[h] = s_lut[rb[16 + gra[h]]]; maa[h] = s_lut[rb[16 + gaa[h]]];
-    }
-    double p0 = 1.0, p1[3], p2[3], p4[3], p5[3], p8[3];  // kid products (p1 carries 2^nkids, p4 4^nkids, p5 2^nkids)
-#pragma unroll
-    for (int h = 0; h < 3; h++) p1[h] = p2[h] = p4[h] = p5[h] = p8[h] = 1.0;
-    for (int k = 0; k < nkids; k++) {
-      double drr, dra[3], daa[3];
-      if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
-        const uint4 rk = recs[first + 2 + k];
-        double l[10];
-        l[0] = s_lut[__byte_perm(rk.x, 0, 0x4440)]; l[1] = s_lut[__byte_perm(rk.x, 0, 0x4441)];
-        l[2] = s_lut[__byte_perm(rk.x, 0, 0x4442)]; l[3] = s_lut[__byte_perm(rk.x, 0, 0x4443)];
-        l[4] = s_lut[__byte_perm(rk.y, 0, 0x4440)]; l[5] = s_lut[__byte_perm(rk.y, 0, 0x4441)];
-        l[6] = s_lut[__byte_perm(rk.y, 0, 0x4442)]; l[7] = s_lut[__byte_perm(rk.y, 0, 0x4443)];
-        l[8] = s_lut[__byte_perm(rk.z, 0, 0x4440)]; l[9] = s_lut[__byte_perm(rk.z, 0, 0x4441)];
-        auto row = [&](int g) {
-          const double2 *r = reinterpret_cast<const double2 *>(s_mut + g * 10);
-          double a = 0.0, c = 0.0;
-#pragma unroll
-          for (int i = 0; i < 5; i++) { const double2 x = r[i]; a = fma(x.x, l[2 * i], a); c = fma(x.y, l[2 * i + 1], c); }
-          return a + c;
-        };
-        drr = row(grr);
-#pragma unroll
-        for (int h = 0; h < 3; h++) { dra[h] = row(gra[h]); daa[h] = row(gaa[h]); }
-      } else {
-        const uint8_t *kb = reinterpret_cast<const uint8_t *>(recs + first + 2 + k);
-        drr = s_lut[kb[grr]];
-#pragma unroll
-        for (int h = 0; h < 3; h++) { dra[h] = s_lut[kb[gra[h]]]; daa[h] = s_lut[kb[gaa[h]]]; }
-      }
-      // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome), the halves and quarters taken out
-      p0 *= drr;
-#pragma unroll
-      for (int h = 0; h < 3; h++) {
-        p1[h] *= drr + dra[h];
-        p2[h] *= dra[h];
-        p4[h] *= fma(2.0, dra[h], drr) + daa[h];
-        p5[h] *= dra[h] + daa[h];
-        p8[h] *= daa[h];
-      }
-    }
-    const double h1 = __hiloint2double((1023 + 1 - nkids) << 20, 0), h4 = __hiloint2double((1023 + 2 - 2 * nkids) << 20, 0);
-    const double b4 = p0 * (frr * mrr);
-#pragma unroll
-    for (int h = 0; h < 3; h++) {
-      b[h][4] = b4;
-      b[h][3] = (p1[h] * h1) * fma(frr, mra[h], fra[h] * mrr);
-      b[h][2] = fma(p4[h] * h4, fra[h] * mra[h], p2[h] * fma(frr, maa[h], faa[h] * mrr));
-      b[h][1] = (p5[h] * h1) * fma(fra[h], maa[h], faa[h] * mra[h]);
-      b[h][0] = p8[h] * (faa[h] * maa[h]);
-    }
-  }
+  unit_h123(recs, first, nkids, ref, denovo, b);
   ret.c0 = scale_slot(b[0], nkids >= 0, out0);
   ret.c1 = scale_slot(b[1], nkids >= 0, out1);
   ret.c2 = scale_slot(b[2], nkids >= 0, out2);
@@ -839,6 +839,129 @@ struct WideEval {
     else rounds<false>(B, Kall, rare, ctx);
   }
 
+  // ---- H1..H3 (and H0 under --denovo) of an autosomal site in ONE pass ------------------------------------
+  // The three (ref, alt) hypotheses share the walk over the records (unit_h123) and the points of the monotone path do
+  // not depend on the data, so: unit by unit, the coefficients of the three hypotheses are built in registers and
+  // multiplied into 3 x 10 running products straight away — they are never stored — then one block barrier, warp 0 takes
+  // the 30 logarithms (lane = hypothesis * 10 + point; lane 31: H0) and checks the three paths with one ballot.  If every
+  // hypothesis stays on its path (any monomorphic site) thread 0 calls done(ll1, ll2, ll3, ll_h0) and the site has cost two
+  // barriers; otherwise (a path left, a fragile unit, a path longer than ten points) nothing has been written and the
+  // caller goes through optimize() hypothesis by hypothesis.  Same evaluation order as optimize(): the same bits.
+  // fm / fe: per-warp partials, entry (lane, warp) at lane * nwp + warp.
+  static constexpr int kF3Pts = 10;
+  template <typename Done>
+  __device__ __forceinline__ bool fast3(int ref, bool dn, double *fm, int *fe, int nwp, Done done) {
+    constexpr int NP = kF3Pts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (T + 31) >> 5;
+    const int ns = s_ws.spec_n;
+    if (!s_ws.spec_complete || ns > NP) return false;
+    double acc[3][NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) {
+      const double qf = s_ws.spec_q[j < ns ? j : ns - 1];
+#pragma unroll
+      for (int h = 0; h < 3; h++) acc[h][j] = qf;
+    }
+    int Kall[3] = {0, 0, 0}, K0 = 0;
+    ME h0;
+    h0.m = 1.0; h0.e = 0;
+    int bail = 0;
+#pragma unroll 1
+    for (int k = 0; k < U; k++) {
+      const int u = t + k * T;
+      double c[3][5];
+      if (u < n_units) {
+        const int4 du = __ldg(reinterpret_cast<const int4 *>(run->units + u));  // first, nkids, kid0, sex
+        double b[3][5];
+        unit_h123(recs, du.x, du.y, ref, dn ? 1 : 0, b);
+#pragma unroll
+        for (int h = 0; h < 3; h++) {
+          const int code = scale_slot(b[h], du.y >= 0, c[h]);
+          if (code & kSlotFragile) { bail = 1; Kall[h] += 2; }
+          else { const int e = (code << 12) >> 12; Kall[h] += e; if (h == 0) K0 += e; }
+        }
+        if (dn) me_mul(h0, c[0][4]);
+      } else {
+#pragma unroll
+        for (int h = 0; h < 3; h++) { c[h][0] = 0.25; c[h][1] = 1.0; c[h][2] = 1.5; c[h][3] = 1.0; c[h][4] = 0.25; Kall[h] += 2; }
+      }
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        const double r = s_ws.spec_r[j < ns ? j : ns - 1];
+#pragma unroll
+        for (int h = 0; h < 3; h++) acc[h][j] *= fma(fma(fma(fma(c[h][4], r, c[h][3]), r, c[h][2]), r, c[h][1]), r, c[h][0]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+#pragma unroll
+      for (int j0 = 0; j0 < NP; j0 += 5) {
+        double m[5];
+        int e[5];
+        bool zero[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          const double vv = acc[h][j0 + j];
+          const ME x = me_split_pos(vv);
+          zero[j] = !(vv > 0.0);
+          m[j] = x.m; e[j] = x.e + Kall[h];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int j = 0; j < 5; j++) m[j] *= __shfl_xor_sync(0xffffffffu, m[j], o);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+          const int es = __reduce_add_sync(0xffffffffu, e[j]);
+          const bool anyz = __any_sync(0xffffffffu, zero[j]);
+          if (lane == 0) {
+            const ME w = me_split_pos(m[j]);
+            fm[(h * NP + j0 + j) * nwp + warp] = anyz ? 0.0 : w.m; fe[(h * NP + j0 + j) * nwp + warp] = w.e + es;
+          }
+        }
+      }
+    }
+    if (dn) {  // H0 = prod_u B4_u (the likelihood at p = 1), same scaling as H1
+      h0.e += K0;
+      const bool hz = !(h0.m > 0.0);
+      double hm = hz ? 1.0 : h0.m;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) hm *= __shfl_xor_sync(0xffffffffu, hm, o);
+      const int he = __reduce_add_sync(0xffffffffu, h0.e);
+      const bool anyz = __any_sync(0xffffffffu, hz);
+      if (lane == 0) { const ME w = me_split_pos(hm); fm[31 * nwp + warp] = anyz ? 0.0 : w.m; fe[31 * nwp + warp] = w.e + he; }
+    }
+    if (__syncthreads_or(bail)) return false;
+    if (warp == 0) {
+      const int hh = lane / NP, j = lane - hh * NP;
+      double ll = 0.0;
+      if (lane < 3 * NP || (dn && lane == 31)) {
+        double m0 = 1.0, m1 = 1.0;
+        int es = 0;
+        for (int w = 0; w < nwarp; w++) {
+          const double x = fm[lane * nwp + w];
+          es += fe[lane * nwp + w];
+          if (w & 1) m1 *= x; else m0 *= x;
+        }
+        const double mm = m0 * m1;
+        const ME a = me_split_pos(mm);
+        ll = mm > 0.0 ? log10_me(a.m, a.e + es) : -CUDART_INF;
+      }
+      const double first = __shfl_sync(0xffffffffu, ll, hh < 3 ? hh * NP : 0);
+      const bool ok = lane >= 3 * NP || j == 0 || j >= ns || ll < first;  // f_k > f_0 (a NaN or -inf leaves the path)
+      const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+      const double l1 = __shfl_sync(0xffffffffu, ll, 0), l2 = __shfl_sync(0xffffffffu, ll, NP), l3 = __shfl_sync(0xffffffffu, ll, 2 * NP);
+      const double lh = __shfl_sync(0xffffffffu, ll, 31);
+      if (lane == 0) {
+        const bool good = okmask == 0xffffffffu;
+        s_ws.ibcast[0] = good ? 1 : 0;
+        if (good) done(l1, l2, l3, lh);
+      }
+    }
+    block_sync();
+    return s_ws.ibcast[0] != 0;
+  }
+
   template <bool DRIVER>
   __device__ __forceinline__ void rounds(const double (&B)[U][5], const int Kall, const bool rare, const RareCtx &ctx) {
     constexpr int PER = U >= 4 ? U / 4 : 1;
@@ -901,6 +1024,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
                                                            int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *const ws = &s_ws;
+  constexpr int F3W = MAXT <= 32 ? 1 : MAXT / 32 + 1;  // warps per block (+1: an odd stride for the 32 lanes that read the partials)
   if (NA ? ((err[1] == 0 && run->site_filter != 2) || run->site_filter == 1) : run->site_filter == 2) return;
   const int np = run->n_person;
   unsigned char *site_base = smem_raw;  // the dynamic part is the site buffer alone
@@ -1007,56 +1131,67 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
       // polymorphic de novo call (main:567-573).
       const bool dn = run->denovo != 0;
       int step = vcf ? 0 : 1;
-      // H1..H3 are built together, in one pass over the site's records (autosomal instance, no units in the L2 scratch)
-#ifdef PM_NO_FUSE  // A/B builds only
-      const bool fuse = false;
-#else
-      // (measured on B200: +14 % on 50 trios + 50 quartets at U = 4; at U = 8 the three coefficient sets waiting in local memory
-      // cost as much DRAM write-back as the shared look-ups save: 8.6 against 8.7 M sites/s on 1,000 trios)
-      const bool fuse = !NA && !vcf && ev.spill == nullptr && U <= 4;
-#endif
-      double pre[3][U][5];
-      int pre_codes[3][U];
-      if (fuse) ev.setup3(ref, dn, pre, pre_codes);
+      // after H3 / H6 (thread 0): posterior over the hypotheses so far; H4..H6 wanted?  else the decisions of main:539-574
+      auto decide = [&](int at) {
+        bool more = false;
+        if (at == 3) {
+          if (!dn) ws->r.varllk[0] = run->cls_log[cls][0] + ws->lk_mono;
+          ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->cls_log[cls][0];
+          ws->r.varfreq[0] = 1.0;
+          var_posterior_ol(&ws->r, ref, 4);
+          more = ws->r.var_post_prob < 0.99;  // main:499
+        } else {
+          var_posterior_ol(&ws->r, ref, 7);
+        }
+        ws->ibcast[1] = more;
+        ws->ibcast[2] = more ? 0 : site_decide_ol(run, &ws->r, ws->lk_mono);
+      };
+      bool decided = false;
+      if constexpr (!NA && !ES) {
+        // H1..H3 (+ H0) in one pass wherever every hypothesis stays on Brent's monotone path: any monomorphic site
+        __shared__ double f3_m[32 * F3W];
+        __shared__ int f3_e[32 * F3W];
+        if (!vcf && ev.spill == nullptr) {
+          decided = ev.fast3(ref, dn, f3_m, f3_e, F3W, [&](double l1, double l2, double l3, double lh0) {
+            const double p0 = ws->spec_p[0];
+            site_store_hyp(run, ws->r, 1, l1, p0, cls);
+            site_store_hyp(run, ws->r, 2, l2, p0, cls);
+            site_store_hyp(run, ws->r, 3, l3, p0, cls);
+            if (dn) ws->r.varllk[0] = run->cls_log[cls][0] + lh0;
+            n_hyp += dn ? 4 : 3; n_eval += 3 * (unsigned)ws->spec_n + (dn ? 1 : 0);
+            decide(3);
+          });
+          if (decided) step = 3;
+        }
+      }
       if (vcf && threadIdx.x == 0) { memset(&ws->r, 0, sizeof ws->r); ws->r.site = (uint32_t)s; }
       for (;;) {
-        int a1, a2;
-        bool dnc = false, with_h0 = false;
-        if (step == 0) { a1 = ref; a2 = h.reserved & 0xff; }
-        else if (step <= 6) { hyp_alleles(step, ref, a1, a2); dnc = dn; with_h0 = dn && step == 1; }
-        else { a1 = ws->r.allele1; a2 = ws->r.allele2; }
-        if (fuse && step >= 1 && step <= 3) ev.optimize(a1, a2, dnc, with_h0, pre[step - 1], pre_codes[step - 1]);
-        else ev.optimize(a1, a2, dnc, with_h0);
-        // (optimize ends with a block barrier: thread 0's state is final)
-        if (threadIdx.x == 0) { n_hyp += with_h0 ? 2 : 1; n_eval += ws->n_eval + (with_h0 ? 1 : 0); }
-        if (step == 0) {
-          if (threadIdx.x == 0) vcf_record_result(run, ws->r, a1, a2, (h.reserved & 0x100) != 0, mono_all[s], -ws->brent.fmin, ws->brent.min);
-          break;
-        }
-        if (step == 7) {
-          if (threadIdx.x == 0) site_finish_refit(run, ws->r, -ws->brent.fmin, ws->brent.min);
-          break;
-        }
-        if (threadIdx.x == 0) {
-          site_store_hyp(run, ws->r, step, -ws->brent.fmin, ws->brent.min, cls);
-          if (with_h0) ws->r.varllk[0] = run->cls_log[cls][0] + ws->h0;
-        }
-        if (step != 3 && step != 6) { step++; continue; }
-        if (threadIdx.x == 0) {
-          bool more = false;
-          if (step == 3) {
-            if (!dn) ws->r.varllk[0] = run->cls_log[cls][0] + ws->lk_mono;
-            ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->cls_log[cls][0];
-            ws->r.varfreq[0] = 1.0;
-            var_posterior_ol(&ws->r, ref, 4);
-            more = ws->r.var_post_prob < 0.99;  // main:499
-          } else {
-            var_posterior_ol(&ws->r, ref, 7);
+        if (!decided) {
+          int a1, a2;
+          bool dnc = false, with_h0 = false;
+          if (step == 0) { a1 = ref; a2 = h.reserved & 0xff; }
+          else if (step <= 6) { hyp_alleles(step, ref, a1, a2); dnc = dn; with_h0 = dn && step == 1; }
+          else { a1 = ws->r.allele1; a2 = ws->r.allele2; }
+          ev.optimize(a1, a2, dnc, with_h0);
+          // (optimize ends with a block barrier: thread 0's state is final)
+          if (threadIdx.x == 0) { n_hyp += with_h0 ? 2 : 1; n_eval += ws->n_eval + (with_h0 ? 1 : 0); }
+          if (step == 0) {
+            if (threadIdx.x == 0) vcf_record_result(run, ws->r, a1, a2, (h.reserved & 0x100) != 0, mono_all[s], -ws->brent.fmin, ws->brent.min);
+            break;
           }
-          ws->ibcast[1] = more;
-          ws->ibcast[2] = more ? 0 : site_decide_ol(run, &ws->r, ws->lk_mono);
+          if (step == 7) {
+            if (threadIdx.x == 0) site_finish_refit(run, ws->r, -ws->brent.fmin, ws->brent.min);
+            break;
+          }
+          if (threadIdx.x == 0) {
+            site_store_hyp(run, ws->r, step, -ws->brent.fmin, ws->brent.min, cls);
+            if (with_h0) ws->r.varllk[0] = run->cls_log[cls][0] + ws->h0;
+          }
+          if (step != 3 && step != 6) { step++; continue; }
+          if (threadIdx.x == 0) decide(step);
+          __syncthreads();
         }
-        __syncthreads();
+        decided = false;
         if (ws->ibcast[1]) step = 4;
         else if (ws->ibcast[2]) step = 7;
         else break;

@@ -1,10 +1,13 @@
 #include "glf_ingest.h"
 
+#include <fcntl.h>
 #include <sys/resource.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
 #include <climits>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,7 +21,7 @@ static const uint8_t kTranslateBase[16] = {0, 1, 2, 0, 3, 0, 0, 0, 4, 0, 0, 0, 0
 static double g_t[4];
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 GlfBatchReader::~GlfBatchReader() {
-  for (auto &s : streams_) if (s.f) gzclose(s.f);
+  for (auto &s : streams_) { if (s.f) gzclose(s.f); else if (s.fd >= 0) close(s.fd); }
   if (getenv("PM_TIMING")) fprintf(stderr, "[pm timing] ingest: decode %.3f s, window+mark %.3f s, rows %.3f s, fill %.3f s\n", g_t[0], g_t[1], g_t[2], g_t[3]);
 }
 
@@ -50,6 +53,13 @@ bool GlfBatchReader::Stream::fill(size_t need) {
   }
   if (raw_dec + need > raw.size()) raw.resize(std::max(raw.size() * 2, raw_dec + need + (1 << 16)));  // an indel record can carry 2 x 32 KiB of allele text
   while (raw_end - raw_dec < need && !file_eof) {
+    if (!f) {  // an uncompressed GLF: straight from the page cache into the record buffer (no second copy through zlib)
+      const ssize_t n = read(fd, raw.data() + raw_end, std::min<size_t>(raw.size() - raw_end, (size_t)1 << 30));
+      if (n < 0) { if (errno == EINTR) continue; throw std::runtime_error(std::string("GLF stream: read error (") + strerror(errno) + ")"); }
+      if (n == 0) { file_eof = true; break; }
+      raw_end += (size_t)n;
+      continue;
+    }
     int got = gzread(f, raw.data() + raw_end, (unsigned)std::min<size_t>(raw.size() - raw_end, 1u << 30));
     if (got < 0) {  // a damaged .gz is an error, not the end of the chromosome (the run would exit 0 with a partial VCF)
       int errnum = 0;
@@ -155,9 +165,16 @@ bool GlfBatchReader::open(const std::vector<std::string> &paths, int threads, st
       if (paths[(size_t)i].empty()) continue;
       Stream &s = streams_[(size_t)i];
       const std::string &path = paths[(size_t)i];
-      s.f = gzopen(path.c_str(), "rb");
-      if (!s.f) { errs[(size_t)i] = "GLF file " + path + " can  not be opened!"; continue; }
-      gzbuffer(s.f, 1 << 17);
+      s.fd = ::open(path.c_str(), O_RDONLY | O_CLOEXEC);
+      if (s.fd < 0) { errs[(size_t)i] = "GLF file " + path + " can  not be opened!"; continue; }
+      unsigned char magic[2] = {0, 0};
+      const bool gz = pread(s.fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+      if (gz) {  // gzip / BGZF: through zlib; anything else is read as it is (what gzread's transparent mode would do)
+        s.f = gzdopen(s.fd, "rb");
+        if (!s.f) { close(s.fd); s.fd = -1; errs[(size_t)i] = "GLF file " + path + " can  not be opened!"; continue; }
+        gzbuffer(s.f, 1 << 17);
+      }
+      s.live = true;
       s.raw.resize(1 << 16);
       if (!s.fill(8) || memcmp(s.raw.data(), "GLF\3", 4) != 0) { errs[(size_t)i] = "GLF file " + path + ": invalid format or unsupported version"; continue; }
       uint32_t hl;
@@ -176,7 +193,7 @@ bool GlfBatchReader::open(const std::vector<std::string> &paths, int threads, st
   });
   for (size_t i = 0; i < paths.size(); i++) {
     if (!errs[i].empty()) { if (err) *err = errs[i]; return false; }
-    if (lead_ < 0 && streams_[i].f) lead_ = (int)i;
+    if (lead_ < 0 && streams_[i].live) lead_ = (int)i;
   }
   if (lead_ < 0) { if (err) *err = "no GLF file could be opened"; return false; }
   section_done_ = true;
@@ -189,7 +206,7 @@ bool GlfBatchReader::next_section() {
   parallel_streams([&](int lo, int hi, int) {
     for (int i = lo; i < hi; i++) {
       Stream &s = streams_[(size_t)i];
-      if (!s.f) continue;
+      if (!s.live) continue;
       while (!s.ended) { s.head = s.pos.size(); s.decode(4096); }  // drain the old section
       s.pos.clear(); s.off.clear(); s.head = 0; s.raw_keep = s.raw_dec;
       s.position = 0; s.last_pos = -1;
@@ -213,7 +230,7 @@ bool GlfBatchReader::next_section() {
   // the reference walks the streams in order and stops at the first that has no further section
   for (size_t i = 0; i < streams_.size(); i++) {
     const Stream &s = streams_[i];
-    if (!s.f) continue;
+    if (!s.live) continue;
     if (ok[i] && ok[(size_t)lead_] && (s.max_position != lead.max_position || s.label != lead.label))
       throw std::runtime_error("GLF files are not compatible:\n\tsection " + lead.label + " with " + std::to_string(lead.max_position) +
                                " entries vs section " + s.label + " with " + std::to_string(s.max_position) + " entries");
@@ -235,7 +252,7 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   parallel_streams([&](int lo, int hi, int) {
     for (int i = lo; i < hi; i++) {
       Stream &s = streams_[(size_t)i];
-      if (s.f && !s.ended && s.pending() < want) s.decode(want);
+      if (s.live && !s.ended && s.pending() < want) s.decode(want);
     }
   });
   const double t1 = now_s();
@@ -243,7 +260,7 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   long long base = LLONG_MAX, wend = LLONG_MAX;
   long long T = LLONG_MAX;  // min over ended streams of their last base-record position (-1: none at all)
   for (const Stream &s : streams_) {
-    if (!s.f) continue;
+    if (!s.live) continue;
     if (s.pending()) base = std::min<long long>(base, s.pos[s.head]);
     if (s.ended) T = std::min<long long>(T, s.last_pos);
     else wend = std::min<long long>(wend, s.pos.back());
@@ -252,7 +269,7 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   const long long cap = (long long)std::max<size_t>(1 << 16, 4 * max_sites);
   if (wend == LLONG_MAX) {  // every stream has been decoded to its end: the rest of the section is known
     wend = base;
-    for (const Stream &s : streams_) if (s.f && s.pending()) wend = std::max<long long>(wend, s.pos.back());
+    for (const Stream &s : streams_) if (s.live && s.pending()) wend = std::max<long long>(wend, s.pos.back());
   }
   wend = std::max(base, std::min(wend, base + cap - 1));
   const size_t width = (size_t)(wend - base + 1);
@@ -260,7 +277,7 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   parallel_streams([&](int lo, int hi, int) {
     for (int i = lo; i < hi; i++) {
       const Stream &s = streams_[(size_t)i];
-      if (!s.f) continue;
+      if (!s.live) continue;
       for (size_t k = s.head; k < s.pos.size() && s.pos[k] <= wend; k++) mark_[(size_t)(s.pos[k] - base)] = 1;
     }
   });
@@ -286,58 +303,58 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   const int Tn = std::max(1, std::min(threads_, (int)np));
   owner_.assign(n * (size_t)Tn, UINT32_MAX);
   parallel_streams([&](int lo, int hi, int t) {
-    // tiles of 4 columns (one 64-byte line of a site's row) x 256 rows: the four streams are read sequentially, every
-    // line of the batch is written once and completely
+    // Blocks of 64 rows x tiles of 4 columns (one 64-byte line of a site's row): inside a block of rows the thread goes
+    // through all its columns, so the lines it writes there — its stretch of 64 rows, 64 pages — stay in reach of the
+    // TLB while every stream is still read sequentially (64 records at a time).  Measured on the GPU box's 16 cores, 3,000
+    // streams: 180 k sites/s against 165 k with the columns outermost; non-temporal stores were slower (148 k).
     uint32_t *own = owner_.data() + (size_t)t * n;
     constexpr int CW = 4;
-    constexpr size_t RB = 256;
-    for (int c0 = lo; c0 < hi; c0 += CW) {
-      const int cw = std::min(CW, hi - c0);
-      const int32_t *pp[CW], *pe[CW];
-      const uint32_t *op[CW];
-      const unsigned char *rawp[CW];
-      uint32_t prio[CW];
-      for (int j = 0; j < cw; j++) {
-        const Stream &s = streams_[(size_t)(c0 + j)];
-        pp[j] = s.pos.data() + s.head; pe[j] = s.pos.data() + s.pos.size();
-        op[j] = s.off.data() + s.head; rawp[j] = s.raw.data();
-        prio[j] = ((c0 + j == lead_) ? 0u : (uint32_t)(c0 + j) + 1u) << 8;
-      }
-      for (size_t r0 = 0; r0 < n; r0 += RB) {
-        const size_t r1 = std::min(n, r0 + RB);
+    constexpr size_t RB = 64;
+    struct Cur { const int32_t *pp, *pe; const uint32_t *op; const unsigned char *raw; uint32_t prio; };
+    std::vector<Cur> cur((size_t)(hi - lo));
+    for (int c = lo; c < hi; c++) {
+      const Stream &s = streams_[(size_t)c];
+      Cur &k = cur[(size_t)(c - lo)];
+      k.pp = s.pos.data() + s.head; k.pe = s.pos.data() + s.pos.size();
+      k.op = s.off.data() + s.head; k.raw = s.raw.data();
+      k.prio = ((c == lead_) ? 0u : (uint32_t)c + 1u) << 8;
+    }
+    for (size_t r0 = 0; r0 < n; r0 += RB) {
+      const size_t r1 = std::min(n, r0 + RB);
+      for (int c0 = lo; c0 < hi; c0 += CW) {
+        const int cw = std::min(CW, hi - c0);
+        Cur *const ck = cur.data() + (c0 - lo);
         for (size_t r = r0; r < r1; r++) {
           const int32_t p = rowpos_[r];
           pm_person_site *row = out + r * np + (size_t)c0;
           uint32_t best = own[r];
           for (int j = 0; j < cw; j++) {
-            pm_person_site &o = row[j];
-            if (pp[j] < pe[j] && *pp[j] == p) {
+            Cur &k = ck[j];
+            uint64_t lo8 = 0, hi8 = 0;
+            if (k.pp < k.pe && *k.pp == p) {
               // 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
               // 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) as two 8-byte words (little endian)
-              const unsigned char *rec = rawp[j] + *op[j];
-              uint64_t lo8;
+              const unsigned char *rec = k.raw + *k.op;
               uint32_t dm;
               uint16_t lk89;
               memcpy(&lo8, rec + 10, 8);
               memcpy(&lk89, rec + 18, 2);
               memcpy(&dm, rec + 5, 4);
-              const uint64_t hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
-              memcpy(reinterpret_cast<unsigned char *>(&o), &lo8, 8);
-              memcpy(reinterpret_cast<unsigned char *>(&o) + 8, &hi8, 8);
-              const uint32_t v = prio[j] | kTranslateBase[rec[0] & 0xf];
+              hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
+              const uint32_t v = k.prio | kTranslateBase[rec[0] & 0xf];
               if (v < best) best = v;
-              pp[j]++; op[j]++;
-            } else {
-              memset(&o, 0, sizeof o);
+              k.pp++; k.op++;
             }
+            memcpy(reinterpret_cast<unsigned char *>(row + j), &lo8, 8);
+            memcpy(reinterpret_cast<unsigned char *>(row + j) + 8, &hi8, 8);
           }
           own[r] = best;
         }
       }
-      for (int j = 0; j < cw; j++) {
-        Stream &s = streams_[(size_t)(c0 + j)];
-        s.head = (size_t)(pp[j] - s.pos.data());
-      }
+    }
+    for (int c = lo; c < hi; c++) {
+      Stream &s = streams_[(size_t)c];
+      s.head = (size_t)(cur[(size_t)(c - lo)].pp - s.pos.data());
     }
   });
   for (size_t r = 0; r < n; r++) {

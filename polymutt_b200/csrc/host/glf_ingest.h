@@ -40,7 +40,9 @@ class GlfBatchReader {
 
  private:
   struct Stream {
-    gzFile f = nullptr;
+    gzFile f = nullptr;               // gzip / BGZF input; nullptr for an uncompressed file, which is read through fd
+    int fd = -1;
+    bool live = false;                // the column has a GLF
     // Bytes of the (inflated) stream: [raw_keep, raw_dec) holds the records that are decoded but not consumed yet,
     // [raw_dec, raw_end) what has been read but not looked at.  Base records are never copied out: a pending record is
     // (pos[k], off[k]) = its position and the offset of its 20 bytes in `raw`.

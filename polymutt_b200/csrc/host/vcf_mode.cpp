@@ -104,6 +104,22 @@ inline bool nth_field(const Tok &t, char sep, int k, Tok *out) {
   return true;
 }
 
+// fields ia and ib (':'-separated, -1 = none) of a sample token in one pass; has_x = the token has that many fields
+inline void two_fields(const Tok &t, int ia, int ib, Tok *fa, bool *has_a, Tok *fb, bool *has_b) {
+  *has_a = *has_b = false;
+  const char *end = t.p + t.n, *fs = t.p;
+  int k = 0;
+  for (const char *q = t.p;; q++) {
+    if (q == end || *q == ':') {
+      if (k == ia) { fa->p = fs; fa->n = (uint32_t)(q - fs); *has_a = true; }
+      if (k == ib) { fb->p = fs; fb->n = (uint32_t)(q - fs); *has_b = true; }
+      if (q == end) break;
+      k++; fs = q + 1;
+      if (k > ia && k > ib) break;
+    }
+  }
+}
+
 // atof() of a token that is not NUL-terminated
 inline double tok_atof(const Tok &t) {
   if (t.n == 0) return 0.0;
@@ -301,8 +317,11 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   std::vector<pm_person_result> pres;   // per-sample results, or (engines with call_vcf_calls) ...
   std::vector<uint16_t> calls;           // ... best | gq << 8 per sample
   const bool compact = engine.call_vcf_calls != nullptr;
-  std::vector<std::string> text;
+  std::vector<std::string> text, text_w;  // rows being formatted / rows being written
+  std::thread writer;
   std::vector<std::vector<double>> scratch((size_t)threads, std::vector<double>((size_t)np));
+  struct SampF { Tok dp, lk; bool has_dp, has_lk; };  // the DP and PL / GL fields of one sample token
+  std::vector<std::vector<SampF>> fscratch((size_t)threads, std::vector<SampF>(n_names));
   static const char *lab[3] = {"0/0", "0/1", "1/1"};
 
   // FillPenetrance for one line (FLSeq_VCF.cpp:267-383); everything it writes belongs to the line
@@ -332,15 +351,40 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     for (size_t i = 0; i < n_names; i++) {
       const int c = vcf2col[i];
       if (c < 0) continue;
-      Tok field, g[3], extra;
-      const bool missing = fi < 0 || !nth_field(toks[L.samp0 + i], ':', fi, &field) || field.n == 0;
-      if (missing) break;  // the reference returns from FillPenetrance here: later samples keep likelihood 1
-      if (!nth_field(field, ',', 0, &g[0]) || !nth_field(field, ',', 1, &g[1]) || !nth_field(field, ',', 2, &g[2]) || nth_field(field, ',', 3, &extra)) {
-        L.kind = L_ERROR;
-        L.err = "GL or PL filed does not have 3 values separated by commas at: " + L.col[0].str() + " " + L.col[1].str() + "!";
-        return;
+      double G[3];
+      // fast path: the field is three runs of decimal digits "a,b,c" (every PL a caller writes): one pass over the
+      // sample's bytes, no memchr calls; anything else (GL floats, empty or missing values, a fourth value) goes the
+      // general way below with the same result
+      bool fast = false;
+      if (fi >= 0) {
+        const Tok &st = toks[L.samp0 + i];
+        const char *b = st.p, *end = st.p + st.n;
+        int k = 0;
+        while (k < fi && b < end) if (*b++ == ':') k++;
+        if (k == fi && b < end && *b != ':') {
+          unsigned v[3] = {0, 0, 0};
+          int idx = 0, digits = 0;
+          bool ok = true;
+          for (const char *q = b; q < end && *q != ':'; q++) {
+            const unsigned ch = (unsigned char)*q;
+            if (ch - '0' <= 9u) { v[idx] = v[idx] * 10 + (ch - '0'); if (++digits > 8) { ok = false; break; } }
+            else if (ch == ',' && digits > 0 && idx < 2) { idx++; digits = 0; }
+            else { ok = false; break; }
+          }
+          if (ok && idx == 2 && digits > 0) { G[0] = (double)v[0]; G[1] = (double)v[1]; G[2] = (double)v[2]; fast = true; }
+        }
       }
-      const double G[3] = {tok_atof(g[0]), tok_atof(g[1]), tok_atof(g[2])};
+      if (!fast) {
+        Tok field, g[3], extra;
+        const bool missing = fi < 0 || !nth_field(toks[L.samp0 + i], ':', fi, &field) || field.n == 0;
+        if (missing) break;  // the reference returns from FillPenetrance here: later samples keep likelihood 1
+        if (!nth_field(field, ',', 0, &g[0]) || !nth_field(field, ',', 1, &g[1]) || !nth_field(field, ',', 2, &g[2]) || nth_field(field, ',', 3, &extra)) {
+          L.kind = L_ERROR;
+          L.err = "GL or PL filed does not have 3 values separated by commas at: " + L.col[0].str() + " " + L.col[1].str() + "!";
+          return;
+        }
+        G[0] = tok_atof(g[0]); G[1] = tok_atof(g[1]); G[2] = tok_atof(g[2]);
+      }
       if (G[0] != 0.0 || G[1] != 0.0 || G[2] != 0.0) withdata++;
       for (int k = 0; k < 3; k++) {
         const double ll = PL_idx > 0 ? (G[k] > 255 ? -255 / 10.0 : -G[k] / 10.0) : (-10 * G[k] > 255 ? -255 / 10.0 : G[k]);
@@ -360,7 +404,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   };
 
   // FamilyLikelihoodSeq_VCF::OutputVCF (FLSeq_VCF.cpp:437-521) for one line, into text[li]
-  auto format_line = [&](size_t li, int) {
+  auto format_line = [&](size_t li, int tid) {
     const LineRec &L = lines[li];
     std::string &o = text[li];
     o.clear();
@@ -378,16 +422,20 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     auto best_of = [&](int c) { return pr ? (int)pr[c].best : (cl ? (int)(cl[c] & 0xff) : last_best[(size_t)c]); };
     auto gq_of = [&](int c) { return pr ? (int)pr[c].gq : (cl ? (int)(cl[c] >> 8) : last_gq[(size_t)c]); };
     const int dpi = L.dp_index;
+    const int fi = PL_idx > 0 ? PL_idx : GL_idx;
     int AC = 0, totalDepth = 0;
     bool missing = false;
-    Tok f;
+    // the DP and PL / GL fields of every sample, located once (one pass over the sample's bytes)
+    std::vector<SampF> &sf = fscratch[(size_t)tid];
     for (size_t i = 0; i < n_names; i++) {
       if (vcf2col[i] < 0) continue;
+      SampF &x = sf[i];
+      two_fields(toks[L.samp0 + i], dpi > 0 ? dpi : -1, fi >= 0 ? fi : -1, &x.dp, &x.has_dp, &x.lk, &x.has_lk);
       AC += best_of(vcf2col[i]);
       int dp = 0;
       if (dpi > 0) {
-        missing = !nth_field(toks[L.samp0 + i], ':', dpi, &f) || f.n == 0;
-        dp = missing ? 0 : tok_atoi(f);
+        missing = !x.has_dp || x.dp.n == 0;
+        dp = missing ? 0 : tok_atoi(x.dp);
       }
       if (missing) continue;
       totalDepth += dp;
@@ -404,28 +452,42 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     o += ";AC="; append_int(o, AC);
     o += ";DP="; append_int(o, totalDepth);
     o += PL_idx > 0 ? "\tGT:GQ:DP:PL" : "\tGT:GQ:DP:GL";
-    const int fi = PL_idx > 0 ? PL_idx : GL_idx;
+    // the sample columns through a raw pointer: label ':' GQ ':' DP ':' PL, at most 24 bytes beside the copied fields
+    const size_t head = o.size();
+    o.resize(head + L.line.n + 24 * n_names + 8);
+    char *w = &o[head];
     for (size_t i = 0; i < n_names; i++) {
       if (vcf2col[i] < 0) continue;
       const int c = vcf2col[i];
-      const Tok &s = toks[L.samp0 + i];
+      const SampF &x = sf[i];
       const int gq = gq_of(c);
-      o.push_back('\t');
+      *w++ = '\t';
       const int sex = col_sex[(size_t)c];
       const char *label = !labeled ? "" : (lcls == PM_CHR_Y && sex == 2) ? "."
                           : (lcls == PM_CHR_Y || lcls == PM_CHR_MT || (lcls == PM_CHR_X && sex == 1)) ? lab_hap[best_of(c)] : lab[best_of(c)];
-      o += (gq > 0 || !strcmp(label, ".")) ? label : "./.";   // FLSeq_VCF.cpp:507
-      o.push_back(':'); append_int(o, gq); o.push_back(':');
+      const char *shown = (gq > 0 || (label[0] == '.' && label[1] == 0)) ? label : "./.";   // FLSeq_VCF.cpp:507
+      while (*shown) *w++ = *shown++;
+      *w++ = ':';
+      {  // GQ (0..255 from the engine; any int from the stale state)
+        char tmp[12];
+        int n = 0;
+        unsigned v = gq < 0 ? 0u - (unsigned)gq : (unsigned)gq;
+        do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+        if (gq < 0) *w++ = '-';
+        while (n) *w++ = tmp[--n];
+      }
+      *w++ = ':';
       Tok dps; dps.p = "."; dps.n = 1;
       if (dpi > 0) {
-        missing = !nth_field(s, ':', dpi, &f) || f.n == 0;
-        if (!missing) dps = f;
+        missing = !x.has_dp || x.dp.n == 0;
+        if (!missing) dps = x.dp;
       }
-      if (missing) o.push_back('.'); else o.append(dps.p, dps.n);
-      o.push_back(':');
-      missing = fi < 0 || !nth_field(s, ':', fi, &f) || f.n == 0;
-      if (missing) o.push_back('.'); else o.append(f.p, f.n);
+      if (missing) *w++ = '.'; else { memcpy(w, dps.p, dps.n); w += dps.n; }
+      *w++ = ':';
+      missing = fi < 0 || !x.has_lk || x.lk.n == 0;
+      if (missing) *w++ = '.'; else { memcpy(w, x.lk.p, x.lk.n); w += x.lk.n; }
     }
+    o.resize((size_t)(w - o.data()));
     o.push_back('\n');
   };
 
@@ -486,10 +548,11 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
         PL_idx = format_index(L.col[8], "PL");
         if (GL_idx < 0 && PL_idx < 0) {
           fprintf(stderr, "NO GL or PL field was found. Please check the vcf file at chr:%s and position:%d", L.col[0].str().c_str(), tok_atoi(L.col[1]));
+          if (writer.joinable()) writer.join();
           engine.destroy(ctx); fclose(out);
           return 1;
         }
-        if (n_in_both == 0) { engine.destroy(ctx); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
+        if (n_in_both == 0) { if (writer.joinable()) writer.join(); engine.destroy(ctx); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
         break;
       }
     }
@@ -533,8 +596,13 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     if (text.size() < nl) text.resize(nl);
     parallel_for(n_use, threads, format_line);
     const auto t_format = std::chrono::steady_clock::now();
-    for (size_t li = 0; li < n_use; li++) if (!text[li].empty()) fwrite(text[li].data(), 1, text[li].size(), out);
-    fflush(out);
+    // the rows of this chunk are written by a helper thread while the next chunk is read, parsed and computed
+    if (writer.joinable()) writer.join();
+    text.swap(text_w);
+    writer = std::thread([&text_w, n_use, out]() {
+      for (size_t li = 0; li < n_use; li++) if (!text_w[li].empty()) fwrite(text_w[li].data(), 1, text_w[li].size(), out);
+      fflush(out);
+    });
     const auto t_write = std::chrono::steady_clock::now();
     tm[0] += secs(t_begin, t_read); tm[1] += secs(t_read, t_parse); tm[2] += secs(t_parse, t_engine); tm[3] += secs(t_engine, t_format); tm[4] += secs(t_format, t_write);
     if (n_rows) {  // what the next chunk's leading no-data records print
@@ -546,6 +614,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       }
     }
   }
+  if (writer.joinable()) writer.join();
   if (getenv("PM_TIMING"))
     printf("[pm timing] vcf mode: read %.3f s, tokenise+parse %.3f s, engine %.3f s, format %.3f s, write %.3f s; %d threads\n", tm[0], tm[1], tm[2], tm[3], tm[4], threads);
   std::string err = rc == PM_OK ? std::string() : std::string("engine '") + engine.name + "': " + engine.last_error();

@@ -418,16 +418,17 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
   if (second)
     CUDA_TRY(pm::launch_sites(c->plan_x, c->d_run_x, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_spill, c->d_res_all, d_status_out, c->d_err, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  const bool with_ab = !c->par.denovo && !c->par.vcf_input;  // the allele balance is printed by the non-de-novo GLF writer only
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                            out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
-                           d_person_out, c->sm_count, c->stream));
+                           d_person_out, c->sm_count, with_ab, c->stream));
   if (second)
     CUDA_TRY(pm::launch_post(c->d_run_x, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                              out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
-                             d_person_out, c->sm_count, c->stream));
+                             d_person_out, c->sm_count, false, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-  c->launches = 4;  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact, k_post
+  c->launches = 4 + (with_ab ? 1 : 0);  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact, k_post [, k_post_ab]
   if (c->par.quick_call) c->launches += 3;
   if (second) c->launches += 3;
   c->timing_cached = false;
@@ -694,8 +695,10 @@ extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
   if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
   if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", c->plan.units_per_thread, c->plan.threads);
   else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site, %d units/thread in registers (%d units, %d in the L2 scratch), persistent grid %d (%d blocks/SM), "
-                "one TMA bulk copy per site, one block barrier per Brent round",
-                c->plan.units_per_thread, c->plan.threads, c->plan.units_per_thread, c->n_units, c->plan.n_spill, c->plan.grid, c->plan.blocks_per_sm);
+                "one TMA bulk copy per site, %s",
+                c->plan.units_per_thread, c->plan.threads, c->plan.units_per_thread, c->n_units, c->plan.n_spill, c->plan.grid, c->plan.blocks_per_sm,
+                c->plan.f3_offset && !c->plan.n_spill && !c->plan.es ? "H1-H3 of an autosomal site in one pass over Brent's monotone path (3 block barriers per monomorphic site)"
+                                                                      : "one hypothesis at a time over Brent's monotone path");
   return PM_OK;
 }
 

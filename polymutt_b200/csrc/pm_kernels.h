@@ -23,6 +23,8 @@ struct LaunchPlan {
   int blocks_per_sm;
   int es;                 // wide: the pedigree has extended families too (the ES instances of the kernel)
   int n_person;
+  int smem_bytes;         // wide: dynamic shared memory per block (site buffer [+ the one-pass partials])
+  int f3_offset;          // wide: byte offset of the one-pass H1..H3 partials in it, 0 = no room for them (that path is off)
 };
 
 // force_wide (tests, tuning scripts): {variant, threads} overrides the choice and sends even small pedigrees to the wide kernel
@@ -46,7 +48,7 @@ cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d
 cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                         const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
-                        int sm_count, cudaStream_t stream);
+                        int sm_count, bool with_ab, cudaStream_t stream);
 
 cudaError_t launch_pack_calls(const pm_person_result *d_person, size_t n, uint16_t *d_calls, int sm_count, cudaStream_t stream);
 

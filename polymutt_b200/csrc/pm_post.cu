@@ -269,26 +269,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
       if (nonauto) {
         r.ab = 0.0;  // not computed and not printed there (NucFam:1791-1800)
       } else if (!dn && !run->vcf_mode) {
-        double A = 0.0, Bsum = 0.0;
-        const double f0 = r.freq;
-        const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
-        for (int i = 0; i < np; i++) {
-          uint4 rec = recs[i];
-          int depth = rec_depth(rec);
-          int u11 = rec_lk(rec, g11), u12 = rec_lk(rec, g12), u22 = rec_lk(rec, g22);
-          double l11 = lut[u11], l12 = lut[u12], l22 = lut[u22];
-          double phet = (p12 * l12) / (p11 * l11 + p12 * l12 + p22 * l22);
-          if (phet > 1e-05 && depth > 0) {
-            int scale = u22 + u11 - 2 * u12 + 6 * depth;
-            int minimum = abs(u22 - u11);
-            if (scale < 4) scale = 4;
-            if (scale < minimum) scale = minimum;
-            int nref = (int)(0.5 * depth * (1 + (u22 - u11) / (scale + 1e-30)));
-            A += phet * nref;
-            Bsum += phet * depth;
-          }
-        }
-        r.ab = (0.05 + A) / (0.1 + Bsum);
+        r.ab = 0.5;  // k_post_ab, launched right behind this kernel, puts the allele balance here (a sum over ALL persons of the site)
       } else {
         r.ab = 0.5;
       }
@@ -298,10 +279,66 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
 }
 
 
+// CalculateAB (NucFam:1006-1039) for the emitted autosomal rows of a run without --denovo: one block per row, the persons
+// spread over its threads (the loop is 3,000 divisions long for 1,000 trios: on one thread of k_post it took longer than
+// everything else in the batch).  Per-person terms exactly as the reference's; their sum is taken as a tree (the printed
+// digits do not see the difference in the last bits).
+__global__ void __launch_bounds__(128) k_post_ab(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                                 const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
+                                                 const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
+                                                 size_t res_cap, pm_site_result *__restrict__ res_out) {
+  __shared__ double s_lut[256];
+  __shared__ double s_red[2][4];
+  if (run->denovo != 0 || run->vcf_mode != 0) return;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = run->lut[i];
+  __syncthreads();
+  const uint32_t n_emit = *n_emit_ptr;
+  const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
+  const int np = run->n_person;
+  for (size_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const uint32_t s = emit_sites[row];
+    const int cls = hdr[s].chr_class;
+    if ((run->site_filter == 1 && cls != PM_CHR_AUTO) || (run->site_filter == 2 && cls == PM_CHR_AUTO)) continue;
+    const pm_site_result *r = res_all + s;
+    if (r->status != PM_SITE_EMITTED || cls != PM_CHR_AUTO) continue;
+    const int a1 = r->allele1, a2 = r->allele2;
+    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+    const double f0 = r->freq;
+    const double p11 = f0 * f0, p12 = 2 * f0 * (1 - f0), p22 = (1 - f0) * (1 - f0);
+    const uint4 *recs = recs_all + (size_t)s * np;
+    double A = 0.0, Bsum = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      const uint4 rec = recs[i];
+      const int depth = rec_depth(rec);
+      const int u11 = rec_lk(rec, g11), u12 = rec_lk(rec, g12), u22 = rec_lk(rec, g22);
+      const double l11 = s_lut[u11], l12 = s_lut[u12], l22 = s_lut[u22];
+      const double phet = (p12 * l12) / (p11 * l11 + p12 * l12 + p22 * l22);
+      if (phet > 1e-05 && depth > 0) {
+        int scale = u22 + u11 - 2 * u12 + 6 * depth;
+        const int minimum = abs(u22 - u11);
+        if (scale < 4) scale = 4;
+        if (scale < minimum) scale = minimum;
+        const int nref = (int)(0.5 * depth * (1 + (u22 - u11) / (scale + 1e-30)));
+        A += phet * nref;
+        Bsum += phet * depth;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) { A += __shfl_xor_sync(0xffffffffu, A, o); Bsum += __shfl_xor_sync(0xffffffffu, Bsum, o); }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = A; s_red[1][threadIdx.x >> 5] = Bsum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) { a += s_red[0][w]; b += s_red[1][w]; }
+      res_out[row].ab = (0.05 + a) / (0.1 + b);
+    }
+    __syncthreads();
+  }
+}
+
 cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                         const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
-                        int sm_count, cudaStream_t stream) {
+                        int sm_count, bool with_ab, cudaStream_t stream) {
   if (max_rows == 0) return cudaSuccess;
   static_assert(sizeof(PostSmem) <= 48 * 1024, "k_post's tables fit in the default dynamic shared memory limit");
   size_t want = (max_rows * (size_t)n_fam + 127) / 128;
@@ -309,6 +346,9 @@ cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if (grid == 0) grid = 1;
   k_post<<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out);
+  if (!with_ab) return cudaGetLastError();
+  const size_t ab_cap = (size_t)sm_count * 8;
+  k_post_ab<<<(unsigned)(max_rows < ab_cap ? max_rows : ab_cap), 128, 0, stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out);
   return cudaGetLastError();
 }
 

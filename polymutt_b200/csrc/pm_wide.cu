@@ -52,10 +52,11 @@ struct WideShared {
   int red_e[32];
   double red0_m[32];                  // the H0 product (first round of H1 under --denovo)
   int red0_e[32];
-  int red_i[4 * 32];                  // per-warp integer partials (depth, samples, mapq, lk sum)
+  int4 red_i[2][32];                  // per-warp integer partials (depth, samples, mapq, lk sum), double-buffered by site parity
   double next[4];                     // broadcast by thread 0 after every round: p, r = p/q, q^(4 * units per partial product)
   // The monotone path (see spec_table_ol): evaluation points Brent visits when no point beats the first one
   double spec_p[kMaxSpec], spec_r[kMaxSpec], spec_q[kMaxSpec];  // p, p/q, q^(4 * units per speculative partial product)
+  double spec_qn[9][kMaxSpec];        // q^(4 n), n = 0..8 units of a thread (the one-pass H1..H3 evaluation)
   double spec_m[kMaxSpec][17];        // per point, per warp: partial products of the speculative round (17: bank padding)
   int spec_e[kMaxSpec][17];
   double spec_ll[kMaxSpec];           // log10 likelihood at every point of the path
@@ -319,6 +320,15 @@ __device__ __forceinline__ int scale_slot(const double (&b)[5], bool nuclear, do
   out[0] = b[0] * sc; out[1] = b[1] * sc; out[2] = b[2] * sc; out[3] = b[3] * sc; out[4] = b[4] * sc;
   return (ex - 1023) & 0xfffff;
 }
+// The same without the fragile branch (the one-pass evaluation gives a site with a fragile unit up anyway): the scaled
+// coefficients are always written, the code carries kSlotFragile where scale_slot would have returned it.
+__device__ __forceinline__ int scale_slot_nb(const double (&b)[5], bool nuclear, double (&out)[5]) {
+  const double sum = ((b[0] + b[1]) + (b[2] + b[3])) + b[4];
+  const int ex = (__double2hiint(sum) >> 20) & 0x7ff;
+  const double sc = __hiloint2double((2046 - ex) << 20, 0);
+  out[0] = b[0] * sc; out[1] = b[1] * sc; out[2] = b[2] * sc; out[3] = b[3] * sc; out[4] = b[4] * sc;
+  return ((ex - 1023) & 0xfffff) | ((ex < 66 && nuclear) ? kSlotFragile : 0);
+}
 __device__ __forceinline__ int one_slot(const uint4 *recs, int d, int g11, int g12, int g22, int mode, double *out);
 
 // Two slots of a thread per call (slot = packed unit descriptor, -1 = none): when both are nuclear families with the
@@ -369,14 +379,13 @@ __device__ PM_SLOT_INLINE int slot_single_ol(const uint4 *recs, int d, int g11, 
   return one_slot(recs, d, g11, g12, g22, mode, out);
 }
 
-// One slot, the three hypotheses H1..H3 = (ref, ts), (ref, tv1), (ref, tv2) of a site at once (autosome).  They share the
-// reference-homozygous genotype and, above all, every byte extraction and table look-up of the slot's records: the
+// One unit, the three hypotheses H1..H3 = (ref, ts), (ref, tv1), (ref, tv2) of a site at once (autosome).  They share the
+// reference-homozygous genotype and, above all, every byte extraction and table look-up of the unit's records: the
 // ten likelihoods of a kid are fetched once, seven rows of the mutation matrix (ref/ref, three ref/alt, three alt/alt)
 // give the mutation-mixed likelihoods of all three hypotheses — 70 multiply-adds and 11 look-ups per kid instead of
 // 90 and 30 — and the seventeen independent dependency chains keep the FP64 pipe busy where one hypothesis alone
-// waits on latency.  out0..out2: 5 scaled coefficients each; returns the three slot codes (scale_slot).
-struct Codes3 { int c0, c1, c2; };
-// The unscaled coefficients b[h][0..4] of one unit (first column, nkids; -1 = a single founder) for H1..H3.
+// waits on latency.  b[h][0..4]: the unscaled coefficients (first column, nkids; -1 = a single founder); bit for bit
+// what nuclear_quartic_n / one_slot give for each hypothesis on its own.
 __device__ __forceinline__ void unit_h123(const uint4 *recs, int first, int nkids, int ref, int denovo, double (&b)[3][5]) {
   const int alt[3] = {poly_ts(ref), poly_tvs1(ref), poly_tvs2(ref)};
   const int grr = geno_index(ref, ref);
@@ -393,11 +402,8 @@ __device__ __forceinline__ void unit_h123(const uint4 *recs, int first, int nkid
     }
     return;
   }
-  double p0 = 1.0, p1[3], p2[3], p4[3], p5[3], p8[3];  // kid products (p1 carries 2^nkids, p4 4^nkids, p5 2^nkids)
-#pragma unroll
-  for (int h = 0; h < 3; h++) p1[h] = p2[h] = p4[h] = p5[h] = p8[h] = 1.0;
-  for (int k = 0; k < nkids; k++) {
-    double drr, dra[3], daa[3];
+  // the mutation-mixed (or plain) likelihoods of kid k under the seven genotypes the three hypotheses name
+  auto kid = [&](int k, double &drr, double (&dra)[3], double (&daa)[3]) {
     if (denovo) {  // CalcDenovoMutLk, NucFam:1553-1562
       const uint4 rk = recs[first + 2 + k];
       double l[10];
@@ -422,7 +428,28 @@ __device__ __forceinline__ void unit_h123(const uint4 *recs, int first, int nkid
 #pragma unroll
       for (int h = 0; h < 3; h++) { dra[h] = s_lut[kb[gra[h]]]; daa[h] = s_lut[kb[gaa[h]]]; }
     }
-    // likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome), the halves and quarters taken out
+  };
+  // kid products (p1 carries 2^nkids, p4 4^nkids, p5 2^nkids); likelihoodONEKid{,_denovo}, NucFam:1202-1296 (autosome),
+  // the halves and quarters taken out.  The first kid starts them (1.0 * x = x exactly: same bits as a loop from 1.0).
+  double p0 = 1.0, p1[3], p2[3], p4[3], p5[3], p8[3];
+#pragma unroll
+  for (int h = 0; h < 3; h++) p1[h] = p2[h] = p4[h] = p5[h] = p8[h] = 1.0;
+  if (nkids > 0) {
+    double drr, dra[3], daa[3];
+    kid(0, drr, dra, daa);
+    p0 = drr;
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      p1[h] = drr + dra[h];
+      p2[h] = dra[h];
+      p4[h] = fma(2.0, dra[h], drr) + daa[h];
+      p5[h] = dra[h] + daa[h];
+      p8[h] = daa[h];
+    }
+  }
+  for (int k = 1; k < nkids; k++) {
+    double drr, dra[3], daa[3];
+    kid(k, drr, dra, daa);
     p0 *= drr;
 #pragma unroll
     for (int h = 0; h < 3; h++) {
@@ -447,24 +474,6 @@ __device__ __forceinline__ void unit_h123(const uint4 *recs, int first, int nkid
     b[h][0] = p8[h] * (faa * maa);
   }
 }
-__device__ __noinline__ Codes3 slot_h123_ol(const uint4 *recs, int d, int ref, int denovo, double *out0, double *out1, double *out2) {
-  Codes3 ret;
-  double *const out[3] = {out0, out1, out2};
-  if (d < 0) {
-#pragma unroll
-    for (int h = 0; h < 3; h++) { out[h][0] = 0.25; out[h][1] = 1.0; out[h][2] = 1.5; out[h][3] = 1.0; out[h][4] = 0.25; }
-    ret.c0 = ret.c1 = ret.c2 = kSlotNeutral;
-    return ret;
-  }
-  const int first = d & 0xfffff, nkids = ((d >> 20) & 0xff) - 1;
-  double b[3][5];
-  unit_h123(recs, first, nkids, ref, denovo, b);
-  ret.c0 = scale_slot(b[0], nkids >= 0, out0);
-  ret.c1 = scale_slot(b[1], nkids >= 0, out1);
-  ret.c2 = scale_slot(b[2], nkids >= 0, out2);
-  return ret;
-}
-
 // chrX / chrY / MT slot; mode = denovo | chr_class << 1
 __device__ __noinline__ int slot_na_ol(const uint4 *recs, int d, int g11, int g12, int g22, int mode, double *out) {
   if (d < 0) { out[0] = 0.25; out[1] = 1.0; out[2] = 1.5; out[3] = 1.0; out[4] = 0.25; return kSlotNeutral; }
@@ -554,6 +563,35 @@ __device__ __noinline__ ME rare_factor_ol(const RareCtx *c, double p, double r, 
 }
 
 __device__ __noinline__ void var_posterior_ol(pm_site_result *r, int ref, int n) { var_posterior(*r, ref, n); }
+// The same by a whole warp (all 32 lanes call it; *r is final and visible to them): lane i takes the exp10 of hypothesis
+// i, the sum is formed in the reference's order — same bits as var_posterior, a third of its dependent latency.  Lane 0
+// writes the result.
+__device__ __noinline__ void var_posterior_warp_ol(pm_site_result *r, int ref, int n) {
+  const int lane = threadIdx.x & 31;
+  int maxidx = 0;
+  double mx = r->varllk[0];
+  for (int i = 0; i < n; i++) if (mx < r->varllk[i]) { mx = r->varllk[i]; maxidx = i; }
+  const double e = lane < n ? exp10(r->varllk[lane] - mx) : 0.0;
+  double sum = 0.0;
+  for (int i = 0; i < n; i++) sum += __shfl_sync(0xffffffffu, e, i);
+  if (lane == 0) {
+    r->var_post_prob = 1 / sum;
+    int a1, a2;
+    if (maxidx == 0) {
+      int idx = 1;
+      double m2 = r->varllk[1];
+      for (int i = 1; i < 4; i++) if (m2 < r->varllk[i]) { m2 = r->varllk[i]; idx = i; }
+      hyp_alleles(idx, ref, a1, a2);
+    } else {
+      hyp_alleles(maxidx, ref, a1, a2);
+    }
+    r->allele1 = (uint8_t)a1; r->allele2 = (uint8_t)a2;
+    r->maxidx = (int8_t)maxidx;
+    r->n_hyp = (uint8_t)n;
+    r->poly_qual = (r->var_post_prob > 0.9999999999) ? 100.0 : -10 * log10(1 - r->var_post_prob);
+  }
+  __syncwarp();
+}
 __device__ __noinline__ int site_decide_ol(const DevRun *run, pm_site_result *r, double lk_mono) { return site_decide(run, *r, lk_mono) ? 1 : 0; }
 
 __device__ __forceinline__ void publish_next(double p, int log2per) {
@@ -605,6 +643,11 @@ __device__ __noinline__ void spec_table_ol(double tol, int log2sper) {
     qa *= qa;
     for (int i = 0; i < log2sper; i++) qa *= qa;
     s_ws.spec_p[n] = p; s_ws.spec_r[n] = p * fast_rcp(q); s_ws.spec_q[n] = qa;
+    {
+      const double q4 = (q * q) * (q * q);
+      double qn = 1.0;
+      for (int i = 0; i <= 8; i++) { s_ws.spec_qn[i][n] = qn; qn *= q4; }
+    }
     n++;
     if (!brent_feed_fast(st, n == 1 ? 0.0 : 1.0, tol)) { complete = 1; break; }
   }
@@ -655,17 +698,7 @@ struct WideEval {
   // PolymorphismLogLikelihood (FLSeq:91-104) for alleles (a1, a2).  On return (after a block barrier) s_ws.brent holds
   // min / fmin, s_ws.n_eval the rounds, s_ws.h0 the H0 term.
   // with_h0: also the product of the p^4 coefficients (the hom-ref hypothesis under --denovo, main:455-462).
-  // Coefficients of H1..H3 for all my slots in one pass over the site (slot_h123_ol): pre[h][k][0..4], codes[h][k].
-  __device__ __forceinline__ void setup3(int ref, bool denovo, double (&pre)[3][U][5], int (&codes)[3][U]) {
-#pragma unroll
-    for (int k = 0; k < U; k++) {
-      const Codes3 c = slot_h123_ol(recs, desc[k], ref, denovo ? 1 : 0, pre[0][k], pre[1][k], pre[2][k]);
-      codes[0][k] = c.c0; codes[1][k] = c.c1; codes[2][k] = c.c2;
-    }
-  }
-
-  // pre / pre_codes: this hypothesis' coefficients from setup3, or nullptr to build them here.
-  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo, bool with_h0, const double (*pre)[5] = nullptr, const int *pre_codes = nullptr) {
+  __device__ __forceinline__ void optimize(int a1, int a2, bool denovo, bool with_h0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (T + 31) >> 5;
     const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
     const int mode = (denovo ? 1 : 0) | (NA ? (cls << 1) : 0);
@@ -684,14 +717,7 @@ struct WideEval {
     // The out-of-line slot builders write into a staging array in local memory (their results would be spilled around
     // the calls anyway); the coefficients move to registers once, after the last call.
     double stage[U][5];
-    if (pre) {
-#pragma unroll
-      for (int k = 0; k < U; k++) {
-        account(pre_codes[k], k);
-#pragma unroll
-        for (int a = 0; a < 5; a++) stage[k][a] = pre[k][a];
-      }
-    } else if constexpr (NA) {
+    if constexpr (NA) {
 #pragma unroll
       for (int k = 0; k < U; k++) account(slot_na_ol(recs, desc[k], g11, g12, g22, mode, stage[k]), k);
     } else if constexpr (U == 1) {
@@ -844,7 +870,7 @@ struct WideEval {
   // not depend on the data, so: unit by unit, the coefficients of the three hypotheses are built in registers and
   // multiplied into 3 x 10 running products straight away — they are never stored — then one block barrier, warp 0 takes
   // the 30 logarithms (lane = hypothesis * 10 + point; lane 31: H0) and checks the three paths with one ballot.  If every
-  // hypothesis stays on its path (any monomorphic site) thread 0 calls done(ll1, ll2, ll3, ll_h0) and the site has cost two
+  // hypothesis stays on its path (any monomorphic site) warp 0 calls done(ll1, ll2, ll3, ll_h0) and the site has cost two
   // barriers; otherwise (a path left, a fragile unit, a path longer than ten points) nothing has been written and the
   // caller goes through optimize() hypothesis by hypothesis.  Same evaluation order as optimize(): the same bits.
   // fm / fe: per-warp partials, entry (lane, warp) at lane * nwp + warp.
@@ -855,36 +881,34 @@ struct WideEval {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (T + 31) >> 5;
     const int ns = s_ws.spec_n;
     if (!s_ws.spec_complete || ns > NP) return false;
+    // my units are t, t + T, ...: the first `mine` slots (no neutral slots here: the products start from q^(4 mine))
+    const int mine = t < n_units ? min(U, (n_units - t + T - 1) / T) : 0;
     double acc[3][NP];
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-      const double qf = s_ws.spec_q[j < ns ? j : ns - 1];
+      const double qf = s_ws.spec_qn[mine][j < ns ? j : ns - 1];
 #pragma unroll
       for (int h = 0; h < 3; h++) acc[h][j] = qf;
     }
-    int Kall[3] = {0, 0, 0}, K0 = 0;
+    int Kall[3] = {0, 0, 0};
     ME h0;
     h0.m = 1.0; h0.e = 0;
     int bail = 0;
 #pragma unroll 1
-    for (int k = 0; k < U; k++) {
-      const int u = t + k * T;
+    for (int k = 0; k < mine; k++) {
+      const int4 du = __ldg(reinterpret_cast<const int4 *>(run->units + (t + k * T)));  // first, nkids, kid0, sex
       double c[3][5];
-      if (u < n_units) {
-        const int4 du = __ldg(reinterpret_cast<const int4 *>(run->units + u));  // first, nkids, kid0, sex
+      {
         double b[3][5];
         unit_h123(recs, du.x, du.y, ref, dn ? 1 : 0, b);
 #pragma unroll
         for (int h = 0; h < 3; h++) {
-          const int code = scale_slot(b[h], du.y >= 0, c[h]);
-          if (code & kSlotFragile) { bail = 1; Kall[h] += 2; }
-          else { const int e = (code << 12) >> 12; Kall[h] += e; if (h == 0) K0 += e; }
+          const int code = scale_slot_nb(b[h], du.y >= 0, c[h]);
+          bail |= code & kSlotFragile;
+          Kall[h] += (code << 12) >> 12;  // sign-extend the 20-bit exponent
         }
-        if (dn) me_mul(h0, c[0][4]);
-      } else {
-#pragma unroll
-        for (int h = 0; h < 3; h++) { c[h][0] = 0.25; c[h][1] = 1.0; c[h][2] = 1.5; c[h][3] = 1.0; c[h][4] = 0.25; Kall[h] += 2; }
       }
+      if (dn) me_mul(h0, c[0][4]);
 #pragma unroll
       for (int j = 0; j < NP; j++) {
         const double r = s_ws.spec_r[j < ns ? j : ns - 1];
@@ -892,6 +916,7 @@ struct WideEval {
         for (int h = 0; h < 3; h++) acc[h][j] *= fma(fma(fma(fma(c[h][4], r, c[h][3]), r, c[h][2]), r, c[h][1]), r, c[h][0]);
       }
     }
+    const int K0 = Kall[0];
 #pragma unroll
     for (int h = 0; h < 3; h++) {
 #pragma unroll
@@ -931,7 +956,9 @@ struct WideEval {
       const bool anyz = __any_sync(0xffffffffu, hz);
       if (lane == 0) { const ME w = me_split_pos(hm); fm[31 * nwp + warp] = anyz ? 0.0 : w.m; fe[31 * nwp + warp] = w.e + he; }
     }
+    PM_TICK(2);
     if (__syncthreads_or(bail)) return false;
+    PM_TICK(6);
     if (warp == 0) {
       const int hh = lane / NP, j = lane - hh * NP;
       double ll = 0.0;
@@ -952,13 +979,12 @@ struct WideEval {
       const unsigned okmask = __ballot_sync(0xffffffffu, ok);
       const double l1 = __shfl_sync(0xffffffffu, ll, 0), l2 = __shfl_sync(0xffffffffu, ll, NP), l3 = __shfl_sync(0xffffffffu, ll, 2 * NP);
       const double lh = __shfl_sync(0xffffffffu, ll, 31);
-      if (lane == 0) {
-        const bool good = okmask == 0xffffffffu;
-        s_ws.ibcast[0] = good ? 1 : 0;
-        if (good) done(l1, l2, l3, lh);
-      }
+      const bool good = okmask == 0xffffffffu;
+      if (lane == 0) s_ws.ibcast[0] = good ? 1 : 0;
+      if (good) done(l1, l2, l3, lh);  // all lanes of warp 0
     }
     block_sync();
+    PM_TICK(3);
     return s_ws.ibcast[0] != 0;
   }
 
@@ -1019,12 +1045,12 @@ struct WideEval {
 template <int U, int MAXT, int MINB, bool NA, bool ES>
 __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                                            const uint4 *__restrict__ recs_all, const double *__restrict__ mono_all,
-                                                           size_t n_sites, double *__restrict__ spill_all, int n_spill,
+                                                           size_t n_sites, double *__restrict__ spill_all, int n_spill, int f3_off,
                                                            pm_site_result *__restrict__ res, uint16_t *__restrict__ status,
                                                            int *__restrict__ err) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   WideShared *const ws = &s_ws;
-  constexpr int F3W = MAXT <= 32 ? 1 : MAXT / 32 + 1;  // warps per block (+1: an odd stride for the 32 lanes that read the partials)
+  constexpr int F3W = MAXT <= 32 ? 1 : MAXT / 32 + 1;  // warps per block (+1: an odd stride for the 32 lanes that read the partials); plan_wide knows it too
   if (NA ? ((err[1] == 0 && run->site_filter != 2) || run->site_filter == 1) : run->site_filter == 2) return;
   const int np = run->n_person;
   unsigned char *site_base = smem_raw;  // the dynamic part is the site buffer alone
@@ -1073,6 +1099,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
     if (NA) ev.cls = cls;
     const bool bad = ref < 1 || ref > 4 || bad_cls;
     unsigned n_hyp = 0, n_eval = 0;
+    bool synced = false;  // a block barrier since the wait: every iteration needs one (nobody may run two sites ahead:
+                          // the mbarrier's parity tells adjacent phases apart only; the site buffer is refilled behind it)
     if (NA ? (bad || cls == PM_CHR_AUTO) : (!bad && cls != PM_CHR_AUTO)) {  // the other instance's site
       if (!NA && threadIdx.x == 0) atomicExch(err + 1, 1);
       skip = true;
@@ -1098,20 +1126,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
       }
       dsum = __reduce_add_sync(0xffffffffu, dsum); nsamp = __reduce_add_sync(0xffffffffu, nsamp);
       mq = __reduce_add_sync(0xffffffffu, mq); lksum = __reduce_add_sync(0xffffffffu, lksum);
-      if (lane == 0) { ws->red_i[warp] = dsum; ws->red_i[32 + warp] = nsamp; ws->red_i[64 + warp] = mq; ws->red_i[96 + warp] = lksum; }
+      const int par = (int)(phase & 1);  // (flipped after the wait: the buffer of this site)
+      if (lane == 0) ws->red_i[par][warp] = make_int4(dsum, nsamp, mq, lksum);
       block_sync();
-      if (threadIdx.x == 0) {  // the totals, two divisions and the filters: one thread, the verdict is broadcast
-        int D = 0, NS = 0, MQ = 0, LK = 0;
-        for (int w = 0; w < nwarp; w++) { D += ws->red_i[w]; NS += ws->red_i[32 + w]; MQ += ws->red_i[64 + w]; LK += ws->red_i[96 + w]; }
-        double perc_samp = 0.0, avg_mq = 0.0;
-        if (NS > 0) { avg_mq = (double)MQ / (double)NS; perc_samp = (double)NS / (double)np; }
-        int st = 0;
-        if (D < run->min_total_depth) st = PM_SITE_MIN_DEPTH;
-        else if (run->max_total_depth > 0 && D > run->max_total_depth) st = PM_SITE_MAX_DEPTH;
-        else if (perc_samp * 100 < run->min_ps) st = PM_SITE_MIN_PS;
-        else if (avg_mq < run->min_map_quality) st = PM_SITE_MIN_MAPQ;
+      synced = true;
+      // the totals, two divisions and the filters: every thread for itself (no second barrier, no broadcast)
+      int D = 0, NS = 0, MQ = 0, LK = 0;
+      for (int w = 0; w < nwarp; w++) { const int4 x = ws->red_i[par][w]; D += x.x; NS += x.y; MQ += x.z; LK += x.w; }
+      double perc_samp = 0.0, avg_mq = 0.0;
+      if (NS > 0) { avg_mq = (double)MQ / (double)NS; perc_samp = (double)NS / (double)np; }
+      int st = 0;
+      if (D < run->min_total_depth) st = PM_SITE_MIN_DEPTH;
+      else if (run->max_total_depth > 0 && D > run->max_total_depth) st = PM_SITE_MAX_DEPTH;
+      else if (perc_samp * 100 < run->min_ps) st = PM_SITE_MIN_PS;
+      else if (avg_mq < run->min_map_quality) st = PM_SITE_MIN_MAPQ;
+      if (threadIdx.x == 0) {
         ws->lk_mono = -(double)LK / 10.0;  // sum_i -lk_i/10 with the integer sum taken first (exact), one division
-        ws->ibcast[3] = st;
         pm_site_result &r = ws->r;
         memset(&r, 0, sizeof r);
         r.site = (uint32_t)s; r.maxidx = -1;
@@ -1120,8 +1150,6 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
         r.reserved = (uint16_t)ref;
         if (st != 0) { res[s] = r; status[s] = status_word(r); }
       }
-      block_sync();
-      const int st = ws->ibcast[3];
       PM_TICK(1);
       skip = st != 0;
     }
@@ -1149,17 +1177,30 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
       bool decided = false;
       if constexpr (!NA && !ES) {
         // H1..H3 (+ H0) in one pass wherever every hypothesis stays on Brent's monotone path: any monomorphic site
-        __shared__ double f3_m[32 * F3W];
-        __shared__ int f3_e[32 * F3W];
-        if (!vcf && ev.spill == nullptr) {
+        // (the per-warp partials of that pass sit behind the site buffer where the block's shared memory has room for them)
+        double *const f3_m = reinterpret_cast<double *>(smem_raw + f3_off);
+        int *const f3_e = reinterpret_cast<int *>(f3_m + 32 * F3W);
+        if (f3_off != 0 && !vcf && ev.spill == nullptr) {
           decided = ev.fast3(ref, dn, f3_m, f3_e, F3W, [&](double l1, double l2, double l3, double lh0) {
-            const double p0 = ws->spec_p[0];
-            site_store_hyp(run, ws->r, 1, l1, p0, cls);
-            site_store_hyp(run, ws->r, 2, l2, p0, cls);
-            site_store_hyp(run, ws->r, 3, l3, p0, cls);
-            if (dn) ws->r.varllk[0] = run->cls_log[cls][0] + lh0;
-            n_hyp += dn ? 4 : 3; n_eval += 3 * (unsigned)ws->spec_n + (dn ? 1 : 0);
-            decide(3);
+            if (lane == 0) {
+              PM_TICK(4);
+              const double p0 = ws->spec_p[0];
+              site_store_hyp(run, ws->r, 1, l1, p0, cls);
+              site_store_hyp(run, ws->r, 2, l2, p0, cls);
+              site_store_hyp(run, ws->r, 3, l3, p0, cls);
+              ws->r.varllk[0] = run->cls_log[cls][0] + (dn ? lh0 : ws->lk_mono);
+              ws->r.varllk_noprior[0] = ws->r.varllk[0] - run->cls_log[cls][0];
+              ws->r.varfreq[0] = 1.0;
+              n_hyp += dn ? 4 : 3; n_eval += 3 * (unsigned)ws->spec_n + (dn ? 1 : 0);
+              PM_TICK(7);
+            }
+            __syncwarp();
+            var_posterior_warp_ol(&ws->r, ref, 4);  // (as decide(3), the posterior by the whole warp)
+            if (lane == 0) {
+              const bool more = ws->r.var_post_prob < 0.99;  // main:499
+              ws->ibcast[1] = more;
+              ws->ibcast[2] = more ? 0 : site_decide_ol(run, &ws->r, ws->lk_mono);
+            }
           });
           if (decided) step = 3;
         }
@@ -1213,13 +1254,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
 #endif
       }
     }
-    __syncthreads();  // ws->r is final; nobody reads the site buffer any more
-    if (threadIdx.x == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
-    if (!skip && warp == 0) {  // the 256-byte result leaves as one coalesced 32 x 8-byte store
-      static_assert(sizeof(pm_site_result) == 256, "pm_site_result must be 256 bytes");
-      reinterpret_cast<unsigned long long *>(&res[s])[lane] = reinterpret_cast<const unsigned long long *>(&ws->r)[lane];
+    // Every path that read the site buffer has passed a block barrier since (the statistics' one, or the one an
+    // optimisation ends with): the buffer can be refilled.  ws->r is thread 0's; the other lanes of warp 0 only help to
+    // store it.  No block barrier here: the other warps are already waiting for the next site.
+    if (skip && !synced) __syncthreads();
+    if (warp == 0) {
+      __syncwarp();
+      if (lane == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
+      if (!skip) {  // the 256-byte result leaves as one coalesced 32 x 8-byte store
+        static_assert(sizeof(pm_site_result) == 256, "pm_site_result must be 256 bytes");
+        reinterpret_cast<unsigned long long *>(&res[s])[lane] = reinterpret_cast<const unsigned long long *>(&ws->r)[lane];
+      }
+      __syncwarp();
     }
-    __syncthreads();  // ws->r is reused by the next iteration
   }
 }
 
@@ -1239,18 +1286,42 @@ static size_t wide_smem_bytes(int n_person) {  // dynamic part = the site buffer
 //   variant 4: U=8 T=64..128   ..1024         168 registers, 3 blocks/SM at T=128 (measured on B200, 1,000 trios --denovo:
 //                                             9.7 M sites/s; U=16 T=64: 7.4 M; U=8 T=128 at 128 registers, 4 blocks/SM: 8.3 M)
 //   variant 5: U=8 T=160..512  ..4096 (+ the L2 scratch beyond)   128 registers
+//   (also measured with the one-pass H1..H3 evaluation: 160 threads x 3 blocks at 96 registers 10.0 M, 256 x 2 at 128 registers
+//    8.8 M, 192 x 3 at 112 registers 8.0 M against 13.1 M for 128 x 3 at 168 registers: the spills cost more than the warps bring)
 #define PM_WIDE_VARIANTS(X) X(0, 1, 32, 16) X(1, 2, 32, 16) X(2, 4, 32, 12) X(3, 8, 32, 10) X(4, 8, 128, 3) X(5, 8, 512, 1)
+#define X(V_, U_, MT_, MB_) U_,
+static const int kVariantU[] = {PM_WIDE_VARIANTS(X)};
+#undef X
+#define X(V_, U_, MT_, MB_) MT_,
+static const int kVariantMaxT[] = {PM_WIDE_VARIANTS(X)};
+#undef X
+static const int kNumVariants = (int)(sizeof(kVariantU) / sizeof(kVariantU[0]));
 
+// The dynamic shared-memory limit of a kernel is a property of the (instantiation, device) pair, shared by every context
+// of the process: it is raised to everything the SM offers beside the kernel's static part, never to one pedigree's
+// need (a second engine with a smaller pedigree on the same instantiation must not lower it under the first one).
+template <typename K>
+static cudaError_t wide_raise_smem(K kernel, size_t smem) {
+  int dev = 0, optin = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  const long long room = (long long)optin - (long long)fa.sharedSizeBytes;
+  if ((long long)smem > room) return cudaErrorInvalidValue;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
+}
 template <int U, int MAXT, int MINB>
 static cudaError_t wide_attr(bool es, size_t smem, int threads, int *per_sm) {
   cudaError_t e;
   if (es) {
-    e = cudaFuncSetAttribute(k_sites_wide<U, MAXT, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U, MAXT, MINB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, true>, smem);
+    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, true>, smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, true>, threads, smem);
   } else {
-    e = cudaFuncSetAttribute(k_sites_wide<U, MAXT, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sites_wide<U, MAXT, MINB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, false>, smem);
+    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, false>, smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, false>, threads, smem);
   }
   return e;
@@ -1261,17 +1332,17 @@ static void wide_launch(const LaunchPlan &plan, unsigned grid, size_t smem, cuda
                         const uint4 *d_recs, const double *d_mono, size_t n_sites, double *d_spill, pm_site_result *d_res, uint16_t *d_status,
                         int *d_err) {
   if (plan.es) {
-    k_sites_wide<U, MAXT, MINB, false, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, d_res, d_status, d_err);
-    k_sites_wide<U, MAXT, MINB, true, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, false, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, true, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
   } else {
-    k_sites_wide<U, MAXT, MINB, false, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, d_res, d_status, d_err);
-    k_sites_wide<U, MAXT, MINB, true, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, false, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, true, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
   }
 }
 
 cudaError_t launch_sites_wide(const LaunchPlan &plan, const DevRun *d_run, const pm_site_hdr *d_hdr, const uint4 *d_recs, const double *d_mono,
                               size_t n_sites, double *d_spill, pm_site_result *d_res, uint16_t *d_status, int *d_err, cudaStream_t stream) {
-  const size_t smem = wide_smem_bytes(plan.n_person);
+  const size_t smem = (size_t)plan.smem_bytes;
   const unsigned grid = (unsigned)(n_sites < (size_t)plan.grid ? n_sites : (size_t)plan.grid);
   cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
@@ -1298,23 +1369,33 @@ cudaError_t plan_wide(LaunchPlan *plan, int n_person, int n_units, int n_es, int
   else if (n_units <= 1024) { variant = 4; U = 8; T = up32((n_units + 7) / 8); }
   else { variant = 5; U = 8; T = up32((n_units + 7) / 8); if (T > 512) T = 512; }
   if (force) {
-    static const int vu[] = {1, 2, 4, 8, 8, 8}, vmax[] = {32, 32, 32, 32, 128, 512};
-    if (force[0] < 0 || force[0] > 5 || force[1] < 32 || force[1] % 32 || force[1] > vmax[force[0]]) return cudaErrorInvalidValue;
-    variant = force[0]; T = force[1]; U = vu[variant];
+    if (force[0] < 0 || force[0] >= kNumVariants || force[1] < 32 || force[1] % 32 || force[1] > kVariantMaxT[force[0]]) return cudaErrorInvalidValue;
+    variant = force[0]; T = force[1]; U = kVariantU[variant];
   }
   plan->variant = variant;
   plan->threads = T;
   plan->units_per_thread = U;
   plan->n_spill = n_units > T * U ? n_units - T * U : 0;
   if (plan->n_spill > 32 * T) return cudaErrorNotSupported;  // the fragile-unit mask of the spilled units is 32 bits per thread
-  const size_t smem = wide_smem_bytes(n_person);
-  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  const size_t site_smem = wide_smem_bytes(n_person);
+  if (site_smem > 227 * 1024) return cudaErrorNotSupported;
+  // the one-pass H1..H3 evaluation keeps 32 x (warps + 1) partial products (8 + 4 bytes) behind the site buffer; a
+  // pedigree that fills the SM's shared memory by itself goes without that pass (same results, one hypothesis at a time)
+  const int f3w = kVariantMaxT[variant] <= 32 ? 1 : kVariantMaxT[variant] / 32 + 1;
+  const size_t f3_bytes = (size_t)32 * f3w * 12;
   int per_sm = 1;
   cudaError_t e = cudaErrorInvalidValue;
-  switch (variant) {
+  for (int with_f3 = 1; with_f3 >= 0; with_f3--) {
+    const size_t smem = site_smem + (with_f3 ? f3_bytes : 0);
+    switch (variant) {
 #define X(V_, U_, MT_, MB_) case V_: e = wide_attr<U_, MT_, MB_>(plan->es != 0, smem, T, &per_sm); break;
-    PM_WIDE_VARIANTS(X)
+      PM_WIDE_VARIANTS(X)
 #undef X
+    }
+    plan->smem_bytes = (int)smem;
+    plan->f3_offset = with_f3 ? (int)site_smem : 0;
+    if (e == cudaSuccess && per_sm >= 1) break;
+    (void)cudaGetLastError();
   }
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;

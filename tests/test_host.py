@@ -224,6 +224,20 @@ def test_batched_multithreaded_ingest_equals_the_one_site_at_a_time_merge(tools_
     for o in outs[1:]:
         assert len(o.hdr) == len(ref.hdr)
         assert np.array_equal(o.hdr, ref.hdr) and np.array_equal(o.recs, ref.recs)
+    # every other file gzip-compressed in place (told apart by their first two bytes: gzip goes through zlib, plain files are
+    # read as they are): same batch
+    import gzip
+    for l in gif:
+        key, path = l.split()
+        if int(key) % 2 and key != "10":
+            raw = open(path, "rb").read()
+            with gzip.open(path, "wb", compresslevel=1) as z:
+                z.write(raw)
+    out = str(d / "outz.pmpk")
+    subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out, "--batched", "3"],
+                   check=True, stderr=subprocess.DEVNULL)
+    z = load_pmpk(out)
+    assert np.array_equal(z.hdr, ref.hdr) and np.array_equal(z.recs, ref.recs)
 
 
 def test_synthetic_generator_is_seeded_and_well_formed():

@@ -695,8 +695,9 @@ extern "C" int pm_describe_plan(pm_ctx *c, char *buf, size_t len) {
   if (!c || !buf || !len) return fail(PM_EINVAL, "null argument");
   if (c->plan.kind == pm::LaunchPlan::NARROW) snprintf(buf, len, "k_sites_narrow<%d>: one thread per site, %d threads/block", c->plan.units_per_thread, c->plan.threads);
   else snprintf(buf, len, "k_sites_wide<U=%d>: one block of %d threads per site, %d units/thread in registers (%d units, %d in the L2 scratch), persistent grid %d (%d blocks/SM), "
-                "one TMA bulk copy per site, %s",
+                "%s, %s",
                 c->plan.units_per_thread, c->plan.threads, c->plan.units_per_thread, c->n_units, c->plan.n_spill, c->plan.grid, c->plan.blocks_per_sm,
+                c->plan.variant == 6 ? "the site's records read from global memory (too large for shared memory)" : "one TMA bulk copy per site",
                 c->plan.f3_offset && !c->plan.n_spill && !c->plan.es ? "H1-H3 of an autosomal site in one pass over Brent's monotone path (3 block barriers per monomorphic site)"
                                                                       : "one hypothesis at a time over Brent's monotone path");
   return PM_OK;

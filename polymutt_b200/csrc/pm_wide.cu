@@ -571,11 +571,16 @@ __device__ __noinline__ void var_posterior_warp_ol(pm_site_result *r, int ref, i
   int maxidx = 0;
   double mx = r->varllk[0];
   for (int i = 0; i < n; i++) if (mx < r->varllk[i]) { mx = r->varllk[i]; maxidx = i; }
-  const double e = lane < n ? exp10(r->varllk[lane] - mx) : 0.0;
+  // (on a monomorphic site of a large pedigree every other hypothesis lies hundreds of log10 units below the best one:
+  // 10^x is exactly 0 below x = -400 and exactly 1 at x = 0, so the warp usually skips exp10 altogether — same bits)
+  const double x = lane < n ? r->varllk[lane] - mx : -1000.0;
+  const bool trivial = x == 0.0 || x < -400.0;
+  double e = x == 0.0 ? 1.0 : 0.0;
+  if (!__all_sync(0xffffffffu, trivial)) e = lane < n ? exp10(x) : 0.0;
   double sum = 0.0;
   for (int i = 0; i < n; i++) sum += __shfl_sync(0xffffffffu, e, i);
   if (lane == 0) {
-    r->var_post_prob = 1 / sum;
+    r->var_post_prob = sum == 1.0 ? 1.0 : 1 / sum;
     int a1, a2;
     if (maxidx == 0) {
       int idx = 1;
@@ -1042,7 +1047,9 @@ struct WideEval {
 // NA = false: the autosomal instance; sites on chrX / chrY / MT are left untouched and flagged in err[1].
 // NA = true: launched right behind it, returns at once unless err[1] is set, then does only those sites.
 // ES = the pedigree also has extended families (evaluated by es_factor); again separate instances.
-template <int U, int MAXT, int MINB, bool NA, bool ES>
+// GM = the site's records do not fit in shared memory (more than ~13,800 people): they are read where they lie, in
+// global memory (L2; the next site of the block is prefetched there as always), no staging copy.
+template <int U, int MAXT, int MINB, bool NA, bool ES, bool GM>
 __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                                            const uint4 *__restrict__ recs_all, const double *__restrict__ mono_all,
                                                            size_t n_sites, double *__restrict__ spill_all, int n_spill, int f3_off,
@@ -1069,7 +1076,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
   __syncthreads();
   uint32_t phase = 0;
   const uint32_t site_bytes = (uint32_t)np * 16u;
-  if (threadIdx.x == 0 && blockIdx.x < n_sites) tma_issue_site(site_base, recs_all + (size_t)blockIdx.x * np, site_bytes, &ws->mbar);
+  if (!GM && threadIdx.x == 0 && blockIdx.x < n_sites) tma_issue_site(site_base, recs_all + (size_t)blockIdx.x * np, site_bytes, &ws->mbar);
   WideEval<U, NA, ES> ev;
   ev.run = run; ev.T = blockDim.x; ev.t = threadIdx.x; ev.cls = PM_CHR_AUTO;
   ev.n_units = run->n_units; ev.tol = run->precision;
@@ -1084,11 +1091,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
 
   for (size_t s = blockIdx.x; s < n_sites; s += gridDim.x) {
     const size_t nxt = s + gridDim.x;
+    if constexpr (GM) { site = recs_all + s * (size_t)np; ev.recs = site; }
     if (threadIdx.x == 0 && nxt < n_sites) tma_prefetch_l2(recs_all + nxt * (size_t)np, site_bytes);  // next site -> L2 meanwhile
 #ifdef PM_PHASE_TIMING
     if (threadIdx.x == 0) ws->t_last = clock64();
 #endif
-    mbar_wait(&ws->mbar, phase);
+    if constexpr (!GM) mbar_wait(&ws->mbar, phase);
     phase ^= 1;
     PM_TICK(0);
     const pm_site_hdr h = hdr[s];
@@ -1260,7 +1268,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
     if (skip && !synced) __syncthreads();
     if (warp == 0) {
       __syncwarp();
-      if (lane == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
+      if (!GM && lane == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
       if (!skip) {  // the 256-byte result leaves as one coalesced 32 x 8-byte store
         static_assert(sizeof(pm_site_result) == 256, "pm_site_result must be 256 bytes");
         reinterpret_cast<unsigned long long *>(&res[s])[lane] = reinterpret_cast<const unsigned long long *>(&ws->r)[lane];
@@ -1288,11 +1296,12 @@ static size_t wide_smem_bytes(int n_person) {  // dynamic part = the site buffer
 //   variant 5: U=8 T=160..512  ..4096 (+ the L2 scratch beyond)   128 registers
 //   (also measured with the one-pass H1..H3 evaluation: 160 threads x 3 blocks at 96 registers 10.0 M, 256 x 2 at 128 registers
 //    8.8 M, 192 x 3 at 112 registers 8.0 M against 13.1 M for 128 x 3 at 168 registers: the spills cost more than the warps bring)
-#define PM_WIDE_VARIANTS(X) X(0, 1, 32, 16) X(1, 2, 32, 16) X(2, 4, 32, 12) X(3, 8, 32, 10) X(4, 8, 128, 3) X(5, 8, 512, 1)
-#define X(V_, U_, MT_, MB_) U_,
+//   variant 6: as 5, the site's records read from global memory (pedigrees whose site does not fit in shared memory)
+#define PM_WIDE_VARIANTS(X) X(0, 1, 32, 16, false) X(1, 2, 32, 16, false) X(2, 4, 32, 12, false) X(3, 8, 32, 10, false) X(4, 8, 128, 3, false) X(5, 8, 512, 1, false) X(6, 8, 512, 1, true)
+#define X(V_, U_, MT_, MB_, GM_) U_,
 static const int kVariantU[] = {PM_WIDE_VARIANTS(X)};
 #undef X
-#define X(V_, U_, MT_, MB_) MT_,
+#define X(V_, U_, MT_, MB_, GM_) MT_,
 static const int kVariantMaxT[] = {PM_WIDE_VARIANTS(X)};
 #undef X
 static const int kNumVariants = (int)(sizeof(kVariantU) / sizeof(kVariantU[0]));
@@ -1312,31 +1321,31 @@ static cudaError_t wide_raise_smem(K kernel, size_t smem) {
   if ((long long)smem > room) return cudaErrorInvalidValue;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
 }
-template <int U, int MAXT, int MINB>
+template <int U, int MAXT, int MINB, bool GM>
 static cudaError_t wide_attr(bool es, size_t smem, int threads, int *per_sm) {
   cudaError_t e;
   if (es) {
-    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, true>, smem);
-    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, true>, smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, true>, threads, smem);
+    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, true, GM>, smem);
+    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, true, GM>, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, true, GM>, threads, smem);
   } else {
-    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, false>, smem);
-    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, false>, smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, false>, threads, smem);
+    e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, true, false, GM>, smem);
+    if (e == cudaSuccess) e = wide_raise_smem(k_sites_wide<U, MAXT, MINB, false, false, GM>, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, k_sites_wide<U, MAXT, MINB, false, false, GM>, threads, smem);
   }
   return e;
 }
 
-template <int U, int MAXT, int MINB>
+template <int U, int MAXT, int MINB, bool GM>
 static void wide_launch(const LaunchPlan &plan, unsigned grid, size_t smem, cudaStream_t stream, const DevRun *d_run, const pm_site_hdr *d_hdr,
                         const uint4 *d_recs, const double *d_mono, size_t n_sites, double *d_spill, pm_site_result *d_res, uint16_t *d_status,
                         int *d_err) {
   if (plan.es) {
-    k_sites_wide<U, MAXT, MINB, false, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
-    k_sites_wide<U, MAXT, MINB, true, true><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, false, true, GM><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, true, true, GM><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
   } else {
-    k_sites_wide<U, MAXT, MINB, false, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
-    k_sites_wide<U, MAXT, MINB, true, false><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, false, false, GM><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
+    k_sites_wide<U, MAXT, MINB, true, false, GM><<<grid, plan.threads, smem, stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, plan.n_spill, plan.f3_offset, d_res, d_status, d_err);
   }
 }
 
@@ -1347,7 +1356,7 @@ cudaError_t launch_sites_wide(const LaunchPlan &plan, const DevRun *d_run, const
   cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
   switch (plan.variant) {
-#define X(V_, U_, MT_, MB_) case V_: wide_launch<U_, MT_, MB_>(plan, grid, smem, stream, d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, d_res, d_status, d_err); break;
+#define X(V_, U_, MT_, MB_, GM_) case V_: wide_launch<U_, MT_, MB_, GM_>(plan, grid, smem, stream, d_run, d_hdr, d_recs, d_mono, n_sites, d_spill, d_res, d_status, d_err); break;
     PM_WIDE_VARIANTS(X)
 #undef X
     default: return cudaErrorInvalidValue;
@@ -1377,26 +1386,38 @@ cudaError_t plan_wide(LaunchPlan *plan, int n_person, int n_units, int n_es, int
   plan->units_per_thread = U;
   plan->n_spill = n_units > T * U ? n_units - T * U : 0;
   if (plan->n_spill > 32 * T) return cudaErrorNotSupported;  // the fragile-unit mask of the spilled units is 32 bits per thread
-  const size_t site_smem = wide_smem_bytes(n_person);
-  if (site_smem > 227 * 1024) return cudaErrorNotSupported;
-  // the one-pass H1..H3 evaluation keeps 32 x (warps + 1) partial products (8 + 4 bytes) behind the site buffer; a
-  // pedigree that fills the SM's shared memory by itself goes without that pass (same results, one hypothesis at a time)
-  const int f3w = kVariantMaxT[variant] <= 32 ? 1 : kVariantMaxT[variant] / 32 + 1;
-  const size_t f3_bytes = (size_t)32 * f3w * 12;
+  // Shared memory per block: the site buffer and, behind it, the 32 x (warps + 1) partial products (8 + 4 bytes) of the
+  // one-pass H1..H3 evaluation.  A pedigree whose site nearly fills the SM's shared memory goes without that pass (same
+  // results, one hypothesis at a time); one whose site does not fit at all (more than ~13,800 people) takes the
+  // instantiation that reads the records from global memory.
   int per_sm = 1;
   cudaError_t e = cudaErrorInvalidValue;
-  for (int with_f3 = 1; with_f3 >= 0; with_f3--) {
-    const size_t smem = site_smem + (with_f3 ? f3_bytes : 0);
-    switch (variant) {
-#define X(V_, U_, MT_, MB_) case V_: e = wide_attr<U_, MT_, MB_>(plan->es != 0, smem, T, &per_sm); break;
-      PM_WIDE_VARIANTS(X)
+  auto fit = [&](int v, size_t site_smem) {
+    const int f3w = kVariantMaxT[v] <= 32 ? 1 : kVariantMaxT[v] / 32 + 1;
+    const size_t f3_bytes = (size_t)32 * f3w * 12;
+    for (int with_f3 = 1; with_f3 >= 0; with_f3--) {
+      const size_t smem = site_smem + (with_f3 ? f3_bytes : 0);
+      per_sm = 0;
+      switch (v) {
+#define X(V_, U_, MT_, MB_, GM_) case V_: e = wide_attr<U_, MT_, MB_, GM_>(plan->es != 0, smem, T, &per_sm); break;
+        PM_WIDE_VARIANTS(X)
 #undef X
+      }
+      plan->smem_bytes = (int)smem;
+      plan->f3_offset = with_f3 ? (int)site_smem : 0;
+      if (e == cudaSuccess && per_sm >= 1) return true;
+      (void)cudaGetLastError();
     }
-    plan->smem_bytes = (int)smem;
-    plan->f3_offset = with_f3 ? (int)site_smem : 0;
-    if (e == cudaSuccess && per_sm >= 1) break;
-    (void)cudaGetLastError();
+    return false;
+  };
+  constexpr int kGlobalVariant = 6, kLargestVariant = 5;
+  bool ok = variant == kGlobalVariant ? fit(variant, 16) : fit(variant, wide_smem_bytes(n_person));
+  if (!ok && variant == kLargestVariant) {
+    variant = kGlobalVariant;
+    plan->variant = variant;
+    ok = fit(variant, 16);
   }
+  if (!ok) return e != cudaSuccess ? e : cudaErrorNotSupported;
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
 #ifdef PM_PHASE_TIMING  // measurement builds only (scripts/gpu_phase_timing.py): fewer resident blocks, to tell latency from contention

@@ -267,7 +267,7 @@ def test_large_extended_families(case, oracle_built):
 
 # ---- the block-per-site kernel on the edge cases, every instantiation ------------------------------
 # (variant, threads) of pm_wide.cu's PM_WIDE_VARIANTS; test.mix.ped has 10 units, so every plan holds it
-WIDE_PLANS = [(0, 32), (1, 32), (2, 32), (3, 32), (4, 64), (4, 128), (5, 256)]
+WIDE_PLANS = [(0, 32), (1, 32), (2, 32), (3, 32), (4, 64), (4, 128), (5, 256), (6, 128)]  # (variant 6: the site read from global memory)
 
 
 def _run_wide(ped, params, hdr, recs, plan):
@@ -331,10 +331,11 @@ def test_wide_kernel_family_likelihood_underflow_gives_minus_infinity(kw, oracle
     assert both_inf.all()
 
 
-@pytest.mark.parametrize("n_fam,kw", [(4400, dict(denovo=True)), (4500, dict())], ids=["4400_trios_denovo", "4500_trios_ba"])
+@pytest.mark.parametrize("n_fam,kw", [(4400, dict(denovo=True)), (4500, dict()), (5000, dict(denovo=True))],
+                         ids=["4400_trios_denovo", "4500_trios_ba", "5000_trios_denovo_site_in_global_memory"])
 def test_wide_kernel_more_units_than_registers_hold(n_fam, kw, oracle_built):
-    """More than 4,096 units: 512 threads x 8 units in registers, the rest in the L2 scratch.  (What bounds the pedigree
-    now is the site buffer: one site's 16 bytes x persons must fit in shared memory, about 14,000 people.)"""
+    """More than 4,096 units: 512 threads x 8 units in registers, the rest in the L2 scratch.  A site of more than
+    ~13,800 people (16 bytes each) does not fit in an SM's shared memory: its records are read from global memory."""
     ped = synth.trios(n_fam)
     n = 24
     h, r = synth.generate_sites(ped, n, seed=78, cfg=synth.SynthConfig(poly_boost=5.0, injected_denovo=0.1))
@@ -343,6 +344,7 @@ def test_wide_kernel_more_units_than_registers_hold(n_fam, kw, oracle_built):
     params = Params(**kw)
     eng = Engine(ped, params)
     assert "in the L2 scratch" in eng.describe_plan() and f"{n_fam - 4096} in the L2" in eng.describe_plan()
+    assert ("read from global memory" in eng.describe_plan()) == (n_fam == 5000), eng.describe_plan()
     g = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
     eng.close()
     ora = OracleEngine(ped, params)

@@ -117,8 +117,10 @@ def test_large_pedigrees(n_fam, kw, oracle_built):
 
 
 def test_unsupported_shapes_fail_loudly():
-    # one site of 15,000 people (240 KB) does not fit in an SM's shared memory
+    # more than 512 threads x (8 + 32) units: the per-thread mask of fragile units in the L2 scratch is 32 bits wide
+    # (a site of more than ~13,800 people no longer fits in shared memory either, but that is served from global memory:
+    # test_wide_kernel_more_units_than_registers_hold)
     with pytest.raises(RuntimeError, match="not supported"):
-        Engine(synth.trios(5000), Params())
+        Engine(synth.trios(21000), Params())
     with pytest.raises(RuntimeError, match="quick_call"):
         Engine(synth.trios(3), Params(quick_call=True, vcf_input=True))

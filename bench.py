@@ -480,6 +480,9 @@ def main():
             "frac": max(fp_frac, hbm_frac), "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
             "peak_source": "DFMA microbenchmark measured live on this GPU (pm_measure_fp64_peak; method and history: profiles/fp64_peak.json); "
                            "MEASURED_PEAKS.json has no FP64 figure",
+            "note": "achieved = the REFERENCE formulation's flops per site (SURVEY.md 8d: H x set-up + E x evaluation, H and E counted by the kernel) / "
+                    "kernel time. The kernels execute fewer: quartic units about a quarter of them, the factorised ten-state Elston-Stewart peel about a "
+                    "tenth -- so the fraction of an extended-pedigree workload can pass 1; the FP64 pipe's own utilisation is in the ncu summaries under profiles/",
             "flops_per_site": flops_per_site, "hypotheses_per_site": hyp_per_site, "evaluations_per_site": ev_per_site, "kernel_ms_per_launch": main_ms,
             "fp64": {"achieved": achieved_tflops, "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": fp_frac},
             "hbm": {"achieved": bytes_per_launch / (main_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_frac,

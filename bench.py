@@ -285,7 +285,7 @@ def main():
     ap.add_argument("--workload", default="trios1000_dn", choices=["trios1000_dn", "ceph20_ba", "ceph20_dn", "vcf200x5", "mixed100"])
     ap.add_argument("--sites-per-step", type=int, default=0, help="0 = the workload's default")
     ap.add_argument("--resident-batches", type=int, default=2)
-    ap.add_argument("--e2e-sites", type=int, default=0, help="0 = about 400 MB of packed input")
+    ap.add_argument("--e2e-sites", type=int, default=0, help="0 = about 400 MB of wire-format input")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-sites-per-core", type=int, default=300)
     ap.add_argument("--cpu-baseline-sites-per-core", type=int, default=300)
@@ -356,14 +356,16 @@ def main():
     cap = S if vcf else max(4096, S // 16)
     status = torch.empty(S, dtype=torch.uint16, device=dev)
     res_out = torch.empty((cap, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    per_out = torch.empty((cap, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    # per-person results: 96-byte rows for the emitted GLF sites; VCF input: 2 bytes per sample (best | gq << 8: what its writer prints from)
+    per_out = (torch.empty((cap, npers), dtype=torch.uint16, device=dev) if vcf else
+               torch.empty((cap, npers, capi.PERSON_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev))
     n_res = torch.zeros(1, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
 
     def step(i):
         hdr, recs, mono = batches[i % R]
         if vcf:
-            eng.call_vcf_records_device(hdr.data_ptr(), recs.data_ptr(), mono.data_ptr(), S, False, status.data_ptr(), res_out.data_ptr(), per_out.data_ptr())
+            eng.call_vcf_records_calls_device(hdr.data_ptr(), recs.data_ptr(), mono.data_ptr(), S, False, status.data_ptr(), res_out.data_ptr(), per_out.data_ptr())
         else:
             eng.call_glf_sites_device(hdr.data_ptr(), recs.data_ptr(), S, capi.PM_OUT_EMITTED, status.data_ptr(), res_out.data_ptr(),
                                       per_out.data_ptr(), cap, n_res.data_ptr())
@@ -402,10 +404,20 @@ def main():
 
     # ---- e2e through the host-buffer C-ABI call, pinned host memory: every rank at the same time (they share the
     # host's memory and PCIe root complexes), whole-job value = all ranks' sites / the slowest rank's time ----
-    Se = min(args.e2e_sites or max(2048, (400 << 20) // (npers * 16)), S)
+    Se = min(args.e2e_sites or max(2048, (400 << 20) // (npers * (3 if vcf else 14))), S)
     h_hdr = torch.empty((Se, 8), dtype=torch.uint8, pin_memory=True)
-    h_recs = torch.empty((Se, npers, 16), dtype=torch.uint8, pin_memory=True)
-    h_hdr.copy_(batches[0][0][:Se]); h_recs.copy_(batches[0][1][:Se])
+    # the wire forms of the records: GLF 14 bytes per (site, person) (pm_person_site_wire), VCF 3 PL bytes per (record, sample)
+    h_hdr.copy_(batches[0][0][:Se])
+    if vcf:
+        ref = batches[0][0][:Se, 4].long(); alt = batches[0][0][:Se, 6].long()
+        g = torch.stack([gi(ref, ref), gi(ref, alt), gi(alt, alt)], dim=1)
+        rec_bytes = 3
+        h_recs = torch.empty((Se, npers, 3), dtype=torch.uint8, pin_memory=True)
+        h_recs.copy_(batches[0][1][:Se].gather(2, g[:, None, :].expand(Se, npers, 3)))
+    else:
+        rec_bytes = 14
+        h_recs = torch.empty((Se, npers, 14), dtype=torch.uint8, pin_memory=True)
+        h_recs.copy_(batches[0][1][:Se, :, :14])
     cap_e = Se if vcf else max(1024, Se // 8)
     h_status = torch.empty(Se, dtype=torch.uint16, pin_memory=True)
     h_res = torch.empty((cap_e, capi.SITE_RESULT_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
@@ -420,11 +432,11 @@ def main():
 
     def e2e_step():
         if vcf:
-            rc = eng.lib.pm_call_vcf_records_calls(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), h_mono.data_ptr(), Se, h_res.data_ptr(), h_calls.data_ptr())
+            rc = eng.lib.pm_call_vcf_records_pl(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), h_mono.data_ptr(), Se, h_res.data_ptr(), h_calls.data_ptr())
             nres.value = Se
         else:
-            rc = eng.lib.pm_call_glf_sites(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
-                                           h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
+            rc = eng.lib.pm_call_glf_sites_wire(eng.ctx, h_hdr.data_ptr(), h_recs.data_ptr(), Se, capi.PM_OUT_EMITTED, h_status.data_ptr(),
+                                                h_res.data_ptr(), h_per.data_ptr(), cap_e, C.byref(nres))
         if rc != 0:
             raise RuntimeError(eng.lib.pm_last_error().decode())
 
@@ -440,11 +452,12 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_dt = float(te.item())
     rows = nres.value
-    e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * 16 + 8 + (8 if vcf else 0)),
+    e2e = {"value": world * Se / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": world * Se * (npers * rec_bytes + 8 + (8 if vcf else 0)),
            "d2h_bytes_per_step": world * (Se * (capi.SITE_RESULT_DTYPE.itemsize + npers * 2) if vcf else
                                           Se * 2 + rows * (capi.SITE_RESULT_DTYPE.itemsize + npers * capi.PERSON_RESULT_DTYPE.itemsize) + 4),
            "sites_per_step": world * Se, "ms_per_step": e2e_dt * 1e3, "n_gpus": world,
-           "note": ("pm_call_vcf_records_calls" if vcf else "pm_call_glf_sites") + " from pinned host buffers; H2D of the packed sites and D2H of status + "
+           "note": ("pm_call_vcf_records_pl (3 PL bytes per sample in, 2 bytes per sample out)" if vcf else "pm_call_glf_sites_wire (14-byte records)") +
+                   " from pinned host buffers; H2D of the sites and D2H of status + "
                    "result rows inside the timed region; all ranks run it at the same time, time = max over ranks"}
 
     if rank == 0:

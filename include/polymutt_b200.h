@@ -124,6 +124,15 @@ typedef struct pm_person_site {
   uint8_t pad[2];
 } pm_person_site;
 
+/* The same record without the two pad bytes, 14 bytes: what a host buffer needs to carry per (site, person).
+ * record (s, i) lives at wire + 14*(s*n_person + i).  pm_call_glf_sites_wire copies this form over PCIe (12.5 % fewer
+ * bytes on a link-bound path) and widens it to pm_person_site on the device (k_unpack_wire). */
+typedef struct pm_person_site_wire {
+  uint8_t lk[PM_NGENO];   /* glfEntry::lk */
+  uint8_t depth[3];       /* glfEntry::depth, 24-bit little endian */
+  uint8_t map_quality;    /* glfEntry::mapQuality */
+} pm_person_site_wire;
+
 /* What happened to a site (the `continue`s of src/main.cpp:339-574, in order). */
 enum {
   PM_SITE_EMITTED       = 0,  /* a VCF row is due */
@@ -207,6 +216,13 @@ int pm_call_glf_sites(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site 
                       pm_site_result *res_out, pm_person_result *person_out, size_t res_cap,
                       size_t *n_res);
 
+/* The same call on 14-byte records (pm_person_site_wire): same results, 14/16 of the bytes over PCIe.  Replaces the
+ * same reference loop (src/main.cpp:325-594 over PedigreeGLF::glf[i].data, core/glfHandler.h:21-42). */
+int pm_call_glf_sites_wire(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site_wire *person_site_wire,
+                           size_t n_sites, int out_mode, uint16_t *status_out,
+                           pm_site_result *res_out, pm_person_result *person_out, size_t res_cap,
+                           size_t *n_res);
+
 /* Same computation on buffers that already live in this ctx's device memory (cudaMalloc pointers,
  * e.g. torch tensors' data_ptr()).  Asynchronous on the ctx stream; call pm_sync before reading. */
 int pm_call_glf_sites_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
@@ -236,12 +252,24 @@ int pm_call_vcf_records(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_sit
 int pm_call_vcf_records_calls(pm_ctx *ctx, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
                               size_t n_records, pm_site_result *res_out, uint16_t *calls_out);
 
+/* The same from the wire form of a VCF record's likelihoods: pl3[n_records * n_person * 3] holds, per sample, int(PL) (or
+ * int(-10*GL)) capped at 255 of the genotypes (a1,a1), (a1,a2), (a2,a2) -- the three numbers the reference reads from a
+ * sample's PL / GL field (src/FamilyLikelihoodSeq_VCF.cpp:340-382); 0,0,0 for a sample without data.  3 bytes per sample
+ * go over PCIe instead of 16; the device widens them to pm_person_site records (k_unpack_pl3). */
+int pm_call_vcf_records_pl(pm_ctx *ctx, const pm_site_hdr *hdr, const uint8_t *pl3, const double *mono,
+                           size_t n_records, pm_site_result *res_out, uint16_t *calls_out);
+
 /* The same on buffers in this ctx's device memory (asynchronous on the ctx stream, pm_sync before reading).  Every
  * record gets a row: d_res_out[n_records], d_person_out[n_records * n_person], d_status_out[n_records].
  * has_nonauto: the batch holds chrX / chrY / MT records (they take a second pass over the batch). */
 int pm_call_vcf_records_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
                                size_t n_records, int has_nonauto, uint16_t *d_status_out, pm_site_result *d_res_out,
                                pm_person_result *d_person_out);
+
+/* Device-buffer variant of pm_call_vcf_records_calls: d_calls_out[n_records * n_person] = best | gq << 8. */
+int pm_call_vcf_records_calls_device(pm_ctx *ctx, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                                     size_t n_records, int has_nonauto, uint16_t *d_status_out, pm_site_result *d_res_out,
+                                     uint16_t *d_calls_out);
 
 /* Page-locked host memory for the buffers handed to pm_call_glf_sites (lets its H2D/D2H copies overlap
  * the kernels).  Optional: pageable buffers are accepted too. */

@@ -186,6 +186,33 @@ class PedigreeArrays:
 _LIB = None
 
 
+def to_wire(recs: np.ndarray) -> np.ndarray:
+    """16-byte pm_person_site records -> 14-byte pm_person_site_wire records (uint8 [..., 14])."""
+    raw = np.ascontiguousarray(recs, dtype=PERSON_SITE_DTYPE).view(np.uint8).reshape(-1, 16)
+    return np.ascontiguousarray(raw[:, :14])
+
+
+def geno_index(b1: int, b2: int) -> int:
+    """core/glfHandler.h:102-106 (bases 1..4)."""
+    if b1 > b2:
+        b1, b2 = b2, b1
+    return (b1 - 1) * (10 - b1) // 2 + (b2 - b1)
+
+
+def to_pl3(hdr: np.ndarray, recs: np.ndarray, n_person: int) -> np.ndarray:
+    """VCF-input records -> the three PL bytes per sample (a1a1, a1a2, a2a2) pm_call_vcf_records_pl takes."""
+    hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+    raw = np.ascontiguousarray(recs, dtype=PERSON_SITE_DTYPE).view(np.uint8).reshape(len(hdr), n_person, 16)
+    out = np.zeros((len(hdr), n_person, 3), dtype=np.uint8)
+    a1 = hdr["ref_base"].astype(np.int64)
+    a2 = (hdr["reserved"] & 0xff).astype(np.int64)
+    gi = np.vectorize(geno_index)
+    if len(hdr):
+        for k, g in enumerate((gi(a1, a1), gi(a1, a2), gi(a2, a2))):
+            out[:, :, k] = np.take_along_axis(raw[:, :, :10], g[:, None, None].astype(np.int64), axis=2)[:, :, 0]
+    return out
+
+
 def _declare(lib):
     lib.pm_create.restype = C.c_void_p
     lib.pm_create.argtypes = [C.POINTER(_PmPedigree), C.POINTER(_PmParams), C.c_void_p, C.c_int]
@@ -194,6 +221,12 @@ def _declare(lib):
     lib.pm_call_glf_sites.restype = C.c_int
     lib.pm_call_glf_sites.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.pm_call_glf_sites_wire.restype = C.c_int
+    lib.pm_call_glf_sites_wire.argtypes = lib.pm_call_glf_sites.argtypes
+    lib.pm_call_vcf_records_pl.restype = C.c_int
+    lib.pm_call_vcf_records_pl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.pm_call_vcf_records_calls_device.restype = C.c_int
+    lib.pm_call_vcf_records_calls_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pm_call_vcf_records.restype = C.c_int
     lib.pm_call_vcf_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.pm_call_glf_sites_device.restype = C.c_int
@@ -297,6 +330,38 @@ class Engine:
                                                res.ctypes.data, per.ctypes.data, cap, C.byref(n_res)))
         k = n_res.value
         return status, res[:k], per[:k]
+
+    def call_glf_sites_wire(self, hdr: np.ndarray, recs: np.ndarray, out_mode: int = PM_OUT_ALL, res_cap: Optional[int] = None):
+        """pm_call_glf_sites_wire: the same call on 14-byte records (`recs` as for call_glf_sites; packed here)."""
+        hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+        wire = to_wire(recs)
+        n, npers = len(hdr), self.ped.n_person
+        assert wire.size == n * npers * 14, (wire.size, n, npers)
+        cap = n if res_cap is None else res_cap
+        status = np.zeros(n, dtype=np.uint16)
+        res = np.zeros(max(cap, 1), dtype=SITE_RESULT_DTYPE)
+        per = np.zeros((max(cap, 1), npers), dtype=PERSON_RESULT_DTYPE)
+        n_res = C.c_size_t(0)
+        self._check(self.lib.pm_call_glf_sites_wire(self.ctx, hdr.ctypes.data, wire.ctypes.data, n, out_mode, status.ctypes.data,
+                                                    res.ctypes.data, per.ctypes.data, cap, C.byref(n_res)))
+        k = n_res.value
+        return status, res[:k], per[:k]
+
+    def call_vcf_records_pl(self, hdr: np.ndarray, recs: np.ndarray, mono: np.ndarray):
+        """pm_call_vcf_records_pl: VCF-input entry point on three PL bytes per sample (`recs` as for call_vcf_records;
+        the triplets are taken from them here).  Returns (results[n], calls[n, n_person] = best | gq << 8)."""
+        hdr = np.ascontiguousarray(hdr, dtype=SITE_HDR_DTYPE)
+        mono = np.ascontiguousarray(mono, dtype=np.float64)
+        n, npers = len(hdr), self.ped.n_person
+        pl3 = to_pl3(hdr, recs, npers)
+        res = np.zeros(max(n, 1), dtype=SITE_RESULT_DTYPE)
+        calls = np.zeros((max(n, 1), npers), dtype=np.uint16)
+        self._check(self.lib.pm_call_vcf_records_pl(self.ctx, hdr.ctypes.data, pl3.ctypes.data, mono.ctypes.data, n, res.ctypes.data, calls.ctypes.data))
+        return res[:n], calls[:n]
+
+    def call_vcf_records_calls_device(self, d_hdr: int, d_recs: int, d_mono: int, n: int, has_nonauto: bool, d_status: int, d_res: int, d_calls: int):
+        """Device-buffer VCF entry point with 2 bytes per sample out (raw device pointers); asynchronous."""
+        self._check(self.lib.pm_call_vcf_records_calls_device(self.ctx, d_hdr, d_recs, d_mono, n, 1 if has_nonauto else 0, d_status, d_res, d_calls))
 
     def call_vcf_records(self, hdr: np.ndarray, recs: np.ndarray, mono: np.ndarray):
         """VCF-input entry point.  Returns (results[n], persons[n, n_person])."""

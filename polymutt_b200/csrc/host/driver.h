@@ -30,6 +30,9 @@ struct Engine {
   // optional: page-locked allocation for the batch buffers (nullptr = plain malloc)
   void *(*host_alloc)(size_t bytes) = nullptr;
   void (*host_free)(void *p) = nullptr;
+  // optional: pm_call_vcf_records_pl -- three PL bytes per sample in (a1a1, a1a2, a2a2), calls out; used when present
+  int (*call_vcf_pl)(void *ctx, const pm_site_hdr *, const uint8_t *pl3, const double *mono, size_t n, pm_site_result *res,
+                     uint16_t *calls) = nullptr;
 };
 
 // Returns the process exit code (0 on success, 1 after a fatal error, like the reference's error()).

@@ -18,9 +18,12 @@ static int call_vcf_calls(void *ctx, const pm_site_hdr *hdr, const pm_person_sit
                           uint16_t *calls) {
   return pm_call_vcf_records_calls((pm_ctx *)ctx, hdr, ps, mono, n, res, calls);
 }
+static int call_vcf_pl(void *ctx, const pm_site_hdr *hdr, const uint8_t *pl3, const double *mono, size_t n, pm_site_result *res, uint16_t *calls) {
+  return pm_call_vcf_records_pl((pm_ctx *)ctx, hdr, pl3, mono, n, res, calls);
+}
 static void destroy(void *ctx) { pm_destroy((pm_ctx *)ctx); }
 
 int main(int argc, char **argv) {
-  pmh::Engine e{"cuda-sm100a", create, call_glf, destroy, pm_last_error, call_vcf, call_vcf_calls, pm_host_alloc, pm_host_free};
+  pmh::Engine e{"cuda-sm100a", create, call_glf, destroy, pm_last_error, call_vcf, call_vcf_calls, pm_host_alloc, pm_host_free, call_vcf_pl};
   return pmh::run_cli(argc, argv, e);
 }

@@ -160,15 +160,33 @@ struct LineRec {
   std::string err;       // L_ERROR / L_WARN text
 };
 
-// Reads the (plain or gzip) file in large blocks and hands out chunks of whole lines.
+// Reads the (plain or gzip) file in large blocks and hands out chunks of whole lines.  The next block is read (and
+// inflated) by a helper thread while the current chunk is tokenised, computed and formatted.
 struct ChunkReader {
   gzFile f = nullptr;
   std::vector<char> buf;
   size_t have = 0;       // bytes in buf
   size_t start = 0;      // first unconsumed byte
   bool eof = false;
+  static constexpr size_t kBlock = (size_t)24 << 20;  // a chunk's worth of text
+  std::vector<char> ahead;      // the block being read ahead
+  size_t ahead_n = 0;
+  bool ahead_eof = false;
+  std::thread ahead_thread;
   bool open(const std::string &path) { f = gzopen(path.c_str(), "rb"); if (f) gzbuffer(f, 1 << 20); return f != nullptr; }
-  ~ChunkReader() { if (f) gzclose(f); }
+  ~ChunkReader() { if (ahead_thread.joinable()) ahead_thread.join(); if (f) gzclose(f); }
+  void read_ahead() {
+    ahead.resize(kBlock);
+    ahead_thread = std::thread([this]() {
+      size_t n = 0;
+      while (n < kBlock) {
+        const int got = gzread(f, ahead.data() + n, (unsigned)(kBlock - n));
+        if (got <= 0) { ahead_eof = true; break; }
+        n += (size_t)got;
+      }
+      ahead_n = n;
+    });
+  }
   // Next line (without its terminator); false at end of input.  Pointers stay valid until the next refill().
   bool next_line(Tok *out, bool allow_refill) {
     for (;;) {
@@ -193,17 +211,19 @@ struct ChunkReader {
       refill();
     }
   }
-  // Drops consumed bytes and reads more; invalidates every pointer handed out before.
+  // Drops consumed bytes and appends the block the helper has read; invalidates every pointer handed out before.
   void refill() {
     if (start > 0) { memmove(buf.data(), buf.data() + start, have - start); have -= start; start = 0; }
-    if (buf.size() - have < ((size_t)8 << 20)) buf.resize(buf.size() + ((size_t)32 << 20));
-    while (!eof && buf.size() - have > 1) {
-      const size_t room = buf.size() - have - 1;
-      int n = gzread(f, buf.data() + have, (unsigned)(room > ((size_t)1 << 30) ? ((size_t)1 << 30) : room));
-      if (n <= 0) { eof = true; break; }
-      have += (size_t)n;
-      if (have >= ((size_t)24 << 20)) break;  // a chunk's worth of text
+    if (!eof) {
+      if (!ahead_thread.joinable()) read_ahead();  // the first block
+      ahead_thread.join();
+      if (buf.size() < have + ahead_n + 1) buf.resize(have + ahead_n + 1);
+      memcpy(buf.data() + have, ahead.data(), ahead_n);
+      have += ahead_n;
+      ahead_n = 0;
+      if (ahead_eof) eof = true; else read_ahead();
     }
+    if (buf.size() < have + 1) buf.resize(have + 1);
     buf[have] = 0;
   }
 };
@@ -311,12 +331,15 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   std::vector<LineRec> lines;
   std::vector<Tok> toks;
   std::vector<pm_site_hdr> hdr;
+  // per (line, pedigree column): the three PL bytes of the record's genotypes (a1a1, a1a2, a2a2); engines without the
+  // pl3 entry point (the CPU oracle behind the same front end) get them widened to 16-byte records below
+  std::vector<uint8_t> pl3;
   std::vector<pm_person_site> recs;
   std::vector<double> mono;
   std::vector<pm_site_result> res;
   std::vector<pm_person_result> pres;   // per-sample results, or (engines with call_vcf_calls) ...
   std::vector<uint16_t> calls;           // ... best | gq << 8 per sample
-  const bool compact = engine.call_vcf_calls != nullptr;
+  const bool compact = engine.call_vcf_calls != nullptr || engine.call_vcf_pl != nullptr;
   std::vector<std::string> text, text_w;  // rows being formatted / rows being written
   std::thread writer;
   std::vector<std::vector<double>> scratch((size_t)threads, std::vector<double>((size_t)np));
@@ -341,11 +364,10 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     }
     L.ref = (uint8_t)ref; L.alt = (uint8_t)alt; L.indel = indel;
     L.dp_here = format_index(L.col[8], "DP");
-    pm_person_site *row = &recs[li * (size_t)np];
-    memset(row, 0, sizeof(pm_person_site) * (size_t)np);
+    uint8_t *row = &pl3[li * (size_t)np * 3];
+    memset(row, 0, (size_t)np * 3);
     std::vector<double> &loglk_rr = scratch[(size_t)tid];
     std::fill(loglk_rr.begin(), loglk_rr.end(), 0.0);
-    const int gi[3] = {genotype_index(ref, ref), genotype_index(ref, alt), genotype_index(alt, alt)};
     const int fi = GL_idx > 0 ? GL_idx : PL_idx;
     int withdata = 0;
     for (size_t i = 0; i < n_names; i++) {
@@ -392,7 +414,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
         int pl = int(PL_idx > 0 ? G[k] : -10 * G[k]);
         if (pl < 0) { L.kind = L_ERROR; L.err = "Phred-scaled likelihood " + std::to_string(pl) + " can not be negative"; return; }
         if (pl > 255) pl = 255;
-        row[c].lk[gi[k]] = (uint8_t)pl;
+        row[3 * c + k] = (uint8_t)pl;
       }
     }
     if (withdata == 0) { L.kind = L_NODATA; return; }  // PedVCF.cpp:122: printed with whatever the previous record left behind
@@ -557,7 +579,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       }
     }
     if (!announced) { printf("Total samples in both VCF and PED files: %d\n\n", n_in_both); announced = true; }
-    if (recs.size() < nl * (size_t)np) recs.resize(nl * (size_t)np);
+    if (pl3.size() < nl * (size_t)np * 3) pl3.resize(nl * (size_t)np * 3);
     parallel_for(nl, threads, parse_line);
     const auto t_parse = std::chrono::steady_clock::now();
     // ---- in line order: warnings, the first error, engine rows, which row each line prints ----
@@ -573,7 +595,7 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
       L.dp_index = DP_index;
       if (L.kind == L_COMPUTED) {
         L.row = (long)n_rows;
-        if (n_rows != li) memmove(&recs[n_rows * (size_t)np], &recs[li * (size_t)np], sizeof(pm_person_site) * (size_t)np);
+        if (n_rows != li) memmove(&pl3[n_rows * (size_t)np * 3], &pl3[li * (size_t)np * 3], (size_t)np * 3);
         mono[n_rows] = L.mono;
         pm_site_hdr &h = hdr[n_rows];
         memset(&h, 0, sizeof h);
@@ -588,8 +610,21 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     }
     if (n_rows) {
       if (res.size() < n_rows) { res.resize(n_rows); if (compact) calls.resize(n_rows * (size_t)np); else pres.resize(n_rows * (size_t)np); }
-      rc = compact ? engine.call_vcf_calls(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), calls.data())
-                   : engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
+      if (engine.call_vcf_pl) {
+        rc = engine.call_vcf_pl(ctx, hdr.data(), pl3.data(), mono.data(), n_rows, res.data(), calls.data());
+      } else {
+        if (recs.size() < n_rows * (size_t)np) recs.resize(n_rows * (size_t)np);
+        parallel_for(n_rows, threads, [&](size_t r, int) {
+          const int a1 = hdr[r].ref_base, a2 = hdr[r].reserved & 0xff;
+          const int gi[3] = {genotype_index(a1, a1), genotype_index(a1, a2), genotype_index(a2, a2)};
+          pm_person_site *row = &recs[r * (size_t)np];
+          memset(row, 0, sizeof(pm_person_site) * (size_t)np);
+          for (int c = 0; c < np; c++)
+            for (int k = 0; k < 3; k++) row[c].lk[gi[k]] = pl3[(r * (size_t)np + (size_t)c) * 3 + (size_t)k];
+        });
+        rc = compact ? engine.call_vcf_calls(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), calls.data())
+                     : engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
+      }
       if (rc != PM_OK) break;
     }
     const auto t_engine = std::chrono::steady_clock::now();

@@ -70,9 +70,16 @@ struct pm_ctx {
   // staging for the host-buffer entry point
   size_t cap_in_sites = 0, cap_out_rows = 0;
   double *d_mono[2] = {nullptr, nullptr}; size_t cap_mono = 0;
-  uint16_t *d_calls = nullptr; size_t cap_calls = 0;
   pm_site_hdr *d_hdr[2] = {nullptr, nullptr};   // two input slots: H2D of chunk k+1 overlaps compute of chunk k
   uint4 *d_recs[2] = {nullptr, nullptr};
+  // VCF input (vcf_records_chunked): 3-byte PL triplets as they arrive, two output slots, a stream for the results
+  uint8_t *d_pl3[2] = {nullptr, nullptr}; size_t cap_pl3 = 0;
+  pm_site_result *d_vres[2] = {nullptr, nullptr}; size_t cap_vres = 0;
+  pm_person_result *d_vperson[2] = {nullptr, nullptr}; size_t cap_vperson = 0;
+  uint16_t *d_vcalls[2] = {nullptr, nullptr}; size_t cap_vcalls = 0;
+  cudaStream_t stream_d2h = nullptr;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+  unsigned char *d_wire[2] = {nullptr, nullptr}; size_t cap_wire_sites = 0;   // 14-byte records as they arrive (pm_call_glf_sites_wire)
   cudaStream_t stream_h2d = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   uint32_t *h_rows = nullptr;                   // pinned
@@ -371,10 +378,14 @@ extern "C" void pm_destroy(pm_ctx *c) {
   cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
   cudaFree(c->d_err); cudaFree(c->d_spill); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
-  for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
+  for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); cudaFree(c->d_wire[k]); cudaFree(c->d_pl3[k]); cudaFree(c->d_vres[k]); cudaFree(c->d_vperson[k]); cudaFree(c->d_vcalls[k]);
+    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+    if (c->ev_d2h[k]) cudaEventDestroy(c->ev_d2h[k]);
+    if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]); }
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
+  if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
   if (c->h_rows) cudaFreeHost(c->h_rows);
-  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono[0]); cudaFree(c->d_mono[1]); cudaFree(c->d_calls);
+  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono[0]); cudaFree(c->d_mono[1]);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -386,7 +397,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
 
 static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
                       size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
-                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res);
+                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res, uint16_t *d_calls_out = nullptr);
 static int check_device_error(pm_ctx *c);
 
 extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
@@ -397,11 +408,12 @@ extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, con
   return run_device(c, d_hdr, d_person_site, nullptr, n_sites, out_mode, d_status_out, d_res_out, d_person_out, res_cap, d_n_res);
 }
 
+// d_calls_out != nullptr: the per-person results leave as 2 bytes (best | gq << 8) there and d_person_out is not used
 static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
                       size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
-                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res) {
+                      pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res, uint16_t *d_calls_out) {
   if (n_sites == 0) { if (d_n_res) CUDA_TRY(cudaMemsetAsync(d_n_res, 0, sizeof(uint32_t), c->stream)); return PM_OK; }
-  if (!d_hdr || !d_person_site || !d_status_out || !d_res_out || !d_person_out)
+  if (!d_hdr || !d_person_site || !d_status_out || !d_res_out || (!d_person_out && !d_calls_out))
     return fail(PM_EINVAL, "pm_call_glf_sites_device: null buffer");
   if (n_sites > 0xffffffffull) return fail(PM_EINVAL, "at most 2^32-1 sites per call");
   if (out_mode == PM_OUT_ALL && res_cap < n_sites) return fail(PM_EINVAL, "PM_OUT_ALL needs res_cap >= n_sites");
@@ -418,15 +430,16 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
   if (second)
     CUDA_TRY(pm::launch_sites(c->plan_x, c->d_run_x, d_hdr, (const uint4 *)d_person_site, d_mono, n_sites, c->d_spill, c->d_res_all, d_status_out, c->d_err, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  const bool ten_state = c->par.denovo && !c->par.vcf_input;
   const bool with_ab = !c->par.denovo && !c->par.vcf_input;  // the allele balance is printed by the non-de-novo GLF writer only
   CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                            out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
-                           d_person_out, c->sm_count, with_ab, c->stream));
+                           d_person_out, d_calls_out, c->n_es > 0, ten_state, c->sm_count, with_ab, c->stream));
   if (second)
     CUDA_TRY(pm::launch_post(c->d_run_x, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                              out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
-                             d_person_out, c->sm_count, false, c->stream));
+                             d_person_out, d_calls_out, true, ten_state, c->sm_count, false, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
   c->launches = 4 + (with_ab ? 1 : 0);  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact, k_post [, k_post_ab]
   if (c->par.quick_call) c->launches += 3;
@@ -464,9 +477,11 @@ extern "C" int pm_last_timing(pm_ctx *c, float *ms_main_kernel, float *ms_total,
 // call runs at the slower of PCIe and the kernels instead of their sum.  Results of a chunk are copied
 // back as soon as its row count is known.  Pinned host buffers (pm_host_alloc) make the copies truly
 // asynchronous; pageable buffers work too, just without the overlap.
-extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, size_t n_sites,
-                                 int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
-                                 size_t res_cap, size_t *n_res) {
+// rec_bytes: 16 (pm_person_site) or 14 (pm_person_site_wire: copied into a staging slot and widened on the device by
+// k_unpack_wire, on the compute stream right in front of the chunk's kernels).
+static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_site, size_t rec_bytes, size_t n_sites,
+                          int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
+                          size_t res_cap, size_t *n_res) {
   if (!c) return fail(PM_EINVAL, "null context");
   if (n_res) *n_res = 0;
   if (n_sites == 0) return PM_OK;
@@ -496,6 +511,13 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
     c->cap_out_rows = chunk;
   }
+  const bool wire = rec_bytes != sizeof(pm_person_site);
+  if (wire && chunk > c->cap_wire_sites) {
+    c->cap_wire_sites = 0;
+    for (int k = 0; k < 2; k++)
+      if ((rc = dev_alloc(&c->d_wire[k], chunk * np * rec_bytes + 16))) return rc;  // + 16: the unpack kernel reads whole uint4s
+    c->cap_wire_sites = chunk;
+  }
   if (!c->h_rows) CUDA_TRY(cudaHostAlloc((void **)&c->h_rows, sizeof(uint32_t), cudaHostAllocDefault));
   const size_t n_chunks = (n_sites + chunk - 1) / chunk;
   auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n_sites - k * chunk; };
@@ -503,7 +525,9 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, n = chunk_len(k);
     cudaError_t e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_recs[slot], person_site + base * np, n * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(wire ? (void *)c->d_wire[slot] : (void *)c->d_recs[slot], (const unsigned char *)person_site + base * np * rec_bytes,
+                          n * np * rec_bytes, cudaMemcpyHostToDevice, c->stream_h2d);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_h2d[slot], c->stream_h2d);
     return e;
   };
@@ -521,6 +545,8 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
     if (k + 1 < n_chunks && (e = issue_h2d(k + 1)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
     if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
+    if (wire && (e = pm::launch_unpack_wire(c->d_wire[slot], c->d_recs[slot], n * np, c->sm_count, c->stream)) != cudaSuccess)
+      return bail(fail(PM_ECUDA, "k_unpack_wire: %s", cudaGetErrorString(e)));
     rc = pm_call_glf_sites_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], n, out_mode, c->d_status, c->d_res_out,
                                   c->d_person_out, c->cap_out_rows, c->d_n_emit);
     if (rc) return bail(rc);
@@ -530,7 +556,7 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
     if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites chunk %zu: %s", k, cudaGetErrorString(e)));
     float a = 0.f, b = 0.f;
     pm_last_timing(c, &a, &b, nullptr);
-    ms_main += a; ms_total += b; launches += c->launches;
+    ms_main += a; ms_total += b; launches += c->launches + (wire ? 1 : 0);
     const uint32_t rows = *c->h_rows;
     if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
     if (rows) {
@@ -551,6 +577,19 @@ extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_per
   return PM_OK;
 }
 
+extern "C" int pm_call_glf_sites(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, size_t n_sites,
+                                 int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
+                                 size_t res_cap, size_t *n_res) {
+  return glf_sites_host(c, hdr, person_site, sizeof(pm_person_site), n_sites, out_mode, status_out, res_out, person_out, res_cap, n_res);
+}
+
+extern "C" int pm_call_glf_sites_wire(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site_wire *person_site_wire, size_t n_sites,
+                                      int out_mode, uint16_t *status_out, pm_site_result *res_out, pm_person_result *person_out,
+                                      size_t res_cap, size_t *n_res) {
+  static_assert(sizeof(pm_person_site_wire) == 14, "pm_person_site_wire must be 14 bytes");
+  return glf_sites_host(c, hdr, person_site_wire, sizeof(pm_person_site_wire), n_sites, out_mode, status_out, res_out, person_out, res_cap, n_res);
+}
+
 // Checks the device-side error word (set by a kernel that met a site it cannot handle); one small blocking copy, so once per call.
 static int check_device_error(pm_ctx *c) {
   int err = 0;
@@ -563,15 +602,17 @@ static int check_device_error(pm_ctx *c) {
   return PM_OK;
 }
 
-// VCF-input records from host buffers, in chunks of ~48 MB of packed input through two input slots: the H2D copy of
-// chunk k+1 runs on its own stream while chunk k is computed and its results are copied back.  person_out (96 bytes per
-// sample) and calls_out (2 bytes per sample: best | gq << 8, all the --in_vcf writer prints from) are both optional.
-static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono, size_t n,
-                               pm_site_result *res_out, pm_person_result *person_out, uint16_t *calls_out) {
+// VCF-input records from host buffers, in chunks of ~128 MB of 16-byte records, through two input slots and two output
+// slots on three streams: while chunk k is computed, chunk k+1 comes in and chunk k-1's results go out; nothing waits for
+// the host inside the loop.  Input: 16-byte records, or (pl3) three PL bytes per sample widened on the device.  Output per
+// sample: person_out (96 bytes) or calls_out (2 bytes: best | gq << 8, all the --in_vcf writer prints from, written by
+// k_post directly) -- either is optional.
+static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const uint8_t *pl3, const double *mono,
+                               size_t n, pm_site_result *res_out, pm_person_result *person_out, uint16_t *calls_out) {
   if (!c) return fail(PM_EINVAL, "null context");
   if (!c->par.vcf_input) return fail(PM_EINVAL, "pm_call_vcf_records: the ctx was not created with pm_params.vcf_input = 1");
   if (n == 0) return PM_OK;
-  if (!hdr || !person_site || !mono || !res_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
+  if (!hdr || (!person_site && !pl3) || !mono || !res_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
   for (size_t s = 0; s < n; s++) {
     const int a2 = hdr[s].reserved & 0xff;
     if (hdr[s].ref_base < 1 || hdr[s].ref_base > 4 || a2 < 1 || a2 > 4 || a2 == hdr[s].ref_base)
@@ -582,7 +623,7 @@ static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_perso
   }
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t np = (size_t)c->n_person;
-  size_t chunk = ((size_t)48 << 20) / (np * sizeof(pm_person_site));
+  size_t chunk = ((size_t)128 << 20) / (np * sizeof(pm_person_site));
   if (chunk < 256) chunk = 256;
   if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
   if (chunk > n) chunk = n;
@@ -596,78 +637,115 @@ static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_perso
     if ((rc = dev_alloc(&c->d_status, chunk))) return rc;
     c->cap_in_sites = chunk;
   }
-  if (chunk > c->cap_out_rows) {
-    c->cap_out_rows = 0;
-    if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
-    if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
-    c->cap_out_rows = chunk;
+  if (pl3 && chunk > c->cap_pl3) {
+    c->cap_pl3 = 0;
+    for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_pl3[k], chunk * np * 3))) return rc;
+    c->cap_pl3 = chunk;
+  }
+  if (chunk > c->cap_vres) {
+    c->cap_vres = 0;
+    for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_vres[k], chunk))) return rc;
+    c->cap_vres = chunk;
+  }
+  if (person_out && chunk > c->cap_vperson) {
+    c->cap_vperson = 0;
+    for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_vperson[k], chunk * np))) return rc;
+    c->cap_vperson = chunk;
+  }
+  if (calls_out && chunk > c->cap_vcalls) {
+    c->cap_vcalls = 0;
+    for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_vcalls[k], chunk * np))) return rc;
+    c->cap_vcalls = chunk;
   }
   if (chunk > c->cap_mono) {
     c->cap_mono = 0;
     for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_mono[k], chunk))) return rc;
     c->cap_mono = chunk;
   }
-  if (calls_out && chunk * np > c->cap_calls) {
-    c->cap_calls = 0;
-    if ((rc = dev_alloc(&c->d_calls, chunk * np))) return rc;
-    c->cap_calls = chunk * np;
+  if (!c->stream_d2h) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
+    }
   }
   const size_t n_chunks = (n + chunk - 1) / chunk;
   auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n - k * chunk; };
   auto issue_h2d = [&](size_t k) -> cudaError_t {
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, m = chunk_len(k);
-    cudaError_t e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_recs[slot], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream_h2d);
+    cudaError_t e = cudaSuccess;
+    if (k >= 2) e = cudaStreamWaitEvent(c->stream_h2d, c->ev_done[slot], 0);  // the slot's last reader: chunk k-2's kernels
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, m * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess && pl3) e = cudaMemcpyAsync(c->d_pl3[slot], pl3 + base * np * 3, m * np * 3, cudaMemcpyHostToDevice, c->stream_h2d);
+    if (e == cudaSuccess && !pl3) e = cudaMemcpyAsync(c->d_recs[slot], person_site + base * np, m * np * sizeof(pm_person_site), cudaMemcpyHostToDevice, c->stream_h2d);
     if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_mono[slot], mono + base, m * sizeof(double), cudaMemcpyHostToDevice, c->stream_h2d);
     if (e == cudaSuccess) e = cudaEventRecord(c->ev_h2d[slot], c->stream_h2d);
     return e;
   };
-  auto bail = [&](int code) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); return code; };  // nothing may still read the caller's buffers
+  // nothing may still read or write the caller's buffers when the call returns, error or not
+  auto drain = [&]() -> cudaError_t {
+    cudaError_t e0 = cudaStreamSynchronize(c->stream_h2d), e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->stream_d2h);
+    return e0 != cudaSuccess ? e0 : (e1 != cudaSuccess ? e1 : e2);
+  };
+  auto bail = [&](int code) { drain(); return code; };
   cudaError_t e = issue_h2d(0);
   if (e != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
-  float ms_main = 0.f, ms_total = 0.f;
   int launches = 0;
   for (size_t k = 0; k < n_chunks; k++) {
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, m = chunk_len(k);
-    // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
     if (k + 1 < n_chunks && (e = issue_h2d(k + 1)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
     if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
+    // the output slot was last copied out for chunk k-2
+    if (k >= 2 && (e = cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
     c->batch_has_nonauto = false;
     for (size_t r = 0; r < m; r++) c->batch_has_nonauto |= hdr[base + r].chr_class != PM_CHR_AUTO;
-    rc = run_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], c->d_mono[slot], m, PM_OUT_ALL, c->d_status, c->d_res_out,
-                    c->d_person_out, c->cap_out_rows, c->d_n_emit);
+    if (pl3 && (e = pm::launch_unpack_pl3(c->d_hdr[slot], c->d_pl3[slot], c->d_recs[slot], m, (int)np, c->sm_count, c->stream)) != cudaSuccess)
+      return bail(fail(PM_ECUDA, "k_unpack_pl3: %s", cudaGetErrorString(e)));
+    rc = run_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], c->d_mono[slot], m, PM_OUT_ALL, c->d_status, c->d_vres[slot],
+                    person_out ? c->d_vperson[slot] : nullptr, m, c->d_n_emit, calls_out ? c->d_vcalls[slot] : nullptr);
     if (rc) return bail(rc);
-    e = cudaMemcpyAsync(res_out + base, c->d_res_out, m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && person_out)
-      e = cudaMemcpyAsync(person_out + base * np, c->d_person_out, m * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && calls_out) {
-      e = pm::launch_pack_calls(c->d_person_out, m * np, c->d_calls, c->sm_count, c->stream);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(calls_out + base * np, c->d_calls, m * np * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
+    launches += c->launches + (pl3 ? 1 : 0);
+    if (person_out && calls_out) {  // both asked for: the rows come from k_post, the calls from the rows
+      e = pm::launch_pack_calls(c->d_vperson[slot], m * np, c->d_vcalls[slot], c->sm_count, c->stream);
+      launches++;
+      if (e != cudaSuccess) return bail(fail(PM_ECUDA, "k_pack_calls: %s", cudaGetErrorString(e)));
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    e = cudaEventRecord(c->ev_done[slot], c->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream_d2h, c->ev_done[slot], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(res_out + base, c->d_vres[slot], m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream_d2h);
+    if (e == cudaSuccess && person_out)
+      e = cudaMemcpyAsync(person_out + base * np, c->d_vperson[slot], m * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream_d2h);
+    if (e == cudaSuccess && calls_out)
+      e = cudaMemcpyAsync(calls_out + base * np, c->d_vcalls[slot], m * np * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream_d2h);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_d2h[slot], c->stream_d2h);
     if (e != cudaSuccess) return bail(fail(PM_ECUDA, "VCF records chunk %zu: %s", k, cudaGetErrorString(e)));
-    float a = 0.f, b = 0.f;
-    pm_last_timing(c, &a, &b, nullptr);
-    ms_main += a; ms_total += b; launches += c->launches;
-    for (size_t r = 0; r < m; r++) res_out[base + r].site += (uint32_t)base;
   }
-  c->ms_main = ms_main; c->ms_total = ms_total; c->launches = launches;
-  c->timing_cached = true;
+  if ((e = drain()) != cudaSuccess) return fail(PM_ECUDA, "VCF records: %s", cudaGetErrorString(e));
+  for (size_t k = 1; k < n_chunks; k++)
+    for (size_t r = 0, base = k * chunk, m = chunk_len(k); r < m; r++) res_out[base + r].site += (uint32_t)base;
+  c->launches = launches;
+  c->timing_cached = false;  // (the events hold the last chunk's times)
   return check_device_error(c);
 }
 
 extern "C" int pm_call_vcf_records(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
                                    size_t n, pm_site_result *res_out, pm_person_result *person_out) {
-  if (n && !person_out) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
-  return vcf_records_chunked(c, hdr, person_site, mono, n, res_out, person_out, nullptr);
+  if (n && (!person_out || !person_site)) return fail(PM_EINVAL, "pm_call_vcf_records: null buffer");
+  return vcf_records_chunked(c, hdr, person_site, nullptr, mono, n, res_out, person_out, nullptr);
 }
 
 extern "C" int pm_call_vcf_records_calls(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const double *mono,
                                          size_t n, pm_site_result *res_out, uint16_t *calls_out) {
-  if (n && !calls_out) return fail(PM_EINVAL, "pm_call_vcf_records_calls: null buffer");
-  return vcf_records_chunked(c, hdr, person_site, mono, n, res_out, nullptr, calls_out);
+  if (n && (!calls_out || !person_site)) return fail(PM_EINVAL, "pm_call_vcf_records_calls: null buffer");
+  return vcf_records_chunked(c, hdr, person_site, nullptr, mono, n, res_out, nullptr, calls_out);
+}
+
+extern "C" int pm_call_vcf_records_pl(pm_ctx *c, const pm_site_hdr *hdr, const uint8_t *pl3, const double *mono, size_t n,
+                                      pm_site_result *res_out, uint16_t *calls_out) {
+  if (n && (!calls_out || !pl3)) return fail(PM_EINVAL, "pm_call_vcf_records_pl: null buffer");
+  return vcf_records_chunked(c, hdr, nullptr, pl3, mono, n, res_out, nullptr, calls_out);
 }
 
 // Device-buffer variant of pm_call_vcf_records (bench.py's device-resident leg): every record gets a row.
@@ -680,6 +758,18 @@ extern "C" int pm_call_vcf_records_device(pm_ctx *c, const pm_site_hdr *d_hdr, c
   if (n && !d_mono) return fail(PM_EINVAL, "pm_call_vcf_records_device: null buffer");
   c->batch_has_nonauto = has_nonauto != 0;
   return run_device(c, d_hdr, d_person_site, d_mono, n, PM_OUT_ALL, d_status_out, d_res_out, d_person_out, n, c->d_n_emit);
+}
+
+// The same with 2 bytes per sample out (d_calls_out[n * n_person] = best | gq << 8) instead of the 96-byte rows.
+extern "C" int pm_call_vcf_records_calls_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site, const double *d_mono,
+                                                size_t n, int has_nonauto, uint16_t *d_status_out, pm_site_result *d_res_out,
+                                                uint16_t *d_calls_out) {
+  if (!c) return fail(PM_EINVAL, "null context");
+  if (!c->par.vcf_input) return fail(PM_EINVAL, "pm_call_vcf_records_calls_device: the ctx was not created with pm_params.vcf_input = 1");
+  if (has_nonauto && !c->have_x) return fail(PM_EUNSUPPORTED, "chrX/chrY/MT records need every family peeled, which the device kernels cannot do for this pedigree");
+  if (n && (!d_mono || !d_calls_out)) return fail(PM_EINVAL, "pm_call_vcf_records_calls_device: null buffer");
+  c->batch_has_nonauto = has_nonauto != 0;
+  return run_device(c, d_hdr, d_person_site, d_mono, n, PM_OUT_ALL, d_status_out, d_res_out, nullptr, n, c->d_n_emit, d_calls_out);
 }
 
 extern "C" void *pm_host_alloc(size_t bytes) {

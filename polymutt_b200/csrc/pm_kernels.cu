@@ -9,6 +9,7 @@
 //
 // All arithmetic is FP64; inputs are uint8 phred likelihoods.  See DESIGN.md for the data layout and
 // the roofline of each kernel.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <math_constants.h>
@@ -275,6 +276,60 @@ __global__ void __launch_bounds__(1024) k_compact(const uint16_t *__restrict__ s
 }
 
 // ================================================================================================
+// 14-byte wire records (pm_person_site_wire) -> 16-byte pm_person_site records the site kernels load as one uint4.
+// HBM-bound byte shuffling: 14 bytes read + 16 written per record.  A block moves tiles of 1,024 records: 896 coalesced
+// 16-byte loads into shared memory, then thread t builds records t, t+256, ... from 32-bit words (record r starts at
+// byte 14 r: word 7 (r/2), plus half a word for odd r) and stores them as coalesced uint4s.
+// ================================================================================================
+constexpr int kUnpackThreads = 256;
+constexpr int kUnpackTile = 1024;                       // records per tile: 14,336 bytes in, 16,384 out
+constexpr int kUnpackWordsIn = kUnpackTile * 14 / 4;    // 3,584
+__global__ void __launch_bounds__(kUnpackThreads) k_unpack_wire(const uint4 *__restrict__ wire, uint4 *__restrict__ recs, size_t n_recs) {
+  __shared__ __align__(16) uint32_t w[kUnpackWordsIn];
+  const size_t n_tiles = (n_recs + kUnpackTile - 1) / kUnpackTile;
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const size_t r0 = tile * kUnpackTile;
+    const int nr = (int)(n_recs - r0 < (size_t)kUnpackTile ? n_recs - r0 : (size_t)kUnpackTile);
+    const int nq = (nr * 14 + 15) / 16;                 // (the wire buffer is allocated with 16 bytes of slack)
+    const uint4 *src = wire + r0 * 14 / 16;             // a tile starts on a 16-byte boundary (1,024 * 14 = 896 * 16)
+    for (int q = threadIdx.x; q < nq; q += kUnpackThreads) reinterpret_cast<uint4 *>(w)[q] = __ldg(src + q);
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += kUnpackThreads) {
+      const int sh = (r & 1) << 4;                      // odd records start in the middle of a word
+      const uint32_t *p = w + 7 * (r >> 1) + 3 * (r & 1);
+      const uint32_t a = p[0], b = p[1], c = p[2], d = p[3];
+      uint4 o;
+      o.x = __funnelshift_r(a, b, sh); o.y = __funnelshift_r(b, c, sh); o.z = __funnelshift_r(c, d, sh);
+      o.w = (d >> sh) & 0xffffu;
+      recs[r0 + (size_t)r] = o;                         // bytes 14, 15 (pm_person_site::pad) are zero
+    }
+    __syncthreads();
+  }
+}
+
+// VCF input, wire form: three bytes per (record, sample) -- int(PL) capped at 255 of the genotypes (a1,a1), (a1,a2),
+// (a2,a2) (FamilyLikelihoodSeq_VCF.cpp:275-279) -- widened to the 16-byte record whose lk[] holds them at the genotype
+// indices of the record's two alleles, every other byte 0.  One thread per (record, sample): a warp reads 96 contiguous
+// bytes and writes 512.
+__global__ void __launch_bounds__(256) k_unpack_pl3(const pm_site_hdr *__restrict__ hdr, const uint8_t *__restrict__ pl3,
+                                                    uint4 *__restrict__ recs, size_t n_records, int np) {
+  const size_t total = n_records * (size_t)np;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const pm_site_hdr h = hdr[i / (size_t)np];
+    const int a1 = h.ref_base, a2 = h.reserved & 0xff;
+    const int g[3] = {geno_index(a1, a1), geno_index(a1, a2), geno_index(a2, a2)};
+    const uint8_t *p = pl3 + 3 * i;
+    uint32_t w[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t v = (uint32_t)__ldg(p + k) << ((g[k] & 3) * 8);
+      w[0] |= g[k] < 4 ? v : 0u; w[1] |= (g[k] >= 4 && g[k] < 8) ? v : 0u; w[2] |= g[k] >= 8 ? v : 0u;
+    }
+    recs[i] = make_uint4(w[0], w[1], w[2], 0u);
+  }
+}
+
+// ================================================================================================
 // microbenchmarks used as roofline denominators
 // ================================================================================================
 __global__ void k_dfma_peak(double *out, int iters) {
@@ -337,6 +392,22 @@ cudaError_t launch_quick_merge(const uint16_t *d_status_q, size_t n_sites, pm_si
 cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,
                            cudaStream_t stream) {
   k_compact<<<1, 1024, 0, stream>>>(d_status, n_sites, d_emit_sites, d_n_emit, all);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_wire(const void *d_wire, uint4 *d_recs, size_t n_recs, int sm_count, cudaStream_t stream) {
+  if (n_recs == 0) return cudaSuccess;
+  const size_t n_tiles = (n_recs + kUnpackTile - 1) / kUnpackTile;
+  const unsigned grid = (unsigned)std::min<size_t>(n_tiles, (size_t)sm_count * 8);  // 8 resident blocks of 256 threads per SM
+  k_unpack_wire<<<grid, kUnpackThreads, 0, stream>>>((const uint4 *)d_wire, d_recs, n_recs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_pl3(const pm_site_hdr *d_hdr, const uint8_t *d_pl3, uint4 *d_recs, size_t n_records, int np, int sm_count, cudaStream_t stream) {
+  const size_t total = n_records * (size_t)np;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)sm_count * 8);
+  k_unpack_pl3<<<grid, 256, 0, stream>>>(d_hdr, d_pl3, d_recs, n_records, np);
   return cudaGetLastError();
 }
 

@@ -48,9 +48,15 @@ cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d
 cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                         const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
-                        int sm_count, bool with_ab, cudaStream_t stream);
+                        uint16_t *d_calls_out, bool has_es, bool ten_state, int sm_count, bool with_ab, cudaStream_t stream);  // ten_state: --denovo on GLF input  // d_calls_out != nullptr: 2 bytes per person instead of d_person_out's 96
 
 cudaError_t launch_pack_calls(const pm_person_result *d_person, size_t n, uint16_t *d_calls, int sm_count, cudaStream_t stream);
+
+// 14-byte wire records -> 16-byte records (d_wire: n_recs * 14 bytes, 16-byte aligned, readable up to the next multiple of 16)
+cudaError_t launch_unpack_wire(const void *d_wire, uint4 *d_recs, size_t n_recs, int sm_count, cudaStream_t stream);
+
+// VCF input: 3 PL bytes per (record, sample) -> 16-byte records (genotype indices from the record's alleles in d_hdr)
+cudaError_t launch_unpack_pl3(const pm_site_hdr *d_hdr, const uint8_t *d_pl3, uint4 *d_recs, size_t n_records, int np, int sm_count, cudaStream_t stream);
 
 cudaError_t launch_dfma_peak(double *d_out, int blocks, int threads, int iters, cudaStream_t stream);
 cudaError_t launch_copy(const void *src, void *dst, size_t bytes, int sm_count, cudaStream_t stream);

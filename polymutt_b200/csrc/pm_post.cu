@@ -30,6 +30,29 @@ __device__ inline void store_person3(pm_person_result &o, double p0, double p1, 
   o.reserved[0] = o.reserved[1] = 0;
 }
 
+// Where a person's result goes: the 96-byte pm_person_result row, or (CALLS: what the --in_vcf writer prints from,
+// FamilyLikelihoodSeq_VCF.cpp:499-517) two bytes, best | gq << 8 -- same arithmetic up to the stored values either way.
+template <bool CALLS>
+struct PersonSink {
+  pm_person_result *out;
+  uint16_t *calls;
+  __device__ __forceinline__ void put3(int i, double p0, double p1, double p2, int best) const {
+    if (CALLS) calls[i] = (uint16_t)(best | ((unsigned)gq_of(best == 0 ? p0 : (best == 1 ? p1 : p2)) << 8));
+    else store_person3(out[i], p0, p1, p2, best);
+  }
+  __device__ __forceinline__ void put10(int i, const double *post, int best) const {
+    if (CALLS) { calls[i] = (uint16_t)(best | ((unsigned)gq_of(post[best]) << 8)); return; }
+    pm_person_result &o = out[i];
+    for (int g = 0; g < 10; g++) o.post[g] = post[g];
+    o.dosage = 0.0; o.best = best; o.gq = gq_of(post[best]); o.ten_state = 1;
+    o.reserved[0] = o.reserved[1] = 0;
+  }
+  __device__ __forceinline__ void zero(int i) const {
+    if (CALLS) calls[i] = 0;
+    else memset(&out[i], 0, sizeof(pm_person_result));
+  }
+};
+
 // likelihoodKidGenotype on chrX / chrY / MT (NucFam:1334-1443) for configurations 1, 2, 6, 7 (0 and 8 have no
 // special case there, 3..5 are zero); `sex` is the kid's own.
 __device__ inline void kid_cfg_nonauto(int cls, int sex, int cfg, double l11, double l12, double l22, double &lk, double &x11,
@@ -55,11 +78,12 @@ __device__ inline void kid_cfg_nonauto(int cls, int sex, int cfg, double l11, do
   }
 }
 
+template <bool CALLS, bool ES, bool DN>
 __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                               const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
                                               const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
                                               size_t res_cap, pm_site_result *__restrict__ res_out,
-                                              pm_person_result *__restrict__ person_out) {
+                                              pm_person_result *__restrict__ person_out, uint16_t *__restrict__ calls_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
   load_tables(run, &sm->t);
@@ -76,17 +100,17 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
     if ((run->site_filter == 1 && hdr[s].chr_class != PM_CHR_AUTO) || (run->site_filter == 2 && hdr[s].chr_class == PM_CHR_AUTO)) continue;
     pm_site_result r = res_all[s];
     const uint4 *recs = recs_all + (size_t)s * np;
-    pm_person_result *out = person_out + row * (size_t)np;
+    const PersonSink<CALLS> out{CALLS ? nullptr : person_out + row * (size_t)np, CALLS ? calls_out + row * (size_t)np : nullptr};
     const DevFam f = run->fams[fi];
     if (r.status != PM_SITE_EMITTED) {  // PM_OUT_ALL rows of sites that print nothing
       if (fi == 0) res_out[row] = r;
-      for (int j = 0; j < f.size; j++) memset(&out[f.first + j], 0, sizeof(pm_person_result));
+      for (int j = 0; j < f.size; j++) out.zero(f.first + j);
       continue;
     }
     const int a1 = r.allele1, a2 = r.allele2;
     const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
     const bool mono = (r.flags & PM_FLAG_MONO) != 0;
-    const bool dn = run->denovo != 0 && !run->vcf_mode;
+    const bool dn = DN && run->denovo != 0 && !run->vcf_mode;  // (instances for runs without --denovo leave the ten-state code out)
     // frequency the posteriors are taken at (main:576-587)
     const double freq = mono ? (dn ? 1.0 : 1.0 - run->theta) : r.freq;
     const double q = 1.0 - freq;
@@ -104,8 +128,8 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
         double m12 = lut[rec_lk(rec, g12)] * pr1;
         double m22 = lut[rec_lk(rec, g22)] * pr2;
         double sum = m11 + m12 + m22;
-        if (sum == 0 || (cls == PM_CHR_Y && sex == 2)) store_person3(out[f.first + j], 0, 0, 0, best3(m11, m12, m22));  // NucFam:781, 788
-        else store_person3(out[f.first + j], m11 / sum, m12 / sum, m22 / sum, best3(m11, m12, m22));
+        if (sum == 0 || (cls == PM_CHR_Y && sex == 2)) out.put3(f.first + j, 0, 0, 0, best3(m11, m12, m22));  // NucFam:781, 788
+        else out.put3(f.first + j, m11 / sum, m12 / sum, m22 / sum, best3(m11, m12, m22));
       }
     } else if (f.kind == 1) {  // nuclear: NucFam:590-752
       const int nk = f.size - 2;
@@ -128,12 +152,12 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
       {
         double p11 = pm9[0] + pm9[1] + pm9[2], p12 = pm9[3] + pm9[4] + pm9[5], p22 = pm9[6] + pm9[7] + pm9[8];
         double sum = p11 + p12 + p22;
-        if (sum == 0) store_person3(out[f.first], 0, 0, 0, best3(p11, p12, p22));
-        else store_person3(out[f.first], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+        if (sum == 0) out.put3(f.first, 0, 0, 0, best3(p11, p12, p22));
+        else out.put3(f.first, p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
         p11 = pm9[0] + pm9[3] + pm9[6]; p12 = pm9[1] + pm9[4] + pm9[7]; p22 = pm9[2] + pm9[5] + pm9[8];
         sum = p11 + p12 + p22;
-        if (sum == 0) store_person3(out[f.first + 1], 0, 0, 0, best3(p11, p12, p22));
-        else store_person3(out[f.first + 1], p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
+        if (sum == 0) out.put3(f.first + 1, 0, 0, 0, best3(p11, p12, p22));
+        else out.put3(f.first + 1, p11 / sum, p12 / sum, p22 / sum, best3(p11, p12, p22));
       }
       // parentGLF * parentPrior per configuration (NucFam:815-823)
       double w9[9];
@@ -149,7 +173,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
         for (int j = 0; j < 9; j++) w9[j] = (fl[j / 3] * ml[j % 3]) * pp[j];
       }
       for (int kid = 0; kid < nk; kid++) {
-        pm_person_result &o = out[f.first + 2 + kid];
+        const int o = f.first + 2 + kid;
         if (!dn) {
           // KidJointGenoLikelihood + likelihoodKidGenotype, NucFam:798-835, 1334-1443
           double J[3] = {0, 0, 0};
@@ -179,7 +203,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
           double sum = J[0] + J[1] + J[2];
           double p0 = 0, p1 = 0, p2 = 0;
           if (sum != 0.0) { p0 = J[0] / sum; p1 = J[1] / sum; p2 = J[2] / sum; }
-          store_person3(o, p0, p1, p2, best3(p0, p1, p2));
+          out.put3(o, p0, p1, p2, best3(p0, p1, p2));
         } else {
           // KidJointGenoLikelihood_denovo, NucFam:838-868, 1446-1551
           double geno[10];
@@ -229,24 +253,23 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
           int best = 0;
           for (int g = 0; g < 10; g++) {
             double pg = sum == 0.0 ? 0.0 : geno[g] / sum;
-            o.post[g] = pg;
+            geno[g] = pg;
             if (mx < pg) { mx = pg; best = g; }
           }
-          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
-          o.reserved[0] = o.reserved[1] = 0;
+          out.put10(o, geno, best);
         }
       }
-    } else {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216)
+    } else if (ES) {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216); instances for pedigrees without one leave it out
       for (int j = 0; j < f.size; j++) {
-        pm_person_result &o = out[f.first + j];
+        const int o = f.first + j;
         if (!dn) {
-          if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { store_person3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
+          if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { out.put3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
           double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g11, cls);
           double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g12, cls);
           double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g22, cls);
           double sum = l11 + l12 + l22;
-          if (sum == 0) store_person3(o, 0, 0, 0, best3(l11, l12, l22));
-          else store_person3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
+          if (sum == 0) out.put3(o, 0, 0, 0, best3(l11, l12, l22));
+          else out.put3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
         } else {
           double lk[10], sum = 0.0;
           for (int g = 0; g < 10; g++) {
@@ -256,11 +279,10 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
           double mx = 0.0;
           int best = 0;
           for (int g = 0; g < 10; g++) {
-            o.post[g] = sum == 0 ? 0.0 : lk[g] / sum;
             if (mx < lk[g]) { mx = lk[g]; best = g; }
+            lk[g] = sum == 0 ? 0.0 : lk[g] / sum;
           }
-          o.dosage = 0.0; o.best = best; o.gq = gq_of(o.post[best]); o.ten_state = 1;
-          o.reserved[0] = o.reserved[1] = 0;
+          out.put10(o, lk, best);
         }
       }
     }
@@ -338,14 +360,20 @@ __global__ void __launch_bounds__(128) k_post_ab(const DevRun *__restrict__ run,
 cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr, const uint4 *d_recs,
                         const pm_site_result *d_res_all, const uint32_t *d_emit_sites, const uint32_t *d_n_emit,
                         size_t max_rows, size_t res_cap, pm_site_result *d_res_out, pm_person_result *d_person_out,
-                        int sm_count, bool with_ab, cudaStream_t stream) {
+                        uint16_t *d_calls_out, bool has_es, bool ten_state, int sm_count, bool with_ab, cudaStream_t stream) {
   if (max_rows == 0) return cudaSuccess;
   static_assert(sizeof(PostSmem) <= 48 * 1024, "k_post's tables fit in the default dynamic shared memory limit");
   size_t want = (max_rows * (size_t)n_fam + 127) / 128;
   size_t cap = (size_t)sm_count * 16;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if (grid == 0) grid = 1;
-  k_post<<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out);
+#define PM_POST(CALLS_, ES_, DN_) \
+  k_post<CALLS_, ES_, DN_><<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out, d_calls_out)
+#define PM_POST2(CALLS_, ES_) do { if (ten_state) PM_POST(CALLS_, ES_, true); else PM_POST(CALLS_, ES_, false); } while (0)
+  if (d_calls_out) { if (has_es) PM_POST2(true, true); else PM_POST2(true, false); }
+  else             { if (has_es) PM_POST2(false, true); else PM_POST2(false, false); }
+#undef PM_POST2
+#undef PM_POST
   if (!with_ab) return cudaGetLastError();
   const size_t ab_cap = (size_t)sm_count * 8;
   k_post_ab<<<(unsigned)(max_rows < ab_cap ? max_rows : ab_cap), 128, 0, stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out);

@@ -657,6 +657,11 @@ __device__ __noinline__ void spec_table_ol(double tol, int log2sper) {
     if (!brent_feed_fast(st, n == 1 ? 0.0 : 1.0, tol)) { complete = 1; break; }
   }
   s_ws.spec_n = n; s_ws.spec_complete = complete;
+  // the slots behind the last point repeat it: the one-pass evaluation works on a fixed number of points without selects
+  for (int j = n; j < kMaxSpec; j++) {
+    s_ws.spec_p[j] = s_ws.spec_p[n - 1]; s_ws.spec_r[j] = s_ws.spec_r[n - 1]; s_ws.spec_q[j] = s_ws.spec_q[n - 1];
+    for (int i = 0; i <= 8; i++) s_ws.spec_qn[i][j] = s_ws.spec_qn[i][n - 1];
+  }
 }
 
 // After the speculative round (thread 0): the likelihoods at all points of the monotone path are in spec_ll.  If none
@@ -891,7 +896,7 @@ struct WideEval {
     double acc[3][NP];
 #pragma unroll
     for (int j = 0; j < NP; j++) {
-      const double qf = s_ws.spec_qn[mine][j < ns ? j : ns - 1];
+      const double qf = s_ws.spec_qn[mine][j];  // (slots >= ns repeat the last point)
 #pragma unroll
       for (int h = 0; h < 3; h++) acc[h][j] = qf;
     }
@@ -916,7 +921,7 @@ struct WideEval {
       if (dn) me_mul(h0, c[0][4]);
 #pragma unroll
       for (int j = 0; j < NP; j++) {
-        const double r = s_ws.spec_r[j < ns ? j : ns - 1];
+        const double r = s_ws.spec_r[j];
 #pragma unroll
         for (int h = 0; h < 3; h++) acc[h][j] *= fma(fma(fma(fma(c[h][4], r, c[h][3]), r, c[h][2]), r, c[h][1]), r, c[h][0]);
       }
@@ -1245,6 +1250,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
         else if (ws->ibcast[2]) step = 7;
         else break;
       }
+      // (every way out of the loop above ends with a block barrier behind the last read of the site buffer: the next site's
+      // copy starts before thread 0 books the result, the other warps are already waiting for it)
+      if (!GM && threadIdx.x == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
       if (threadIdx.x == 0) {
         pm_site_result &r = ws->r;
         if (!vcf) {
@@ -1268,7 +1276,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_sites_wide(const DevRun *__restr
     if (skip && !synced) __syncthreads();
     if (warp == 0) {
       __syncwarp();
-      if (!GM && lane == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
+      if (!GM && skip && lane == 0 && nxt < n_sites) tma_issue_site(site_base, recs_all + nxt * (size_t)np, site_bytes, &ws->mbar);
       if (!skip) {  // the 256-byte result leaves as one coalesced 32 x 8-byte store
         static_assert(sizeof(pm_site_result) == 256, "pm_site_result must be 256 bytes");
         reinterpret_cast<unsigned long long *>(&res[s])[lane] = reinterpret_cast<const unsigned long long *>(&ws->r)[lane];

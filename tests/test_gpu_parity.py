@@ -44,7 +44,10 @@ EXAMPLE_CASES = [
 def _run_both(ped, params, hdr, recs):
     eng = Engine(ped, params)
     st_g, res_g, per_g = eng.call_glf_sites(hdr, recs, capi.PM_OUT_ALL)
+    # the same sites as 14-byte wire records (pm_call_glf_sites_wire, widened on the device): identical bytes out
+    st_w, res_w, per_w = eng.call_glf_sites_wire(hdr, recs, capi.PM_OUT_ALL)
     eng.close()
+    assert np.array_equal(st_w, st_g) and res_w.tobytes() == res_g.tobytes() and per_w.tobytes() == per_g.tobytes()
     ora = OracleEngine(ped, params)
     st_o, res_o, per_o = ora.call_glf_sites(hdr, recs)
     ora.close()
@@ -393,10 +396,13 @@ def test_vcf_records_parity_wide_plans(shape, n, oracle_built):
     eng = Engine(ped, params, lut=lut)
     assert "k_sites_wide" in eng.describe_plan()
     res_g, per_g = eng.call_vcf_records(h, r, mono)
-    res_c, calls = eng.call_vcf_records_calls(h, r, mono)   # the compact form the executable uses: best | gq << 8
+    res_c, calls = eng.call_vcf_records_calls(h, r, mono)   # the compact form: best | gq << 8, written by k_post directly
+    res_p, calls_p = eng.call_vcf_records_pl(h, r, mono)    # the same from three PL bytes per sample (what the executable sends)
     eng.close()
     assert np.array_equal(calls, (per_g["best"].astype(np.uint16) & 0xff) | (per_g["gq"].astype(np.uint16) << 8))
-    assert np.array_equal(res_c["poly_qual"], res_g["poly_qual"]) and np.array_equal(res_c["freq"], res_g["freq"])
+    assert np.array_equal(calls_p, calls)
+    for f in ("poly_qual", "freq", "varllk", "varllk_noprior", "allele1", "allele2", "site"):
+        assert np.array_equal(res_c[f], res_g[f]) and np.array_equal(res_p[f], res_g[f]), f
     ora = OracleEngine(eng.ped, params, lut=lut)
     res_o, per_o = ora.call_vcf_records(h, r, mono)
     ora.close()
@@ -435,7 +441,11 @@ def test_vcf_records_parity(pedfile, n, mixed_classes, example12, oracle_built, 
     params = Params(vcf_input=True)
     eng = Engine(ped, params, lut=lut)
     res_g, per_g = eng.call_vcf_records(h, r, mono)
+    res_p, calls_p = eng.call_vcf_records_pl(h, r, mono)    # three PL bytes per sample in, two bytes per sample out
     eng.close()
+    assert np.array_equal(calls_p, (per_g["best"].astype(np.uint16) & 0xff) | (per_g["gq"].astype(np.uint16) << 8))
+    for f in ("poly_qual", "freq", "varllk", "allele1", "allele2", "site"):
+        assert np.array_equal(res_p[f], res_g[f]), f
     ora = OracleEngine(eng.ped, params, lut=lut)
     res_o, per_o = ora.call_vcf_records(h, r, mono)
     ora.close()

@@ -182,7 +182,7 @@ int run_cli(int argc, char **argv, const Engine &engine) {
   // batch buffers: page-locked when the engine offers it, so H2D/D2H overlap the kernels
   struct HostBuf {
     const Engine &e; void *p = nullptr;
-    HostBuf(const Engine &eng, size_t bytes) : e(eng) { p = e.host_alloc ? e.host_alloc(bytes) : malloc(bytes); if (p) memset(p, 0, bytes); }
+    HostBuf(const Engine &eng, size_t bytes) : e(eng) { p = e.host_alloc ? e.host_alloc(bytes) : calloc(bytes ? bytes : 1, 1); }  // (every byte the engine or the writer reads is written first)
     ~HostBuf() { if (e.host_free) e.host_free(p); else free(p); }
     HostBuf(const HostBuf &) = delete;
   };

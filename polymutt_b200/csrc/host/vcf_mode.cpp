@@ -228,6 +228,34 @@ struct ChunkReader {
   }
 };
 
+// The buffers that cross the engine boundary: page-locked when the engine offers an allocator (the CUDA engine's copies
+// are then asynchronous and at link speed), plain memory otherwise.  The few std::vector members the loop uses.
+template <typename T>
+struct HostVec {
+  const Engine &e;
+  T *p = nullptr;
+  size_t n = 0, cap = 0;
+  explicit HostVec(const Engine &eng) : e(eng) {}
+  HostVec(const HostVec &) = delete;
+  ~HostVec() { release(p); }
+  void release(T *q) { if (!q) return; if (e.host_alloc && e.host_free) e.host_free(q); else free(q); }
+  void resize(size_t m) {
+    if (m > cap) {
+      const size_t want = std::max(m, cap + cap / 2);
+      T *q = (T *)((e.host_alloc && e.host_free) ? e.host_alloc(want * sizeof(T)) : malloc(want * sizeof(T)));
+      if (!q) throw std::bad_alloc();
+      if (n) memcpy(q, p, n * sizeof(T));
+      release(p);
+      p = q; cap = want;
+    }
+    n = m;
+  }
+  size_t size() const { return n; }
+  T *data() { return p; }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+};
+
 template <typename F>
 void parallel_for(size_t n, int threads, F fn) {
   if (threads <= 1 || n < 2) { for (size_t i = 0; i < n; i++) fn(i, 0); return; }
@@ -330,15 +358,15 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
 
   std::vector<LineRec> lines;
   std::vector<Tok> toks;
-  std::vector<pm_site_hdr> hdr;
+  HostVec<pm_site_hdr> hdr(engine);
   // per (line, pedigree column): the three PL bytes of the record's genotypes (a1a1, a1a2, a2a2); engines without the
   // pl3 entry point (the CPU oracle behind the same front end) get them widened to 16-byte records below
-  std::vector<uint8_t> pl3;
+  HostVec<uint8_t> pl3(engine);
   std::vector<pm_person_site> recs;
-  std::vector<double> mono;
-  std::vector<pm_site_result> res;
+  HostVec<double> mono(engine);
+  HostVec<pm_site_result> res(engine);
   std::vector<pm_person_result> pres;   // per-sample results, or (engines with call_vcf_calls) ...
-  std::vector<uint16_t> calls;           // ... best | gq << 8 per sample
+  HostVec<uint16_t> calls(engine);       // ... best | gq << 8 per sample
   const bool compact = engine.call_vcf_calls != nullptr || engine.call_vcf_pl != nullptr;
   std::vector<std::string> text, text_w;  // rows being formatted / rows being written
   std::thread writer;

@@ -66,6 +66,7 @@ struct pm_ctx {
   size_t cap_sites = 0;
   pm_site_result *d_res_all = nullptr;
   uint32_t *d_emit_sites = nullptr;
+  uint32_t *d_tile_scratch = nullptr;   // k_compact_*: emitted sites per tile of 1,024
   uint32_t *d_n_emit = nullptr;
   // staging for the host-buffer entry point
   size_t cap_in_sites = 0, cap_out_rows = 0;
@@ -83,9 +84,14 @@ struct pm_ctx {
   cudaStream_t stream_h2d = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr};
   uint32_t *h_rows = nullptr;                   // pinned
-  uint16_t *d_status = nullptr;
-  pm_site_result *d_res_out = nullptr;
-  pm_person_result *d_person_out = nullptr;
+  uint16_t *d_status = nullptr;                 // VCF input: the per-record status words (not copied back)
+  // GLF host path: two output slots (status, compacted rows, row count)
+  uint16_t *d_gstatus[2] = {nullptr, nullptr};
+  pm_site_result *d_gres[2] = {nullptr, nullptr};
+  pm_person_result *d_gperson[2] = {nullptr, nullptr};
+  uint32_t *d_gemit[2] = {nullptr, nullptr};
+  struct RowFix { size_t first, rows; uint32_t base; };
+  std::vector<RowFix> row_fix;
   // timing of the last call
   float ms_main = 0.f, ms_total = 0.f;
   int launches = 0;
@@ -121,6 +127,7 @@ int ensure_scratch(pm_ctx *c, size_t n_sites) {
   c->cap_sites = 0;
   if ((rc = dev_alloc(&c->d_res_all, n_sites))) return rc;
   if ((rc = dev_alloc(&c->d_emit_sites, n_sites))) return rc;
+  if ((rc = dev_alloc(&c->d_tile_scratch, (n_sites + 1023) / 1024))) return rc;
   if (c->par.quick_call) {
     if ((rc = dev_alloc(&c->d_res_q, n_sites))) return rc;
     if ((rc = dev_alloc(&c->d_status_q, n_sites))) return rc;
@@ -290,6 +297,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
   run.vcf_log_indel = log10(prior);
 
   e = pm::plan_launch(&c->plan, c->n_person, c->n_units, c->n_es, c->sm_count, nullptr);
+  c->plan.ten_state = par->denovo != 0;  // (DevRun::denovo, which the kernels read)
   if (e == cudaErrorNotSupported) {
     fail(PM_EUNSUPPORTED, "pedigree shape not supported by the device kernels yet (%d quartic units, %d extended families, %d persons)", c->n_units, c->n_es, c->n_person);
     delete c; return nullptr;
@@ -323,6 +331,7 @@ extern "C" pm_ctx *pm_create(const pm_pedigree *ped, const pm_params *par, const
     pm::DevRun run_x = run;
     run_x.n_units = (int)D1.units.size(); run_x.n_es = (int)D1.es.size(); run_x.n_kids = 0; run_x.site_filter = 2;
     cudaError_t ex = pm::plan_launch(&c->plan_x, c->n_person, run_x.n_units, run_x.n_es, c->sm_count, nullptr);
+    c->plan_x.ten_state = run_x.denovo != 0;
     if (ex == cudaSuccess) {
       ok = dev_alloc(&c->d_run_x, 1) == PM_OK && dev_alloc(&c->d_fams_x, D1.fams.size()) == PM_OK && dev_alloc(&c->d_units_x, D1.units.size()) == PM_OK &&
            dev_alloc(&c->d_es_x, D1.es.size()) == PM_OK && dev_alloc(&c->d_steps_x, D1.steps.size()) == PM_OK;
@@ -377,7 +386,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   cudaFree(c->d_run_x); cudaFree(c->d_fams_x); cudaFree(c->d_units_x); cudaFree(c->d_es_x); cudaFree(c->d_steps_x);
   cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);
-  cudaFree(c->d_err); cudaFree(c->d_spill); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_n_emit);
+  cudaFree(c->d_err); cudaFree(c->d_spill); cudaFree(c->d_counters); cudaFree(c->d_res_all); cudaFree(c->d_emit_sites); cudaFree(c->d_tile_scratch); cudaFree(c->d_n_emit);
   for (int k = 0; k < 2; k++) { cudaFree(c->d_hdr[k]); cudaFree(c->d_recs[k]); cudaFree(c->d_wire[k]); cudaFree(c->d_pl3[k]); cudaFree(c->d_vres[k]); cudaFree(c->d_vperson[k]); cudaFree(c->d_vcalls[k]);
     if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
     if (c->ev_d2h[k]) cudaEventDestroy(c->ev_d2h[k]);
@@ -385,7 +394,9 @@ extern "C" void pm_destroy(pm_ctx *c) {
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
   if (c->h_rows) cudaFreeHost(c->h_rows);
-  cudaFree(c->d_status); cudaFree(c->d_res_out); cudaFree(c->d_person_out); cudaFree(c->d_mono[0]); cudaFree(c->d_mono[1]);
+  cudaFree(c->d_status);
+  for (int k = 0; k < 2; k++) { cudaFree(c->d_gstatus[k]); cudaFree(c->d_gres[k]); cudaFree(c->d_gperson[k]); cudaFree(c->d_gemit[k]); }
+  cudaFree(c->d_mono[0]); cudaFree(c->d_mono[1]);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -399,6 +410,17 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                       size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
                       pm_person_result *d_person_out, size_t res_cap, uint32_t *d_n_res, uint16_t *d_calls_out = nullptr);
 static int check_device_error(pm_ctx *c);
+
+// the result stream and the per-slot events of the host-buffer entry points, made on first use
+static int ensure_copy_streams(pm_ctx *c) {
+  if (c->stream_d2h) return PM_OK;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
+  }
+  return PM_OK;
+}
 
 extern "C" int pm_call_glf_sites_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site *d_person_site,
                                         size_t n_sites, int out_mode, uint16_t *d_status_out, pm_site_result *d_res_out,
@@ -432,7 +454,7 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
   CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
   const bool ten_state = c->par.denovo && !c->par.vcf_input;
   const bool with_ab = !c->par.denovo && !c->par.vcf_input;  // the allele balance is printed by the non-de-novo GLF writer only
-  CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->stream));
+  CUDA_TRY(pm::launch_compact(d_status_out, n_sites, c->d_emit_sites, d_cnt, out_mode == PM_OUT_ALL, c->d_tile_scratch, c->stream));
   CUDA_TRY(pm::launch_post(c->d_run, c->n_fam, d_hdr, (const uint4 *)d_person_site, c->d_res_all, c->d_emit_sites, d_cnt,
                            out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
                            d_person_out, d_calls_out, c->n_es > 0, ten_state, c->sm_count, with_ab, c->stream));
@@ -441,7 +463,9 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                              out_mode == PM_OUT_ALL ? n_sites : (res_cap < n_sites ? res_cap : n_sites), res_cap, d_res_out,
                              d_person_out, d_calls_out, true, ten_state, c->sm_count, false, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-  c->launches = 4 + (with_ab ? 1 : 0);  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact, k_post [, k_post_ab]
+  // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact (three launches for long batches) or
+  // k_all_rows, k_post [, k_post_es10] [, k_post_ab]
+  c->launches = 2 + ((out_mode != PM_OUT_ALL && n_sites > 8 * 1024) ? 3 : 1) + 1 + ((ten_state && c->n_es > 0) ? 1 : 0) + (with_ab ? 1 : 0);
   if (c->par.quick_call) c->launches += 3;
   if (second) c->launches += 3;
   c->timing_cached = false;
@@ -472,11 +496,11 @@ extern "C" int pm_last_timing(pm_ctx *c, float *ms_main_kernel, float *ms_total,
   return PM_OK;
 }
 
-// Host-buffer entry point.  The batch is cut into chunks of ~48 MB of packed input; chunk k+1 is
-// copied host->device on a second stream while chunk k is being computed (two input slots), so the
-// call runs at the slower of PCIe and the kernels instead of their sum.  Results of a chunk are copied
-// back as soon as its row count is known.  Pinned host buffers (pm_host_alloc) make the copies truly
-// asynchronous; pageable buffers work too, just without the overlap.
+// Host-buffer entry point.  The batch is cut into chunks of ~48 MB of packed input that go through two input slots and
+// two output slots on three streams: while chunk k is computed, chunk k+1 is copied in and the rows of chunk k-1 are
+// copied out -- the host only waits for a chunk's row count (it sizes the copy of its rows) after the next chunk's
+// kernels are already queued, so the call runs at the slower of PCIe and the kernels.  Pinned host buffers
+// (pm_host_alloc) make the copies truly asynchronous; pageable buffers work too, just without the overlap.
 // rec_bytes: 16 (pm_person_site) or 14 (pm_person_site_wire: copied into a staging slot and widened on the device by
 // k_unpack_wire, on the compute stream right in front of the chunk's kernels).
 static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_site, size_t rec_bytes, size_t n_sites,
@@ -502,13 +526,16 @@ static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_
       if ((rc = dev_alloc(&c->d_hdr[k], chunk))) return rc;
       if ((rc = dev_alloc(&c->d_recs[k], chunk * np))) return rc;
     }
-    if ((rc = dev_alloc(&c->d_status, chunk))) return rc;
     c->cap_in_sites = chunk;
   }
   if (chunk > c->cap_out_rows) {  // a chunk can emit at most `chunk` rows
     c->cap_out_rows = 0;
-    if ((rc = dev_alloc(&c->d_res_out, chunk))) return rc;
-    if ((rc = dev_alloc(&c->d_person_out, chunk * np))) return rc;
+    for (int k = 0; k < 2; k++) {
+      if ((rc = dev_alloc(&c->d_gstatus[k], chunk))) return rc;
+      if ((rc = dev_alloc(&c->d_gres[k], chunk))) return rc;
+      if ((rc = dev_alloc(&c->d_gperson[k], chunk * np))) return rc;
+      if ((rc = dev_alloc(&c->d_gemit[k], 1))) return rc;
+    }
     c->cap_out_rows = chunk;
   }
   const bool wire = rec_bytes != sizeof(pm_person_site);
@@ -518,13 +545,16 @@ static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_
       if ((rc = dev_alloc(&c->d_wire[k], chunk * np * rec_bytes + 16))) return rc;  // + 16: the unpack kernel reads whole uint4s
     c->cap_wire_sites = chunk;
   }
-  if (!c->h_rows) CUDA_TRY(cudaHostAlloc((void **)&c->h_rows, sizeof(uint32_t), cudaHostAllocDefault));
+  if (!c->h_rows) CUDA_TRY(cudaHostAlloc((void **)&c->h_rows, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+  if ((rc = ensure_copy_streams(c))) return rc;
   const size_t n_chunks = (n_sites + chunk - 1) / chunk;
   auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n_sites - k * chunk; };
   auto issue_h2d = [&](size_t k) -> cudaError_t {
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, n = chunk_len(k);
-    cudaError_t e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
+    cudaError_t e = cudaSuccess;
+    if (k >= 2) e = cudaStreamWaitEvent(c->stream_h2d, c->ev_done[slot], 0);  // the slot's last reader: chunk k-2's kernels
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_hdr[slot], hdr + base, n * sizeof(pm_site_hdr), cudaMemcpyHostToDevice, c->stream_h2d);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(wire ? (void *)c->d_wire[slot] : (void *)c->d_recs[slot], (const unsigned char *)person_site + base * np * rec_bytes,
                           n * np * rec_bytes, cudaMemcpyHostToDevice, c->stream_h2d);
@@ -532,45 +562,58 @@ static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_
     return e;
   };
   // an error return must not leave a copy in flight that still reads (or writes) the caller's buffers
-  auto bail = [&](int code) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); return code; };
+  auto bail = [&](int code) { cudaStreamSynchronize(c->stream_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream_d2h); return code; };
   size_t total_rows = 0;
   bool overflow = false;
-  float ms_main = 0.f, ms_total = 0.f;
   int launches = 0;
-  cudaError_t e = issue_h2d(0);
-  if (e != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
+  cudaError_t e = cudaSuccess;
+  // chunk k's kernels have been queued: wait for its row count and send its rows home (on the result stream)
+  auto finish = [&](size_t k) -> int {
+    const int slot = (int)(k & 1);
+    const size_t base = k * chunk;
+    if ((e = cudaEventSynchronize(c->ev_done[slot])) != cudaSuccess) return fail(PM_ECUDA, "GLF sites chunk %zu: %s", k, cudaGetErrorString(e));
+    const uint32_t rows = c->h_rows[slot];
+    if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; return PM_OK; }
+    if (rows) {
+      e = cudaMemcpyAsync(res_out + total_rows, c->d_gres[slot], rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream_d2h);
+      if (e == cudaSuccess && person_out)
+        e = cudaMemcpyAsync(person_out + total_rows * np, c->d_gperson[slot], rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream_d2h);
+      if (e != cudaSuccess) return fail(PM_ECUDA, "GLF sites chunk %zu results: %s", k, cudaGetErrorString(e));
+      c->row_fix.push_back({total_rows, (size_t)rows, (uint32_t)base});
+    }
+    if ((e = cudaEventRecord(c->ev_d2h[slot], c->stream_d2h)) != cudaSuccess) return fail(PM_ECUDA, "cudaEventRecord: %s", cudaGetErrorString(e));
+    total_rows += rows;
+    return PM_OK;
+  };
+  c->row_fix.clear();
+  if ((e = issue_h2d(0)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
   for (size_t k = 0; k < n_chunks; k++) {
     const int slot = (int)(k & 1);
     const size_t base = k * chunk, n = chunk_len(k);
-    // slot (k+1)&1 was last read by chunk k-1, whose completion we waited for in the previous iteration
     if (k + 1 < n_chunks && (e = issue_h2d(k + 1)) != cudaSuccess) return bail(fail(PM_ECUDA, "H2D copy: %s", cudaGetErrorString(e)));
     if ((e = cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
+    // the output slot was last copied out for chunk k-2 (finish(k-2) recorded the event, rows or not)
+    if (k >= 2 && (e = cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0)) != cudaSuccess) return bail(fail(PM_ECUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)));
     if (wire && (e = pm::launch_unpack_wire(c->d_wire[slot], c->d_recs[slot], n * np, c->sm_count, c->stream)) != cudaSuccess)
       return bail(fail(PM_ECUDA, "k_unpack_wire: %s", cudaGetErrorString(e)));
-    rc = pm_call_glf_sites_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], n, out_mode, c->d_status, c->d_res_out,
-                                  c->d_person_out, c->cap_out_rows, c->d_n_emit);
+    rc = pm_call_glf_sites_device(c, c->d_hdr[slot], (const pm_person_site *)c->d_recs[slot], n, out_mode, c->d_gstatus[slot], c->d_gres[slot],
+                                  c->d_gperson[slot], c->cap_out_rows, c->d_gemit[slot]);
     if (rc) return bail(rc);
-    e = cudaMemcpyAsync(c->h_rows, c->d_n_emit, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out + base, c->d_status, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    launches += c->launches + (wire ? 1 : 0);
+    e = cudaMemcpyAsync(c->h_rows + slot, c->d_gemit[slot], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && status_out) e = cudaMemcpyAsync(status_out + base, c->d_gstatus[slot], n * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_done[slot], c->stream);
     if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites chunk %zu: %s", k, cudaGetErrorString(e)));
-    float a = 0.f, b = 0.f;
-    pm_last_timing(c, &a, &b, nullptr);
-    ms_main += a; ms_total += b; launches += c->launches + (wire ? 1 : 0);
-    const uint32_t rows = *c->h_rows;
-    if (total_rows + rows > res_cap) { overflow = true; total_rows += rows; continue; }
-    if (rows) {
-      e = cudaMemcpyAsync(res_out + total_rows, c->d_res_out, rows * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess && person_out)
-        e = cudaMemcpyAsync(person_out + total_rows * np, c->d_person_out, rows * np * sizeof(pm_person_result), cudaMemcpyDeviceToHost, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-      if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites chunk %zu results: %s", k, cudaGetErrorString(e)));
-      for (size_t r = 0; r < rows; r++) res_out[total_rows + r].site += (uint32_t)base;
-    }
-    total_rows += rows;
+    if (k >= 1 && (rc = finish(k - 1))) return bail(rc);
   }
-  c->ms_main = ms_main; c->ms_total = ms_total; c->launches = launches;
-  c->timing_cached = true;
+  if ((rc = finish(n_chunks - 1))) return bail(rc);
+  e = cudaStreamSynchronize(c->stream_d2h);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return bail(fail(PM_ECUDA, "GLF sites: %s", cudaGetErrorString(e)));
+  for (const pm_ctx::RowFix &f : c->row_fix)   // site indices of a chunk's rows are chunk-relative on the device
+    for (size_t r = 0; r < f.rows; r++) res_out[f.first + r].site += f.base;
+  c->launches = launches;
+  c->timing_cached = false;  // (the events hold the last chunk's times)
   if (n_res) *n_res = total_rows;
   if ((rc = check_device_error(c))) return rc;  // the error word a kernel sets: polled once per call
   if (overflow) return fail(PM_EINVAL, "pm_call_glf_sites: res_cap %zu too small, %zu rows needed", res_cap, total_rows);
@@ -606,7 +649,7 @@ static int check_device_error(pm_ctx *c) {
 // slots on three streams: while chunk k is computed, chunk k+1 comes in and chunk k-1's results go out; nothing waits for
 // the host inside the loop.  Input: 16-byte records, or (pl3) three PL bytes per sample widened on the device.  Output per
 // sample: person_out (96 bytes) or calls_out (2 bytes: best | gq << 8, all the --in_vcf writer prints from, written by
-// k_post directly) -- either is optional.
+// k_post directly) -- exactly one of the two.
 static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_person_site *person_site, const uint8_t *pl3, const double *mono,
                                size_t n, pm_site_result *res_out, pm_person_result *person_out, uint16_t *calls_out) {
   if (!c) return fail(PM_EINVAL, "null context");
@@ -662,13 +705,7 @@ static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_perso
     for (int k = 0; k < 2; k++) if ((rc = dev_alloc(&c->d_mono[k], chunk))) return rc;
     c->cap_mono = chunk;
   }
-  if (!c->stream_d2h) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; k++) {
-      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
-      CUDA_TRY(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
-    }
-  }
+  if ((rc = ensure_copy_streams(c))) return rc;
   const size_t n_chunks = (n + chunk - 1) / chunk;
   auto chunk_len = [&](size_t k) { return k + 1 < n_chunks ? chunk : n - k * chunk; };
   auto issue_h2d = [&](size_t k) -> cudaError_t {
@@ -707,11 +744,6 @@ static int vcf_records_chunked(pm_ctx *c, const pm_site_hdr *hdr, const pm_perso
                     person_out ? c->d_vperson[slot] : nullptr, m, c->d_n_emit, calls_out ? c->d_vcalls[slot] : nullptr);
     if (rc) return bail(rc);
     launches += c->launches + (pl3 ? 1 : 0);
-    if (person_out && calls_out) {  // both asked for: the rows come from k_post, the calls from the rows
-      e = pm::launch_pack_calls(c->d_vperson[slot], m * np, c->d_vcalls[slot], c->sm_count, c->stream);
-      launches++;
-      if (e != cudaSuccess) return bail(fail(PM_ECUDA, "k_pack_calls: %s", cudaGetErrorString(e)));
-    }
     e = cudaEventRecord(c->ev_done[slot], c->stream);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream_d2h, c->ev_done[slot], 0);
     if (e == cudaSuccess) e = cudaMemcpyAsync(res_out + base, c->d_vres[slot], m * sizeof(pm_site_result), cudaMemcpyDeviceToHost, c->stream_d2h);
@@ -806,6 +838,7 @@ extern "C" int pm_force_wide_plan(pm_ctx *c, int variant, int threads) {
   if (e == cudaErrorInvalidValue) return fail(PM_EINVAL, "pm_force_wide_plan: no variant %d with %d threads", variant, threads);
   if (e == cudaErrorNotSupported) return fail(PM_EUNSUPPORTED, "pm_force_wide_plan: variant %d with %d threads cannot hold this pedigree", variant, threads);
   if (e != cudaSuccess) return fail(PM_ECUDA, "pm_force_wide_plan: %s", cudaGetErrorString(e));
+  p.ten_state = c->par.denovo != 0;
   c->plan = p;
   return ensure_spill(c);
 }

@@ -32,7 +32,9 @@ struct NarrowSmem {
 
 // NA = the instance for chrX / chrY / MT sites (see k_sites_wide): the autosomal one has none of those rules compiled in.
 // ES = the pedigree has extended families (the peel's registers are only paid for where there is something to peel)
-template <int UMAX, bool NA, bool ES>
+// DN = false: the instance for runs without --denovo of pedigrees with extended families -- the ten-state peel and its
+// workspace (the bulk of the stack frame) are not compiled in
+template <int UMAX, bool NA, bool ES, bool DN>
 struct NarrowEval {
   const DevRun *run;
   const uint4 *recs;  // this site's records
@@ -72,7 +74,7 @@ struct NarrowEval {
     if constexpr (ES)
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
-      double lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
+      double lk = (DN && denovo) ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
                          : es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
       sum += log10(lk);
     }
@@ -100,7 +102,7 @@ struct NarrowEval {
   }
 };
 
-template <int UMAX, bool NA, bool ES>
+template <int UMAX, bool NA, bool ES, bool DN>
 __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
                                                                   const pm_site_hdr *__restrict__ hdr,
                                                                   const uint4 *__restrict__ recs_all,
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   const double log_1m_prior = run->cls_log[cls][0];
   if (run->vcf_mode) {  // one record of a VCF: mono is given, one Brent run for (REF, ALT)
     const int a2 = h.reserved & 0xff;
-    NarrowEval<UMAX, NA, ES> ev;
+    NarrowEval<UMAX, NA, ES, DN> ev;
     ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
     double freq = 0.0;
     const double poly = ev.optimize(ref, a2, false, &freq);
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *_
   else if (r.avg_map_qual < run->min_map_quality) r.status = PM_SITE_MIN_MAPQ;
   if (r.status != 0) { res[s] = r; status[s] = status_word(r); return; }
 
-  NarrowEval<UMAX, NA, ES> ev;
+  NarrowEval<UMAX, NA, ES, DN> ev;
   ev.run = run; ev.recs = recs; ev.sm = sm; ev.cls = cls;
   r.reserved = (uint16_t)ref;
   // H0 (main:447-462)
@@ -275,6 +277,67 @@ __global__ void __launch_bounds__(1024) k_compact(const uint16_t *__restrict__ s
   if (tid == 0) *n_emit = base;
 }
 
+// The same in three small launches for long batches (the single block takes ~1.3 us per 1,024 sites: 2.6 ms of a 23 ms
+// step at 2 Mi sites): emitted sites per tile of 1,024 -> exclusive scan of the tile counts (one block) -> scatter.
+__global__ void __launch_bounds__(1024) k_compact_count(const uint16_t *__restrict__ status, size_t n_sites, uint32_t *__restrict__ tile_count) {
+  const size_t s = (size_t)blockIdx.x * 1024 + threadIdx.x;
+  const int flag = s < n_sites && (status[s] & 0xf) == PM_SITE_EMITTED;
+  const int c = __syncthreads_count(flag);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(1024) k_compact_scan(uint32_t *__restrict__ tile_count, unsigned n_tiles, uint32_t *__restrict__ n_emit) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) base = 0;
+  __syncthreads();
+  for (unsigned start = 0; start < n_tiles; start += 1024) {
+    const unsigned i = start + tid;
+    const uint32_t v = i < n_tiles ? tile_count[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      warp_tot[lane] = w;
+    }
+    __syncthreads();
+    if (i < n_tiles) tile_count[i] = base + (warp ? warp_tot[warp - 1] : 0) + x - v;  // exclusive prefix: the tile's first row
+    __syncthreads();
+    if (tid == 0) base += warp_tot[31];
+    __syncthreads();
+  }
+  if (tid == 0) *n_emit = base;
+}
+__global__ void __launch_bounds__(1024) k_compact_scatter(const uint16_t *__restrict__ status, size_t n_sites, const uint32_t *__restrict__ tile_first,
+                                                          uint32_t *__restrict__ emit_sites) {
+  __shared__ uint32_t warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t s = (size_t)blockIdx.x * 1024 + tid;
+  const uint32_t flag = s < n_sites && (status[s] & 0xf) == PM_SITE_EMITTED;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_tot[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+    warp_tot[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  if (flag) emit_sites[tile_first[blockIdx.x] + (warp ? warp_tot[warp - 1] : 0) + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)s;
+}
+
+// PM_OUT_ALL (parity tests, VCF input: every record gets a row): row i is site i, no scan needed
+__global__ void k_all_rows(size_t n_sites, uint32_t *__restrict__ emit_sites, uint32_t *__restrict__ n_emit) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_sites; i += (size_t)gridDim.x * blockDim.x) emit_sites[i] = (uint32_t)i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_emit = (uint32_t)n_sites;
+}
+
 // ================================================================================================
 // 14-byte wire records (pm_person_site_wire) -> 16-byte pm_person_site records the site kernels load as one uint4.
 // HBM-bound byte shuffling: 14 bytes read + 16 written per record.  A block moves tiles of 1,024 records: 896 coalesced
@@ -357,15 +420,16 @@ cudaError_t launch_sites(const LaunchPlan &plan, const DevRun *d_run, const pm_s
   const unsigned grid = (unsigned)((n_sites + kNarrowThreads - 1) / kNarrowThreads);
   cudaError_t e = cudaMemsetAsync(d_err + 1, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
-#define PM_NARROW(U_, ES_)                                                                                                                       \
+#define PM_NARROW(U_, ES_, DN_)                                                                                                                  \
   do {                                                                                                                                         \
-    k_sites_narrow<U_, false, ES_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err); \
-    k_sites_narrow<U_, true, ES_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);  \
+    k_sites_narrow<U_, false, ES_, DN_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err); \
+    k_sites_narrow<U_, true, ES_, DN_><<<grid, kNarrowThreads, sizeof(NarrowSmem), stream>>>(d_run, d_hdr, d_recs, d_mono, n_sites, d_res, d_status, d_err);  \
   } while (0)
-  // three instances: quartic units only (nuclear families, singletons), units + extended families, extended families only
-  if (!plan.es) PM_NARROW(kNarrowMaxUnits, false);
-  else if (plan.units_per_thread == 0) PM_NARROW(0, true);
-  else PM_NARROW(kNarrowMaxUnits, true);
+  // instances: quartic units only (nuclear families, singletons), units + extended families, extended families only -- the
+  // last two with and without the ten-state (--denovo) peel
+  if (!plan.es) PM_NARROW(kNarrowMaxUnits, false, true);
+  else if (plan.units_per_thread == 0) { if (plan.ten_state) PM_NARROW(0, true, true); else PM_NARROW(0, true, false); }
+  else { if (plan.ten_state) PM_NARROW(kNarrowMaxUnits, true, true); else PM_NARROW(kNarrowMaxUnits, true, false); }
 #undef PM_NARROW
   return cudaGetLastError();
 }
@@ -390,8 +454,15 @@ cudaError_t launch_quick_merge(const uint16_t *d_status_q, size_t n_sites, pm_si
 }
 
 cudaError_t launch_compact(const uint16_t *d_status, size_t n_sites, uint32_t *d_emit_sites, uint32_t *d_n_emit, int all,
-                           cudaStream_t stream) {
-  k_compact<<<1, 1024, 0, stream>>>(d_status, n_sites, d_emit_sites, d_n_emit, all);
+                           uint32_t *d_tile_scratch, cudaStream_t stream) {
+  const size_t n_tiles = (n_sites + 1023) / 1024;
+  if (all) k_all_rows<<<(unsigned)std::min<size_t>((n_sites + 255) / 256, 1184), 256, 0, stream>>>(n_sites, d_emit_sites, d_n_emit);
+  else if (n_tiles <= 8 || !d_tile_scratch) k_compact<<<1, 1024, 0, stream>>>(d_status, n_sites, d_emit_sites, d_n_emit, 0);
+  else {
+    k_compact_count<<<(unsigned)n_tiles, 1024, 0, stream>>>(d_status, n_sites, d_tile_scratch);
+    k_compact_scan<<<1, 1024, 0, stream>>>(d_tile_scratch, (unsigned)n_tiles, d_n_emit);
+    k_compact_scatter<<<(unsigned)n_tiles, 1024, 0, stream>>>(d_status, n_sites, d_tile_scratch, d_emit_sites);
+  }
   return cudaGetLastError();
 }
 

@@ -78,8 +78,32 @@ __device__ inline void kid_cfg_nonauto(int cls, int sex, int cfg, double l11, do
   }
 }
 
+// likelihoodKidGenotype (NucFam:798-835, 1334-1443) of one kid under parental configuration cfg: lk = the kid's likelihood,
+// x11 / x12 / x22 its split by the kid's own genotype.  na: chrX / chrY / MT rules (sex = the kid's).
+__device__ __forceinline__ void kid_cfg(int cfg, bool na, int cls, int sex, double l11, double l12, double l22, double &lk, double &x11,
+                                        double &x12, double &x22) {
+  if (na && cfg != 0 && cfg != 8) {
+    if (cfg >= 3 && cfg <= 5) { lk = 0.0; x11 = x12 = x22 = 0.0; }
+    else kid_cfg_nonauto(cls, sex, cfg, l11, l12, l22, lk, x11, x12, x22);
+    return;
+  }
+  switch (cfg) {
+    case 0: lk = l11; x11 = l11; x12 = 0; x22 = 0; break;
+    case 1: case 3: lk = 0.5 * (l11 + l12); x11 = l11 * 0.5; x12 = l12 * 0.5; x22 = 0; break;
+    case 2: case 6: lk = l12; x11 = 0; x12 = l12; x22 = 0; break;
+    case 4: lk = 0.25 * l11 + 0.5 * l12 + 0.25 * l22; x11 = l11 * 0.25; x12 = l12 * 0.5; x22 = l22 * 0.25; break;
+    case 5: case 7: lk = 0.5 * (l12 + l22); x11 = 0; x12 = l12 * 0.5; x22 = l22 * 0.5; break;
+    default: lk = l22; x11 = 0; x12 = 0; x22 = l22; break;
+  }
+}
+
+constexpr int kPostMaxKids = 4;  // sibships up to this size take the pass that looks every kid's likelihoods up once
+
+#ifndef PM_POST_MINB
+#define PM_POST_MINB 4   // measured on 200 families x 5 --in_vcf: 1 (254 registers) 15.3, 3 (168) 17.2, 4 (128) 18.1 M records/s
+#endif
 template <bool CALLS, bool ES, bool DN>
-__global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+__global__ void __launch_bounds__(128, (ES || DN) ? 1 : PM_POST_MINB) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                               const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
                                               const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
                                               size_t res_cap, pm_site_result *__restrict__ res_out,
@@ -172,6 +196,50 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
         }
         for (int j = 0; j < 9; j++) w9[j] = (fl[j / 3] * ml[j % 3]) * pp[j];
       }
+      if (!dn && nk <= kPostMaxKids) {
+        // KidJointGenoLikelihood for every kid of a small sibship in one pass: the reference (and the loop below) looks the
+        // nk kids' likelihoods up and runs likelihoodKidGenotype nk x 9 x nk times; here every kid's three likelihoods are
+        // fetched once and its (lk, x11, x12, x22) taken once per configuration.  Same products and sums in the same order.
+        double kl[kPostMaxKids][3];
+        int ksex[kPostMaxKids];
+#pragma unroll
+        for (int kk = 0; kk < kPostMaxKids; kk++) {
+          kl[kk][0] = kl[kk][1] = kl[kk][2] = 1.0; ksex[kk] = 0;
+          if (kk < nk) {
+            const uint4 rk = recs[f.first + 2 + kk];
+            kl[kk][0] = lut[rec_lk(rk, g11)]; kl[kk][1] = lut[rec_lk(rk, g12)]; kl[kk][2] = lut[rec_lk(rk, g22)];
+            if (na) ksex[kk] = run->sex[f.first + 2 + kk];
+          }
+        }
+        double J[kPostMaxKids][3];
+#pragma unroll
+        for (int cfg = 0; cfg < 9; cfg++) {
+          double lkv[kPostMaxKids], xv[kPostMaxKids][3];
+#pragma unroll
+          for (int kk = 0; kk < kPostMaxKids; kk++)
+            kid_cfg(cfg, na, cls, ksex[kk], kl[kk][0], kl[kk][1], kl[kk][2], lkv[kk], xv[kk][0], xv[kk][1], xv[kk][2]);
+#pragma unroll
+          for (int kid = 0; kid < kPostMaxKids; kid++) {
+            double G[3] = {1.0, 1.0, 1.0};
+#pragma unroll
+            for (int kk = 0; kk < kPostMaxKids; kk++) {
+              if (kk >= nk) continue;
+              if (kk != kid) { G[0] *= lkv[kk]; G[1] *= lkv[kk]; G[2] *= lkv[kk]; }
+              else { G[0] *= xv[kk][0]; G[1] *= xv[kk][1]; G[2] *= xv[kk][2]; }
+            }
+#pragma unroll
+            for (int t = 0; t < 3; t++) J[kid][t] = cfg == 0 ? G[t] * w9[cfg] : J[kid][t] + G[t] * w9[cfg];
+          }
+        }
+#pragma unroll
+        for (int kid = 0; kid < kPostMaxKids; kid++) {
+          if (kid >= nk) continue;
+          const double sum = J[kid][0] + J[kid][1] + J[kid][2];
+          double p0 = 0, p1 = 0, p2 = 0;
+          if (sum != 0.0) { p0 = J[kid][0] / sum; p1 = J[kid][1] / sum; p2 = J[kid][2] / sum; }
+          out.put3(f.first + 2 + kid, p0, p1, p2, best3(p0, p1, p2));
+        }
+      } else
       for (int kid = 0; kid < nk; kid++) {
         const int o = f.first + 2 + kid;
         if (!dn) {
@@ -183,18 +251,7 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
               uint4 rk = recs[f.first + 2 + kk];
               double l11 = lut[rec_lk(rk, g11)], l12 = lut[rec_lk(rk, g12)], l22 = lut[rec_lk(rk, g22)];
               double lk, x11, x12, x22;
-              if (na && cfg != 0 && cfg != 8) {
-                if (cfg >= 3 && cfg <= 5) { lk = 0.0; x11 = x12 = x22 = 0.0; }
-                else kid_cfg_nonauto(cls, run->sex[f.first + 2 + kk], cfg, l11, l12, l22, lk, x11, x12, x22);
-              } else
-              switch (cfg) {
-                case 0: lk = l11; x11 = l11; x12 = 0; x22 = 0; break;
-                case 1: case 3: lk = 0.5 * (l11 + l12); x11 = l11 * 0.5; x12 = l12 * 0.5; x22 = 0; break;
-                case 2: case 6: lk = l12; x11 = 0; x12 = l12; x22 = 0; break;
-                case 4: lk = 0.25 * l11 + 0.5 * l12 + 0.25 * l22; x11 = l11 * 0.25; x12 = l12 * 0.5; x22 = l22 * 0.25; break;
-                case 5: case 7: lk = 0.5 * (l12 + l22); x11 = 0; x12 = l12 * 0.5; x22 = l22 * 0.5; break;
-                default: lk = l22; x11 = 0; x12 = 0; x22 = l22; break;
-              }
+              kid_cfg(cfg, na, cls, na ? run->sex[f.first + 2 + kk] : 0, l11, l12, l22, lk, x11, x12, x22);
               if (kk != kid) { G[0] *= lk; G[1] *= lk; G[2] *= lk; }
               else { G[0] *= x11; G[1] *= x12; G[2] *= x22; }
             }
@@ -259,7 +316,8 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
           out.put10(o, geno, best);
         }
       }
-    } else if (ES) {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216); instances for pedigrees without one leave it out
+    } else if (ES && !dn) {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216); instances for pedigrees without one
+                             // leave it out; under --denovo (ten pinned genotypes per person) k_post_es10 does it, a warp per person
       for (int j = 0; j < f.size; j++) {
         const int o = f.first + j;
         if (!dn) {
@@ -270,19 +328,6 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
           double sum = l11 + l12 + l22;
           if (sum == 0) out.put3(o, 0, 0, 0, best3(l11, l12, l22));
           else out.put3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
-        } else {
-          double lk[10], sum = 0.0;
-          for (int g = 0; g < 10; g++) {
-            lk[g] = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, mut, j, g, cls);
-            sum += lk[g];
-          }
-          double mx = 0.0;
-          int best = 0;
-          for (int g = 0; g < 10; g++) {
-            if (mx < lk[g]) { mx = lk[g]; best = g; }
-            lk[g] = sum == 0 ? 0.0 : lk[g] / sum;
-          }
-          out.put10(o, lk, best);
         }
       }
     }
@@ -300,6 +345,62 @@ __global__ void __launch_bounds__(128) k_post(const DevRun *__restrict__ run, co
   }
 }
 
+
+// Ten-state genotype posteriors of extended-family members (--denovo; FLSeq:140-216): every person's ten genotypes are
+// pinned in turn and the family re-peeled -- 200 ten-state peels for a 20-member pedigree.  On one thread of k_post that
+// chain took ~4 ms however few rows a batch emitted (a third of a CEPH --denovo step); here a warp owns one (row, family,
+// person) and lane g < 10 peels with genotype g pinned.  The same es_likelihood<10> per genotype, the ten values summed
+// in genotype order by lane 0: the same bits as the serial loop.
+template <bool CALLS>
+__global__ void __launch_bounds__(128) k_post_es10(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                                   const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
+                                                   const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
+                                                   size_t res_cap, pm_person_result *__restrict__ person_out, uint16_t *__restrict__ calls_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
+  load_tables(run, &sm->t);
+  __syncthreads();
+  if (run->denovo == 0 || run->vcf_mode != 0 || run->n_es == 0) return;
+  const uint32_t n_emit = *n_emit_ptr;
+  const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
+  const int np = run->n_person, lane = threadIdx.x & 31;
+  const size_t per_row = (size_t)run->n_es * kMaxEsPersons;
+  const size_t total = n_rows * per_row;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const double *lut = sm->t.lut, *mut = sm->t.mut;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
+    const size_t row = w / per_row;
+    const int e = (int)((w % per_row) / kMaxEsPersons), j = (int)(w % kMaxEsPersons);
+    const DevFam f = run->fams[run->es_fams[e]];
+    if (j >= f.size) continue;
+    const uint32_t s = emit_sites[row];
+    const int cls = hdr[s].chr_class;
+    if ((run->site_filter == 1 && cls != PM_CHR_AUTO) || (run->site_filter == 2 && cls == PM_CHR_AUTO)) continue;
+    const pm_site_result *r = res_all + s;
+    if (r->status != PM_SITE_EMITTED) continue;  // (k_post has zeroed the row's persons)
+    const int a1 = r->allele1, a2 = r->allele2;
+    const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
+    const double freq = (r->flags & PM_FLAG_MONO) ? 1.0 : r->freq;  // main:576-587 under --denovo
+    const uint4 *recs = recs_all + (size_t)s * np;
+    double mine = 0.0;
+    if (lane < 10) mine = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, mut, j, lane, cls);
+    double lk[10];
+#pragma unroll
+    for (int g = 0; g < 10; g++) lk[g] = __shfl_sync(0xffffffffu, mine, g);
+    if (lane == 0) {
+      double sum = 0.0;
+      for (int g = 0; g < 10; g++) sum += lk[g];
+      double mx = 0.0;
+      int best = 0;
+      for (int g = 0; g < 10; g++) {
+        if (mx < lk[g]) { mx = lk[g]; best = g; }
+        lk[g] = sum == 0 ? 0.0 : lk[g] / sum;
+      }
+      const PersonSink<CALLS> out{CALLS ? nullptr : person_out + row * (size_t)np, CALLS ? calls_out + row * (size_t)np : nullptr};
+      out.put10(f.first + j, lk, best);
+    }
+  }
+}
 
 // CalculateAB (NucFam:1006-1039) for the emitted autosomal rows of a run without --denovo: one block per row, the persons
 // spread over its threads (the loop is 3,000 divisions long for 1,000 trios: on one thread of k_post it took longer than
@@ -374,21 +475,17 @@ cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr
   else             { if (has_es) PM_POST2(false, true); else PM_POST2(false, false); }
 #undef PM_POST2
 #undef PM_POST
+  if (ten_state && has_es) {  // the extended families' members: a warp per (row, family, person)
+    size_t warps = max_rows * 64;  // enough to start with; the kernel strides over the rest
+    const size_t es_cap = (size_t)sm_count * 8 * 4;
+    if (warps > es_cap) warps = es_cap;
+    const unsigned es_grid = (unsigned)((warps + 3) / 4);
+    if (d_calls_out) k_post_es10<true><<<es_grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, nullptr, d_calls_out);
+    else k_post_es10<false><<<es_grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_person_out, nullptr);
+  }
   if (!with_ab) return cudaGetLastError();
   const size_t ab_cap = (size_t)sm_count * 8;
   k_post_ab<<<(unsigned)(max_rows < ab_cap ? max_rows : ab_cap), 128, 0, stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out);
-  return cudaGetLastError();
-}
-
-// The two bytes per sample the VCF-input writer prints from (GT from bestGenoIdx, GQ): best | gq << 8.
-__global__ void k_pack_calls(const pm_person_result *__restrict__ person, size_t n, uint16_t *__restrict__ calls) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    calls[i] = (uint16_t)((person[i].best & 0xff) | ((unsigned)person[i].gq << 8));
-}
-cudaError_t launch_pack_calls(const pm_person_result *d_person, size_t n, uint16_t *d_calls, int sm_count, cudaStream_t stream) {
-  if (n == 0) return cudaSuccess;
-  const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
-  k_pack_calls<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(d_person, n, d_calls);
   return cudaGetLastError();
 }
 

@@ -83,6 +83,9 @@ def vcf_mode(n_rec):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "vcf":   # only the --in_vcf runs: gpu_cli_e2e.py vcf <records>
+        vcf_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 10000)
+        sys.exit(0)
     glf_mode(int(sys.argv[1]) if len(sys.argv) > 1 else 12000)
     glf_mode(int(sys.argv[3]) if len(sys.argv) > 3 else 8000, outdir="/tmp/e2e_glf_all", all_sites_only=True)
     vcf_mode(int(sys.argv[2]) if len(sys.argv) > 2 else 10000)

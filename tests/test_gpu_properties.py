@@ -69,6 +69,17 @@ def test_split_permutation_determinism_and_entry_points(workload):
     r5 = d_res.cpu().numpy().view(capi.SITE_RESULT_DTYPE).reshape(-1)[:len(emitted)]
     p5 = d_per.cpu().numpy().view(capi.PERSON_RESULT_DTYPE).reshape(cap, ped.n_person)[:len(emitted)]
     assert np.array_equal(r5["site"], emitted) and _fields_equal(r5, res[emitted]) and _fields_equal(p5, per[emitted])
+    # host buffers, PM_OUT_EMITTED: 23 chunks in flight on three streams, the rows of all of them compacted in site order
+    # -- as 16-byte records and as 14-byte wire records
+    for call in (eng.call_glf_sites, eng.call_glf_sites_wire):
+        s6, r6, p6 = call(hdr, recs, capi.PM_OUT_EMITTED, res_cap=cap)
+        assert np.array_equal(s6, st) and len(r6) == len(emitted)
+        assert np.array_equal(r6["site"], emitted) and _fields_equal(r6, res[emitted]) and _fields_equal(p6, per[emitted])
+    with pytest.raises(RuntimeError, match="too small"):
+        eng.call_glf_sites(hdr, recs, capi.PM_OUT_EMITTED, res_cap=3)
+    s7, r7, p7 = eng.call_glf_sites(hdr[:5000], recs[:5000], capi.PM_OUT_EMITTED, res_cap=cap)   # the ctx is still good after the error
+    k7 = int(np.sum(emitted < 5000))
+    assert np.array_equal(s7, st[:5000]) and _fields_equal(r7, res[emitted[:k7]])
     # a result buffer that is too small is reported, not overrun
     d_n.zero_()
     eng.call_glf_sites_device(d_hdr.data_ptr(), d_recs.data_ptr(), N_SITES, capi.PM_OUT_EMITTED, d_status.data_ptr(), d_res.data_ptr(),

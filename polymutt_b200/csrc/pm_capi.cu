@@ -464,10 +464,10 @@ static int run_device(pm_ctx *c, const pm_site_hdr *d_hdr, const pm_person_site 
                              d_person_out, d_calls_out, true, ten_state, c->sm_count, false, c->stream));
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
   // the site kernel's autosomal instance + its (normally empty) chrX/Y/MT one, k_compact (three launches for long batches) or
-  // k_all_rows, k_post [, k_post_es10] [, k_post_ab]
-  c->launches = 2 + ((out_mode != PM_OUT_ALL && n_sites > 8 * 1024) ? 3 : 1) + 1 + ((ten_state && c->n_es > 0) ? 1 : 0) + (with_ab ? 1 : 0);
+  // k_all_rows, k_post [, k_post_es] [, k_post_ab]
+  c->launches = 2 + ((out_mode != PM_OUT_ALL && n_sites > 8 * 1024) ? 3 : 1) + 1 + (c->n_es > 0 ? 1 : 0) + (with_ab ? 1 : 0);
   if (c->par.quick_call) c->launches += 3;
-  if (second) c->launches += 3;
+  if (second) c->launches += 4;  // both instances of the site kernel, k_post, k_post_es on the all-families-peeled description
   c->timing_cached = false;
   return PM_OK;
 }

@@ -102,8 +102,8 @@ constexpr int kPostMaxKids = 4;  // sibships up to this size take the pass that 
 #ifndef PM_POST_MINB
 #define PM_POST_MINB 4   // measured on 200 families x 5 --in_vcf: 1 (254 registers) 15.3, 3 (168) 17.2, 4 (128) 18.1 M records/s
 #endif
-template <bool CALLS, bool ES, bool DN>
-__global__ void __launch_bounds__(128, (ES || DN) ? 1 : PM_POST_MINB) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+template <bool CALLS, bool DN>
+__global__ void __launch_bounds__(128, DN ? 1 : PM_POST_MINB) k_post(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
                                               const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
                                               const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
                                               size_t res_cap, pm_site_result *__restrict__ res_out,
@@ -316,21 +316,7 @@ __global__ void __launch_bounds__(128, (ES || DN) ? 1 : PM_POST_MINB) k_post(con
           out.put10(o, geno, best);
         }
       }
-    } else if (ES && !dn) {  // extended pedigree: pin each genotype and re-peel (FLSeq:140-216); instances for pedigrees without one
-                             // leave it out; under --denovo (ten pinned genotypes per person) k_post_es10 does it, a warp per person
-      for (int j = 0; j < f.size; j++) {
-        const int o = f.first + j;
-        if (!dn) {
-          if (cls == PM_CHR_Y && run->sex[f.first + j] == 2) { out.put3(o, 0, 0, 0, 0); continue; }  // FLSeq:181-188
-          double l11 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g11, cls);
-          double l12 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g12, cls);
-          double l22 = es_likelihood<3>(run, f, recs, g11, g12, g22, false, freq, lut, mut, j, g22, cls);
-          double sum = l11 + l12 + l22;
-          if (sum == 0) out.put3(o, 0, 0, 0, best3(l11, l12, l22));
-          else out.put3(o, l11 / sum, l12 / sum, l22 / sum, best3(l11, l12, l22));
-        }
-      }
-    }
+    }  // (extended families: k_post_es, a warp per person)
     if (fi == 0) {
       // CalculateAB (NucFam:1006-1039), only printed by the non-de-novo writer on autosomes
       if (nonauto) {
@@ -346,21 +332,22 @@ __global__ void __launch_bounds__(128, (ES || DN) ? 1 : PM_POST_MINB) k_post(con
 }
 
 
-// Ten-state genotype posteriors of extended-family members (--denovo; FLSeq:140-216): every person's ten genotypes are
-// pinned in turn and the family re-peeled -- 200 ten-state peels for a 20-member pedigree.  On one thread of k_post that
-// chain took ~4 ms however few rows a batch emitted (a third of a CEPH --denovo step); here a warp owns one (row, family,
-// person) and lane g < 10 peels with genotype g pinned.  The same es_likelihood<10> per genotype, the ten values summed
-// in genotype order by lane 0: the same bits as the serial loop.
-template <bool CALLS>
-__global__ void __launch_bounds__(128) k_post_es10(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
-                                                   const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
-                                                   const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
-                                                   size_t res_cap, pm_person_result *__restrict__ person_out, uint16_t *__restrict__ calls_out) {
+// Genotype posteriors of extended-family members (FLSeq:140-216): every person's genotypes are pinned in turn and the
+// family re-peeled -- 3 peels per person bi-allelic, 10 under --denovo: 200 ten-state peels for a 20-member pedigree.
+// On one thread per (row, family) (round 1) that chain took ~4 ms however few rows a batch emitted (a third of a CEPH
+// --denovo step); here a warp owns one (row, family, person) and lane g < A peels with genotype g pinned.  The same
+// es_likelihood<A> per genotype, the values summed in genotype order by lane 0: the same bits as the serial loop.
+template <int A, bool CALLS>
+__global__ void __launch_bounds__(128) k_post_es(const DevRun *__restrict__ run, const pm_site_hdr *__restrict__ hdr,
+                                                 const uint4 *__restrict__ recs_all, const pm_site_result *__restrict__ res_all,
+                                                 const uint32_t *__restrict__ emit_sites, const uint32_t *__restrict__ n_emit_ptr,
+                                                 size_t res_cap, pm_person_result *__restrict__ person_out, uint16_t *__restrict__ calls_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PostSmem *sm = reinterpret_cast<PostSmem *>(smem_raw);
   load_tables(run, &sm->t);
   __syncthreads();
-  if (run->denovo == 0 || run->vcf_mode != 0 || run->n_es == 0) return;
+  constexpr bool dn = A == 10;
+  if ((run->denovo != 0 && run->vcf_mode == 0) != dn || run->n_es == 0) return;
   const uint32_t n_emit = *n_emit_ptr;
   const size_t n_rows = n_emit < res_cap ? n_emit : res_cap;
   const int np = run->n_person, lane = threadIdx.x & 31;
@@ -378,26 +365,38 @@ __global__ void __launch_bounds__(128) k_post_es10(const DevRun *__restrict__ ru
     if ((run->site_filter == 1 && cls != PM_CHR_AUTO) || (run->site_filter == 2 && cls == PM_CHR_AUTO)) continue;
     const pm_site_result *r = res_all + s;
     if (r->status != PM_SITE_EMITTED) continue;  // (k_post has zeroed the row's persons)
+    const PersonSink<CALLS> out{CALLS ? nullptr : person_out + row * (size_t)np, CALLS ? calls_out + row * (size_t)np : nullptr};
+    const int o = f.first + j;
+    if (!dn && cls == PM_CHR_Y && run->sex[o] == 2) {  // FLSeq:181-188
+      if (lane == 0) out.put3(o, 0, 0, 0, 0);
+      continue;
+    }
     const int a1 = r->allele1, a2 = r->allele2;
     const int g11 = geno_index(a1, a1), g12 = geno_index(a1, a2), g22 = geno_index(a2, a2);
-    const double freq = (r->flags & PM_FLAG_MONO) ? 1.0 : r->freq;  // main:576-587 under --denovo
+    // frequency the posteriors are taken at (main:576-587)
+    const double freq = (r->flags & PM_FLAG_MONO) ? (dn ? 1.0 : 1.0 - run->theta) : r->freq;
     const uint4 *recs = recs_all + (size_t)s * np;
+    const int pinned = dn ? lane : (lane == 0 ? g11 : (lane == 1 ? g12 : g22));
     double mine = 0.0;
-    if (lane < 10) mine = es_likelihood<10>(run, f, recs, g11, g12, g22, true, freq, lut, mut, j, lane, cls);
-    double lk[10];
+    if (lane < A) mine = es_likelihood<A>(run, f, recs, g11, g12, g22, dn, freq, lut, mut, j, pinned, cls);
+    double lk[A];
 #pragma unroll
-    for (int g = 0; g < 10; g++) lk[g] = __shfl_sync(0xffffffffu, mine, g);
-    if (lane == 0) {
+    for (int g = 0; g < A; g++) lk[g] = __shfl_sync(0xffffffffu, mine, g);
+    if (lane != 0) continue;
+    if constexpr (!dn) {
+      const double sum = lk[0] + lk[1] + lk[2];
+      if (sum == 0) out.put3(o, 0, 0, 0, best3(lk[0], lk[1], lk[2]));
+      else out.put3(o, lk[0] / sum, lk[1] / sum, lk[2] / sum, best3(lk[0], lk[1], lk[2]));
+    } else {
       double sum = 0.0;
-      for (int g = 0; g < 10; g++) sum += lk[g];
+      for (int g = 0; g < A; g++) sum += lk[g];
       double mx = 0.0;
       int best = 0;
-      for (int g = 0; g < 10; g++) {
+      for (int g = 0; g < A; g++) {
         if (mx < lk[g]) { mx = lk[g]; best = g; }
         lk[g] = sum == 0 ? 0.0 : lk[g] / sum;
       }
-      const PersonSink<CALLS> out{CALLS ? nullptr : person_out + row * (size_t)np, CALLS ? calls_out + row * (size_t)np : nullptr};
-      out.put10(f.first + j, lk, best);
+      out.put10(o, lk, best);
     }
   }
 }
@@ -468,20 +467,21 @@ cudaError_t launch_post(const DevRun *d_run, int n_fam, const pm_site_hdr *d_hdr
   size_t cap = (size_t)sm_count * 16;
   unsigned grid = (unsigned)(want < cap ? want : cap);
   if (grid == 0) grid = 1;
-#define PM_POST(CALLS_, ES_, DN_) \
-  k_post<CALLS_, ES_, DN_><<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out, d_calls_out)
-#define PM_POST2(CALLS_, ES_) do { if (ten_state) PM_POST(CALLS_, ES_, true); else PM_POST(CALLS_, ES_, false); } while (0)
-  if (d_calls_out) { if (has_es) PM_POST2(true, true); else PM_POST2(true, false); }
-  else             { if (has_es) PM_POST2(false, true); else PM_POST2(false, false); }
-#undef PM_POST2
+#define PM_POST(CALLS_, DN_) \
+  k_post<CALLS_, DN_><<<grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_res_out, d_person_out, d_calls_out)
+  if (d_calls_out) { if (ten_state) PM_POST(true, true); else PM_POST(true, false); }
+  else             { if (ten_state) PM_POST(false, true); else PM_POST(false, false); }
 #undef PM_POST
-  if (ten_state && has_es) {  // the extended families' members: a warp per (row, family, person)
+  if (has_es) {  // the extended families' members: a warp per (row, family, person)
     size_t warps = max_rows * 64;  // enough to start with; the kernel strides over the rest
     const size_t es_cap = (size_t)sm_count * 8 * 4;
     if (warps > es_cap) warps = es_cap;
     const unsigned es_grid = (unsigned)((warps + 3) / 4);
-    if (d_calls_out) k_post_es10<true><<<es_grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, nullptr, d_calls_out);
-    else k_post_es10<false><<<es_grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_person_out, nullptr);
+#define PM_POST_ES(A_, CALLS_) \
+  k_post_es<A_, CALLS_><<<es_grid, 128, sizeof(PostSmem), stream>>>(d_run, d_hdr, d_recs, d_res_all, d_emit_sites, d_n_emit, res_cap, d_person_out, d_calls_out)
+    if (ten_state) { if (d_calls_out) PM_POST_ES(10, true); else PM_POST_ES(10, false); }
+    else           { if (d_calls_out) PM_POST_ES(3, true); else PM_POST_ES(3, false); }
+#undef PM_POST_ES
   }
   if (!with_ab) return cudaGetLastError();
   const size_t ab_cap = (size_t)sm_count * 8;

@@ -198,66 +198,83 @@ __device__ double es_likelihood10(const DevRun *__restrict__ run, const DevFam f
   return lk;
 }
 
+// ================================================================================================
+// Three-state peel (bi-allelic).  Arithmetic as the reference's (ES:990-1057 with the _BA tables), but a person's partial
+// lives in local memory only from the moment a peel step multiplies into it: until then it is its initial value, three
+// table look-ups on the person's record, recomputed where it is read (a leaf child is read once).  A run of children of
+// one couple accumulates the nine products of the marriage partial in registers and stores them once.  For the 20-member
+// CEPH pedigree that is 2 persons and one marriage partial in local memory instead of 20 and 14 read-modify-write rounds
+// (ncu of the round-2 kernel: long-scoreboard stall 10 warps per issue cycle, 6 KB of local-memory write-back to DRAM
+// per site).
 // NA = false is the autosomal code with none of the chrX / chrY / MT rules compiled in (cls_ ignored): the rules sit in
 // the innermost loops of the peel and cost the narrow kernel 40 % when they were runtime branches.
-template <int A, bool NA, typename RecPtr>
-__device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
-                                     bool denovo, double freq, const double *__restrict__ lut,
-                                     const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
-  if constexpr (A == 10) return es_likelihood10<NA>(run, f, recs, g11, g12, g22, denovo, freq, lut, mut, pin_person, pin_geno, cls_);
+// ================================================================================================
+template <bool NA, typename RecPtr>
+__device__ double es_likelihood3(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22, double freq,
+                                 const double *__restrict__ lut, int pin_person, int pin_geno, int cls_) {
+  constexpr int A = 3;
   double part[kMaxEsPersons * A];
   double mp[kMaxMp * A * A];
+  unsigned long long live = 0ull;  // bit i: person i's partial has been materialised in part[]
+  static_assert(kMaxEsPersons <= 64, "one bit per family member");
   const int gi[3] = {g11, g12, g22};
   const double q = 1.0 - freq;
   const int cls = NA ? cls_ : PM_CHR_AUTO;
   const uint8_t *sexes = NA ? run->sex + f.first : nullptr;
-  for (int i = 0; i < f.size; i++) {
-    uint4 r = recs[f.first + i];
-    double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+  // SetFounderPriors_BA + InitializePartials_BA, ES:643-687, 1449-1465
+  auto initial = [&](int i, double *o) {
+    const uint4 r = recs[f.first + i];
+    double pr[3] = {freq * freq, 2 * freq * q, q * q};
+    bool yfemale = false;
     if constexpr (NA) {
       const bool male = sexes[i] == 1;
       if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
       else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
+      yfemale = cls == PM_CHR_Y && sexes[i] == 2;
     }
-    if (A == 3) {
-      bool yfemale = false;
-      if constexpr (NA) yfemale = cls == PM_CHR_Y && sexes[i] == 2;
-      for (int j = 0; j < 3; j++) {
-        double pen = lut[rec_lk(r, gi[j])];
-        if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
-        part[i * 3 + j] = yfemale ? 1.0 : ((i < f.founders) ? pr[j] * pen : pen);  // InitializePartials_BA, ES:1449-1465
-      }
-    } else {
-      for (int g = 0; g < 10; g++) {
-        double pen = lut[rec_lk(r, g)];
-        if (i == pin_person && g != pin_geno) pen = 0.0;
-        if (i < f.founders) {  // InitializePartials, ES:1434-1446
-          double prior = g == g11 ? pr[0] : (g == g12 ? pr[1] : (g == g22 ? pr[2] : 0.0));
-          part[i * 10 + g] = prior * pen;
-        } else {
-          part[i * 10 + g] = pen;
-        }
-      }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double pen = lut[rec_lk(r, gi[j])];
+      if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
+      o[j] = yfemale ? 1.0 : ((i < f.founders) ? pr[j] * pen : pen);
     }
-  }
+  };
+  auto load = [&](int i, double *o) {
+    if ((live >> i) & 1ull) { o[0] = part[i * A]; o[1] = part[i * A + 1]; o[2] = part[i * A + 2]; }
+    else initial(i, o);
+  };
   const DevStep *steps = run->steps + f.step_first;
   for (int s = 0; s < f.n_steps; s++) {
     const DevStep st = steps[s];
     if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
-      double *m = mp + st.mp * A * A;
-      const double *pc = part + st.from0 * A;
-      for (int i = 0; i < A; i++)
-        for (int j = 0; j < A; j++) {
-          double sum = 0;
-          if (A == 3) {
-            if constexpr (NA) { for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k]; }
+      double acc[A * A];
+      if (!st.flag) {
+#pragma unroll
+        for (int e = 0; e < A * A; e++) acc[e] = mp[st.mp * A * A + e];
+      }
+      int s2 = s;
+      for (; s2 < f.n_steps; s2++) {
+        const DevStep sk = steps[s2];
+        if (sk.type != PM_PEEL_CHILD_TO_PARENTS || sk.mp != st.mp) break;
+        double pc[A];
+        load(sk.from0, pc);
+#pragma unroll
+        for (int i = 0; i < A; i++)
+#pragma unroll
+          for (int j = 0; j < A; j++) {
+            double sum = 0;
+            if constexpr (NA) { for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[sk.from0], i, j, k) * pc[k]; }
             else { for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k]; }
+            acc[i * A + j] = sk.flag ? sum : acc[i * A + j] * sum;  // a fresh marriage partial starts at 1
           }
-          m[i * A + j] = st.flag ? sum : m[i * A + j] * sum;  // a fresh marriage partial starts at 1
-        }
+      }
+#pragma unroll
+      for (int e = 0; e < A * A; e++) mp[st.mp * A * A + e] = acc[e];
+      s = s2 - 1;
     } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
-      const double *pf = part + st.from0 * A;
-      double *pt = part + st.to0 * A;
+      double pf[A], pt[A];
+      load(st.from0, pf);
+      load(st.to0, pt);
       if (st.mp < 0) {
         double sum = 0.0;
         for (int j = 0; j < A; j++) sum += pf[j];
@@ -271,9 +288,13 @@ __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFa
           pt[i] *= sum;
         }
       }
+      part[st.to0 * A] = pt[0]; part[st.to0 * A + 1] = pt[1]; part[st.to0 * A + 2] = pt[2];
+      live |= 1ull << st.to0;
     } else {
-      const double *pf = part + st.from0 * A, *pm_ = part + st.from1 * A;
-      double *pc = part + st.to0 * A;
+      double pf[A], pm_[A], pc[A];
+      load(st.from0, pf);
+      load(st.from1, pm_);
+      load(st.to0, pc);
       const double *m = st.mp >= 0 ? mp + st.mp * A * A : nullptr;
       for (int k = 0; k < A; k++) {
         double sum = 0.0;
@@ -286,12 +307,24 @@ __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFa
           }
         pc[k] *= sum;
       }
+      part[st.to0 * A] = pc[0]; part[st.to0 * A + 1] = pc[1]; part[st.to0 * A + 2] = pc[2];
+      live |= 1ull << st.to0;
     }
   }
-  const double *pfin = part + steps[f.n_steps - 1].to0 * A;
+  double pfin[A];
+  load(steps[f.n_steps - 1].to0, pfin);
   double lk = 0.0;
   for (int i = 0; i < A; i++) lk += pfin[i];
   return lk;
+}
+
+template <int A, bool NA, typename RecPtr>
+__device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                     bool denovo, double freq, const double *__restrict__ lut,
+                                     const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
+  static_assert(A == 3 || A == 10, "three-state (bi-allelic) or ten-state (--denovo) peel");
+  if constexpr (A == 10) return es_likelihood10<NA>(run, f, recs, g11, g12, g22, denovo, freq, lut, mut, pin_person, pin_geno, cls_);
+  else return es_likelihood3<NA>(run, f, recs, g11, g12, g22, freq, lut, pin_person, pin_geno, cls_);
 }
 
 template <int A, typename RecPtr>

@@ -102,8 +102,11 @@ struct NarrowEval {
   }
 };
 
+#ifndef PM_NARROW_ES3_MINB
+#define PM_NARROW_ES3_MINB 1
+#endif
 template <int UMAX, bool NA, bool ES, bool DN>
-__global__ void __launch_bounds__(kNarrowThreads) k_sites_narrow(const DevRun *__restrict__ run,
+__global__ void __launch_bounds__(kNarrowThreads, (ES && !DN && UMAX == 0) ? PM_NARROW_ES3_MINB : 1) k_sites_narrow(const DevRun *__restrict__ run,
                                                                   const pm_site_hdr *__restrict__ hdr,
                                                                   const uint4 *__restrict__ recs_all,
                                                                   const double *__restrict__ mono_all, size_t n_sites,

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 V="python bench.py --workload vcf200x5 --steps 2 --warmup 3 --sites-per-step 65536 --no-cpu-baseline --e2e-sites 16384 --e2e-steps 1"
 $V > gpurun_out/profb_plain1.json 2> gpurun_out/profb_plain1.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/r02b_launches_vcf200x5.csv $V > gpurun_out/ncub_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^k_|pm::k_|k_sites|k_post|k_unpack|k_compact|k_all_rows" -c 80 --csv --log-file gpurun_out/r02b_launches_vcf200x5.csv $V > gpurun_out/ncub_launch.log 2>&1
 echo "vcf launch list exit=$?"
 $V > gpurun_out/profb_plain2.json 2> gpurun_out/profb_plain2.err && \
 ncu --set full --clock-control none --import-source on -k regex:k_post -s 6 -c 1 -o gpurun_out/r02b_post_vcf200x5 $V > gpurun_out/ncub_full_post.log 2>&1

@@ -516,6 +516,15 @@ static int glf_sites_host(pm_ctx *c, const pm_site_hdr *hdr, const void *person_
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t np = (size_t)c->n_person;
   size_t chunk = ((size_t)48 << 20) / (np * sizeof(pm_person_site));
+  if (c->plan.kind == pm::LaunchPlan::NARROW) {
+    // One thread per site: a launch lasts a whole number of "waves" of resident threads (2 to 5 blocks of 128 per SM by
+    // instance), each as long as one site's serial evaluation (~1 ms for a 20-member peel).  A 48 MB chunk of a 20-person
+    // pedigree is 157 k sites = 2.07 waves of 75.8 k: it paid for 3.  Four times the largest resident set is a whole
+    // number of waves for every instance (up to 256 MB of records).
+    const size_t waves4 = (size_t)4 * (size_t)c->sm_count * 5 * 128;
+    const size_t cap = ((size_t)256 << 20) / (np * sizeof(pm_person_site));
+    chunk = std::max(chunk, std::min(waves4, cap));
+  }
   if (chunk < 256) chunk = 256;
   if (chunk > ((size_t)1 << 20)) chunk = (size_t)1 << 20;
   if (chunk > n_sites) chunk = n_sites;

@@ -318,6 +318,109 @@ __device__ double es_likelihood3(const DevRun *__restrict__ run, const DevFam f,
   return lk;
 }
 
+// The three-state peel as it was before the lazy partials (every partial initialised up front, marriage partials updated in
+// place): smaller code.  The --denovo instances of the thread-per-site kernel use it for their rare bi-allelic refit, where
+// the register-hungry form above, inlined next to the ten-state peel, cost the CEPH --denovo instance 8 %.
+template <bool NA, typename RecPtr>
+__device__ double es_likelihood3_eager(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
+                                     bool denovo, double freq, const double *__restrict__ lut,
+                                     const double *__restrict__ mut, int pin_person, int pin_geno, int cls_) {
+  constexpr int A = 3;
+  double part[kMaxEsPersons * A];
+  double mp[kMaxMp * A * A];
+  const int gi[3] = {g11, g12, g22};
+  const double q = 1.0 - freq;
+  const int cls = NA ? cls_ : PM_CHR_AUTO;
+  const uint8_t *sexes = NA ? run->sex + f.first : nullptr;
+  for (int i = 0; i < f.size; i++) {
+    uint4 r = recs[f.first + i];
+    double pr[3] = {freq * freq, 2 * freq * q, q * q};  // SetFounderPriors{,_BA}, ES:643-687
+    if constexpr (NA) {
+      const bool male = sexes[i] == 1;
+      if (cls == PM_CHR_MT || ((cls == PM_CHR_X || cls == PM_CHR_Y) && male)) { pr[0] = freq; pr[1] = 0.0; pr[2] = q; }
+      else if (cls == PM_CHR_Y) { pr[0] = pr[1] = pr[2] = 1.0; }
+    }
+    if (A == 3) {
+      bool yfemale = false;
+      if constexpr (NA) yfemale = cls == PM_CHR_Y && sexes[i] == 2;
+      for (int j = 0; j < 3; j++) {
+        double pen = lut[rec_lk(r, gi[j])];
+        if (i == pin_person && gi[j] != pin_geno) pen = 0.0;
+        part[i * 3 + j] = yfemale ? 1.0 : ((i < f.founders) ? pr[j] * pen : pen);  // InitializePartials_BA, ES:1449-1465
+      }
+    } else {
+      for (int g = 0; g < 10; g++) {
+        double pen = lut[rec_lk(r, g)];
+        if (i == pin_person && g != pin_geno) pen = 0.0;
+        if (i < f.founders) {  // InitializePartials, ES:1434-1446
+          double prior = g == g11 ? pr[0] : (g == g12 ? pr[1] : (g == g22 ? pr[2] : 0.0));
+          part[i * 10 + g] = prior * pen;
+        } else {
+          part[i * 10 + g] = pen;
+        }
+      }
+    }
+  }
+  const DevStep *steps = run->steps + f.step_first;
+  for (int s = 0; s < f.n_steps; s++) {
+    const DevStep st = steps[s];
+    if (st.type == PM_PEEL_CHILD_TO_PARENTS) {
+      double *m = mp + st.mp * A * A;
+      const double *pc = part + st.from0 * A;
+      for (int i = 0; i < A; i++)
+        for (int j = 0; j < A; j++) {
+          double sum = 0;
+          if (A == 3) {
+            if constexpr (NA) { for (int k = 0; k < 3; k++) sum += tba_cls(cls, sexes[st.from0], i, j, k) * pc[k]; }
+            else { for (int k = 0; k < 3; k++) sum += tba(i, j, k) * pc[k]; }
+          }
+          m[i * A + j] = st.flag ? sum : m[i * A + j] * sum;  // a fresh marriage partial starts at 1
+        }
+    } else if (st.type == PM_PEEL_SPOUSE_TO_SPOUSE) {
+      const double *pf = part + st.from0 * A;
+      double *pt = part + st.to0 * A;
+      if (st.mp < 0) {
+        double sum = 0.0;
+        for (int j = 0; j < A; j++) sum += pf[j];
+        for (int i = 0; i < A; i++) pt[i] *= sum;
+      } else {
+        const double *m = mp + st.mp * A * A;
+        for (int i = 0; i < A; i++) {
+          double sum = 0.0;
+          if (st.flag) for (int j = 0; j < A; j++) sum += pf[j] * m[j * A + i];
+          else for (int j = 0; j < A; j++) sum += pf[j] * m[i * A + j];
+          pt[i] *= sum;
+        }
+      }
+    } else {
+      const double *pf = part + st.from0 * A, *pm_ = part + st.from1 * A;
+      double *pc = part + st.to0 * A;
+      const double *m = st.mp >= 0 ? mp + st.mp * A * A : nullptr;
+      for (int k = 0; k < A; k++) {
+        double sum = 0.0;
+        for (int i = 0; i < A; i++)
+          for (int j = 0; j < A; j++) {
+            double t;
+            if constexpr (NA) t = tba_cls(cls, sexes[st.to0], i, j, k); else t = tba(i, j, k);
+            if (m) sum += pf[i] * m[i * A + j] * pm_[j] * t;
+            else sum += pf[i] * pm_[j] * t;
+          }
+        pc[k] *= sum;
+      }
+    }
+  }
+  const double *pfin = part + steps[f.n_steps - 1].to0 * A;
+  double lk = 0.0;
+  for (int i = 0; i < A; i++) lk += pfin[i];
+  return lk;
+}
+
+template <bool NA, typename RecPtr>
+__device__ __noinline__ double es_likelihood3_ol(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22, double freq,
+                                                 const double *__restrict__ lut, int cls_) {
+  return es_likelihood3<NA>(run, f, recs, g11, g12, g22, freq, lut, -1, -1, cls_);
+}
+
 template <int A, bool NA, typename RecPtr>
 __device__ double es_likelihood_impl(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
                                      bool denovo, double freq, const double *__restrict__ lut,

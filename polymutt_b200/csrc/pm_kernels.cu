@@ -74,8 +74,15 @@ struct NarrowEval {
     if constexpr (ES)
     for (int e = 0; e < run->n_es; e++) {
       const DevFam f = run->fams[run->es_fams[e]];
-      double lk = (DN && denovo) ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
-                         : es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
+      double lk;
+      if constexpr (DN) {
+        // under --denovo the three-state peel only serves the rare bi-allelic refit of a called site: kept out of line so that
+        // it takes no registers from the ten-state peel around it (inlined it cost the CEPH --denovo instance 8 %)
+        lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
+                    : es_likelihood3_eager<NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
+      } else {
+        lk = es_likelihood_impl<3, NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
+      }
       sum += log10(lk);
     }
     return sum;
@@ -103,7 +110,7 @@ struct NarrowEval {
 };
 
 #ifndef PM_NARROW_ES3_MINB
-#define PM_NARROW_ES3_MINB 1
+#define PM_NARROW_ES3_MINB 4   // CEPH bi-allelic: 1 (158 registers) 114.7, 4 (128) 118.0, 5 (96, spills) 117.9 M sites/s
 #endif
 template <int UMAX, bool NA, bool ES, bool DN>
 __global__ void __launch_bounds__(kNarrowThreads, (ES && !DN && UMAX == 0) ? PM_NARROW_ES3_MINB : 1) k_sites_narrow(const DevRun *__restrict__ run,

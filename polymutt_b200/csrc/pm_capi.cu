@@ -383,6 +383,7 @@ extern "C" void pm_destroy(pm_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->stream_h2d) cudaStreamSynchronize(c->stream_h2d);  // a copy issued before an error return may still be reading the caller's buffer
+  if (c->stream_d2h) cudaStreamSynchronize(c->stream_d2h);
   cudaFree(c->d_run_x); cudaFree(c->d_fams_x); cudaFree(c->d_units_x); cudaFree(c->d_es_x); cudaFree(c->d_steps_x);
   cudaFree(c->d_sex); cudaFree(c->d_run_q); cudaFree(c->d_units_q); cudaFree(c->d_res_q); cudaFree(c->d_status_q);
   cudaFree(c->d_run); cudaFree(c->d_fams); cudaFree(c->d_units); cudaFree(c->d_es); cudaFree(c->d_steps);

@@ -320,7 +320,8 @@ __device__ double es_likelihood3(const DevRun *__restrict__ run, const DevFam f,
 
 // The three-state peel as it was before the lazy partials (every partial initialised up front, marriage partials updated in
 // place): smaller code.  The --denovo instances of the thread-per-site kernel use it for their rare bi-allelic refit, where
-// the register-hungry form above, inlined next to the ten-state peel, cost the CEPH --denovo instance 8 %.
+// the register-hungry form above, inlined next to the ten-state peel (or called out of line), cost the CEPH --denovo
+// instance 9 % (33.6-33.9 vs 37.0 M sites/s).
 template <bool NA, typename RecPtr>
 __device__ double es_likelihood3_eager(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22,
                                      bool denovo, double freq, const double *__restrict__ lut,
@@ -413,12 +414,6 @@ __device__ double es_likelihood3_eager(const DevRun *__restrict__ run, const Dev
   double lk = 0.0;
   for (int i = 0; i < A; i++) lk += pfin[i];
   return lk;
-}
-
-template <bool NA, typename RecPtr>
-__device__ __noinline__ double es_likelihood3_ol(const DevRun *__restrict__ run, const DevFam f, RecPtr recs, int g11, int g12, int g22, double freq,
-                                                 const double *__restrict__ lut, int cls_) {
-  return es_likelihood3<NA>(run, f, recs, g11, g12, g22, freq, lut, -1, -1, cls_);
 }
 
 template <int A, bool NA, typename RecPtr>

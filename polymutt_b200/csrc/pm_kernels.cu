@@ -76,8 +76,8 @@ struct NarrowEval {
       const DevFam f = run->fams[run->es_fams[e]];
       double lk;
       if constexpr (DN) {
-        // under --denovo the three-state peel only serves the rare bi-allelic refit of a called site: kept out of line so that
-        // it takes no registers from the ten-state peel around it (inlined it cost the CEPH --denovo instance 8 %)
+        // under --denovo the three-state peel only serves the rare bi-allelic refit of a called site: the small eager form,
+        // which takes no registers from the ten-state peel around it
         lk = denovo ? es_likelihood_impl<10, NA>(run, f, recs, g11, g12, g22, true, p, sm->t.lut, sm->t.mut, -1, -1, cls)
                     : es_likelihood3_eager<NA>(run, f, recs, g11, g12, g22, false, p, sm->t.lut, sm->t.mut, -1, -1, cls);
       } else {

@@ -321,6 +321,7 @@ def main():
     ap.add_argument("--ref-sites-per-core", type=int, default=300)
     ap.add_argument("--cpu-baseline-sites-per-core", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-wide-plan", default="", help="tuning only: 'variant,threads' for pm_force_wide_plan (an instantiation of the block-per-site kernel)")
     ap.add_argument("--cli-e2e-sites", type=int, default=8192, help="sites of the whole-executable run reported as cli_e2e (0 = skip)")
     args = ap.parse_args()
     W = _workloads()
@@ -361,6 +362,8 @@ def main():
     R, K, Wm = args.resident_batches, args.steps, args.warmup
     lut = np.array([pow(10, -float(i) / 10.0) for i in range(256)]) if vcf else None   # FamilyLikelihoodSeq_VCF.cpp:21-22
     eng = Engine(ped, params, device=local_rank, lut=lut)
+    if args.force_wide_plan:
+        eng.force_wide_plan(*[int(x) for x in args.force_wide_plan.split(",")])
 
     # ---- synthetic batches, generated on the device; rank r owns sites [r*R*S, (r+1)*R*S) of the job ----
     gi = lambda a, b: torch.where(a < b, (a - 1) * (10 - a) // 2 + (b - a), (b - 1) * (10 - b) // 2 + (a - b))

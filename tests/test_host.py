@@ -263,3 +263,28 @@ def test_row_formatter_prints_what_printf_prints():
     assert out.returncode == 0, out.stderr
     rep = json.loads(out.stdout)
     assert rep["checked"] > 900000 and rep["fixed_mismatches"] == 0 and rep["int_mismatches"] == 0
+
+
+def test_wire_forms_of_the_records():
+    """capi.to_wire / capi.to_pl3: the byte layouts pm_call_glf_sites_wire and pm_call_vcf_records_pl take
+    (include/polymutt_b200.h: pm_person_site_wire; three PL bytes per sample in the order a1a1, a1a2, a2a2)."""
+    from polymutt_b200 import capi
+    rng = np.random.default_rng(7)
+    n, npers = 5, 4
+    raw = rng.integers(0, 256, size=(n, npers, 16), dtype=np.uint8)
+    recs = raw.view(capi.PERSON_SITE_DTYPE).reshape(n, npers)
+    wire = capi.to_wire(recs)
+    assert wire.shape == (n * npers, 14) and wire.dtype == np.uint8
+    assert np.array_equal(wire.reshape(n, npers, 14), raw[:, :, :14])           # lk[10], depth[3], mapQ; the two pad bytes dropped
+    hdr = np.zeros(n, dtype=capi.SITE_HDR_DTYPE)
+    hdr["ref_base"] = [1, 2, 3, 4, 1]
+    hdr["reserved"] = [2, 4, 1, 3, 4 | 0x100]                                    # ALT allele (| indel flag)
+    pl3 = capi.to_pl3(hdr, recs, npers)
+    assert pl3.shape == (n, npers, 3)
+    for r in range(n):
+        a1, a2 = int(hdr["ref_base"][r]), int(hdr["reserved"][r]) & 0xFF
+        for k, (x, y) in enumerate(((a1, a1), (a1, a2), (a2, a2))):
+            assert np.array_equal(pl3[r, :, k], raw[r, :, capi.geno_index(x, y)])
+    # glfHandler.h:102-106: AA AC AG AT CC CG CT GG GT TT
+    assert [capi.geno_index(a, b) for a in range(1, 5) for b in range(a, 5)] == list(range(10))
+    assert capi.geno_index(3, 1) == capi.geno_index(1, 3)

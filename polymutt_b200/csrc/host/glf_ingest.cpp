@@ -319,36 +319,59 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
       k.op = s.off.data() + s.head; k.raw = s.raw.data();
       k.prio = ((c == lead_) ? 0u : (uint32_t)c + 1u) << 8;
     }
+    // 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
+    // 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) as two 8-byte words (little endian)
+    auto convert = [](const unsigned char *rec, unsigned char *dst) {
+      uint64_t lo8, hi8;
+      uint32_t dm;
+      uint16_t lk89;
+      memcpy(&lo8, rec + 10, 8);
+      memcpy(&lk89, rec + 18, 2);
+      memcpy(&dm, rec + 5, 4);
+      hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
+      memcpy(dst, &lo8, 8);
+      memcpy(dst + 8, &hi8, 8);
+    };
     for (size_t r0 = 0; r0 < n; r0 += RB) {
-      const size_t r1 = std::min(n, r0 + RB);
+      const size_t r1 = std::min(n, r0 + RB), m = r1 - r0;
       for (int c0 = lo; c0 < hi; c0 += CW) {
         const int cw = std::min(CW, hi - c0);
-        Cur *const ck = cur.data() + (c0 - lo);
-        for (size_t r = r0; r < r1; r++) {
-          const int32_t p = rowpos_[r];
-          pm_person_site *row = out + r * np + (size_t)c0;
-          uint32_t best = own[r];
-          for (int j = 0; j < cw; j++) {
-            Cur &k = ck[j];
-            uint64_t lo8 = 0, hi8 = 0;
-            if (k.pp < k.pe && *k.pp == p) {
-              // 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
-              // 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) as two 8-byte words (little endian)
-              const unsigned char *rec = k.raw + *k.op;
-              uint32_t dm;
-              uint16_t lk89;
-              memcpy(&lo8, rec + 10, 8);
-              memcpy(&lk89, rec + 18, 2);
-              memcpy(&dm, rec + 5, 4);
-              hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
-              const uint32_t v = k.prio | kTranslateBase[rec[0] & 0xf];
-              if (v < best) best = v;
-              k.pp++; k.op++;
+        // One column (stream) at a time through the block's rows, its cursor in registers; the four columns of a tile write
+        // the same 64 cache lines one after the other.  (On 8 cores here, 3,000 streams: fill 0.043-0.047 s per 6,000 sites
+        // against 0.052-0.083 s with the rows outermost inside the tile and the cursors re-read per record.)
+        for (int j = 0; j < cw; j++) {
+          Cur &k = cur[(size_t)(c0 + j - lo)];
+          const int32_t *pp = k.pp, *const pe = k.pe;
+          const uint32_t *op = k.op;
+          const unsigned char *const raw = k.raw;
+          unsigned char *dst = reinterpret_cast<unsigned char *>(out + r0 * np + (size_t)(c0 + j));
+          const size_t stride = np * sizeof(pm_person_site);
+          uint32_t *const ownr = own + r0;
+          if ((size_t)(pe - pp) >= m && pp[0] == rowpos_[r0] && pp[m - 1] == rowpos_[r1 - 1]) {
+            // the stream has a record at every row of the block (both position lists increase strictly and the stream's
+            // positions are among the rows'): no compares
+            const uint32_t prio = k.prio;
+            for (size_t i = 0; i < m; i++, dst += stride) {
+              const unsigned char *rec = raw + op[i];
+              convert(rec, dst);
+              const uint32_t v = prio | kTranslateBase[rec[0] & 0xf];
+              if (v < ownr[i]) ownr[i] = v;
             }
-            memcpy(reinterpret_cast<unsigned char *>(row + j), &lo8, 8);
-            memcpy(reinterpret_cast<unsigned char *>(row + j) + 8, &hi8, 8);
+            pp += m; op += m;
+          } else {
+            for (size_t i = 0; i < m; i++, dst += stride) {
+              if (pp < pe && *pp == rowpos_[r0 + i]) {
+                const unsigned char *rec = raw + *op;
+                convert(rec, dst);
+                const uint32_t v = k.prio | kTranslateBase[rec[0] & 0xf];
+                if (v < ownr[i]) ownr[i] = v;
+                pp++; op++;
+              } else {
+                memset(dst, 0, sizeof(pm_person_site));
+              }
+            }
           }
-          own[r] = best;
+          k.pp = pp; k.op = op;
         }
       }
     }

@@ -62,7 +62,7 @@ def _workloads():
                           ped=lambda: S.ceph(), params=Params(), ref_args=[], sites=1 << 21, vcf=False,
                           kernel="k_sites_narrow", nuclear=None, peel=(3, 14, 2, 1, 20)),
         "ceph20_dn": dict(title="configs[2]: 3-generation 20-member CEPH-like pedigree, --denovo (ten-state peel), synthetic GLF sites",
-                          ped=lambda: S.ceph(), params=Params(denovo=True), ref_args=["--denovo"], sites=1 << 18, vcf=False,
+                          ped=lambda: S.ceph(), params=Params(denovo=True), ref_args=["--denovo"], sites=1 << 19, vcf=False,
                           kernel="k_sites_narrow", nuclear=None, peel=(10, 14, 2, 1, 20)),
         "vcf200x5": dict(title="configs[3]: --in_vcf, 200 nuclear families x 5 members (1,000 samples), PL records",
                          ped=lambda: S.families([5] * 200), params=Params(vcf_input=True), ref_args=[], sites=1 << 18, vcf=True,
@@ -542,7 +542,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["title"], "workload_key": args.workload, "sites_per_step_per_gpu": S, "persons": npers,
                        "resident_batches": R, "input_bytes_per_step": S * (npers * 16 + 8),
-                       "l2": "each step reads a different resident batch of %.1f GB, far larger than the 126 MB L2 (no flush needed)" % (S * npers * 16 / 1e9),
+                       "l2": ("each step reads a different resident batch of %.2f GB, larger than the 126 MB L2 (no flush needed)" if S * (npers * 16 + 8) > 126e6
+                              else "WARNING: a resident batch is only %.2f GB, not larger than the 126 MB L2 -- raise --sites-per-step") % (S * (npers * 16 + 8) / 1e9),
                        "kernel_plan": eng.describe_plan(),
                        "emitted_rows_last_step": emitted_last, "result_capacity_rows": cap},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step) * K, "roofline": roofline,

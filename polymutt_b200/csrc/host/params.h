@@ -25,7 +25,7 @@ struct Options {
   // derived (main.cpp:151-153)
   bool force_call = false;
   // extensions of this implementation (not in the reference)
-  int gpus = 1;            // --gpus N: shard consecutive site batches over N GPUs (devices device..device+N-1)
+  int gpus = 1;            // --gpus N: shard consecutive site batches (--in_vcf: record ranges of a chunk) over N GPUs (devices device..device+N-1)
   int ingest_threads = 0;  // --ingest_threads N: GLF decode/merge threads (0 = all cores, capped at 32)
   int device = 0;          // --device
   int batch_sites = 0;     // --batch_sites (0 = automatic)

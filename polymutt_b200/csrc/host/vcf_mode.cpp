@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -334,8 +335,47 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   par.vcf_input = 1;
   double lut[256];
   for (int i = 0; i < 256; i++) lut[i] = pow(10, -double(i) / 10.0);  // PL2LK_table, FLSeq_VCF.cpp:21-22
-  void *ctx = engine.create(ped.view(), &par, lut, opt.device);
-  if (!ctx) { fclose(out); return fatal(std::string("engine '") + engine.name + "': " + engine.last_error()); }
+  // One engine context per GPU (--gpus N, ours): the records of a chunk are independent, so each chunk's rows are cut
+  // into N contiguous ranges, one per context, each on its own host thread; results land in place, in record order.
+  const int n_gpu = opt.gpus > 0 ? opt.gpus : 1;
+  std::vector<void *> ctxs((size_t)n_gpu, nullptr);
+  auto destroy_all = [&]() { for (void *c : ctxs) if (c) engine.destroy(c); ctxs.clear(); };
+  {
+    std::vector<std::string> ctx_err((size_t)n_gpu);
+    std::vector<std::thread> makers;
+    auto make = [&](int g) {
+      ctxs[(size_t)g] = engine.create(ped.view(), &par, lut, opt.device + g);
+      if (!ctxs[(size_t)g]) ctx_err[(size_t)g] = engine.last_error();  // the message is thread-local: keep it
+    };
+    for (int g = 1; g < n_gpu; g++) makers.emplace_back(make, g);
+    make(0);
+    for (auto &t : makers) t.join();
+    for (int g = 0; g < n_gpu; g++)
+      if (!ctxs[(size_t)g]) { destroy_all(); fclose(out); return fatal(std::string("engine '") + engine.name + "': " + ctx_err[(size_t)g]); }
+  }
+  std::string engine_err;
+  // runs call(ctx, first row, number of rows) over the chunk's rows, one contiguous range per context
+  auto sharded = [&](size_t n_rows, const std::function<int(void *, size_t, size_t)> &call) -> int {
+    const size_t n_use = std::min<size_t>((size_t)n_gpu, n_rows);
+    if (n_use <= 1) {
+      const int r = call(ctxs[0], 0, n_rows);
+      if (r != PM_OK) engine_err = engine.last_error();
+      return r;
+    }
+    std::vector<int> rcs(n_use, PM_OK);
+    std::vector<std::string> errs(n_use);
+    std::vector<std::thread> workers;
+    auto part = [&](size_t g) {
+      const size_t lo = n_rows * g / n_use, hi = n_rows * (g + 1) / n_use;
+      rcs[g] = call(ctxs[g], lo, hi - lo);
+      if (rcs[g] != PM_OK) errs[g] = engine.last_error();
+    };
+    for (size_t g = 1; g < n_use; g++) workers.emplace_back(part, g);
+    part(0);
+    for (auto &t : workers) t.join();
+    for (size_t g = 0; g < n_use; g++) if (rcs[g] != PM_OK) { engine_err = errs[g]; return rcs[g]; }
+    return PM_OK;
+  };
 
   const int np = ped.n_person();
   const size_t n_names = names.size();
@@ -599,10 +639,10 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
         if (GL_idx < 0 && PL_idx < 0) {
           fprintf(stderr, "NO GL or PL field was found. Please check the vcf file at chr:%s and position:%d", L.col[0].str().c_str(), tok_atoi(L.col[1]));
           if (writer.joinable()) writer.join();
-          engine.destroy(ctx); fclose(out);
+          destroy_all(); fclose(out);
           return 1;
         }
-        if (n_in_both == 0) { if (writer.joinable()) writer.join(); engine.destroy(ctx); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
+        if (n_in_both == 0) { if (writer.joinable()) writer.join(); destroy_all(); fclose(out); return fatal("NO individual IDs match in the ped and vcf file!"); }
         break;
       }
     }
@@ -639,7 +679,9 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
     if (n_rows) {
       if (res.size() < n_rows) { res.resize(n_rows); if (compact) calls.resize(n_rows * (size_t)np); else pres.resize(n_rows * (size_t)np); }
       if (engine.call_vcf_pl) {
-        rc = engine.call_vcf_pl(ctx, hdr.data(), pl3.data(), mono.data(), n_rows, res.data(), calls.data());
+        rc = sharded(n_rows, [&](void *c, size_t lo, size_t n) {
+          return engine.call_vcf_pl(c, hdr.data() + lo, pl3.data() + lo * (size_t)np * 3, mono.data() + lo, n, res.data() + lo, calls.data() + lo * (size_t)np);
+        });
       } else {
         if (recs.size() < n_rows * (size_t)np) recs.resize(n_rows * (size_t)np);
         parallel_for(n_rows, threads, [&](size_t r, int) {
@@ -650,8 +692,11 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
           for (int c = 0; c < np; c++)
             for (int k = 0; k < 3; k++) row[c].lk[gi[k]] = pl3[(r * (size_t)np + (size_t)c) * 3 + (size_t)k];
         });
-        rc = compact ? engine.call_vcf_calls(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), calls.data())
-                     : engine.call_vcf(ctx, hdr.data(), recs.data(), mono.data(), n_rows, res.data(), pres.data());
+        rc = sharded(n_rows, [&](void *c, size_t lo, size_t n) {
+          const size_t at = lo * (size_t)np;
+          return compact ? engine.call_vcf_calls(c, hdr.data() + lo, recs.data() + at, mono.data() + lo, n, res.data() + lo, calls.data() + at)
+                         : engine.call_vcf(c, hdr.data() + lo, recs.data() + at, mono.data() + lo, n, res.data() + lo, pres.data() + at);
+        });
       }
       if (rc != PM_OK) break;
     }
@@ -680,8 +725,8 @@ int run_vcf_mode(const Options &opt, const Pedigree &ped, const Engine &engine) 
   if (writer.joinable()) writer.join();
   if (getenv("PM_TIMING"))
     printf("[pm timing] vcf mode: read %.3f s, tokenise+parse %.3f s, engine %.3f s, format %.3f s, write %.3f s; %d threads\n", tm[0], tm[1], tm[2], tm[3], tm[4], threads);
-  std::string err = rc == PM_OK ? std::string() : std::string("engine '") + engine.name + "': " + engine.last_error();
-  engine.destroy(ctx);
+  std::string err = rc == PM_OK ? std::string() : std::string("engine '") + engine.name + "': " + engine_err;
+  destroy_all();
   fclose(out);
   if (rc != PM_OK) return fatal(err);
   if (!fail.empty()) return fatal(fail);

@@ -84,6 +84,15 @@ def test_product_cli_small_batches_and_multi_gpu(glfdir, tmp_path):
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)
 
 
+def test_product_cli_vcf_input_on_all_gpus(tmp_path):
+    """--in_vcf --gpus N (every GPU of the box; one context on a one-GPU box): each chunk's records are cut into N
+    contiguous ranges, one per GPU; small chunks, so that some hold fewer computed records than there are GPUs."""
+    import torch
+    n = min(max(1, torch.cuda.device_count()), 8)
+    for case in U.VCF_CASES:
+        U.check_vcf_case(U.PRODUCT_CLI, str(tmp_path), case, gz_input=(case[0] == "vcf_cmd2"), extra=["--gpus", str(n), "--batch_sites", "5"])
+
+
 def test_cli_reports_missing_inputs(tmp_path):
     p = subprocess.run([U.PRODUCT_CLI, "-p", "nope.ped", "-d", "nope.dat", "-g", "nope.gif", "--out_vcf", str(tmp_path / "o.vcf")],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)

@@ -85,9 +85,19 @@ void GlfBatchReader::Stream::compact() {
 
 // glfHandler::NextEntry (core/glfHandler.cpp:186-261) on a byte buffer.  Base records are NOT copied: a pending record
 // is its position and the offset of its 20 bytes in `raw`.
+//
+// A base record with offset 0 right after a base record repeats a position.  The reference's cursor walks through it
+// (src/PedigreeGLF.cpp:282-324: the stream advances to the repeat, stays at currentPos, and the minimum over the streams
+// gives that position again): a second site at the same position, made of the second records of the streams that have one.
+// Here a window holds every position once, so the decoder stops in front of a repeat (dup_wait) until the records
+// before it have been consumed; the repeat then opens the next window, at the same position.
 void GlfBatchReader::Stream::decode(size_t want_records) {
   compact();
-  while (!ended && pending() < want_records) {
+  if (dup_wait) {
+    if (pending() > 0) return;
+    dup_wait = false;
+  }
+  while (!ended && !dup_wait && pending() < want_records) {
     // refill in big steps: the window of undecoded bytes should cover what is still wanted
     if (raw_end - raw_dec < 20) {
       const size_t want_bytes = std::min<size_t>((want_records - pending()) * 20 + 1, (size_t)4 << 20);
@@ -102,23 +112,25 @@ void GlfBatchReader::Stream::decode(size_t want_records) {
         pos.resize(old + n); off.resize(old + n);
         const unsigned char *r = raw.data() + raw_dec;
         size_t k = 0;
-        int p = position, lp = last_pos;
+        int p = position, lp = last_pos, rank = last_rank;
         for (; k < n && (r[0] >> 4) == 1; k++, r += 20) {
           uint32_t offset;
           memcpy(&offset, r + 1, 4);
-          p += (int)offset;
-          if (lp == p && lp >= 0 && offset == 0) {
-            pos.resize(old + k); off.resize(old + k);
-            throw std::runtime_error("GLF stream repeats a position (offset 0): not supported by the batched reader");
+          if (offset == 0 && lp == p && lp >= 0) {
+            if (old + k != head) { dup_wait = true; break; }  // records before the repeat are still pending
+            rank++;
+          } else {
+            rank = 0;
           }
+          p += (int)offset;
           pos[old + k] = p;
           off[old + k] = (uint32_t)(raw_dec + 20 * k);
           lp = p;
         }
-        position = p; last_pos = lp;
+        position = p; last_pos = lp; last_rank = rank;
         raw_dec += 20 * k;
         if (k < n) { pos.resize(old + k); off.resize(old + k); }
-        if (k > 0) continue;
+        if (k > 0 || dup_wait) continue;
       }
     }
     if (!fill(1)) { ended = true; break; }
@@ -209,7 +221,7 @@ bool GlfBatchReader::next_section() {
       if (!s.live) continue;
       while (!s.ended) { s.head = s.pos.size(); s.decode(4096); }  // drain the old section
       s.pos.clear(); s.off.clear(); s.head = 0; s.raw_keep = s.raw_dec;
-      s.position = 0; s.last_pos = -1;
+      s.position = 0; s.last_pos = -1; s.last_rank = 0; s.dup_wait = false;
       int32_t label_len = 0;
       if (!s.fill(4)) { ok[(size_t)i] = 0; continue; }
       memcpy(&label_len, s.raw.data() + s.raw_dec, 4);
@@ -258,11 +270,13 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
   const double t1 = now_s();
   // 2. window: every position <= wend is completely known
   long long base = LLONG_MAX, wend = LLONG_MAX;
-  long long T = LLONG_MAX;  // min over ended streams of their last base-record position (-1: none at all)
+  // Sites are ordered by (position, rank), rank > 0 only for the further sites of a repeated position; kept as one number.
+  auto site_key = [](long long p, long long rank) { return p < 0 ? -1LL : (p << 20) | std::min<long long>(rank, (1 << 20) - 1); };
+  long long T = LLONG_MAX;  // min over ended streams of the site of their last base record (-1: none at all)
   for (const Stream &s : streams_) {
     if (!s.live) continue;
     if (s.pending()) base = std::min<long long>(base, s.pos[s.head]);
-    if (s.ended) T = std::min<long long>(T, s.last_pos);
+    if (s.ended) T = std::min<long long>(T, site_key(s.last_pos, s.last_rank));
     else wend = std::min<long long>(wend, s.pos.back());
   }
   if (base == LLONG_MAX) { section_done_ = true; return 0; }  // nothing left anywhere
@@ -288,10 +302,11 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
     if (!mark_[w]) continue;
     const long long p = base + (long long)w;
     // Move2NextBaseEntry top check: some stream read its end marker in an earlier call
-    if (prev1_ > 0 && T <= prev2_) { section_done_ = true; break; }
+    if (prev1_ >= 0 && (prev1_ >> 20) > 0 && T <= prev2_) { section_done_ = true; break; }
     if (p > max_position_) { section_done_ = true; break; }
     rowpos_.push_back((int32_t)p);
-    prev2_ = prev1_; prev1_ = p;
+    const long long rank = (prev1_ >= 0 && (prev1_ >> 20) == p) ? (prev1_ & ((1 << 20) - 1)) + 1 : 0;
+    prev2_ = prev1_; prev1_ = site_key(p, rank);
   }
   const size_t n = rowpos_.size();
   if (n == 0) { section_done_ = true; return 0; }

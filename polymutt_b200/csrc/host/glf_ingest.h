@@ -55,6 +55,8 @@ class GlfBatchReader {
     int position = 0;                 // running position of the decoder
     bool ended = true;                // end-of-section marker (or end of file) reached by the decoder
     int last_pos = -1;                // position of the last base record of the section (valid once ended)
+    int last_rank = 0;                // how many base records right before it sit at that same position (a repeated position)
+    bool dup_wait = false;            // the next record repeats last_pos: not decoded before everything pending is consumed
     std::string label;
     int max_position = 0;
     bool fill(size_t need);           // makes `need` undecoded bytes available at raw_dec
@@ -68,7 +70,7 @@ class GlfBatchReader {
   std::string label_;
   int max_position_ = 0;
   bool section_done_ = true;
-  long long prev1_ = -1, prev2_ = -1; // positions of the last two sites handed out (termination rule)
+  long long prev1_ = -1, prev2_ = -1; // the last two sites handed out, as (position << 20 | rank) (termination rule)
   std::vector<uint8_t> mark_;         // per position of the window: some stream has a record
   std::vector<int32_t> rowpos_;       // position of every row of the batch
   std::vector<uint32_t> owner_;       // per (thread, row): (priority << 8) | ref base of the best stream of that thread's column range

@@ -13,10 +13,13 @@ _BACK = np.array([15, 1, 2, 4, 8], dtype=np.uint8)  # glfHandler::backTranslateB
 
 
 def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_base: np.ndarray, recs: np.ndarray,
-              indel_every: int = 0, end_marker: bool = True):
+              indel_every: int = 0, end_marker: bool = True, repeats=()):
     """recs: [n_sites] PERSON_SITE_DTYPE for one person; rows that are all zero are left out.
     indel_every > 0 interleaves an indel record (type 2, offset 0) after every indel_every-th base record;
-    end_marker=False leaves the section without its terminating byte (a truncated file)."""
+    end_marker=False leaves the section without its terminating byte (a truncated file);
+    repeats: site indices whose record is followed by one more base record with offset 0 -- a repeated position --
+    carrying the data of the person's next record (an index listed k times gets k repeats; sites without a record are
+    skipped)."""
     depth = recs["depth"][:, 0].astype(np.uint32) | (recs["depth"][:, 1].astype(np.uint32) << 8) | (recs["depth"][:, 2].astype(np.uint32) << 16)
     keep = (depth > 0) | (recs["map_quality"] > 0) | (recs["lk"].max(axis=1) > 0)
     p = pos[keep].astype(np.int64)
@@ -26,6 +29,21 @@ def write_glf(path: str, label: str, max_position: int, pos: np.ndarray, ref_bas
     out["depth_minllk"] = depth[keep]
     out["mapq"] = recs["map_quality"][keep]
     out["lk"] = recs["lk"][keep]
+    if len(repeats) and len(out):
+        site_to_rec = np.cumsum(keep) - 1
+        at, extra = [], []
+        for sidx in repeats:
+            if not keep[sidx]:
+                continue
+            k = int(site_to_rec[sidx])
+            rec = out[min(k + 1, len(out) - 1)].copy()
+            rec["tag"] = out[k]["tag"]
+            rec["offset"] = 0
+            at.append(k + 1)
+            extra.append(rec)
+        if at:
+            out = np.insert(out, at, np.array(extra, dtype=_REC))
+        p = np.cumsum(out["offset"].astype(np.int64))
     lab = label.encode() + b"\0"
     with open(path, "wb") as f:
         f.write(b"GLF\x03" + struct.pack("<I", 0))

@@ -105,6 +105,14 @@ MS_CASES = [
     ("ms_denovo", "test.ped", ["--denovo", "--rate_denovo", "1.5e-07", "--chrX", "X"], "ref_ms_denovo.sha"),
     ("ms_y_mt", "ext.ped", ["--chrY", "2", "--MT", "X"], "ref_ms_y_mt.sha"),
 ]
+# GLF files in which some streams repeat a position (a base record with offset 0 after a base record,
+# tests/fixtures_util.py:write_repeat_glfs): the reference's cursor makes one more site at that position out of the repeats
+# alone (src/PedigreeGLF.cpp:282-324)
+REP_CASES = [
+    ("rep_mix", "test.mix.ped", [], "ref_rep_mix.vcf.gz"),
+    ("rep_quartets_dn", "test.ped", ["--denovo", "--rate_denovo", "1.5e-07"], "ref_rep_quartets_dn.sha"),
+    ("rep_ext_all", "ext.ped", ["--pos", os.path.join(GOLDEN, "pos_rep.txt")], "ref_rep_ext_all.vcf.gz"),
+]
 # --quick_call: outputs of the unmodified reference with the everybody-unrelated pre-pass switched on
 QUICK_CASES = [
     ("q_quartets", "test.ped", ["--quick_call"], "ref_q_quartets.sha"),

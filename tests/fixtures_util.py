@@ -57,3 +57,36 @@ def write_multisection_glfs(example12, outdir):
     open(gif_path, "w").write("".join(gif))
     open(os.path.join(outdir, "dat"), "w").write(open(os.path.join(U.GOLDEN, "peds", "test.dat")).read())
     return gif_path
+
+
+def repeat_sites(n_sites, n_streams):
+    """Which sites get a repeated record in which example stream (write_repeat_glfs): 30 seeded sites in streams 1, 4, 5, 8
+    and 11; streams 4 and 5 also share ten sites (two streams repeat the same position), stream 8 repeats five of its
+    sites twice (three records at one position), and stream 11 repeats its last site."""
+    rng = np.random.default_rng(20261019)
+    rep = {g: sorted(int(x) for x in rng.integers(0, n_sites - 1, 30)) for g in (0, 3, 4, 7, 10)}
+    shared = [int(x) for x in rng.integers(0, n_sites - 1, 10)]
+    rep[3] = sorted(rep[3] + shared)
+    rep[4] = sorted(rep[4] + shared)
+    rep[7] = sorted(rep[7] + rep[7][:5])
+    rep[10] = sorted(rep[10] + [n_sites - 1])
+    return rep
+
+
+def write_repeat_glfs(example12, outdir):
+    """The example's 12 GLFs (one section, GLF_Index 1..12) with base records of offset 0 -- repeated positions -- put
+    into five of them (repeat_sites), plus the gif and dat files.  Returns the gif path."""
+    from polymutt_b200 import glfio
+    os.makedirs(outdir, exist_ok=True)
+    hdr, recs = example12.hdr, example12.recs
+    rep = repeat_sites(len(hdr), recs.shape[1])
+    pos = hdr["pos"].astype(np.int64)
+    gif = []
+    for g in range(recs.shape[1]):
+        path = os.path.join(outdir, f"rep{g + 1}.glf")
+        glfio.write_glf(path, example12.label, int(example12.max_position), pos, hdr["ref_base"], recs[:, g], repeats=rep.get(g, ()))
+        gif.append(f"{g + 1} {path}\n")
+    gif_path = os.path.join(outdir, "gif")
+    open(gif_path, "w").write("".join(gif))
+    open(os.path.join(outdir, "dat"), "w").write(open(os.path.join(U.GOLDEN, "peds", "test.dat")).read())
+    return gif_path

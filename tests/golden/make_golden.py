@@ -189,9 +189,48 @@ def make_baseline_shapes(only):
         print(name, len(text), "bytes", text.count(b"\n"), "lines")
 
 
+def make_glf_variants(only):
+    """Goldens on GLF inputs derived from the example (tests/fixtures_util.py): three sections per file (ms_*) and
+    repeated positions (rep_*).  pos_rep.txt lists 40 of the repeated positions (and 20 others), so that the rows of
+    those sites -- both of them where a position has two -- are printed whatever their quality."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import cli_util as U
+    import fixtures_util as F
+    from polymutt_b200 import load_pmpk
+    ex = load_pmpk(os.path.join(HERE, "example12.pmpk.gz"))
+    rep = F.repeat_sites(len(ex.hdr), ex.recs.shape[1])
+    rng = np.random.default_rng(7)
+    sites = sorted(set(int(x) for g in sorted(rep) for x in rep[g][::4]) | set(int(x) for x in rng.integers(0, len(ex.hdr), 20)))
+    open(os.path.join(HERE, "pos_rep.txt"), "w").write("".join("%s\t%d\n" % (ex.label, int(ex.hdr["pos"][i]) + 1) for i in sites))
+    with tempfile.TemporaryDirectory() as tmp:
+        for kind, writer, cases in (("ms", F.write_multisection_glfs, U.MS_CASES), ("rep", F.write_repeat_glfs, U.REP_CASES)):
+            if only and kind not in only and not any(c[0] in only for c in cases):
+                continue
+            d = os.path.join(tmp, kind)
+            writer(ex, d)
+            for name, ped, extra, golden in cases:
+                if only and kind not in only and name not in only:
+                    continue
+                out = os.path.join(tmp, name + ".vcf")
+                subprocess.run([REFBIN, "-p", os.path.join(HERE, "peds", ped), "-d", os.path.join(d, "dat"), "-g", os.path.join(d, "gif"),
+                                "--out_vcf", out] + list(extra), check=True, stdout=subprocess.DEVNULL)
+                text = body(out)
+                if golden.endswith(".vcf.gz"):
+                    with gzip.GzipFile(os.path.join(HERE, golden), "wb", 9, mtime=0) as dst:
+                        dst.write(text)
+                else:
+                    with open(os.path.join(HERE, golden), "w") as f:
+                        f.write("%s %d\n" % (hashlib.sha256(text).hexdigest(), text.count(b"\n")))
+                print(name, len(text), "bytes", text.count(b"\n"), "lines")
+
+
 def main():
     if sys.argv[1:] and all(a.startswith("cfg") for a in sys.argv[1:]):
         return make_baseline_shapes(set(sys.argv[1:]))
+    if sys.argv[1:] and all(a.startswith("ms") or a.startswith("rep") for a in sys.argv[1:]):
+        return make_glf_variants(set(sys.argv[1:]))
     os.makedirs(os.path.join(HERE, "peds"), exist_ok=True)
     for name in ("test.ped", "test.mix.ped", "test.dat"):
         shutil.copy(os.path.join(REF, name), os.path.join(HERE, "peds", name))
@@ -245,6 +284,7 @@ def main():
             print(name, len(text), "bytes", text.count(b"\n"), "lines")
         if not only:
             make_baseline_shapes(set())
+            make_glf_variants(set())
 
 
 if __name__ == "__main__":

@@ -47,6 +47,15 @@ def test_product_cli_multi_section_glfs(case, msdir, glfdir, tmp_path):
     U.check_case(U.PRODUCT_CLI, msdir, str(tmp_path), case)
 
 
+@pytest.mark.parametrize("case", U.REP_CASES, ids=lambda c: c[0])
+def test_product_cli_glfs_with_repeated_positions(case, example12, tools_built, tmp_path):
+    """GLF streams that repeat a position (offset 0): one more site at that position, made of the repeats alone."""
+    import fixtures_util as F
+    d = str(tmp_path / "repeats")
+    F.write_repeat_glfs(example12, d)
+    U.check_case(U.PRODUCT_CLI, d, str(tmp_path), case)
+
+
 @pytest.mark.parametrize("case", U.POS_CASES, ids=lambda c: c[0])
 def test_product_cli_pos_list_matches_reference(case, glfdir, tmp_path):
     U.check_case(U.PRODUCT_CLI, glfdir, str(tmp_path), case)

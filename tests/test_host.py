@@ -240,6 +240,78 @@ def test_batched_multithreaded_ingest_equals_the_one_site_at_a_time_merge(tools_
     assert np.array_equal(z.hdr, ref.hdr) and np.array_equal(z.recs, ref.recs)
 
 
+def _insert_repeats(path, label, at, rng):
+    """Rewrites an uncompressed GLF (base records only) with extra records of offset 0 -- repeats of a position -- after
+    the records whose index is in `at` (an index listed k times gets k repeats)."""
+    raw = open(path, "rb").read()
+    start = 8 + 4 + len(label) + 1 + 4
+    body = raw[start:]
+    has_end = len(body) % 20 == 1
+    n = len(body) // 20
+    out = [raw[:start]]
+    for k in range(n):
+        rec = body[20 * k:20 * (k + 1)]
+        out.append(rec)
+        for _ in range(at.count(k)):
+            lk = bytes(int(x) for x in rng.integers(0, 256, 10))
+            out.append(rec[:1] + (0).to_bytes(4, "little") + int(rng.integers(1, 200)).to_bytes(3, "little") + b"\0" + bytes([int(rng.integers(1, 61))]) + lk)
+    out.append(body[20 * n:] if has_end else b"")
+    open(path, "wb").write(b"".join(out))
+
+
+@pytest.mark.parametrize("case", ["middle", "same_site_two_streams", "triple", "last_record_of_the_first_stream_to_end", "position_zero", "many"])
+def test_batched_ingest_walks_through_repeated_positions_like_the_reference(case, tools_built, tmp_path):
+    """A base record with offset 0 repeats its stream's position.  The reference's cursor (src/PedigreeGLF.cpp:282-324)
+    makes a further site at that position out of the repeats alone; the batched reader must hand out the same sites as
+    the one-site-at-a-time restatement of that cursor: in the middle of a chromosome, with two streams repeating the same
+    position, three records at one position, a repeat that is the last record of the stream that ends the chromosome
+    (the end comes one site after the site that consumed the stream's LAST record), a repeat at position 0, and many."""
+    from polymutt_b200 import glfio, load_pmpk
+    rng = np.random.default_rng(5)
+    ped = synth.concat(synth.trios(2), synth.families([4]))
+    n = 3000
+    h, r = synth.generate_sites(ped, n, seed=33, cfg=synth.SynthConfig(poly_boost=20))
+    hdr = h.numpy().view(capi.SITE_HDR_DTYPE).reshape(-1).copy()
+    recs = r.numpy().view(capi.PERSON_SITE_DTYPE).reshape(n, ped.n_person).copy()
+    steps = rng.choice([1, 1, 2, 7], n)
+    steps[0] = 1
+    hdr["pos"] = np.cumsum(steps) - 1
+    hdr["ref_base"] = rng.integers(1, 5, n)
+    recs["depth"][:, :, 0] |= 1                                            # every person has a record at every site ...
+    ends = {4: 2500}                                                       # ... but stream 4 stops early and ends the chromosome
+    repeats = {"middle": {2: [700]}, "same_site_two_streams": {1: [1200], 6: [1200, 1201]}, "triple": {3: [999, 999], 0: [999]},
+               "last_record_of_the_first_stream_to_end": {4: [2499]}, "position_zero": {5: [0], 0: [0, 0]},
+               "many": {c: sorted(int(x) for x in rng.integers(0, 2400, 40)) for c in range(ped.n_person)}}[case]
+    d = tmp_path / case
+    d.mkdir()
+    lines, gif = [], []
+    col = 0
+    for f in range(ped.n_fam):
+        for j in range(int(ped.fam_size[f])):
+            fa, mo = int(ped.father[col]), int(ped.mother[col])
+            lines.append(f"fam{f + 1}\tp{j + 1}\t{('p%d' % (fa + 1)) if fa >= 0 else 0}\t{('p%d' % (mo + 1)) if mo >= 0 else 0}\t{int(ped.sex[col])}\t{col + 1}\n")
+            rr = recs[:, col].copy()
+            if col in ends:
+                rr[ends[col]:] = np.zeros((), dtype=rr.dtype)
+            path = str(d / f"g{col + 1}.glf")
+            glfio.write_glf(path, "3", int(hdr["pos"].max()) + 1, hdr["pos"].astype(np.int64), hdr["ref_base"], rr)
+            if col in repeats:
+                _insert_repeats(path, "3", repeats[col], rng)
+            gif.append(f"{col + 1} {path}\n")
+            col += 1
+    (d / "ped").write_text("".join(lines)); (d / "dat").write_text("T\tGLF_Index\n"); (d / "gif").write_text("".join(gif))
+    outs = []
+    for extra in ([], ["--batched", "1"], ["--batched", "4"]):
+        out = str(d / ("out%d.pmpk" % len(outs)))
+        subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out] + extra, check=True)
+        outs.append(load_pmpk(out))
+    ref = outs[0]
+    assert len(ref.hdr) > 2400 and int(np.sum(np.diff(ref.hdr["pos"].astype(np.int64)) == 0)) >= 1, "the one-site reader saw no repeated position"
+    for o in outs[1:]:
+        assert len(o.hdr) == len(ref.hdr), (len(o.hdr), len(ref.hdr))
+        assert np.array_equal(o.hdr, ref.hdr) and np.array_equal(o.recs, ref.recs)
+
+
 def test_synthetic_generator_is_seeded_and_well_formed():
     ped = synth.concat(synth.trios(3), synth.families([4, 1]))
     h1, r1 = synth.generate_sites(ped, 500, 11, cfg=synth.SynthConfig(poly_boost=30))

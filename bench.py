@@ -344,7 +344,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from polymutt_b200 import Engine, capi, synth
+    from polymutt_b200 import Engine, capi, shard, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -374,14 +374,17 @@ def main():
     if args.force_wide_plan:
         eng.force_wide_plan(*[int(x) for x in args.force_wide_plan.split(",")])
 
-    # ---- synthetic batches, generated on the device; rank r owns sites [r*R*S, (r+1)*R*S) of the job ----
+    # ---- synthetic batches, generated on the device; rank r owns a contiguous range of the job's world*R*S sites
+    # (polymutt_b200/shard.py, the logic the world-size-2 gloo test covers) ----
+    job_lo, job_hi = shard.site_range(world * R * S, rank, world)
+    assert job_hi - job_lo == R * S
     gi = lambda a, b: torch.where(a < b, (a - 1) * (10 - a) // 2 + (b - a), (b - 1) * (10 - b) // 2 + (a - b))
     batches = []
     for b in range(R):
         hdr = torch.empty((S, 8), dtype=torch.uint8, device=dev)
         recs = torch.empty((S, npers, 16), dtype=torch.uint8, device=dev)
         synth.generate_sites(ped, S, seed=SEED + 1000 * rank + b, device=dev, out_hdr=hdr, out_recs=recs, chunk=max(256, (1 << 24) // npers),
-                             pos0=(rank * R + b) * S, cfg=synth.SynthConfig(poly_boost=50.0) if vcf else None)
+                             pos0=job_lo + b * S, cfg=synth.SynthConfig(poly_boost=50.0) if vcf else None)
         mono = None
         if vcf:
             # a VCF record of the site: (REF, ALT) = (ref, its transition), the three PLs of that pair kept, the rest cleared;
@@ -440,11 +443,8 @@ def main():
     eng.sync()
     main_ms, total_ms, launches_per_step = eng.last_timing()
 
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * K * S / (ms_max * 1e-3)
+    # max over ranks of the device time, sum over ranks of the sites -> whole-job sites/s
+    ms_max, _, value = shard.reduce_timing(ms, K * S, dist if world > 1 else None, dev)
 
     # ---- e2e through the host-buffer C-ABI call, pinned host memory: every rank at the same time (they share the
     # host's memory and PCIe root complexes), whole-job value = all ranks' sites / the slowest rank's time ----

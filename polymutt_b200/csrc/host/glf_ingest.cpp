@@ -13,10 +13,51 @@
 #include <cstring>
 #include <stdexcept>
 #include <thread>
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <tmmintrin.h>
+#endif
 
 namespace pmh {
 
 static const uint8_t kTranslateBase[16] = {0, 1, 2, 0, 3, 0, 0, 0, 4, 0, 0, 0, 0, 0, 0, 0};  // core/glfHandler.cpp:4
+
+// 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
+// 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) for a run of records of one stream that sit at consecutive
+// rows of the batch (no position compares: the caller has established the run).  dst advances by one row per record.
+static void convert_run_scalar(const unsigned char *raw, const uint32_t *op, size_t count, unsigned char *dst, size_t stride) {
+  for (size_t i = 0; i < count; i++, dst += stride) {
+    const unsigned char *rec = raw + op[i];
+    uint64_t lo8, hi8;
+    uint32_t dm;
+    uint16_t lk89;
+    memcpy(&lo8, rec + 10, 8);
+    memcpy(&lk89, rec + 18, 2);
+    memcpy(&dm, rec + 5, 4);
+    hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
+    memcpy(dst, &lo8, 8);
+    memcpy(dst + 8, &hi8, 8);
+  }
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+// the same with one 16-byte load of record bytes 4..19, one byte shuffle and one store per record
+__attribute__((target("ssse3"))) static void convert_run_ssse3(const unsigned char *raw, const uint32_t *op, size_t count, unsigned char *dst, size_t stride) {
+  const __m128i pick = _mm_setr_epi8(6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 1, 2, 3, 5, (char)0x80, (char)0x80);
+  for (size_t i = 0; i < count; i++, dst += stride) {
+    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i *>(raw + op[i] + 4));
+    _mm_storeu_si128(reinterpret_cast<__m128i *>(dst), _mm_shuffle_epi8(v, pick));
+  }
+}
+#endif
+typedef void (*ConvertRun)(const unsigned char *, const uint32_t *, size_t, unsigned char *, size_t);
+static bool g_portable_convert = false;
+void GlfBatchReader::use_portable_convert(bool on) { g_portable_convert = on; }
+static ConvertRun pick_convert_run() {
+#if defined(__x86_64__) && defined(__GNUC__)
+  static const bool have_ssse3 = __builtin_cpu_supports("ssse3");
+  if (have_ssse3 && !g_portable_convert) return convert_run_ssse3;
+#endif
+  return convert_run_scalar;
+}
 
 static double g_t[4];
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -334,57 +375,52 @@ size_t GlfBatchReader::next_batch(pm_site_hdr *hdr, pm_person_site *out, size_t 
       k.op = s.off.data() + s.head; k.raw = s.raw.data();
       k.prio = ((c == lead_) ? 0u : (uint32_t)c + 1u) << 8;
     }
-    // 20-byte glfEntry (core/glfHandler.h:21-42: type/ref, offset u32, depth:24 | minLLK:8, mapQ, lk[10]) ->
-    // 16-byte pm_person_site (lk[10], depth[3], mapQ, pad[2]) as two 8-byte words (little endian)
-    auto convert = [](const unsigned char *rec, unsigned char *dst) {
-      uint64_t lo8, hi8;
-      uint32_t dm;
-      uint16_t lk89;
-      memcpy(&lo8, rec + 10, 8);
-      memcpy(&lk89, rec + 18, 2);
-      memcpy(&dm, rec + 5, 4);
-      hi8 = (uint64_t)lk89 | ((uint64_t)(dm & 0xffffffu) << 16) | ((uint64_t)rec[9] << 40);
-      memcpy(dst, &lo8, 8);
-      memcpy(dst + 8, &hi8, 8);
-    };
+    const ConvertRun convert_run = pick_convert_run();
+    const int32_t *const rowpos = rowpos_.data();
+    const size_t stride = np * sizeof(pm_person_site);
     for (size_t r0 = 0; r0 < n; r0 += RB) {
       const size_t r1 = std::min(n, r0 + RB), m = r1 - r0;
+      const int32_t *const rp = rowpos + r0;
+      uint32_t *const ownr = own + r0;
+      // The reference base of a row comes from the lowest column that has a record there (the lead stream is the lowest
+      // live column).  The thread goes through its columns in increasing order, so the first record it sees at a row
+      // settles the row; once every row of the block is settled the columns that follow skip the bookkeeping.
+      size_t unowned = m;
       for (int c0 = lo; c0 < hi; c0 += CW) {
         const int cw = std::min(CW, hi - c0);
         // One column (stream) at a time through the block's rows, its cursor in registers; the four columns of a tile write
-        // the same 64 cache lines one after the other.  (On 8 cores here, 3,000 streams: fill 0.043-0.047 s per 6,000 sites
-        // against 0.052-0.083 s with the rows outermost inside the tile and the cursors re-read per record.)
+        // the same 64 cache lines one after the other.
         for (int j = 0; j < cw; j++) {
           Cur &k = cur[(size_t)(c0 + j - lo)];
           const int32_t *pp = k.pp, *const pe = k.pe;
           const uint32_t *op = k.op;
           const unsigned char *const raw = k.raw;
           unsigned char *dst = reinterpret_cast<unsigned char *>(out + r0 * np + (size_t)(c0 + j));
-          const size_t stride = np * sizeof(pm_person_site);
-          uint32_t *const ownr = own + r0;
-          if ((size_t)(pe - pp) >= m && pp[0] == rowpos_[r0] && pp[m - 1] == rowpos_[r1 - 1]) {
-            // the stream has a record at every row of the block (both position lists increase strictly and the stream's
-            // positions are among the rows'): no compares
-            const uint32_t prio = k.prio;
-            for (size_t i = 0; i < m; i++, dst += stride) {
-              const unsigned char *rec = raw + op[i];
-              convert(rec, dst);
-              const uint32_t v = prio | kTranslateBase[rec[0] & 0xf];
-              if (v < ownr[i]) ownr[i] = v;
-            }
-            pp += m; op += m;
-          } else {
-            for (size_t i = 0; i < m; i++, dst += stride) {
-              if (pp < pe && *pp == rowpos_[r0 + i]) {
-                const unsigned char *rec = raw + *op;
-                convert(rec, dst);
-                const uint32_t v = k.prio | kTranslateBase[rec[0] & 0xf];
-                if (v < ownr[i]) ownr[i] = v;
-                pp++; op++;
-              } else {
-                memset(dst, 0, sizeof(pm_person_site));
+          // Runs of rows at which the stream has a record, separated by single rows at which it has none.  Both position
+          // lists increase strictly and the stream's positions are among the rows', so "the stream's L-th pending record
+          // sits at the L-th row from here" holds for a prefix of L and fails from there on: the end of a run is found by
+          // bisection, and a stream with a record at every row left (the common case) by one compare.
+          size_t i = 0;
+          while (i < m) {
+            const size_t lim = std::min(m - i, (size_t)(pe - pp));
+            size_t run = lim;
+            if (lim > 0 && pp[lim - 1] != rp[i + lim - 1]) {
+              size_t ok = 0, bad = lim - 1;  // records [0, ok) match; record `bad` does not
+              while (ok < bad) {
+                const size_t mid = (ok + bad) / 2;
+                if (pp[mid] == rp[i + mid]) ok = mid + 1; else bad = mid;
               }
+              run = ok;
             }
+            if (run) {
+              convert_run(raw, op, run, dst, stride);
+              if (unowned) {
+                for (size_t q = 0; q < run; q++)
+                  if (ownr[i + q] == UINT32_MAX) { ownr[i + q] = k.prio | kTranslateBase[raw[op[q]] & 0xf]; unowned--; }
+              }
+              pp += run; op += run; i += run; dst += run * stride;
+            }
+            if (i < m) { memset(dst, 0, sizeof(pm_person_site)); i++; dst += stride; }  // no record of this stream at this row
           }
           k.pp = pp; k.op = op;
         }

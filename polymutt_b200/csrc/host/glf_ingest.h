@@ -37,6 +37,9 @@ class GlfBatchReader {
   const std::string &label() const { return label_; }
   int max_position() const { return max_position_; }
   int n_person() const { return (int)streams_.size(); }
+  // The record conversion has an SSSE3 form (chosen at run time where the CPU has it) and a portable one; this switches
+  // every reader of the process to the portable form (pm-tools pack --portable: the tests compare the two).
+  static void use_portable_convert(bool on);
 
  private:
   struct Stream {

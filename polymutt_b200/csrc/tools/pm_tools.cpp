@@ -47,6 +47,7 @@ static int do_pack(int argc, char **argv) {
   for (int i = 2; i + 1 < argc; i += 2) {
     std::string k = argv[i];
     if (k == "--batched") batched = atoi(argv[i + 1]);
+    if (k == "--portable") GlfBatchReader::use_portable_convert(atoi(argv[i + 1]) != 0);  // --portable 1: no SSSE3 in the record conversion
     if (k == "-p") ped_path = argv[i + 1];
     else if (k == "-d") dat_path = argv[i + 1];
     else if (k == "-g") gif_path = argv[i + 1];

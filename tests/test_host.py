@@ -214,7 +214,7 @@ def test_batched_multithreaded_ingest_equals_the_one_site_at_a_time_merge(tools_
     (d / "gif").write_text("".join(l for l in gif if not l.startswith("10 ")))
     (d / "ped").write_text("".join(l.rsplit("\t", 1)[0] + "\t0\n" if l.endswith("\t10\n") else l for l in lines))
     outs = []
-    for extra in ([], ["--batched", "1"], ["--batched", "3"]):
+    for extra in ([], ["--batched", "1"], ["--batched", "3"], ["--batched", "2", "--portable", "1"]):   # --portable: the record conversion without SSSE3
         out = str(d / ("outb%d.pmpk" % len(outs)))
         subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out] + extra,
                        check=True, stderr=subprocess.DEVNULL)
@@ -301,7 +301,7 @@ def test_batched_ingest_walks_through_repeated_positions_like_the_reference(case
             col += 1
     (d / "ped").write_text("".join(lines)); (d / "dat").write_text("T\tGLF_Index\n"); (d / "gif").write_text("".join(gif))
     outs = []
-    for extra in ([], ["--batched", "1"], ["--batched", "4"]):
+    for extra in ([], ["--batched", "1"], ["--batched", "4"], ["--batched", "3", "--portable", "1"]):
         out = str(d / ("out%d.pmpk" % len(outs)))
         subprocess.run([U.PM_TOOLS, "pack", "-p", str(d / "ped"), "-d", str(d / "dat"), "-g", str(d / "gif"), "-o", out] + extra, check=True)
         outs.append(load_pmpk(out))

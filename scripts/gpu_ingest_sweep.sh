@@ -1,5 +1,6 @@
-# Host GLF ingest on the GPU box's cores: 3,000 uncompressed GLFs (1,000 trios), block size of the fill loop and
-# non-temporal stores, three runs each (pm-tools ingest-bench; no GPU work).
+# Host GLF ingest on the GPU box's cores: 3,000 uncompressed GLFs (1,000 trios), thread counts 1..all, three runs each
+# (pm-tools ingest-bench; no GPU work).  (The round-2 sweep of the fill loop's row-block size and of non-temporal stores,
+# profiles/r02_host_ingest_sweep.txt, used build-time switches that are gone.)
 mkdir -p gpurun_out
 python - <<'PY'
 import sys, time
@@ -12,13 +13,9 @@ t = time.time(); glfio.write_run_dir('/tmp/ing', ped, hdr, recs); print('wrote',
 PY
 nproc
 cd /tmp/ing
-for thr in 8 16 0; do
-for cfg in "64 1" "64 0" "512 1" "4096 1" "4096 0"; do
-  set -- $cfg
-  if [ "$2" = "0" ]; then export PM_NO_NT=1; else unset PM_NO_NT; fi
+for thr in 1 4 8 16 0; do
   for i in 1 2 3; do
-    echo -n "threads=$thr RB=$1 NT=$2: "
-    PM_RB=$1 PM_TIMING=1 $GRAFT_REPO_ROOT/polymutt_b200/bin/pm-tools ingest-bench -p run.ped -d run.dat -g run.gif --batched $thr --batch 4096 2>&1 | grep -o 'decode [0-9.]* s\|fill [0-9.]* s\|sites_per_s": [0-9]*' | tr '\n' ' '; echo
+    echo -n "threads=$thr: "
+    PM_TIMING=1 $GRAFT_REPO_ROOT/polymutt_b200/bin/pm-tools ingest-bench -p run.ped -d run.dat -g run.gif --batched $thr --batch 4096 2>&1 | grep -o 'decode [0-9.]* s\|fill [0-9.]* s\|sites_per_s": [0-9]*' | tr '\n' ' '; echo
   done
-done
 done
